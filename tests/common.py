@@ -1,0 +1,62 @@
+"""Shared helpers for the parity tests: golden loading, stream regeneration, row comparison."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from oracle.streams import bench_stream, stress_embeddings, stress_stream
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+BYTETRACK_YAML = dict(min_conf=0.1, track_thresh=0.6, track_buffer=30, match_thresh=0.9, frame_rate=30)
+BOTSORT_YAML = dict(
+    track_high_thresh=0.6296854875023994, track_low_thresh=0.1014392537025336,
+    new_track_thresh=0.6246494191492591, track_buffer=40, match_thresh=0.7722224024589055,
+    proximity_thresh=0.6084297894561342, appearance_thresh=0.6188818853936099,
+    unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
+    unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329, fuse_first_associate=True,
+    frame_rate=30, with_reid=True)
+
+# name -> (tracker kind, kwargs, frames factory, embeddings factory or None)
+CASES = {
+    "bytetrack_bench64": ("bytetrack", BYTETRACK_YAML, lambda: bench_stream(64, 300)[1], None),
+    "bytetrack_stress96": ("bytetrack", BYTETRACK_YAML, lambda: stress_stream(96, 300), None),
+    "bytetrack_stress48_gaps": ("bytetrack", BYTETRACK_YAML,
+                                lambda: stress_stream(48, 200, seed=19, n_classes=3, empty_every=37), None),
+    "botsort_stress96": ("botsort", BOTSORT_YAML, lambda: stress_stream(96, 300),
+                         lambda fr: stress_embeddings(fr, 96)),
+    "botsort_stress48_gaps": ("botsort", BOTSORT_YAML,
+                              lambda: stress_stream(48, 200, seed=19, n_classes=3, empty_every=37),
+                              lambda fr: stress_embeddings(fr, 48, seed=5)),
+    "botsort_noreid_stress64": ("botsort", dict(with_reid=False), lambda: stress_stream(64, 200, seed=23), None),
+    "botsort_bench256": ("botsort", BOTSORT_YAML, lambda: bench_stream(256, 40)[1],
+                         lambda fr: stress_embeddings(fr, 256, seed=3)),
+}
+
+
+def load_golden(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    rows, off = z["rows"], z["offsets"]
+    frames = [rows[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    snaps = {}
+    for k in z.files:
+        if k.startswith("snap") and k.endswith("_ids"):
+            f = int(k[4:-4])
+            snaps[f] = (z[k], z[f"snap{f}_mean"], z[f"snap{f}_cov"])
+    return frames, snaps
+
+
+def assert_rows_match(got, want, frame, *, exact_boxes=False, box_rtol=1e-4):
+    """ids / det_ind / conf / cls bit-exact; boxes bit-exact or within the stated relative tolerance."""
+    got = np.asarray(got, dtype=np.float32).reshape(-1, 8)
+    want = np.asarray(want, dtype=np.float32).reshape(-1, 8)
+    assert got.shape == want.shape, f"frame {frame}: {got.shape} vs {want.shape}"
+    if got.size == 0:
+        return
+    assert np.array_equal(got[:, 4:], want[:, 4:]), f"frame {frame}: id/conf/cls/det_ind differ"
+    if exact_boxes:
+        assert np.array_equal(got[:, :4], want[:, :4]), f"frame {frame}: boxes differ"
+    else:
+        np.testing.assert_allclose(got[:, :4], want[:, :4], rtol=box_rtol, atol=1e-3,
+                                   err_msg=f"frame {frame}: boxes")

@@ -1,0 +1,107 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) in this container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Inputs are regenerated from seeds by oracle/streams.py at test time; only the reference OUTPUTS are stored
+(per-frame `(M,8)` rows, plus Kalman mean/cov snapshots keyed by track id on a few frames).  The reference is
+imported through tests/golden/refharness.py (stubs for gdown/ftfy/yacs; `lap` -> oracle/lap.py because lapx is
+not installed -- SURVEY section 8(c)); CMC is disabled; the ByteTrack id counter is reset per
+stream.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(HERE.parents[1]))
+
+import refharness  # noqa: E402
+
+refharness.install_reference()
+
+from boxmot.trackers.bbox.botsort.botsort import BotSort  # noqa: E402
+from boxmot.trackers.bbox.bytetrack import basetrack as bt_base  # noqa: E402
+from boxmot.trackers.bbox.bytetrack.bytetrack import ByteTrack  # noqa: E402
+
+from oracle.streams import bench_stream, stress_embeddings, stress_stream  # noqa: E402
+
+BYTETRACK_YAML = dict(min_conf=0.1, track_thresh=0.6, track_buffer=30, match_thresh=0.9, frame_rate=30)
+BOTSORT_YAML = dict(
+    track_high_thresh=0.6296854875023994, track_low_thresh=0.1014392537025336,
+    new_track_thresh=0.6246494191492591, track_buffer=40, match_thresh=0.7722224024589055,
+    proximity_thresh=0.6084297894561342, appearance_thresh=0.6188818853936099,
+    unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
+    unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329, fuse_first_associate=True,
+    frame_rate=30, with_reid=True)
+SNAP_FRAMES = (1, 2, 10, 50, 150, 299)
+
+
+def _snapshot(tracker):
+    ids, means, covs = [], [], []
+    for t in list(tracker.active_tracks) + list(tracker.lost_stracks):
+        ids.append(t.id)
+        means.append(np.asarray(t.mean, dtype=np.float64))
+        covs.append(np.asarray(t.covariance, dtype=np.float64))
+    return (np.asarray(ids, dtype=np.int64), np.asarray(means).reshape(-1, 8), np.asarray(covs).reshape(-1, 8, 8))
+
+
+def run(tracker, frames, img, embs=None):
+    rows, offsets, snaps = [], [0], {}
+    for f, dets in enumerate(frames):
+        e = None if embs is None else embs[f].copy()
+        out = np.asarray(tracker.update(dets.copy(), img, e) if e is not None else tracker.update(dets.copy(), img))
+        out = out.reshape(-1, 8) if out.size else np.empty((0, 8), np.float32)
+        rows.append(out.astype(np.float32))
+        offsets.append(offsets[-1] + len(out))
+        if (f + 1) in SNAP_FRAMES:
+            ids, m, c = _snapshot(tracker)
+            snaps[f"snap{f + 1}_ids"] = ids
+            snaps[f"snap{f + 1}_mean"] = m
+            snaps[f"snap{f + 1}_cov"] = c
+    return dict(rows=np.concatenate(rows, 0), offsets=np.asarray(offsets, np.int64), **snaps)
+
+
+def main():
+    img = np.zeros((360, 640, 3), np.uint8)
+
+    bt_base.BaseTrack._count = 0
+    _, frames = bench_stream(64, 300)
+    np.savez_compressed(HERE / "bytetrack_bench64.npz", **run(ByteTrack(**BYTETRACK_YAML), frames, img))
+
+    bt_base.BaseTrack._count = 0
+    frames = stress_stream(96, 300)
+    np.savez_compressed(HERE / "bytetrack_stress96.npz", **run(ByteTrack(**BYTETRACK_YAML), frames, img))
+
+    bt_base.BaseTrack._count = 0
+    frames = stress_stream(48, 200, seed=19, n_classes=3, empty_every=37)
+    np.savez_compressed(HERE / "bytetrack_stress48_gaps.npz", **run(ByteTrack(**BYTETRACK_YAML), frames, img))
+
+    frames = stress_stream(96, 300)
+    embs = stress_embeddings(frames, 96)
+    np.savez_compressed(HERE / "botsort_stress96.npz",
+                        **run(BotSort(reid_model=None, use_cmc=False, **BOTSORT_YAML), frames, img, embs))
+
+    frames = stress_stream(48, 200, seed=19, n_classes=3, empty_every=37)
+    embs = stress_embeddings(frames, 48, seed=5)
+    np.savez_compressed(HERE / "botsort_stress48_gaps.npz",
+                        **run(BotSort(reid_model=None, use_cmc=False, **BOTSORT_YAML), frames, img, embs))
+
+    # constructor defaults instead of YAML defaults, no appearance
+    frames = stress_stream(64, 200, seed=23)
+    np.savez_compressed(HERE / "botsort_noreid_stress64.npz",
+                        **run(BotSort(reid_model=None, use_cmc=False, with_reid=False), frames, img))
+
+    _, frames = bench_stream(256, 40)
+    embs = stress_embeddings(frames, 256, seed=3)
+    np.savez_compressed(HERE / "botsort_bench256.npz",
+                        **run(BotSort(reid_model=None, use_cmc=False, **BOTSORT_YAML), frames, img, embs))
+    for p in sorted(HERE.glob("*.npz")):
+        print(p.name, p.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()
