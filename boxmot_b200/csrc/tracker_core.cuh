@@ -1,0 +1,971 @@
+// tracker_core.cuh -- the per-stream, per-frame track update for the STrack family (ByteTrack, BoT-SORT).
+//
+// One CTA owns one video stream and runs the whole frame: detection split, Kalman predict over the pool,
+// IoU / appearance cost build, three linear-assignment rounds, Kalman update, EMA appearance update, the
+// track state machine and output row assembly.  All track state is structure-of-arrays in HBM and never
+// leaves the device; a frame costs one launch for every stream resident on the GPU.
+//
+// What it replaces in the reference (relative to /root/reference/boxmot):
+//   trackers/bbox/bytetrack/bytetrack.py:259-447    ByteTrack._update_impl (+ joint/sub/remove_duplicate)
+//   trackers/bbox/botsort/botsort.py:177-500        BotSort._update_impl
+//   trackers/bbox/botsort/botsort_track.py:16-115,232-282   STrack feature EMA, class vote, update paths
+//   motion/kalman_filters/base.py:234-355 + xyah.py / xywh.py  initiate / multi_predict / project / update
+//   trackers/association/matching.py:28-147         iou_distance, embedding gates, fuse_score, lapjv
+//   trackers/association/iou.py:134-150             iou_batch
+//
+// The same source compiles for the host (BMB_HOSTSIM, one "thread") so the control flow can be checked
+// against the golden vectors in a container without a GPU; that build lives under tests/ only and is never
+// linked into the product library.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(BMB_HOSTSIM)
+#define BMB_FN __device__ __forceinline__
+#define BMB_TID ((int)threadIdx.x)
+#define BMB_NT ((int)blockDim.x)
+#define BMB_SYNC() __syncthreads()
+#define BMB_LANE ((int)(threadIdx.x & 31))
+#define BMB_NL 32
+#define BMB_WARP ((int)(threadIdx.x >> 5))
+#define BMB_NW ((int)(blockDim.x >> 5))
+#define BMB_SYNCWARP() __syncwarp()
+#define BMB_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define BMB_POPC(x) __popc(x)
+#define BMB_SHFL_DOWN_D(v, o) __shfl_down_sync(0xffffffffu, (v), (o))
+#define BMB_SHFL_DOWN_I(v, o) __shfl_down_sync(0xffffffffu, (v), (o))
+#define BMB_SHFL_D(v, l) __shfl_sync(0xffffffffu, (v), (l))
+#define BMB_SHFL_I(v, l) __shfl_sync(0xffffffffu, (v), (l))
+#define BMB_SHFL_XOR_F(v, o) __shfl_xor_sync(0xffffffffu, (v), (o))
+#define BMB_DEVICE 1
+#else
+#define BMB_FN static inline
+#define BMB_TID 0
+#define BMB_NT 1
+#define BMB_SYNC() ((void)0)
+#define BMB_LANE 0
+#define BMB_NL 1
+#define BMB_WARP 0
+#define BMB_NW 1
+#define BMB_SYNCWARP() ((void)0)
+#define BMB_BALLOT(p) ((p) ? 1u : 0u)
+#define BMB_POPC(x) ((int)((x) & 1u))
+#define BMB_SHFL_DOWN_D(v, o) (v)
+#define BMB_SHFL_DOWN_I(v, o) (v)
+#define BMB_SHFL_D(v, l) (v)
+#define BMB_SHFL_I(v, l) (v)
+#define BMB_SHFL_XOR_F(v, o) (v)
+#define BMB_DEVICE 0
+#endif
+
+namespace bmb {
+
+enum { ST_NEW = 0, ST_TRACKED = 1, ST_LOST = 2, ST_REMOVED = 3 };
+enum { KIND_XYAH = 0, KIND_XYWH = 1 };
+enum { HIST_CAP = 8 };  // distinct classes remembered per track by the BoT-SORT class vote
+enum {
+    SC_N_ACTIVE = 0, SC_N_LOST, SC_FRAME, SC_NEXT_ID, SC_RING_HEAD, SC_RING_COUNT, SC_ERROR, SC_N_OUT,
+    SC_LAP_STEPS, SC_COUNT = 16
+};
+enum { ERR_NONE = 0, ERR_TRACK_CAPACITY = 1, ERR_CLS_HIST = 2, ERR_DET_CAPACITY = 3 };
+
+struct TrkCfg {
+    int kind;             // KIND_XYAH (ByteTrack) / KIND_XYWH (BoT-SORT)
+    int with_reid;        // appearance gates active
+    int fuse_first;       // fuse_score in the first association round
+    int proximity_mask;   // BoT-SORT proximity gate (rounds 1 and 3)
+    int max_time_lost;
+    int removed_cap;      // 0: unbounded removed set (ByteTrack); >0: deque(maxlen) of ids (BoT-SORT)
+    int feat_dim;
+    int cap_tracks;       // CT
+    int cap_dets;         // CD
+    int vote_cls;         // BoT-SORT class vote
+    double high_thresh, low_thresh;
+    float new_thresh_f32;  // np.float32 conf < python float compares in float32 (NEP 50)
+    double match1, match2, match3;
+    double proximity, appearance, unc_emb_scale;
+};
+
+struct TrkStream {
+    // persistent track table (slot indexed)
+    double* mean;  // [CT][8]
+    double* cov;   // [CT][64]
+    int* state;
+    int* activated;
+    int* id;
+    int* frame_id;
+    int* start_frame;
+    int* tracklet_len;
+    float* conf;
+    float* cls;
+    float* det_ind;
+    float* smooth;     // [CT][F]
+    float* hist_cls;   // [CT][HIST_CAP]
+    float* hist_sum;   // [CT][HIST_CAP]
+    int* hist_n;       // [CT]
+    int* in_removed;   // [CT]   unbounded removed set as a slot flag
+    int* removed_ring; // [removed_cap] ids
+    int* active;       // [CT] ordered slot list
+    int* lost;         // [CT] ordered slot list
+    int* scalars;      // [SC_COUNT]
+    // per-frame inputs
+    const float* dets;  // [CD][6]
+    const int* n_dets;  // [1]
+    // per-frame scratch
+    float* dxywh;   // [CD][4]
+    float* dmeas;   // [CD][4]
+    float* dxyxy;   // [CD][4]
+    float* dfeat;   // [CD][F]  detection appearance after the reference's two in-place normalisations
+    double* embd;   // [CT][CD] max(0, cosine distance(smooth[slot], dfeat[det])) by the wide kernel
+    double* cost;   // [CT][CD]
+    double* txyxy;  // [CT][4]
+    int* first;     // [CD]
+    int* second;    // [CD]
+    int* rest;      // [CD]
+    int* pool;      // [CT]
+    int* unconf;    // [CT]
+    int* rtracked;  // [CT]
+    int* act_l;     // [CT+CD]
+    int* refind_l;  // [CT]
+    int* lostnow_l; // [CT]
+    int* remnow_l;  // [CT]
+    int* tmp_a;     // [CT]
+    int* tmp_b;     // [CT]
+    int* mark;      // [CT]
+    int* free_l;    // [CT]
+    // linear assignment scratch
+    int* lap_x;       // [CT]
+    int* lap_y;       // [CD]
+    double* lap_u;    // [CT]
+    double* lap_v;    // [CD]
+    double* lap_spc;  // [CD]
+    int* lap_path;    // [CD]
+    int* lap_insc;    // [CD]
+    int* lap_tl;      // [CD]
+    int* lap_sc;      // [CD]
+    int* csr_ptr;     // [CT+1]
+    int* csr_col;     // [CT*CD]
+    // output
+    float* out;  // [CD][8]
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small geometry helpers (float32 detection geometry exactly as numpy evaluates it)
+// ---------------------------------------------------------------------------------------------------
+BMB_FN void det_geometry(const TrkCfg& c, const float* d, float* xywh, float* meas, float* xyxy) {
+    // xyxy2xywh on a float32 row (trackers/common/geometry.py:10-24)
+    float cx = (d[0] + d[2]) / 2.0f;
+    float cy = (d[1] + d[3]) / 2.0f;
+    float w = d[2] - d[0];
+    float h = d[3] - d[1];
+    xywh[0] = cx; xywh[1] = cy; xywh[2] = w; xywh[3] = h;
+    if (c.kind == KIND_XYAH) {
+        // xywh2tlwh then tlwh2xyah (bytetrack.py:37-40)
+        float t0 = cx - w / 2.0f;
+        float t1 = cy - h / 2.0f;
+        meas[0] = t0 + (w / 2.0f);
+        meas[1] = t1 + (h / 2.0f);
+        meas[2] = w / h;
+        meas[3] = h;
+    } else {
+        meas[0] = cx; meas[1] = cy; meas[2] = w; meas[3] = h;
+    }
+    // STrack.xyxy of a not-yet-activated detection: xywh2xyxy(self.xywh) in float32
+    xyxy[0] = cx - w / 2.0f;
+    xyxy[1] = cy - h / 2.0f;
+    xyxy[2] = cx + w / 2.0f;
+    xyxy[3] = cy + h / 2.0f;
+}
+
+BMB_FN void track_xyxy(const TrkCfg& c, const double* m, double* o) {
+    double w = m[2], h = m[3];
+    if (c.kind == KIND_XYAH) w = w * h;
+    o[0] = m[0] - w / 2.0;
+    o[1] = m[1] - h / 2.0;
+    o[2] = m[0] + w / 2.0;
+    o[3] = m[1] + h / 2.0;
+}
+
+// 1 - IoU between a float64 track box and a float32 detection box; numpy computes the detection area in
+// float32 before promotion (association/iou.py:134-150).
+BMB_FN double iou_dist_td(const double* a, const float* b) {
+    double b0 = (double)b[0], b1 = (double)b[1], b2 = (double)b[2], b3 = (double)b[3];
+    double xx1 = a[0] > b0 ? a[0] : b0;
+    double yy1 = a[1] > b1 ? a[1] : b1;
+    double xx2 = a[2] < b2 ? a[2] : b2;
+    double yy2 = a[3] < b3 ? a[3] : b3;
+    double w = xx2 - xx1; w = w > 0.0 ? w : 0.0;
+    double h = yy2 - yy1; h = h > 0.0 ? h : 0.0;
+    double wh = w * h;
+    double area_a = (a[2] - a[0]) * (a[3] - a[1]);
+    float area_b = (b[2] - b[0]) * (b[3] - b[1]);
+    double o = wh / (area_a + (double)area_b - wh);
+    return 1.0 - o;
+}
+
+BMB_FN double iou_dist_tt(const double* a, const double* b) {
+    double xx1 = a[0] > b[0] ? a[0] : b[0];
+    double yy1 = a[1] > b[1] ? a[1] : b[1];
+    double xx2 = a[2] < b[2] ? a[2] : b[2];
+    double yy2 = a[3] < b[3] ? a[3] : b[3];
+    double w = xx2 - xx1; w = w > 0.0 ? w : 0.0;
+    double h = yy2 - yy1; h = h > 0.0 ? h : 0.0;
+    double wh = w * h;
+    double o = wh / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - wh);
+    return 1.0 - o;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Kalman filter (float64).  W_POS = 1/20, W_VEL = 1/160 as python evaluates them.
+// ---------------------------------------------------------------------------------------------------
+#define BMB_W_POS 0.05
+#define BMB_W_VEL 0.00625
+
+BMB_FN void kf_sizes(const TrkCfg& c, const double* v, double* s) {
+    if (c.kind == KIND_XYAH) { s[0] = v[3]; s[1] = v[3]; s[2] = v[3]; s[3] = v[3]; }
+    else { s[0] = v[2]; s[1] = v[3]; s[2] = v[2]; s[3] = v[3]; }
+}
+
+// base.py:234-244 + xyah.py:22-37 / xywh.py:22-36; measurement arrives as float32 and is widened first.
+BMB_FN void kf_initiate(const TrkCfg& c, const float* meas32, double* mean, double* cov) {
+    double m[4] = {(double)meas32[0], (double)meas32[1], (double)meas32[2], (double)meas32[3]};
+    double s[4];
+    kf_sizes(c, m, s);
+    double sd[8];
+    const double two_wp = 2 * BMB_W_POS, ten_wv = 10 * BMB_W_VEL;
+    for (int i = 0; i < 4; ++i) { sd[i] = two_wp * s[i]; sd[4 + i] = ten_wv * s[i]; }
+    if (c.kind == KIND_XYAH) { sd[2] = 1e-2; sd[6] = 1e-5; }
+    for (int i = 0; i < 64; ++i) cov[i] = 0.0;
+    for (int i = 0; i < 8; ++i) cov[i * 8 + i] = sd[i] * sd[i];
+    for (int i = 0; i < 4; ++i) { mean[i] = m[i]; mean[4 + i] = 0.0; }
+    if (mean[2] < 1e-4) mean[2] = 1e-4;
+    if (mean[3] < 1e-4) mean[3] = 1e-4;
+}
+
+// base.py:311-327 (+ STrack.multi_predict velocity zeroing for non-Tracked tracks).  In place.
+BMB_FN void kf_predict(const TrkCfg& c, int tracked, double* mean, double* cov) {
+    if (!tracked) {
+        if (c.kind == KIND_XYAH) mean[7] = 0.0;
+        else { mean[6] = 0.0; mean[7] = 0.0; }
+    }
+    double s[4], q[8];
+    kf_sizes(c, mean, s);   // process noise from the PRIOR mean
+    for (int i = 0; i < 4; ++i) {
+        double sp = BMB_W_POS * s[i], sv = BMB_W_VEL * s[i];
+        q[i] = sp * sp; q[4 + i] = sv * sv;
+    }
+    if (c.kind == KIND_XYAH) { q[2] = 1e-2 * 1e-2; q[6] = 1e-5 * 1e-5; }
+    for (int i = 0; i < 4; ++i) mean[i] = mean[i] + mean[4 + i];
+    // left = F P ; P' = left F^T + Q, with the reference's summation order
+    double L[64];
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) L[i * 8 + j] = (i < 4) ? (cov[i * 8 + j] + cov[(i + 4) * 8 + j]) : cov[i * 8 + j];
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) {
+            double v = (j < 4) ? (L[i * 8 + j] + L[i * 8 + j + 4]) : L[i * 8 + j];
+            if (i == j) v = v + q[i];
+            cov[i * 8 + j] = v;
+        }
+    if (mean[2] < 1e-4) mean[2] = 1e-4;
+    if (mean[3] < 1e-4) mean[3] = 1e-4;
+}
+
+// base.py:286-309,329-355: S = HPH^T + R, Cholesky, K = P H^T S^-1, x += K y, P -= K S K^T (non-Joseph).
+BMB_FN void kf_update(const TrkCfg& c, const float* meas32, double* mean, double* cov) {
+    double s[4], S[16], Lc[16];
+    kf_sizes(c, mean, s);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) S[i * 4 + j] = cov[i * 8 + j];
+    for (int i = 0; i < 4; ++i) {
+        double sd = BMB_W_POS * s[i];
+        if (c.kind == KIND_XYAH && i == 2) sd = 1e-1;
+        sd = 1.0 * sd;  // (1 - confidence) with confidence = 0
+        S[i * 4 + i] = S[i * 4 + i] + sd * sd;
+    }
+    // lower Cholesky S = Lc Lc^T
+    for (int i = 0; i < 16; ++i) Lc[i] = 0.0;
+    for (int j = 0; j < 4; ++j) {
+        double d = S[j * 4 + j];
+        for (int k = 0; k < j; ++k) d -= Lc[j * 4 + k] * Lc[j * 4 + k];
+        d = sqrt(d);
+        Lc[j * 4 + j] = d;
+        for (int i = j + 1; i < 4; ++i) {
+            double v = S[i * 4 + j];
+            for (int k = 0; k < j; ++k) v -= Lc[i * 4 + k] * Lc[j * 4 + k];
+            Lc[i * 4 + j] = v / d;
+        }
+    }
+    // K^T (4x8) = S^-1 (P H^T)^T ; column r of (P H^T)^T is row r of P restricted to the first 4 columns
+    double KT[32];
+    for (int r = 0; r < 8; ++r) {
+        double y[4];
+        for (int i = 0; i < 4; ++i) {
+            double v = cov[r * 8 + i];
+            for (int k = 0; k < i; ++k) v -= Lc[i * 4 + k] * y[k];
+            y[i] = v / Lc[i * 4 + i];
+        }
+        for (int i = 3; i >= 0; --i) {
+            double v = y[i];
+            for (int k = i + 1; k < 4; ++k) v -= Lc[k * 4 + i] * KT[k * 8 + r];
+            KT[i * 8 + r] = v / Lc[i * 4 + i];
+        }
+    }
+    double inn[4];
+    for (int i = 0; i < 4; ++i) inn[i] = (double)meas32[i] - mean[i];
+    for (int r = 0; r < 8; ++r) {
+        double acc = 0.0;
+        for (int i = 0; i < 4; ++i) acc += inn[i] * KT[i * 8 + r];
+        mean[r] = mean[r] + acc;
+    }
+    // M = S K^T (4x8); P -= K M
+    double M[32];
+    for (int i = 0; i < 4; ++i)
+        for (int r = 0; r < 8; ++r) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += S[i * 4 + k] * KT[k * 8 + r];
+            M[i * 8 + r] = acc;
+        }
+    for (int a = 0; a < 8; ++a)
+        for (int b = 0; b < 8; ++b) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; ++k) acc += KT[k * 8 + a] * M[k * 8 + b];
+            cov[a * 8 + b] = cov[a * 8 + b] - acc;
+        }
+    if (mean[2] < 1e-4) mean[2] = 1e-4;
+    if (mean[3] < 1e-4) mean[3] = 1e-4;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// appearance: the float32 normalisations and EMA of botsort_track.py:58-67, one warp per vector
+// ---------------------------------------------------------------------------------------------------
+BMB_FN float warp_sum_f(float v) {
+#if BMB_DEVICE
+    for (int o = 16; o > 0; o >>= 1) v += BMB_SHFL_XOR_F(v, o);
+#endif
+    return v;
+}
+
+BMB_FN float vec_norm_f32(const float* x, int n) {
+    float acc = 0.0f;
+    for (int k = BMB_LANE; k < n; k += BMB_NL) acc += x[k] * x[k];
+    acc = warp_sum_f(acc);
+    return sqrtf(acc);
+}
+
+// dst = src / ||src|| twice (update_features on a fresh STrack: feat /= norm; smooth_feat is the same array
+// and is normalised again in place).  Warp-cooperative.
+BMB_FN void feat_prepare(const float* src, float* dst, int n) {
+    float nr = vec_norm_f32(src, n);
+    for (int k = BMB_LANE; k < n; k += BMB_NL) dst[k] = src[k] / nr;
+    BMB_SYNCWARP();
+    nr = vec_norm_f32(dst, n);
+    BMB_SYNCWARP();
+    for (int k = BMB_LANE; k < n; k += BMB_NL) dst[k] = dst[k] / nr;
+    BMB_SYNCWARP();
+}
+
+// track.update_features(det.curr_feat): det feature normalised a third time in place, then the EMA.
+BMB_FN void feat_ema(float* smooth, float* dfeat, int n) {
+    float nr = vec_norm_f32(dfeat, n);
+    BMB_SYNCWARP();
+    for (int k = BMB_LANE; k < n; k += BMB_NL) {
+        float f = dfeat[k] / nr;
+        dfeat[k] = f;
+        float a = 0.9f * smooth[k];
+        float b = 0.1f * f;
+        smooth[k] = a + b;
+    }
+    BMB_SYNCWARP();
+    nr = vec_norm_f32(smooth, n);
+    BMB_SYNCWARP();
+    for (int k = BMB_LANE; k < n; k += BMB_NL) smooth[k] = smooth[k] / nr;
+    BMB_SYNCWARP();
+}
+
+// botsort_track.py:69-82
+BMB_FN void vote_cls(const TrkCfg& c, TrkStream& s, int slot, float cls, float conf) {
+    float* hc = s.hist_cls + slot * HIST_CAP;
+    float* hs = s.hist_sum + slot * HIST_CAP;
+    int n = s.hist_n[slot];
+    float best = 0.0f;
+    int seen = 0;
+    for (int k = 0; k < n; ++k) {
+        if (cls == hc[k]) { hs[k] = hs[k] + conf; seen = 1; }
+        if (hs[k] > best) { best = hs[k]; s.cls[slot] = hc[k]; }
+    }
+    if (!seen) {
+        if (n < HIST_CAP) { hc[n] = cls; hs[n] = conf; s.hist_n[slot] = n + 1; }
+        else s.scalars[SC_ERROR] = ERR_CLS_HIST;
+        s.cls[slot] = cls;
+    }
+}
+
+// max(0, cosine distance) of two float32 vectors evaluated in float64, as scipy's cdist(..., 'cosine') does
+// after widening (matching.py:85-107): 1 - u.v / (|u| |v|), cosine clipped to [-1, 1].
+BMB_FN double cosine_cost_f64(const float* a, const float* b, int n) {
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int k = 0; k < n; ++k) {
+        double x = (double)a[k], y = (double)b[k];
+        dot += x * y; na += x * x; nb += y * y;
+    }
+    double cs = dot / (sqrt(na) * sqrt(nb));
+    if (fabs(cs) > 1.0) cs = cs > 0 ? 1.0 : -1.0;
+    double d = 1.0 - cs;
+    return d > 0.0 ? d : (d != d ? d : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Linear assignment with lapjv(extend_cost=True, cost_limit=thresh) semantics (matching.py:28-43).
+//
+// lapjv pads the T x D problem to (T+D)^2 with thresh/2 everywhere outside the real block and 0 in the
+// dummy-dummy block: a real pair is worth matching iff it beats leaving both ends unmatched (thresh).  That
+// is exactly: every row either takes a real column at c[i][j] or its private "stay unmatched" column at
+// thresh.  Entries with c >= thresh can never be part of an optimum, so the graph is sparse (a track overlaps
+// few detections).  We solve it exactly with shortest augmenting paths (row by row, dual prices u/v in
+// float64) on CSR candidate lists; one warp runs the search, lanes relax candidates and reduce the frontier.
+// Unique optimum  =>  same matches as lapjv (ties have measure zero on continuous costs).
+// ---------------------------------------------------------------------------------------------------
+BMB_FN void lap_build_csr(TrkStream& s, int T, int D, int ld, double thresh) {
+    // count (parallel over rows), prefix (thread 0), fill (parallel over rows)
+    for (int i = BMB_TID; i < T; i += BMB_NT) {
+        const double* ci = s.cost + (size_t)i * ld;
+        int n = 0;
+        for (int j = 0; j < D; ++j) n += (ci[j] < thresh) ? 1 : 0;
+        s.lap_x[i] = n;  // temporarily the row count
+    }
+    BMB_SYNC();
+    if (BMB_TID == 0) {
+        int acc = 0;
+        for (int i = 0; i < T; ++i) { s.csr_ptr[i] = acc; acc += s.lap_x[i]; }
+        s.csr_ptr[T] = acc;
+    }
+    BMB_SYNC();
+    for (int i = BMB_TID; i < T; i += BMB_NT) {
+        const double* ci = s.cost + (size_t)i * ld;
+        int p = s.csr_ptr[i];
+        for (int j = 0; j < D; ++j)
+            if (ci[j] < thresh) s.csr_col[p++] = j;
+    }
+    BMB_SYNC();
+}
+
+// Called by the whole CTA; result in lap_x[0..T) (column or -1) and lap_y[0..D) (row or -1).
+BMB_FN void lap_solve(TrkStream& s, int T, int D, int ld, double thresh) {
+    if (T == 0 || D == 0) {
+        for (int i = BMB_TID; i < T; i += BMB_NT) s.lap_x[i] = -1;
+        for (int j = BMB_TID; j < D; j += BMB_NT) s.lap_y[j] = -1;
+        BMB_SYNC();
+        return;
+    }
+    lap_build_csr(s, T, D, ld, thresh);
+    for (int i = BMB_TID; i < T; i += BMB_NT) { s.lap_x[i] = -1; s.lap_u[i] = 0.0; }
+    for (int j = BMB_TID; j < D; j += BMB_NT) {
+        s.lap_y[j] = -1; s.lap_v[j] = 0.0; s.lap_spc[j] = INFINITY; s.lap_insc[j] = 0;
+    }
+    BMB_SYNC();
+    if (BMB_WARP == 0) {
+        const int lane = BMB_LANE;
+        const double INF = INFINITY;
+        int steps = 0;
+        for (int cur = 0; cur < T; ++cur) {
+            if (s.csr_ptr[cur + 1] == s.csr_ptr[cur]) continue;  // no candidate: stays unmatched
+            double minval = 0.0;
+            int i = cur;
+            int n_tl = 0, n_sc = 0;
+            int sink = -1;
+            double dmin = INF;   // cheapest "leave row r unmatched" terminal seen so far
+            int drow = -1;
+            while (true) {
+                ++steps;
+                double ui = s.lap_u[i];
+                double cand = (minval + thresh) - ui;
+                if (cand < dmin) { dmin = cand; drow = i; }
+                // relax the candidates of row i
+                const int e0 = s.csr_ptr[i], e1 = s.csr_ptr[i + 1];
+                const double* ci = s.cost + (size_t)i * ld;
+                for (int base = e0; base < e1; base += BMB_NL) {
+                    int e = base + lane;
+                    int fresh = 0;
+                    int j = -1;
+                    if (e < e1) {
+                        j = s.csr_col[e];
+                        if (!s.lap_insc[j]) {
+                            double r = ((minval + ci[j]) - ui) - s.lap_v[j];
+                            double old = s.lap_spc[j];
+                            if (r < old) {
+                                s.lap_spc[j] = r;
+                                s.lap_path[j] = i;
+                                fresh = (old == INF) ? 1 : 0;
+                            }
+                        }
+                    }
+                    unsigned m = BMB_BALLOT(fresh);
+                    if (fresh) {
+#if BMB_DEVICE
+                        int pos = n_tl + __popc(m & ((1u << lane) - 1u));
+#else
+                        int pos = n_tl;
+#endif
+                        s.lap_tl[pos] = j;
+                    }
+                    n_tl += BMB_POPC(m);
+                }
+                BMB_SYNCWARP();
+                // frontier minimum over touched, unscanned columns
+                double best = INF;
+                int bj = -1;
+                for (int k = lane; k < n_tl; k += BMB_NL) {
+                    int j = s.lap_tl[k];
+                    if (!s.lap_insc[j]) {
+                        double v = s.lap_spc[j];
+                        if (v < best || (v == best && j < bj)) { best = v; bj = j; }
+                    }
+                }
+#if BMB_DEVICE
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = BMB_SHFL_DOWN_D(best, o);
+                    int oj = BMB_SHFL_DOWN_I(bj, o);
+                    if (oj >= 0 && (bj < 0 || ov < best || (ov == best && oj < bj))) { best = ov; bj = oj; }
+                }
+                best = BMB_SHFL_D(best, 0);
+                bj = BMB_SHFL_I(bj, 0);
+#endif
+                if (bj < 0 || dmin <= best) {  // cheapest way out is to leave `drow` unmatched
+                    minval = dmin;
+                    sink = -1;
+                    break;
+                }
+                minval = best;
+                if (lane == 0) { s.lap_insc[bj] = 1; s.lap_sc[n_sc] = bj; }
+                ++n_sc;
+                BMB_SYNCWARP();
+                if (s.lap_y[bj] < 0) { sink = bj; break; }
+                i = s.lap_y[bj];
+            }
+            // dual update (lanes over the scanned columns)
+            for (int k = lane; k < n_sc; k += BMB_NL) {
+                int j = s.lap_sc[k];
+                double dj = s.lap_spc[j];
+                int r = s.lap_y[j];
+                if (r >= 0) s.lap_u[r] = s.lap_u[r] + (minval - dj);
+                s.lap_v[j] = s.lap_v[j] - (minval - dj);
+            }
+            if (lane == 0) s.lap_u[cur] = s.lap_u[cur] + minval;
+            BMB_SYNCWARP();
+            // augment (sequential walk back along the path)
+            if (lane == 0) {
+                int j;
+                bool go = true;
+                if (sink >= 0) {
+                    j = sink;
+                } else if (drow == cur) {
+                    go = false;  // cur itself stays unmatched
+                    j = -1;
+                } else {
+                    j = s.lap_x[drow];
+                    s.lap_x[drow] = -1;
+                }
+                while (go) {
+                    int r = s.lap_path[j];
+                    s.lap_y[j] = r;
+                    int prev = s.lap_x[r];
+                    s.lap_x[r] = j;
+                    j = prev;
+                    if (r == cur) go = false;
+                }
+            }
+            // reset the touched columns
+            for (int k = lane; k < n_tl; k += BMB_NL) {
+                int j = s.lap_tl[k];
+                s.lap_spc[j] = INF;
+                s.lap_insc[j] = 0;
+            }
+            BMB_SYNCWARP();
+        }
+        if (lane == 0) s.scalars[SC_LAP_STEPS] += steps;
+    }
+    BMB_SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// match application: Kalman update (thread per match), appearance EMA (warp per match), bookkeeping
+// ---------------------------------------------------------------------------------------------------
+// rows[i] = slot of LAP row i, cols[j] = detection index of LAP column j.
+BMB_FN void apply_matches(const TrkCfg& c, TrkStream& s, int T, const int* rows, const int* cols, int frame,
+                          int force_update_branch, int use_feat, int* n_act, int* n_refind) {
+    // 1) Kalman update, one thread per matched row
+    for (int i = BMB_TID; i < T; i += BMB_NT) {
+        int j = s.lap_x[i];
+        if (j < 0) continue;
+        int slot = rows[i];
+        int det = cols[j];
+        kf_update(c, s.dmeas + det * 4, s.mean + slot * 8, s.cov + slot * 64);
+    }
+    // 2) appearance EMA, one warp per matched row
+    if (use_feat) {
+        for (int i = BMB_WARP; i < T; i += BMB_NW) {
+            int j = s.lap_x[i];
+            if (j < 0) continue;
+            feat_ema(s.smooth + (size_t)rows[i] * c.feat_dim, s.dfeat + (size_t)cols[j] * c.feat_dim, c.feat_dim);
+        }
+    }
+    BMB_SYNC();
+    // 3) bookkeeping in ascending row order (list order is output order)
+    if (BMB_TID == 0) {
+        int na = *n_act, nr = *n_refind;
+        for (int i = 0; i < T; ++i) {
+            int j = s.lap_x[i];
+            if (j < 0) continue;
+            int slot = rows[i];
+            int det = cols[j];
+            const float* d = s.dets + det * 6;
+            if (force_update_branch || s.state[slot] == ST_TRACKED) {
+                s.frame_id[slot] = frame;
+                s.tracklet_len[slot] += 1;
+                s.act_l[na++] = slot;
+            } else {
+                s.tracklet_len[slot] = 0;
+                s.frame_id[slot] = frame;
+                s.refind_l[nr++] = slot;
+            }
+            s.state[slot] = ST_TRACKED;
+            s.activated[slot] = 1;
+            s.conf[slot] = d[4];
+            s.cls[slot] = d[5];
+            s.det_ind[slot] = (float)det;
+            if (c.vote_cls) vote_cls(c, s, slot, d[5], d[4]);
+        }
+        *n_act = na;
+        *n_refind = nr;
+    }
+    BMB_SYNC();
+}
+
+// removed-set membership of a live track (ByteTrack: unbounded list -> slot flag; BoT-SORT: deque of ids)
+BMB_FN int in_removed_set(const TrkCfg& c, const TrkStream& s, int slot) {
+    if (c.removed_cap == 0) return s.in_removed[slot];
+    int id = s.id[slot];
+    int n = s.scalars[SC_RING_COUNT];
+    for (int k = 0; k < n; ++k)
+        if (s.removed_ring[k] == id) return 1;
+    return 0;
+}
+
+BMB_FN void push_removed(const TrkCfg& c, TrkStream& s, int slot) {
+    if (c.removed_cap == 0) { s.in_removed[slot] = 1; return; }
+    int head = s.scalars[SC_RING_HEAD], n = s.scalars[SC_RING_COUNT];
+    if (n < c.removed_cap) {
+        s.removed_ring[(head + n) % c.removed_cap] = s.id[slot];
+        s.scalars[SC_RING_COUNT] = n + 1;
+    } else {
+        s.removed_ring[head] = s.id[slot];
+        s.scalars[SC_RING_HEAD] = (head + 1) % c.removed_cap;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the frame
+// ---------------------------------------------------------------------------------------------------
+BMB_FN void tracker_frame(const TrkCfg& c, TrkStream& s) {
+    const int CT = c.cap_tracks, CD = c.cap_dets, F = c.feat_dim;
+    int D = *s.n_dets;
+    if (D > CD) {
+        if (BMB_TID == 0) s.scalars[SC_ERROR] = ERR_DET_CAPACITY;
+        D = CD;
+    }
+    const int frame = s.scalars[SC_FRAME] + 1;
+    BMB_SYNC();
+
+    // ---- S0: detection geometry + confidence split (botsort.py:251-261, bytetrack.py:273-282) ----
+    for (int d = BMB_TID; d < D; d += BMB_NT)
+        det_geometry(c, s.dets + d * 6, s.dxywh + d * 4, s.dmeas + d * 4, s.dxyxy + d * 4);
+    // counts produced by thread 0 are broadcast through the first 8 ints of free_l (a mailbox)
+    int n_first = 0, n_second = 0;
+    if (BMB_TID == 0) {
+        for (int d = 0; d < D; ++d) {
+            double cf = (double)s.dets[d * 6 + 4];
+            if (cf > c.high_thresh) s.first[n_first++] = d;
+            else if (cf > c.low_thresh && cf < c.high_thresh) s.second[n_second++] = d;
+        }
+        s.free_l[0] = n_first;
+        s.free_l[1] = n_second;
+    }
+    BMB_SYNC();
+    n_first = s.free_l[0];
+    n_second = s.free_l[1];
+    BMB_SYNC();
+
+    // ---- S1: unconfirmed / tracked split, pool = tracked ++ lost (joint by identity) ----
+    int n_pool = 0, n_unc = 0;
+    if (BMB_TID == 0) {
+        int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
+        for (int k = 0; k < CT; ++k) s.mark[k] = 0;
+        for (int k = 0; k < na; ++k) {
+            int t = s.active[k];
+            if (!s.activated[t]) s.unconf[n_unc++] = t;
+            else { s.pool[n_pool++] = t; s.mark[t] = 1; }
+        }
+        for (int k = 0; k < nl; ++k) {
+            int t = s.lost[k];
+            if (!s.mark[t]) { s.pool[n_pool++] = t; s.mark[t] = 1; }
+        }
+        s.free_l[0] = n_pool;
+        s.free_l[1] = n_unc;
+    }
+    BMB_SYNC();
+    n_pool = s.free_l[0];
+    n_unc = s.free_l[1];
+    BMB_SYNC();
+
+    // ---- S2: Kalman predict over the pool (state is updated in place, as the reference does) ----
+    for (int k = BMB_TID; k < n_pool; k += BMB_NT) {
+        int t = s.pool[k];
+        kf_predict(c, s.state[t] == ST_TRACKED, s.mean + t * 8, s.cov + t * 64);
+        track_xyxy(c, s.mean + t * 8, s.txyxy + t * 4);
+    }
+    for (int k = BMB_TID; k < n_unc; k += BMB_NT) {
+        int t = s.unconf[k];
+        track_xyxy(c, s.mean + t * 8, s.txyxy + t * 4);
+    }
+    BMB_SYNC();
+
+    // ---- S3: first-association cost (botsort.py:306-317 / bytetrack.py:303-305) ----
+    for (int e = BMB_TID; e < n_pool * n_first; e += BMB_NT) {
+        int i = e / n_first, j = e - i * n_first;
+        int t = s.pool[i], d = s.first[j];
+        double iou_d = iou_dist_td(s.txyxy + t * 4, s.dxyxy + d * 4);
+        int far = iou_d > c.proximity;
+        if (c.fuse_first) {
+            double sim = 1.0 - iou_d;
+            double fs = sim * (double)s.dets[d * 6 + 4];
+            iou_d = 1.0 - fs;
+        }
+        double v = iou_d;
+        if (c.with_reid) {
+            double em = s.embd[(size_t)t * CD + d];
+            if (em > c.appearance) em = 1.0;
+            if (c.proximity_mask && far) em = 1.0;
+            v = (iou_d != iou_d || em != em) ? NAN : (iou_d < em ? iou_d : em);
+        }
+        s.cost[(size_t)i * CD + j] = v;
+    }
+    BMB_SYNC();
+    lap_solve(s, n_pool, n_first, CD, c.match1);
+
+    int n_act = 0, n_refind = 0, n_lostnow = 0, n_remnow = 0;
+    // scalars that thread 0 accumulates are mirrored through free_l[] after each sequential section
+    if (BMB_TID == 0) { s.free_l[2] = 0; s.free_l[3] = 0; }
+    BMB_SYNC();
+    apply_matches(c, s, n_pool, s.pool, s.first, frame, 0, c.with_reid, &s.free_l[2], &s.free_l[3]);
+
+    // ---- S6: second association: remaining Tracked pool rows x low-confidence detections ----
+    int n_rt = 0, n_rest = 0;
+    if (BMB_TID == 0) {
+        for (int i = 0; i < n_pool; ++i)
+            if (s.lap_x[i] < 0 && s.state[s.pool[i]] == ST_TRACKED) s.rtracked[n_rt++] = s.pool[i];
+        for (int j = 0; j < n_first; ++j)
+            if (s.lap_y[j] < 0) s.rest[n_rest++] = s.first[j];
+        s.free_l[0] = n_rt;
+        s.free_l[1] = n_rest;
+    }
+    BMB_SYNC();
+    n_rt = s.free_l[0];
+    n_rest = s.free_l[1];
+    BMB_SYNC();
+    for (int e = BMB_TID; e < n_rt * n_second; e += BMB_NT) {
+        int i = e / n_second, j = e - i * n_second;
+        s.cost[(size_t)i * CD + j] = iou_dist_td(s.txyxy + s.rtracked[i] * 4, s.dxyxy + s.second[j] * 4);
+    }
+    BMB_SYNC();
+    lap_solve(s, n_rt, n_second, CD, c.match2);
+    apply_matches(c, s, n_rt, s.rtracked, s.second, frame, 0, 0, &s.free_l[2], &s.free_l[3]);
+    if (BMB_TID == 0) {
+        for (int i = 0; i < n_rt; ++i) {
+            if (s.lap_x[i] >= 0) continue;
+            int t = s.rtracked[i];
+            if (s.state[t] != ST_LOST) { s.state[t] = ST_LOST; s.lostnow_l[n_lostnow++] = t; }
+        }
+        s.free_l[4] = n_lostnow;
+    }
+    BMB_SYNC();
+
+    // ---- S7: unconfirmed tracks x detections left over from round 1 ----
+    for (int e = BMB_TID; e < n_unc * n_rest; e += BMB_NT) {
+        int i = e / n_rest, j = e - i * n_rest;
+        int t = s.unconf[i], d = s.rest[j];
+        double iou_d = iou_dist_td(s.txyxy + t * 4, s.dxyxy + d * 4);
+        int far = iou_d > c.proximity;
+        {
+            double sim = 1.0 - iou_d;
+            double fs = sim * (double)s.dets[d * 6 + 4];
+            iou_d = 1.0 - fs;
+        }
+        double v = iou_d;
+        if (c.with_reid) {
+            double em = s.embd[(size_t)t * CD + d] / c.unc_emb_scale;
+            if (em > c.appearance) em = 1.0;
+            if (c.proximity_mask && far) em = 1.0;
+            v = (iou_d != iou_d || em != em) ? NAN : (iou_d < em ? iou_d : em);
+        }
+        s.cost[(size_t)i * CD + j] = v;
+    }
+    BMB_SYNC();
+    lap_solve(s, n_unc, n_rest, CD, c.match3);
+    apply_matches(c, s, n_unc, s.unconf, s.rest, frame, 1, c.with_reid, &s.free_l[2], &s.free_l[3]);
+
+    // ---- S8..S10: removals, births, list algebra, duplicate suppression (sequential bookkeeping) ----
+    if (BMB_TID == 0) {
+        n_act = s.free_l[2];
+        n_refind = s.free_l[3];
+        n_lostnow = s.free_l[4];
+        for (int i = 0; i < n_unc; ++i)
+            if (s.lap_x[i] < 0) { int t = s.unconf[i]; s.state[t] = ST_REMOVED; s.remnow_l[n_remnow++] = t; }
+        // free slots: everything not referenced by the active / lost lists
+        int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
+        for (int k = 0; k < CT; ++k) s.mark[k] = 0;
+        for (int k = 0; k < na; ++k) s.mark[s.active[k]] = 1;
+        for (int k = 0; k < nl; ++k) s.mark[s.lost[k]] = 1;
+        int n_free = 0;
+        for (int k = 0; k < CT; ++k)
+            if (!s.mark[k]) s.free_l[8 + n_free++] = k;  // free_l has CT + 8 entries
+        // births (botsort.py:433-440 / bytetrack.py:368-373); rest[j] with lap_y[j] < 0, ascending
+        int used = 0;
+        int next_id = s.scalars[SC_NEXT_ID];
+        for (int j = 0; j < n_rest; ++j) {
+            if (s.lap_y[j] >= 0) continue;
+            int d = s.rest[j];
+            float cf = s.dets[d * 6 + 4];
+            if (cf < c.new_thresh_f32) continue;
+            if (used >= n_free) { s.scalars[SC_ERROR] = ERR_TRACK_CAPACITY; break; }
+            int t = s.free_l[8 + used++];
+            s.id[t] = ++next_id;
+            s.tmp_a[used - 1] = d;  // remember the detection for the parallel initiation below
+            s.tracklet_len[t] = 0;
+            s.state[t] = ST_TRACKED;
+            s.activated[t] = (frame == 1) ? 1 : 0;
+            s.frame_id[t] = frame;
+            s.start_frame[t] = frame;
+            s.conf[t] = cf;
+            s.cls[t] = s.dets[d * 6 + 5];
+            s.det_ind[t] = (float)d;
+            s.in_removed[t] = 0;
+            s.hist_n[t] = 1;
+            s.hist_cls[t * HIST_CAP] = s.dets[d * 6 + 5];
+            s.hist_sum[t * HIST_CAP] = cf;
+            s.act_l[n_act++] = t;
+        }
+        s.scalars[SC_NEXT_ID] = next_id;
+        s.free_l[5] = used;
+        s.free_l[2] = n_act;
+    }
+    BMB_SYNC();
+    {
+        int n_new = s.free_l[5];
+        for (int k = BMB_TID; k < n_new; k += BMB_NT) {
+            int t = s.free_l[8 + k], d = s.tmp_a[k];
+            kf_initiate(c, s.dmeas + d * 4, s.mean + t * 8, s.cov + t * 64);
+        }
+        if (c.with_reid) {
+            for (int k = BMB_WARP; k < n_new; k += BMB_NW) {
+                int t = s.free_l[8 + k], d = s.tmp_a[k];
+                for (int q = BMB_LANE; q < F; q += BMB_NL) s.smooth[(size_t)t * F + q] = s.dfeat[(size_t)d * F + q];
+            }
+        }
+    }
+    BMB_SYNC();
+    if (BMB_TID == 0) {
+        n_act = s.free_l[2];
+        int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
+        // lost tracks that timed out (botsort.py:472-476)
+        for (int k = 0; k < nl; ++k) {
+            int t = s.lost[k];
+            if (frame - s.frame_id[t] > c.max_time_lost) { s.state[t] = ST_REMOVED; s.remnow_l[n_remnow++] = t; }
+        }
+        // active' = [Tracked in active] ++ activated ++ refind (joint by identity)
+        for (int k = 0; k < CT; ++k) s.mark[k] = 0;
+        int m = 0;
+        for (int k = 0; k < na; ++k) {
+            int t = s.active[k];
+            if (s.state[t] == ST_TRACKED) { s.tmp_a[m++] = t; s.mark[t] = 1; }
+        }
+        for (int k = 0; k < n_act; ++k) {
+            int t = s.act_l[k];
+            if (!s.mark[t]) { s.tmp_a[m++] = t; s.mark[t] = 1; }
+        }
+        for (int k = 0; k < n_refind; ++k) {
+            int t = s.refind_l[k];
+            if (!s.mark[t]) { s.tmp_a[m++] = t; s.mark[t] = 1; }
+        }
+        // lost' = (lost - active') ++ lost_now, minus everything in the removed set
+        int q = 0;
+        for (int k = 0; k < nl; ++k) {
+            int t = s.lost[k];
+            if (!s.mark[t]) s.tmp_b[q++] = t;
+        }
+        for (int k = 0; k < n_lostnow; ++k) s.tmp_b[q++] = s.lostnow_l[k];
+        int q2 = 0;
+        for (int k = 0; k < q; ++k) {
+            int t = s.tmp_b[k];
+            if (!in_removed_set(c, s, t)) s.tmp_b[q2++] = t;
+        }
+        for (int k = 0; k < n_remnow; ++k) push_removed(c, s, s.remnow_l[k]);
+        s.free_l[0] = m;
+        s.free_l[1] = q2;
+    }
+    BMB_SYNC();
+    // duplicate suppression (botsort_utils.py:53-82): IoU distance active' x lost' < 0.15
+    {
+        int m = s.free_l[0], q = s.free_l[1];
+        for (int k = BMB_TID; k < m; k += BMB_NT) track_xyxy(c, s.mean + s.tmp_a[k] * 8, s.txyxy + s.tmp_a[k] * 4);
+        for (int k = BMB_TID; k < q; k += BMB_NT) track_xyxy(c, s.mean + s.tmp_b[k] * 8, s.txyxy + s.tmp_b[k] * 4);
+        BMB_SYNC();
+        // duplicate flags go into `mark` (1 = member of active'): 2 = drop from lost', 3 = drop from active'
+        for (int e = BMB_TID; e < m * q; e += BMB_NT) {
+            int p = e / q, r = e - p * q;
+            int ta = s.tmp_a[p], tb = s.tmp_b[r];
+            double dist = iou_dist_tt(s.txyxy + ta * 4, s.txyxy + tb * 4);
+            if (dist < 0.15) {
+                int tp = s.frame_id[ta] - s.start_frame[ta];
+                int tq = s.frame_id[tb] - s.start_frame[tb];
+                if (tp > tq) s.mark[tb] = 2; else s.mark[ta] = 3;
+            }
+        }
+    }
+    BMB_SYNC();
+    if (BMB_TID == 0) {
+        int m = s.free_l[0], q = s.free_l[1];
+        int na = 0, nl = 0, n_out = 0;
+        for (int k = 0; k < m; ++k) {
+            int t = s.tmp_a[k];
+            if (s.mark[t] == 3) continue;
+            s.active[na++] = t;
+        }
+        for (int k = 0; k < q; ++k) {
+            int t = s.tmp_b[k];
+            if (s.mark[t] == 2) continue;
+            s.lost[nl++] = t;
+        }
+        s.scalars[SC_N_ACTIVE] = na;
+        s.scalars[SC_N_LOST] = nl;
+        s.scalars[SC_FRAME] = frame;
+        // output rows (botsort.py:494-500)
+        for (int k = 0; k < na; ++k) {
+            int t = s.active[k];
+            if (!s.activated[t]) continue;
+            if (n_out >= CD) { s.scalars[SC_ERROR] = ERR_DET_CAPACITY; break; }
+            double b[4];
+            track_xyxy(c, s.mean + t * 8, b);
+            float* o = s.out + n_out * 8;
+            o[0] = (float)b[0]; o[1] = (float)b[1]; o[2] = (float)b[2]; o[3] = (float)b[3];
+            o[4] = (float)s.id[t];
+            o[5] = s.conf[t];
+            o[6] = s.cls[t];
+            o[7] = s.det_ind[t];
+            ++n_out;
+        }
+        s.scalars[SC_N_OUT] = n_out;
+    }
+    BMB_SYNC();
+}
+
+}  // namespace bmb

@@ -1,0 +1,88 @@
+// tracker_layout.h -- carve one contiguous allocation into the per-stream SoA views of TrkStream.
+// Shared by the CUDA engine (device allocation) and by the host-simulation test harness.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "tracker_core.cuh"
+
+namespace bmb {
+
+struct Carver {
+    uint8_t* base;
+    size_t off;
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+// Fills `s` with pointers into `base` (which may be null to only measure) and returns the bytes needed.
+// `persistent_bytes` receives the size of the leading region that must be zeroed on reset.
+inline size_t carve_stream(const TrkCfg& c, uint8_t* base, TrkStream* s, size_t* persistent_bytes) {
+    const size_t CT = (size_t)c.cap_tracks, CD = (size_t)c.cap_dets, F = (size_t)(c.feat_dim > 0 ? c.feat_dim : 1);
+    Carver k{base, 0};
+    TrkStream t{};
+    t.scalars = k.take<int>(SC_COUNT);
+    t.state = k.take<int>(CT);
+    t.activated = k.take<int>(CT);
+    t.id = k.take<int>(CT);
+    t.frame_id = k.take<int>(CT);
+    t.start_frame = k.take<int>(CT);
+    t.tracklet_len = k.take<int>(CT);
+    t.hist_n = k.take<int>(CT);
+    t.in_removed = k.take<int>(CT);
+    t.removed_ring = k.take<int>(c.removed_cap > 0 ? (size_t)c.removed_cap : 1);
+    t.active = k.take<int>(CT);
+    t.lost = k.take<int>(CT);
+    t.conf = k.take<float>(CT);
+    t.cls = k.take<float>(CT);
+    t.det_ind = k.take<float>(CT);
+    t.hist_cls = k.take<float>(CT * HIST_CAP);
+    t.hist_sum = k.take<float>(CT * HIST_CAP);
+    t.mean = k.take<double>(CT * 8);
+    t.cov = k.take<double>(CT * 64);
+    t.smooth = k.take<float>(CT * F);
+    if (persistent_bytes) *persistent_bytes = k.off;
+    // scratch
+    t.dxywh = k.take<float>(CD * 4);
+    t.dmeas = k.take<float>(CD * 4);
+    t.dxyxy = k.take<float>(CD * 4);
+    t.dfeat = k.take<float>(CD * F);
+    t.embd = k.take<double>(CT * CD);
+    t.cost = k.take<double>(CT * CD);
+    t.txyxy = k.take<double>(CT * 4);
+    t.first = k.take<int>(CD);
+    t.second = k.take<int>(CD);
+    t.rest = k.take<int>(CD);
+    t.pool = k.take<int>(CT);
+    t.unconf = k.take<int>(CT);
+    t.rtracked = k.take<int>(CT);
+    t.act_l = k.take<int>(CT + CD);
+    t.refind_l = k.take<int>(CT);
+    t.lostnow_l = k.take<int>(CT);
+    t.remnow_l = k.take<int>(CT);
+    t.tmp_a = k.take<int>(CT);
+    t.tmp_b = k.take<int>(CT);
+    t.mark = k.take<int>(CT);
+    t.free_l = k.take<int>(CT + 8);
+    t.lap_x = k.take<int>(CT);
+    t.lap_y = k.take<int>(CD);
+    t.lap_u = k.take<double>(CT);
+    t.lap_v = k.take<double>(CD);
+    t.lap_spc = k.take<double>(CD);
+    t.lap_path = k.take<int>(CD);
+    t.lap_insc = k.take<int>(CD);
+    t.lap_tl = k.take<int>(CD);
+    t.lap_sc = k.take<int>(CD);
+    t.csr_ptr = k.take<int>(CT + 1);
+    t.csr_col = k.take<int>(CT * CD);
+    t.out = k.take<float>(CD * 8);
+    if (s) *s = t;
+    return (k.off + 255) & ~(size_t)255;
+}
+
+}  // namespace bmb

@@ -1,0 +1,98 @@
+// tests/_hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles boxmot_b200/csrc/tracker_core.cuh for the host (BMB_HOSTSIM: one "thread") so the tracker
+// control flow can be checked against the golden vectors in a container without a GPU.  It is built by
+// tests/test_hostsim_tracker.py with g++, loaded only by that test, and never linked into libboxmot_b200.so.
+#define BMB_HOSTSIM 1
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "tracker_core.cuh"
+#include "tracker_layout.h"
+
+using namespace bmb;
+
+struct HostSim {
+    TrkCfg cfg;
+    TrkStream s;
+    std::vector<uint8_t> mem;
+    std::vector<float> dets;
+    std::vector<float> embs;
+    int n_dets;
+};
+
+extern "C" {
+
+HostSim* hostsim_create(const TrkCfg* cfg) {
+    HostSim* h = new HostSim();
+    h->cfg = *cfg;
+    size_t bytes = carve_stream(h->cfg, nullptr, nullptr, nullptr);
+    h->mem.assign(bytes, 0);
+    carve_stream(h->cfg, h->mem.data(), &h->s, nullptr);
+    h->dets.assign((size_t)cfg->cap_dets * 6, 0.f);
+    h->embs.assign((size_t)cfg->cap_dets * (cfg->feat_dim > 0 ? cfg->feat_dim : 1), 0.f);
+    h->s.dets = h->dets.data();
+    h->s.n_dets = &h->n_dets;
+    return h;
+}
+
+void hostsim_destroy(HostSim* h) { delete h; }
+
+int hostsim_cfg_size() { return (int)sizeof(TrkCfg); }
+
+// returns number of output rows, or -(error code)
+int hostsim_update(HostSim* h, const float* dets, int n, const float* embs, float* out, int* lap_steps) {
+    const TrkCfg& c = h->cfg;
+    if (n > c.cap_dets) return -ERR_DET_CAPACITY;
+    h->n_dets = n;
+    if (n) memcpy(h->dets.data(), dets, sizeof(float) * 6 * n);
+    if (c.with_reid && embs) {
+        const int F = c.feat_dim;
+        for (int d = 0; d < n; ++d) feat_prepare(embs + (size_t)d * F, h->s.dfeat + (size_t)d * F, F);
+        // the wide appearance kernel: every occupied slot against every detection
+        std::vector<char> live(c.cap_tracks, 0);
+        for (int k = 0; k < h->s.scalars[SC_N_ACTIVE]; ++k) live[h->s.active[k]] = 1;
+        for (int k = 0; k < h->s.scalars[SC_N_LOST]; ++k) live[h->s.lost[k]] = 1;
+        for (int t = 0; t < c.cap_tracks; ++t) {
+            if (!live[t]) continue;
+            for (int d = 0; d < n; ++d)
+                h->s.embd[(size_t)t * c.cap_dets + d] =
+                    cosine_cost_f64(h->s.smooth + (size_t)t * F, h->s.dfeat + (size_t)d * F, F);
+        }
+    }
+    h->s.scalars[SC_LAP_STEPS] = 0;
+    tracker_frame(c, h->s);
+    if (lap_steps) *lap_steps = h->s.scalars[SC_LAP_STEPS];
+    if (h->s.scalars[SC_ERROR]) return -h->s.scalars[SC_ERROR];
+    int m = h->s.scalars[SC_N_OUT];
+    memcpy(out, h->s.out, sizeof(float) * 8 * m);
+    return m;
+}
+
+// snapshot of live tracks: ids, means, covs; returns count
+int hostsim_snapshot(HostSim* h, int* ids, double* means, double* covs, int cap) {
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int cnt = h->s.scalars[pass == 0 ? SC_N_ACTIVE : SC_N_LOST];
+        const int* lst = pass == 0 ? h->s.active : h->s.lost;
+        for (int k = 0; k < cnt && n < cap; ++k, ++n) {
+            int t = lst[k];
+            ids[n] = h->s.id[t];
+            memcpy(means + (size_t)n * 8, h->s.mean + (size_t)t * 8, sizeof(double) * 8);
+            memcpy(covs + (size_t)n * 64, h->s.cov + (size_t)t * 64, sizeof(double) * 64);
+        }
+    }
+    return n;
+}
+
+// standalone LAP entry for solver tests: cost is (T, D) row-major
+int hostsim_lap(HostSim* h, const double* cost, int T, int D, double thresh, int* x, int* y) {
+    const TrkCfg& c = h->cfg;
+    if (T > c.cap_tracks || D > c.cap_dets) return -1;
+    for (int i = 0; i < T; ++i) memcpy(h->s.cost + (size_t)i * c.cap_dets, cost + (size_t)i * D, sizeof(double) * D);
+    lap_solve(h->s, T, D, c.cap_dets, thresh);
+    memcpy(x, h->s.lap_x, sizeof(int) * T);
+    memcpy(y, h->s.lap_y, sizeof(int) * D);
+    return 0;
+}
+}

@@ -1,0 +1,127 @@
+"""Host simulation of the device tracker code (tests only; never a product path).
+
+Builds tests/_hostsim/hostsim.cpp with g++ (BMB_HOSTSIM: boxmot_b200/csrc/tracker_core.cuh compiled for one
+host "thread") and exposes it through ctypes so `-m "not gpu"` tests can check the control flow of the CUDA
+tracker against the reference goldens without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+SRC = ROOT / "tests" / "_hostsim" / "hostsim.cpp"
+OUT = ROOT / "tests" / "_hostsim" / "hostsim.so"
+CSRC = ROOT / "boxmot_b200" / "csrc"
+
+
+class TrkCfg(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int), ("with_reid", ctypes.c_int), ("fuse_first", ctypes.c_int),
+        ("proximity_mask", ctypes.c_int), ("max_time_lost", ctypes.c_int), ("removed_cap", ctypes.c_int),
+        ("feat_dim", ctypes.c_int), ("cap_tracks", ctypes.c_int), ("cap_dets", ctypes.c_int),
+        ("vote_cls", ctypes.c_int),
+        ("high_thresh", ctypes.c_double), ("low_thresh", ctypes.c_double),
+        ("new_thresh_f32", ctypes.c_float),
+        ("match1", ctypes.c_double), ("match2", ctypes.c_double), ("match3", ctypes.c_double),
+        ("proximity", ctypes.c_double), ("appearance", ctypes.c_double), ("unc_emb_scale", ctypes.c_double),
+    ]
+
+
+def build():
+    deps = [SRC, CSRC / "tracker_core.cuh", CSRC / "tracker_layout.h"]
+    if OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return OUT
+    tmp = OUT.with_suffix(f".{os.getpid()}.tmp.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+                           f"-I{CSRC}", "-o", str(tmp), str(SRC)])
+    os.replace(tmp, OUT)
+    return OUT
+
+
+def bytetrack_cfg(min_conf=0.1, track_thresh=0.45, match_thresh=0.8, track_buffer=25, frame_rate=30,
+                  cap_tracks=512, cap_dets=256):
+    c = TrkCfg()
+    c.kind, c.with_reid, c.fuse_first, c.proximity_mask = 0, 0, 1, 0
+    c.max_time_lost = int(frame_rate / 30.0 * track_buffer)
+    c.removed_cap, c.feat_dim, c.cap_tracks, c.cap_dets, c.vote_cls = 0, 0, cap_tracks, cap_dets, 0
+    c.high_thresh, c.low_thresh = track_thresh, min_conf
+    c.new_thresh_f32 = np.float32(track_thresh)
+    c.match1, c.match2, c.match3 = match_thresh, 0.5, 0.7
+    c.proximity, c.appearance, c.unc_emb_scale = 0.0, 0.0, 1.0
+    return c
+
+
+def botsort_cfg(track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6, track_buffer=30,
+                match_thresh=0.8, proximity_thresh=0.5, appearance_thresh=0.25, frame_rate=30,
+                fuse_first_associate=False, with_reid=True, second_match_thresh=0.5,
+                unconfirmed_match_thresh=0.7, unconfirmed_emb_scale=2.0, removed_stracks_buffer=100,
+                feat_dim=512, cap_tracks=512, cap_dets=256):
+    c = TrkCfg()
+    c.kind, c.with_reid, c.fuse_first, c.proximity_mask = 1, int(with_reid), int(fuse_first_associate), 1
+    c.max_time_lost = int(frame_rate / 30.0 * track_buffer)
+    c.removed_cap, c.feat_dim = removed_stracks_buffer, (feat_dim if with_reid else 0)
+    c.cap_tracks, c.cap_dets, c.vote_cls = cap_tracks, cap_dets, 1
+    c.high_thresh, c.low_thresh = track_high_thresh, track_low_thresh
+    c.new_thresh_f32 = np.float32(new_track_thresh)
+    c.match1, c.match2, c.match3 = match_thresh, second_match_thresh, unconfirmed_match_thresh
+    c.proximity, c.appearance, c.unc_emb_scale = proximity_thresh, appearance_thresh, unconfirmed_emb_scale
+    return c
+
+
+class HostSimTracker:
+    def __init__(self, cfg: TrkCfg):
+        self.lib = ctypes.CDLL(str(build()))
+        assert self.lib.hostsim_cfg_size() == ctypes.sizeof(TrkCfg)
+        self.lib.hostsim_create.restype = ctypes.c_void_p
+        self.lib.hostsim_create.argtypes = [ctypes.POINTER(TrkCfg)]
+        self.lib.hostsim_update.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.hostsim_snapshot.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        self.lib.hostsim_lap.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.hostsim_destroy.argtypes = [ctypes.c_void_p]
+        self.cfg = cfg
+        self.h = self.lib.hostsim_create(ctypes.byref(cfg))
+        self.lap_steps = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.hostsim_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, img=None, embs=None):
+        dets = np.ascontiguousarray(dets, dtype=np.float32).reshape(-1, 6)
+        n = len(dets)
+        out = np.empty((max(n, 1), 8), np.float32)
+        e = None
+        if embs is not None:
+            e = np.ascontiguousarray(embs, dtype=np.float32)
+            assert len(e) == n
+        steps = ctypes.c_int(0)
+        m = self.lib.hostsim_update(self.h, dets.ctypes.data, n, e.ctypes.data if e is not None else None,
+                                    out.ctypes.data, ctypes.byref(steps))
+        if m < 0:
+            raise RuntimeError(f"hostsim error {-m}")
+        self.lap_steps += steps.value
+        return out[:m].copy()
+
+    def state_snapshot(self):
+        cap = self.cfg.cap_tracks
+        ids = np.empty(cap, np.int32)
+        means = np.empty((cap, 8))
+        covs = np.empty((cap, 8, 8))
+        n = self.lib.hostsim_snapshot(self.h, ids.ctypes.data, means.ctypes.data, covs.ctypes.data, cap)
+        return {int(ids[i]): (means[i].copy(), covs[i].copy()) for i in range(n)}
+
+    def lap(self, cost, thresh):
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        T, D = cost.shape
+        x = np.empty(T, np.int32)
+        y = np.empty(D, np.int32)
+        assert self.lib.hostsim_lap(self.h, cost.ctypes.data, T, D, thresh, x.ctypes.data, y.ctypes.data) == 0
+        return x, y
