@@ -1,0 +1,91 @@
+// engine.h -- internal C++ interfaces shared by the translation units of libboxmot_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/boxmot_b200.h"
+#include "tracker_core.cuh"
+
+namespace bmb {
+
+// One detection crop for the ReID path: source frame index, box, and the row of the output matrix it fills.
+struct CropDesc {
+    float x1, y1, x2, y2;
+    int image;
+    int out_row;
+};
+
+// ---- ReID model (reid_model.cu) -----------------------------------------------------------------------
+struct ReidModel;
+ReidModel* reid_load(const char* blob_path);  // throws std::runtime_error
+void reid_free(ReidModel* m);
+int reid_feature_dim(const ReidModel* m);
+// Enqueue crop -> CNN -> L2-normalised features for up to `max_crops` crops whose descriptors and count live
+// in device memory.  Frames are `image_stride` bytes apart in `d_images` (rows x cols x 3, BGR, uint8).
+// Row r of the result goes to d_out + crops[r].out_row * out_ld.  Returns the number of kernel launches.
+int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int rows, int cols,
+                 const CropDesc* d_crops, const int* d_ncrops, int max_crops, float* d_out, int out_ld,
+                 cudaStream_t stream);
+// staged access for the reid C ABI / tests: the normalised input blob (N,256,128,3) float32 NHWC
+const float* reid_last_input_blob(const ReidModel* m);
+
+// ---- tracker engine (tracker_engine.cu) -----------------------------------------------------------------
+struct Engine {
+    TrkCfg cfg{};
+    int S = 0;
+    cudaStream_t stream = nullptr;
+    ReidModel* reid = nullptr;
+    uint8_t* d_mem = nullptr;
+    size_t stream_bytes = 0, persistent_bytes = 0;
+    TrkStream* d_streams = nullptr;
+    std::vector<TrkStream> h_streams;
+    float* d_dets = nullptr;
+    int* d_ndets = nullptr;
+    float* d_embs = nullptr;
+    float* d_out = nullptr;
+    int* d_scalars_out = nullptr;
+    CropDesc* d_crops = nullptr;
+    int* d_ncrops = nullptr;
+    uint8_t* d_images = nullptr;
+    size_t image_bytes = 0;
+    float* h_dets = nullptr;
+    int* h_ndets = nullptr;
+    float* h_out = nullptr;
+    int* h_scalars = nullptr;
+    float* h_embs = nullptr;
+    uint8_t* h_images = nullptr;
+    cudaEvent_t ev[3]{};
+    int launches = 0;
+    double last_reid_ms = 0.0, last_assoc_ms = 0.0;
+
+    explicit Engine(const BoxMOTB200TrackerConfig& p);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    void reset();
+    void update_batch(const float* const* dets, const int* det_rows, const float* const* embs,
+                      const uint8_t* const* images, int rows, int cols, float* const* out, const int* out_cap,
+                      int* out_rows);
+    void update_device(const float* dets_dev, const int* det_rows, const float* embs_dev,
+                       const uint8_t* images_dev, int rows, int cols, bool sync);
+    void fetch(float* const* out, const int* out_cap, int* out_rows);
+    int snapshot(int stream_index, int* ids, double* means, double* covs, int cap);
+
+   private:
+    void ensure_images(int rows, int cols, bool host_too);
+    void enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total);
+    void enqueue_fetch();
+    void finish_fetch(float* const* out, const int* out_cap, int* out_rows);
+};
+
+void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int* y);
+void standalone_kf(int op, int kind, double* mean, double* cov, const int* tracked, const float* meas, int n);
+void standalone_iou(const double* t, int T, const float* d, int D, double* out);
+void standalone_cosine(const float* a, int T, const float* b, int D, int F, double* out);
+
+}  // namespace bmb

@@ -1,0 +1,526 @@
+// tracker_engine.cu -- host side of the device-resident tracker: memory, launches, and the kernels that wrap
+// tracker_core.cuh.  One Engine owns `n_streams` independent trackers resident on one GPU; a frame for all
+// of them is: H2D (dets [+ embs | frames]) -> [crop list -> ReID] -> appearance prep -> cosine cost (wide
+// grid) -> one CTA per stream running the whole association / Kalman / lifecycle -> D2H rows.
+//
+// Replaces the host loops of BaseTracker.update()/_update_impl (trackers/basetracker.py:120-147,
+// bytetrack.py:259-403, botsort.py:177-249) and the native Update() (native/cpp/trackers/botsort/src/
+// tracker.cpp:329-498) behind the same C ABI.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "tracker_core.cuh"
+#include "tracker_layout.h"
+
+namespace bmb {
+
+#define CUDA_OK(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tracker_frame(const TrkCfg cfg, TrkStream* streams) {
+    TrkStream s = streams[blockIdx.x];
+    tracker_frame(cfg, s);
+}
+
+// detection appearance: the reference normalises each high-confidence row twice in place
+// (botsort_track.py:58-67 on a fresh STrack); one warp per detection row.
+__global__ void __launch_bounds__(256) k_feat_prepare(const TrkCfg cfg, TrkStream* streams, const float* embs) {
+    const TrkStream& s = streams[blockIdx.y];
+    const int D = min(*s.n_dets, cfg.cap_dets);
+    const int F = cfg.feat_dim;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= D) return;
+    const float cf = s.dets[warp * 6 + 4];
+    if (!((double)cf > cfg.high_thresh)) return;  // only first-round detections carry appearance
+    const float* src = embs + ((size_t)blockIdx.y * cfg.cap_dets + warp) * F;
+    feat_prepare(src, s.dfeat + (size_t)warp * F, F);
+}
+
+// max(0, cosine distance) between every live track's smoothed appearance and every first-round detection,
+// float64 accumulate over float32 inputs (scipy cdist semantics, matching.py:85-107).  Tile = 8 track rows x
+// 32 detections per CTA, K staged through shared memory in chunks of 64.
+constexpr int EMB_TR = 8, EMB_TD = 32, EMB_TK = 64;
+__global__ void __launch_bounds__(256) k_embedding_cost(const TrkCfg cfg, TrkStream* streams) {
+    const TrkStream& s = streams[blockIdx.z];
+    const int D = min(*s.n_dets, cfg.cap_dets);
+    const int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
+    const int T = na + nl;
+    const int r0 = blockIdx.y * EMB_TR, d0 = blockIdx.x * EMB_TD;
+    if (r0 >= T || d0 >= D) return;
+    __shared__ float sa[EMB_TR][EMB_TK + 1];
+    __shared__ float sb[EMB_TD][EMB_TK + 1];
+    __shared__ int slot_of[EMB_TR];
+    const int F = cfg.feat_dim;
+    const int tr = threadIdx.x / EMB_TD, td = threadIdx.x % EMB_TD;
+    if (threadIdx.x < EMB_TR) {
+        int r = r0 + threadIdx.x;
+        slot_of[threadIdx.x] = r < T ? (r < na ? s.active[r] : s.lost[r - na]) : -1;
+    }
+    __syncthreads();
+    double dot = 0.0, na2 = 0.0, nb2 = 0.0;
+    for (int k0 = 0; k0 < F; k0 += EMB_TK) {
+        for (int e = threadIdx.x; e < EMB_TR * EMB_TK; e += blockDim.x) {
+            int r = e / EMB_TK, k = e % EMB_TK;
+            int slot = slot_of[r];
+            sa[r][k] = (slot >= 0 && k0 + k < F) ? s.smooth[(size_t)slot * F + k0 + k] : 0.f;
+        }
+        for (int e = threadIdx.x; e < EMB_TD * EMB_TK; e += blockDim.x) {
+            int d = e / EMB_TK, k = e % EMB_TK;
+            sb[d][k] = (d0 + d < D && k0 + k < F) ? s.dfeat[(size_t)(d0 + d) * F + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < EMB_TK; ++k) {
+            double x = (double)sa[tr][k], y = (double)sb[td][k];
+            dot += x * y; na2 += x * x; nb2 += y * y;
+        }
+        __syncthreads();
+    }
+    const int slot = slot_of[tr];
+    if (slot >= 0 && d0 + td < D) {
+        double cs = dot / (sqrt(na2) * sqrt(nb2));
+        if (fabs(cs) > 1.0) cs = cs > 0 ? 1.0 : -1.0;
+        double dist = 1.0 - cs;
+        dist = dist > 0.0 ? dist : (dist != dist ? dist : 0.0);
+        s.embd[(size_t)slot * cfg.cap_dets + d0 + td] = dist;
+    }
+}
+
+// crop list for on-device ReID: one entry per first-round detection, ordered by (stream, detection).
+__global__ void k_build_crops(const TrkCfg cfg, TrkStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    for (int sidx = 0; sidx < n_streams; ++sidx) {
+        const TrkStream& s = streams[sidx];
+        const int D = min(*s.n_dets, cfg.cap_dets);
+        for (int d = 0; d < D; ++d) {
+            const float* r = s.dets + d * 6;
+            if ((double)r[4] > cfg.high_thresh) {
+                CropDesc c;
+                c.x1 = r[0]; c.y1 = r[1]; c.x2 = r[2]; c.y2 = r[3];
+                c.image = sidx;
+                c.out_row = sidx * cfg.cap_dets + d;
+                crops[n++] = c;
+            }
+        }
+    }
+    *n_crops = n;
+}
+
+__global__ void k_reset_streams(TrkStream* streams, size_t persistent_bytes) {
+    // zero the persistent region of one stream (scalars first, so every list is empty and ids restart at 1)
+    TrkStream& s = streams[blockIdx.x];
+    uint8_t* base = reinterpret_cast<uint8_t*>(s.scalars);
+    for (size_t i = threadIdx.x * 16ull; i < persistent_bytes; i += blockDim.x * 16ull)
+        *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------------------------------
+static TrkCfg make_core_cfg(const BoxMOTB200TrackerConfig& p) {
+    TrkCfg c{};
+    const bool bot = p.tracker == BOXMOT_B200_TRACKER_BOTSORT;
+    c.kind = bot ? KIND_XYWH : KIND_XYAH;
+    c.with_reid = bot ? (p.with_reid ? 1 : 0) : 0;
+    c.fuse_first = bot ? (p.fuse_first_associate ? 1 : 0) : 1;
+    c.proximity_mask = bot ? 1 : 0;
+    c.max_time_lost = (int)((double)p.frame_rate / 30.0 * (double)p.track_buffer);
+    c.removed_cap = bot ? p.removed_stracks_buffer : 0;
+    c.feat_dim = c.with_reid ? p.feat_dim : 0;
+    c.cap_tracks = p.cap_tracks;
+    c.cap_dets = p.cap_dets;
+    c.vote_cls = bot ? 1 : 0;
+    c.high_thresh = p.track_high_thresh;
+    c.low_thresh = p.track_low_thresh;
+    c.new_thresh_f32 = (float)p.new_track_thresh;
+    c.match1 = p.match_thresh;
+    c.match2 = p.second_match_thresh;
+    c.match3 = p.unconfirmed_match_thresh;
+    c.proximity = p.proximity_thresh;
+    c.appearance = p.appearance_thresh;
+    c.unc_emb_scale = p.unconfirmed_emb_scale;
+    return c;
+}
+
+Engine::Engine(const BoxMOTB200TrackerConfig& p) {
+    if (p.n_streams < 1) throw std::runtime_error("n_streams must be >= 1");
+    if (p.cap_tracks < 8 || p.cap_dets < 1) throw std::runtime_error("cap_tracks >= 8 and cap_dets >= 1 required");
+    if (p.tracker != BOXMOT_B200_TRACKER_BOTSORT && p.tracker != BOXMOT_B200_TRACKER_BYTETRACK)
+        throw std::runtime_error("unknown tracker kind");
+    if (p.tracker == BOXMOT_B200_TRACKER_BOTSORT && p.removed_stracks_buffer < 1)
+        throw std::runtime_error("removed_stracks_buffer must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device: boxmot_b200 has no CPU fallback");
+    cfg = make_core_cfg(p);
+    if (cfg.with_reid && cfg.feat_dim < 1) throw std::runtime_error("feat_dim must be set when with_reid");
+    S = p.n_streams;
+    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (p.reid_model_path && p.reid_model_path[0]) {
+        reid = reid_load(p.reid_model_path);
+        if (cfg.with_reid && reid_feature_dim(reid) != cfg.feat_dim) {
+            cfg.feat_dim = reid_feature_dim(reid);
+        }
+    }
+    stream_bytes = carve_stream(cfg, nullptr, nullptr, &persistent_bytes);
+    persistent_bytes = (persistent_bytes + 15) & ~(size_t)15;
+    CUDA_OK(cudaMalloc(&d_mem, stream_bytes * S));
+    CUDA_OK(cudaMemset(d_mem, 0, stream_bytes * S));
+    const size_t CD = cfg.cap_dets, F = cfg.feat_dim > 0 ? cfg.feat_dim : 1;
+    CUDA_OK(cudaMalloc(&d_dets, sizeof(float) * 6 * CD * S));
+    CUDA_OK(cudaMalloc(&d_ndets, sizeof(int) * S));
+    CUDA_OK(cudaMemset(d_ndets, 0, sizeof(int) * S));
+    if (cfg.with_reid) {
+        CUDA_OK(cudaMalloc(&d_embs, sizeof(float) * F * CD * S));
+        CUDA_OK(cudaMemset(d_embs, 0, sizeof(float) * F * CD * S));
+    }
+    CUDA_OK(cudaMallocHost(&h_dets, sizeof(float) * 6 * CD * S));
+    CUDA_OK(cudaMallocHost(&h_ndets, sizeof(int) * S));
+    CUDA_OK(cudaMallocHost(&h_out, sizeof(float) * 8 * CD * S));
+    CUDA_OK(cudaMallocHost(&h_scalars, sizeof(int) * SC_COUNT * S));
+    if (cfg.with_reid) CUDA_OK(cudaMallocHost(&h_embs, sizeof(float) * F * CD * S));
+    CUDA_OK(cudaMalloc(&d_out, sizeof(float) * 8 * CD * S));
+    CUDA_OK(cudaMalloc(&d_scalars_out, sizeof(int) * SC_COUNT * S));
+    h_streams.resize(S);
+    for (int i = 0; i < S; ++i) {
+        carve_stream(cfg, d_mem + stream_bytes * i, &h_streams[i], nullptr);
+        h_streams[i].dets = d_dets + (size_t)i * CD * 6;
+        h_streams[i].n_dets = d_ndets + i;
+    }
+    CUDA_OK(cudaMalloc(&d_streams, sizeof(TrkStream) * S));
+    CUDA_OK(cudaMemcpy(d_streams, h_streams.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
+    if (reid) {
+        CUDA_OK(cudaMalloc(&d_crops, sizeof(CropDesc) * CD * S));
+        CUDA_OK(cudaMalloc(&d_ncrops, sizeof(int)));
+    }
+    CUDA_OK(cudaEventCreate(&ev[0]));
+    CUDA_OK(cudaEventCreate(&ev[1]));
+    CUDA_OK(cudaEventCreate(&ev[2]));
+    CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+Engine::~Engine() {
+    cudaStreamSynchronize(stream);
+    if (reid) reid_free(reid);
+    cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
+    cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
+    cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
+    cudaFreeHost(h_embs); cudaFreeHost(h_images);
+    for (auto& e : ev) cudaEventDestroy(e);
+    cudaStreamDestroy(stream);
+}
+
+void Engine::reset() {
+    k_reset_streams<<<S, 256, 0, stream>>>(d_streams, persistent_bytes);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+void Engine::ensure_images(int rows, int cols, bool host_too) {
+    size_t need = (size_t)rows * cols * 3;
+    if (need > image_bytes) {
+        cudaFree(d_images); d_images = nullptr;
+        cudaFreeHost(h_images); h_images = nullptr;
+        CUDA_OK(cudaMalloc(&d_images, need * S));
+        image_bytes = need;
+    }
+    if (host_too && !h_images) CUDA_OK(cudaMallocHost(&h_images, image_bytes * S));
+}
+
+// Enqueue the device work of one frame.  Inputs already in d_dets / d_ndets (+ embs or images).
+void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total) {
+    launches = 0;
+    CUDA_OK(cudaEventRecord(ev[0], stream));
+    if (cfg.with_reid) {
+        const float* src = embs_dev;
+        if (!src) {
+            if (!reid) throw std::runtime_error("with_reid tracker needs embeddings or a ReID model");
+            if (!images_dev) throw std::runtime_error("ReID inside update() needs an image");
+            k_build_crops<<<1, 32, 0, stream>>>(cfg, d_streams, S, d_crops, d_ncrops);
+            ++launches;
+            launches += reid_forward(reid, images_dev, (size_t)rows * cols * 3, rows, cols, d_crops, d_ncrops,
+                                     max_dets_total, d_embs, cfg.feat_dim, stream);
+            src = d_embs;
+        }
+        CUDA_OK(cudaEventRecord(ev[1], stream));
+        dim3 g1((cfg.cap_dets + 7) / 8, S);
+        k_feat_prepare<<<g1, 256, 0, stream>>>(cfg, d_streams, src);
+        dim3 g2((cfg.cap_dets + EMB_TD - 1) / EMB_TD, (cfg.cap_tracks + EMB_TR - 1) / EMB_TR, S);
+        k_embedding_cost<<<g2, 256, 0, stream>>>(cfg, d_streams);
+        launches += 2;
+    } else {
+        CUDA_OK(cudaEventRecord(ev[1], stream));
+    }
+    k_tracker_frame<<<S, 256, 0, stream>>>(cfg, d_streams);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(ev[2], stream));
+}
+
+void Engine::enqueue_fetch() {
+    // gather every stream's rows + scalars into pinned memory (two strided copies)
+    CUDA_OK(cudaMemcpy2DAsync(h_out, sizeof(float) * 8 * cfg.cap_dets, h_streams[0].out, stream_bytes,
+                              sizeof(float) * 8 * cfg.cap_dets, S, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpy2DAsync(h_scalars, sizeof(int) * SC_COUNT, h_streams[0].scalars, stream_bytes,
+                              sizeof(int) * SC_COUNT, S, cudaMemcpyDeviceToHost, stream));
+}
+
+void Engine::finish_fetch(float* const* out, const int* out_cap, int* out_rows) {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < S; ++i) {
+        const int* sc = h_scalars + (size_t)i * SC_COUNT;
+        if (sc[SC_ERROR] != ERR_NONE) {
+            const char* what = sc[SC_ERROR] == ERR_TRACK_CAPACITY ? "track capacity (cap_tracks) exceeded"
+                             : sc[SC_ERROR] == ERR_CLS_HIST      ? "more than 8 distinct classes voted on one track"
+                                                                 : "detection capacity (cap_dets) exceeded";
+            throw std::runtime_error(std::string("stream ") + std::to_string(i) + ": " + what);
+        }
+        const int m = sc[SC_N_OUT];
+        if (out_rows) out_rows[i] = m;
+        if (!out || !out[i]) continue;
+        if (m > out_cap[i]) throw std::runtime_error("out_capacity_rows too small");
+        const float* src = h_out + (size_t)i * cfg.cap_dets * 8;
+        for (int r = 0; r < m; ++r) {
+            float* o = out[i] + (size_t)r * 9;
+            memcpy(o, src + (size_t)r * 8, sizeof(float) * 8);
+            o[8] = 0.f;
+        }
+    }
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    last_reid_ms = a;
+    last_assoc_ms = b;
+}
+
+void Engine::update_batch(const float* const* dets, const int* det_rows, const float* const* embs,
+                          const uint8_t* const* images, int rows, int cols, float* const* out,
+                          const int* out_cap, int* out_rows) {
+    const size_t CD = cfg.cap_dets, F = cfg.feat_dim > 0 ? cfg.feat_dim : 1;
+    int total = 0;
+    bool have_embs = cfg.with_reid && embs != nullptr;
+    for (int i = 0; i < S; ++i) {
+        const int n = det_rows[i];
+        if (n < 0 || n > (int)CD) throw std::runtime_error("det_rows exceeds cap_dets");
+        h_ndets[i] = n;
+        total += n;
+        if (n) {
+            if (!dets[i]) throw std::runtime_error("dets pointer is NULL");
+            memcpy(h_dets + (size_t)i * CD * 6, dets[i], sizeof(float) * 6 * n);
+        }
+        if (have_embs && n) {
+            if (!embs[i]) throw std::runtime_error("embs pointer is NULL for a stream while others pass embeddings");
+            memcpy(h_embs + (size_t)i * CD * F, embs[i], sizeof(float) * F * n);
+        }
+    }
+    CUDA_OK(cudaMemcpyAsync(d_ndets, h_ndets, sizeof(int) * S, cudaMemcpyHostToDevice, stream));
+    // one strided copy moves every stream's occupied prefix; simpler: copy whole staging when small
+    for (int i = 0; i < S; ++i) {
+        if (!h_ndets[i]) continue;
+        CUDA_OK(cudaMemcpyAsync(d_dets + (size_t)i * CD * 6, h_dets + (size_t)i * CD * 6,
+                                sizeof(float) * 6 * h_ndets[i], cudaMemcpyHostToDevice, stream));
+        if (have_embs)
+            CUDA_OK(cudaMemcpyAsync(d_embs + (size_t)i * CD * F, h_embs + (size_t)i * CD * F,
+                                    sizeof(float) * F * h_ndets[i], cudaMemcpyHostToDevice, stream));
+    }
+    const uint8_t* img_dev = nullptr;
+    if (cfg.with_reid && !have_embs) {
+        if (!reid) throw std::runtime_error("with_reid tracker needs embeddings or a ReID model");
+        if (!images || rows <= 0 || cols <= 0) throw std::runtime_error("ReID inside update() needs an image");
+        ensure_images(rows, cols, true);
+        const size_t ib = (size_t)rows * cols * 3;
+        for (int i = 0; i < S; ++i) {
+            if (!images[i]) throw std::runtime_error("image pointer is NULL");
+            memcpy(h_images + ib * i, images[i], ib);
+        }
+        CUDA_OK(cudaMemcpyAsync(d_images, h_images, ib * S, cudaMemcpyHostToDevice, stream));
+        img_dev = d_images;
+    }
+    enqueue_frame(have_embs ? d_embs : nullptr, img_dev, rows, cols, total);
+    enqueue_fetch();
+    finish_fetch(out, out_cap, out_rows);
+}
+
+void Engine::update_device(const float* dets_dev, const int* det_rows, const float* embs_dev,
+                           const uint8_t* images_dev, int rows, int cols, bool sync) {
+    const size_t CD = cfg.cap_dets;
+    int total = 0;
+    for (int i = 0; i < S; ++i) {
+        if (det_rows[i] < 0 || det_rows[i] > (int)CD) throw std::runtime_error("det_rows exceeds cap_dets");
+        h_ndets[i] = det_rows[i];
+        total += det_rows[i];
+    }
+    CUDA_OK(cudaMemcpyAsync(d_ndets, h_ndets, sizeof(int) * S, cudaMemcpyHostToDevice, stream));
+    if (dets_dev != d_dets)
+        CUDA_OK(cudaMemcpyAsync(d_dets, dets_dev, sizeof(float) * 6 * CD * S, cudaMemcpyDeviceToDevice, stream));
+    enqueue_frame(cfg.with_reid ? embs_dev : nullptr, images_dev, rows, cols, total);
+    if (sync) CUDA_OK(cudaStreamSynchronize(stream));
+}
+
+void Engine::fetch(float* const* out, const int* out_cap, int* out_rows) {
+    enqueue_fetch();
+    finish_fetch(out, out_cap, out_rows);
+}
+
+int Engine::snapshot(int sidx, int* ids, double* means, double* covs, int cap) {
+    if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
+    CUDA_OK(cudaStreamSynchronize(stream));
+    const TrkStream& s = h_streams[sidx];
+    const int CT = cfg.cap_tracks;
+    std::vector<int> sc(SC_COUNT), act(CT), lost(CT), idv(CT);
+    std::vector<double> mean((size_t)CT * 8), cov((size_t)CT * 64);
+    CUDA_OK(cudaMemcpy(sc.data(), s.scalars, sizeof(int) * SC_COUNT, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(act.data(), s.active, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(lost.data(), s.lost, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(idv.data(), s.id, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(mean.data(), s.mean, sizeof(double) * 8 * CT, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(cov.data(), s.cov, sizeof(double) * 64 * CT, cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int cnt = sc[pass == 0 ? SC_N_ACTIVE : SC_N_LOST];
+        const std::vector<int>& lst = pass == 0 ? act : lost;
+        for (int k = 0; k < cnt && n < cap; ++k, ++n) {
+            const int t = lst[k];
+            ids[n] = idv[t];
+            memcpy(means + (size_t)n * 8, mean.data() + (size_t)t * 8, sizeof(double) * 8);
+            memcpy(covs + (size_t)n * 64, cov.data() + (size_t)t * 64, sizeof(double) * 64);
+        }
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// standalone kernels for parity tests / micro-benchmarks
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lap_only(const TrkCfg cfg, TrkStream* streams, int T, int D, double thresh) {
+    TrkStream s = streams[blockIdx.x];
+    lap_solve(s, T, D, cfg.cap_dets, thresh);
+}
+
+void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int* y) {
+    if (T < 0 || D < 0) throw std::runtime_error("negative shape");
+    if (T == 0 || D == 0) {
+        for (int i = 0; i < T; ++i) x[i] = -1;
+        for (int j = 0; j < D; ++j) y[j] = -1;
+        return;
+    }
+    TrkCfg c{};
+    c.cap_tracks = T < 8 ? 8 : T;
+    c.cap_dets = D;
+    c.feat_dim = 0;
+    size_t bytes = carve_stream(c, nullptr, nullptr, nullptr);
+    uint8_t* mem = nullptr;
+    TrkStream hs, *ds = nullptr;
+    CUDA_OK(cudaMalloc(&mem, bytes));
+    CUDA_OK(cudaMemset(mem, 0, bytes));
+    carve_stream(c, mem, &hs, nullptr);
+    CUDA_OK(cudaMalloc(&ds, sizeof(TrkStream)));
+    CUDA_OK(cudaMemcpy(ds, &hs, sizeof(TrkStream), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(hs.cost, cost, sizeof(double) * (size_t)T * D, cudaMemcpyHostToDevice));
+    k_lap_only<<<1, 256>>>(c, ds, T, D, thresh);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(x, hs.lap_x, sizeof(int) * T, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(y, hs.lap_y, sizeof(int) * D, cudaMemcpyDeviceToHost);
+    cudaFree(mem);
+    cudaFree(ds);
+    CUDA_OK(e);
+}
+
+__global__ void k_kf_predict(int kind, double* mean, double* cov, const int* tracked, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrkCfg c{};
+    c.kind = kind;
+    kf_predict(c, tracked ? tracked[i] : 1, mean + (size_t)i * 8, cov + (size_t)i * 64);
+}
+__global__ void k_kf_update(int kind, double* mean, double* cov, const float* meas, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrkCfg c{};
+    c.kind = kind;
+    kf_update(c, meas + (size_t)i * 4, mean + (size_t)i * 8, cov + (size_t)i * 64);
+}
+__global__ void k_kf_initiate(int kind, const float* meas, double* mean, double* cov, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrkCfg c{};
+    c.kind = kind;
+    kf_initiate(c, meas + (size_t)i * 4, mean + (size_t)i * 8, cov + (size_t)i * 64);
+}
+__global__ void k_iou_cost(const double* t, int T, const float* d, int D, double* out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)T * D) return;
+    int i = (int)(e / D), j = (int)(e % D);
+    out[e] = iou_dist_td(t + (size_t)i * 4, d + (size_t)j * 4);
+}
+__global__ void k_cosine_cost(const float* a, int T, const float* b, int D, int F, double* out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)T * D) return;
+    int i = (int)(e / D), j = (int)(e % D);
+    out[e] = cosine_cost_f64(a + (size_t)i * F, b + (size_t)j * F, F);
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    explicit DevBuf(size_t count) : n(count) { if (count) CUDA_OK(cudaMalloc(&p, sizeof(T) * count)); }
+    ~DevBuf() { cudaFree(p); }
+    void up(const T* h) { if (n) CUDA_OK(cudaMemcpy(p, h, sizeof(T) * n, cudaMemcpyHostToDevice)); }
+    void down(T* h) { if (n) CUDA_OK(cudaMemcpy(h, p, sizeof(T) * n, cudaMemcpyDeviceToHost)); }
+};
+
+void standalone_kf(int op, int kind, double* mean, double* cov, const int* tracked, const float* meas, int n) {
+    if (n <= 0) return;
+    DevBuf<double> dm((size_t)n * 8), dc((size_t)n * 64);
+    DevBuf<int> dt(tracked ? n : 0);
+    DevBuf<float> dz(meas ? (size_t)n * 4 : 0);
+    if (op != 2) { dm.up(mean); dc.up(cov); }
+    if (tracked) dt.up(tracked);
+    if (meas) dz.up(meas);
+    int g = (n + 127) / 128;
+    if (op == 0) k_kf_predict<<<g, 128>>>(kind, dm.p, dc.p, tracked ? dt.p : nullptr, n);
+    else if (op == 1) k_kf_update<<<g, 128>>>(kind, dm.p, dc.p, dz.p, n);
+    else k_kf_initiate<<<g, 128>>>(kind, dz.p, dm.p, dc.p, n);
+    CUDA_OK(cudaDeviceSynchronize());
+    dm.down(mean);
+    dc.down(cov);
+}
+
+void standalone_iou(const double* t, int T, const float* d, int D, double* out) {
+    if (T <= 0 || D <= 0) return;
+    DevBuf<double> dt((size_t)T * 4), dout((size_t)T * D);
+    DevBuf<float> dd((size_t)D * 4);
+    dt.up(t); dd.up(d);
+    size_t total = (size_t)T * D;
+    k_iou_cost<<<(unsigned)((total + 255) / 256), 256>>>(dt.p, T, dd.p, D, dout.p);
+    CUDA_OK(cudaDeviceSynchronize());
+    dout.down(out);
+}
+
+void standalone_cosine(const float* a, int T, const float* b, int D, int F, double* out) {
+    if (T <= 0 || D <= 0) return;
+    DevBuf<float> da((size_t)T * F), db((size_t)D * F);
+    DevBuf<double> dout((size_t)T * D);
+    da.up(a); db.up(b);
+    size_t total = (size_t)T * D;
+    k_cosine_cost<<<(unsigned)((total + 255) / 256), 256>>>(da.p, T, db.p, D, F, dout.p);
+    CUDA_OK(cudaDeviceSynchronize());
+    dout.down(out);
+}
+
+}  // namespace bmb

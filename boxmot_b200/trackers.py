@@ -1,0 +1,359 @@
+"""Host-side mirror of the reference tracker frontends over the CUDA C ABI.
+
+`ByteTrack` and `BotSort` keep the reference call surface for the per-frame path --
+``update(dets, img, embs=None, masks=None) -> TrackResults`` with the input checks of
+boxmot/trackers/basetracker.py:120-147,356-372 and the constructor arguments of bytetrack.py:226-257 /
+botsort.py:66-118 -- while all track state and arithmetic live on the GPU (csrc/tracker_core.cuh).
+This module is tensor plumbing only; there is no CPU implementation behind it.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error, BoxMOTB200TrackerConfig
+
+# YAML defaults used by the reference's create_tracker (boxmot/configs/trackers/{bytetrack,botsort}.yaml),
+# restated as data: this is the configuration contract of the path.
+TRACKER_DEFAULTS = {
+    "bytetrack": dict(min_conf=0.1, track_thresh=0.6, track_buffer=30, match_thresh=0.9, frame_rate=30),
+    "botsort": dict(
+        track_high_thresh=0.6296854875023994, track_low_thresh=0.1014392537025336,
+        new_track_thresh=0.6246494191492591, track_buffer=40, match_thresh=0.7722224024589055,
+        use_cmc=True, cmc_method="sof", frame_rate=30, fuse_first_associate=True, with_reid=True,
+        proximity_thresh=0.6084297894561342, appearance_thresh=0.6188818853936099,
+        unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
+        unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329),
+}
+
+
+class TrackResults(np.ndarray):
+    """float32 view over the (M, 8) output rows [x1,y1,x2,y2,id,conf,cls,det_ind] (track_results.py:12-31)."""
+
+    def __new__(cls, data):
+        arr = np.asarray(data, dtype=np.float32)
+        if arr.ndim == 1 and arr.size > 0:
+            arr = arr.reshape(1, -1)
+        elif arr.size == 0:
+            cols = arr.shape[1] if arr.ndim == 2 else 0
+            arr = arr.reshape(0, cols)
+        return arr.view(cls)
+
+    @property
+    def xyxy(self):
+        return np.asarray(self[:, :4])
+
+    @property
+    def id(self):
+        return np.asarray(self[:, 4]).astype(int)
+
+    @property
+    def conf(self):
+        return np.asarray(self[:, 5])
+
+    @property
+    def cls(self):
+        return np.asarray(self[:, 6]).astype(int)
+
+    @property
+    def det_ind(self):
+        return np.asarray(self[:, 7]).astype(int)
+
+
+def _check_inputs(dets, img, embs):
+    assert isinstance(dets, np.ndarray), (
+        f"Unsupported 'dets' input format '{type(dets)}', valid format is np.ndarray")
+    assert img is None or isinstance(img, np.ndarray), (
+        f"Unsupported 'img_numpy' input format '{type(img)}', valid format is np.ndarray")
+    assert len(dets.shape) == 2, "Unsupported 'dets' dimensions, valid number of dimensions is two"
+    if embs is not None:
+        assert dets.shape[0] == embs.shape[0], "Missmatch between detections and embeddings sizes"
+    assert dets.shape[1] == 6, (
+        "Unsupported 'dets' 2nd dimension length, valid length is 6 (x1,y1,x2,y2,conf,cls)")
+
+
+class MultiStreamTracker:
+    """`n_streams` independent trackers resident on one GPU, advanced together (one launch sequence/frame).
+
+    Per-stream results equal `n_streams` separate reference trackers (ids start at 1 in every stream)."""
+
+    def __init__(self, tracker: str, n_streams: int = 1, cap_tracks: int = 1024, cap_dets: int = 512,
+                 feat_dim: int = 512, reid_blob: Optional[str] = None, **params: Any):
+        self.lib = _lib.require_device()
+        cfg = BoxMOTB200TrackerConfig()
+        kind = tracker.lower()
+        if kind == "bytetrack":
+            p = dict(min_conf=0.1, track_thresh=0.45, match_thresh=0.8, track_buffer=25, frame_rate=30)
+            unknown = set(params) - set(p)
+            if unknown:
+                raise TypeError(f"unknown ByteTrack parameters: {sorted(unknown)}")
+            p.update(params)
+            cfg.tracker = _lib.TRACKER_BYTETRACK
+            cfg.track_high_thresh = p["track_thresh"]
+            cfg.track_low_thresh = p["min_conf"]
+            cfg.new_track_thresh = p["track_thresh"]
+            cfg.match_thresh = p["match_thresh"]
+            cfg.second_match_thresh = 0.5
+            cfg.unconfirmed_match_thresh = 0.7
+            cfg.removed_stracks_buffer = 0
+            cfg.with_reid = 0
+            cfg.fuse_first_associate = 1
+        elif kind == "botsort":
+            p = dict(track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6, track_buffer=30,
+                     match_thresh=0.8, proximity_thresh=0.5, appearance_thresh=0.25, frame_rate=30,
+                     fuse_first_associate=False, with_reid=True, second_match_thresh=0.5,
+                     unconfirmed_match_thresh=0.7, unconfirmed_emb_scale=2.0, removed_stracks_buffer=100)
+            unknown = set(params) - set(p)
+            if unknown:
+                raise TypeError(f"unknown BotSort parameters: {sorted(unknown)}")
+            p.update(params)
+            cfg.tracker = _lib.TRACKER_BOTSORT
+            cfg.track_high_thresh = p["track_high_thresh"]
+            cfg.track_low_thresh = p["track_low_thresh"]
+            cfg.new_track_thresh = p["new_track_thresh"]
+            cfg.match_thresh = p["match_thresh"]
+            cfg.second_match_thresh = p["second_match_thresh"]
+            cfg.unconfirmed_match_thresh = p["unconfirmed_match_thresh"]
+            cfg.proximity_thresh = p["proximity_thresh"]
+            cfg.appearance_thresh = p["appearance_thresh"]
+            cfg.unconfirmed_emb_scale = p["unconfirmed_emb_scale"]
+            cfg.removed_stracks_buffer = int(p["removed_stracks_buffer"])
+            cfg.with_reid = int(bool(p["with_reid"]))
+            cfg.fuse_first_associate = int(bool(p["fuse_first_associate"]))
+        else:
+            raise ValueError(f"tracker '{tracker}' is not part of the B200 hot path (bytetrack, botsort)")
+        cfg.n_streams = int(n_streams)
+        cfg.cap_tracks = int(cap_tracks)
+        cfg.cap_dets = int(cap_dets)
+        cfg.feat_dim = int(feat_dim)
+        cfg.track_buffer = int(p["track_buffer"])
+        cfg.frame_rate = int(p["frame_rate"])
+        self._blob = str(reid_blob).encode() if reid_blob else None
+        cfg.reid_model_path = self._blob
+        self.kind = kind
+        self.params = p
+        self.n_streams = int(n_streams)
+        self.cap_dets = int(cap_dets)
+        self.cap_tracks = int(cap_tracks)
+        self.feat_dim = int(feat_dim)
+        self.with_reid = bool(cfg.with_reid)
+        self.has_reid_model = reid_blob is not None
+        self.handle = self.lib.boxmot_b200_tracker_create(ctypes.byref(cfg))
+        if not self.handle:
+            raise B200Error(f"tracker create failed: {_lib.last_error(self.lib)}")
+        self.frame_count = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.boxmot_b200_tracker_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        if not self.lib.boxmot_b200_tracker_reset(self.handle):
+            raise B200Error(_lib.last_error(self.lib))
+        self.frame_count = 0
+
+    def update(self, dets: Sequence[np.ndarray], imgs: Optional[Sequence[np.ndarray]] = None,
+               embs: Optional[Sequence[Optional[np.ndarray]]] = None):
+        S = self.n_streams
+        assert len(dets) == S, f"expected {S} detection arrays"
+        d_arr, d_ptr, rows = [], (ctypes.c_void_p * S)(), (ctypes.c_int * S)()
+        for i, d in enumerate(dets):
+            d = np.zeros((0, 6), np.float32) if d is None or len(d) == 0 else d
+            d = np.ascontiguousarray(d, dtype=np.float32)
+            assert d.ndim == 2 and d.shape[1] == 6, (
+                "Unsupported 'dets' 2nd dimension length, valid length is 6 (x1,y1,x2,y2,conf,cls)")
+            d_arr.append(d)
+            d_ptr[i] = d.ctypes.data if len(d) else None
+            rows[i] = len(d)
+        e_ptr = None
+        e_arr = []
+        if embs is not None and self.with_reid:
+            e_ptr = (ctypes.c_void_p * S)()
+            for i, e in enumerate(embs):
+                if rows[i] == 0:
+                    e_ptr[i] = None
+                    continue
+                assert e is not None and len(e) == rows[i], "Missmatch between detections and embeddings sizes"
+                e = np.ascontiguousarray(e, dtype=np.float32)
+                assert e.ndim == 2 and e.shape[1] == self.feat_dim, "embedding width does not match feat_dim"
+                e_arr.append(e)
+                e_ptr[i] = e.ctypes.data
+        i_ptr, ih, iw = None, 0, 0
+        i_arr = []
+        if self.with_reid and e_ptr is None:
+            if imgs is None:
+                raise B200Error("BoT-SORT with_reid needs `embs` or frames (and a ReID blob) to embed detections")
+            i_ptr = (ctypes.c_void_p * S)()
+            for i, im in enumerate(imgs):
+                im = np.ascontiguousarray(im, dtype=np.uint8)
+                assert im.ndim == 3 and im.shape[2] == 3, "img must be HxWx3 uint8 BGR"
+                if i == 0:
+                    ih, iw = im.shape[:2]
+                assert im.shape[:2] == (ih, iw), "all frames of one batch must share a resolution"
+                i_arr.append(im)
+                i_ptr[i] = im.ctypes.data
+        outs = [np.empty((max(int(rows[i]), 1), 9), np.float32) for i in range(S)]
+        o_ptr = (ctypes.c_void_p * S)(*[o.ctypes.data for o in outs])
+        o_cap = (ctypes.c_int * S)(*[len(o) for o in outs])
+        o_rows = (ctypes.c_int * S)()
+        ok = self.lib.boxmot_b200_tracker_update_batch(self.handle, d_ptr, rows, e_ptr, i_ptr, ih, iw, o_ptr, o_cap,
+                                                       o_rows)
+        if not ok:
+            raise B200Error(_lib.last_error(self.lib))
+        self.frame_count += 1
+        return [TrackResults(outs[i][: o_rows[i], :8].copy()) for i in range(S)]
+
+    def snapshot(self, stream: int = 0):
+        cap = self.cap_tracks
+        ids = np.empty(cap, np.int32)
+        means = np.empty((cap, 8))
+        covs = np.empty((cap, 8, 8))
+        n = ctypes.c_int(0)
+        ok = self.lib.boxmot_b200_tracker_snapshot(self.handle, stream, ids.ctypes.data, means.ctypes.data,
+                                                   covs.ctypes.data, cap, ctypes.byref(n))
+        if not ok:
+            raise B200Error(_lib.last_error(self.lib))
+        return {int(ids[i]): (means[i].copy(), covs[i].copy()) for i in range(n.value)}
+
+    def last_launches(self) -> int:
+        n = ctypes.c_int(0)
+        self.lib.boxmot_b200_tracker_last_launches(self.handle, ctypes.byref(n))
+        return n.value
+
+    def last_device_ms(self):
+        a, b = ctypes.c_double(0), ctypes.c_double(0)
+        self.lib.boxmot_b200_tracker_last_device_ms(self.handle, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+
+class _SingleStreamTracker:
+    """BaseTracker-shaped single-stream frontend (basetracker.py:19-147)."""
+
+    _kind = ""
+    provides_reid = False
+    supports_obb = False
+
+    def __init__(self, per_class: bool = False, cap_tracks: int = 2048, cap_dets: int = 1024,
+                 reid_model: Any = None, feat_dim: int = 512, det_thresh: float = 0.3, max_age: int = 30,
+                 max_obs: int = 50, min_hits: int = 3, iou_threshold: float = 0.3, nr_classes: int = 80,
+                 asso_func: str = "iou", is_obb: bool = False, **params: Any):
+        if per_class:
+            raise NotImplementedError("per_class=True is out of scope for the B200 hot path (SURVEY N15)")
+        if is_obb:
+            raise NotImplementedError("OBB detections are out of scope for the B200 hot path")
+        if asso_func != "iou":
+            raise NotImplementedError("only asso_func='iou' is implemented")
+        self.per_class = False
+        self.det_thresh, self.max_age, self.max_obs, self.min_hits = det_thresh, max_age, max_obs, min_hits
+        self.iou_threshold, self.nr_classes, self.is_obb = iou_threshold, nr_classes, False
+        self.model = reid_model
+        blob = getattr(reid_model, "blob_path", None)
+        if reid_model is not None and blob is not None:
+            feat_dim = int(getattr(reid_model, "feature_dim", feat_dim))
+        self._engine = MultiStreamTracker(self._kind, 1, cap_tracks, cap_dets, feat_dim, reid_blob=blob, **params)
+        self.provides_reid = blob is not None
+        self.with_reid = self._engine.with_reid
+        self.frame_count = 0
+
+    def reset(self):
+        self._engine.reset()
+        self.frame_count = 0
+
+    def update(self, dets, img=None, embs=None, masks=None) -> TrackResults:
+        if hasattr(dets, "data") and not isinstance(dets, np.ndarray):
+            dets = dets.data
+        if isinstance(dets, memoryview):
+            dets = np.array(dets, dtype=np.float32)
+        if dets is None or len(dets) == 0:
+            dets = np.empty((0, 6), dtype=np.float32)
+            embs = None if embs is None or len(embs) else embs
+        _check_inputs(dets, img, embs)
+        eng = self._engine
+        if eng.with_reid and embs is None and not eng.has_reid_model:
+            # foreign ReID backend (any object with get_features): embed the first-round detections on its
+            # own device and hand the rows to the tracker, exactly where botsort.py:191-192 calls the model
+            if self.model is None:
+                raise B200Error("with_reid=True needs reid_model=, embs=, or with_reid=False")
+            first = dets[:, 4].astype(np.float64) > eng.params["track_high_thresh"]
+            embs = np.zeros((len(dets), eng.feat_dim), np.float32)
+            if first.any():
+                embs[first] = np.asarray(self.model.get_features(dets[first][:, :4], img), dtype=np.float32)
+        out = eng.update([dets], None if img is None else [img], None if embs is None else [embs])[0]
+        self.frame_count = eng.frame_count
+        return out
+
+    def snapshot(self):
+        return self._engine.snapshot(0)
+
+
+class ByteTrack(_SingleStreamTracker):
+    """ByteTrack on the GPU; arguments as boxmot/trackers/bbox/bytetrack/bytetrack.py:226-257."""
+
+    _kind = "bytetrack"
+
+    def __init__(self, min_conf: float = 0.1, track_thresh: float = 0.45, match_thresh: float = 0.8,
+                 track_buffer: int = 25, frame_rate: int = 30, **kwargs: Any):
+        super().__init__(min_conf=min_conf, track_thresh=track_thresh, match_thresh=match_thresh,
+                         track_buffer=track_buffer, frame_rate=frame_rate, **kwargs)
+
+
+class BotSort(_SingleStreamTracker):
+    """BoT-SORT on the GPU; arguments as boxmot/trackers/bbox/botsort/botsort.py:66-118.
+
+    `use_cmc` must be False: camera-motion estimation is OpenCV image registration outside this hot path
+    (SURVEY N6); the reference's parity and baseline runs disable it the same way."""
+
+    _kind = "botsort"
+
+    def __init__(self, reid_model: Any = None, track_high_thresh: float = 0.5, track_low_thresh: float = 0.1,
+                 new_track_thresh: float = 0.6, track_buffer: int = 30, match_thresh: float = 0.8,
+                 proximity_thresh: float = 0.5, appearance_thresh: float = 0.25, use_cmc: bool = False,
+                 cmc_method: str = "ecc", frame_rate: int = 30, fuse_first_associate: bool = False,
+                 with_reid: bool = True, second_match_thresh: float = 0.5,
+                 unconfirmed_match_thresh: float = 0.7, unconfirmed_emb_scale: float = 2.0,
+                 removed_stracks_buffer: int = 100, **kwargs: Any):
+        if use_cmc:
+            raise NotImplementedError("use_cmc=True: camera-motion compensation is out of scope (pass use_cmc=False)")
+        super().__init__(reid_model=reid_model if with_reid else None, track_high_thresh=track_high_thresh,
+                         track_low_thresh=track_low_thresh, new_track_thresh=new_track_thresh,
+                         track_buffer=track_buffer, match_thresh=match_thresh, proximity_thresh=proximity_thresh,
+                         appearance_thresh=appearance_thresh, frame_rate=frame_rate,
+                         fuse_first_associate=fuse_first_associate, with_reid=with_reid,
+                         second_match_thresh=second_match_thresh,
+                         unconfirmed_match_thresh=unconfirmed_match_thresh,
+                         unconfirmed_emb_scale=unconfirmed_emb_scale,
+                         removed_stracks_buffer=removed_stracks_buffer, **kwargs)
+
+
+def create_tracker(tracker_type: str, reid_weights=None, device=None, half: bool = False, per_class: bool = False,
+                   reid_model: Any = None, **overrides: Any):
+    """YAML-default construction like boxmot/trackers/tracker_zoo.py:33-147 for the two STrack trackers.
+
+    `reid_weights` may be a `.pt` state dict or a `.b200reid` blob; it is converted once and loaded on the GPU.
+    CMC defaults to off (see BotSort)."""
+    kind = tracker_type.lower()
+    if kind not in TRACKER_DEFAULTS:
+        raise ValueError(f"tracker '{tracker_type}' is not part of the B200 hot path")
+    args = dict(TRACKER_DEFAULTS[kind])
+    args.pop("cmc_method", None)
+    args["use_cmc"] = False if kind == "botsort" else None
+    if args["use_cmc"] is None:
+        args.pop("use_cmc")
+    args.update(overrides)
+    if kind == "bytetrack":
+        return ByteTrack(per_class=per_class, **args)
+    if reid_model is None and reid_weights is not None and args.get("with_reid", True):
+        from .reid import B200ReID
+
+        reid_model = B200ReID(reid_weights, half=half)
+    return BotSort(reid_model=reid_model, per_class=per_class, **args)
