@@ -1,0 +1,256 @@
+"""Oracle restatement of the ReID path: crop staging + OSNet forward -- TEST INFRASTRUCTURE ONLY.
+
+Follows (relative to /root/reference/boxmot):
+  * reid/backends/base_backend.py:148-195  get_crops: round -> clip -> slice (blank 256x128 when empty) ->
+    cv2.resize INTER_LINEAR to (128 w, 256 h) -> BGR2RGB -> /255 -> (x - mean) / std, float32 NCHW
+  * reid/core/preprocessing.py:12-18       resize
+  * reid/backends/base_backend.py:197-207  get_features: forward, then row-wise L2 normalisation
+  * reid/backbones/osnet.py:27-260,380-405 ConvLayer / Conv1x1 / Conv1x1Linear / LightConv3x3 / ChannelGate
+    (one gate module shared by the four branches) / OSBlock / OSNet.forward in eval mode
+  * reid/backbones/osnet.py:488,533        osnet_x1_0 (64/256/384/512) and osnet_x0_25 (16/64/96/128)
+`resize_linear_u8` restates OpenCV's 8-bit INTER_LINEAR fixed-point path (third-party, opencv 4.13 in this
+image): 11-bit coefficients from float32 phase, horizontal pass in int32, vertical
+(((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2; x phases are clamped at the borders, y rows are clipped
+at fetch.  It is pinned bit-for-bit against cv2.resize in tests/test_oracle_reid.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+MEAN = (0.485, 0.456, 0.406)
+STD = (0.229, 0.224, 0.225)
+INPUT_HW = (256, 128)
+
+OSNET_ARCHS = {
+    "osnet_x0_25": (16, 64, 96, 128),
+    "osnet_x0_5": (32, 128, 192, 256),
+    "osnet_x0_75": (48, 192, 288, 384),
+    "osnet_x1_0": (64, 256, 384, 512),
+}
+BRANCH_DEPTHS = (("conv2a", 1), ("conv2b", 2), ("conv2c", 3), ("conv2d", 4))
+
+
+# ----------------------------------------------------------------------------------------------------
+# crop staging
+# ----------------------------------------------------------------------------------------------------
+def _linear_coeffs(dst_n: int, src_n: int, clamp: bool):
+    inv_scale = float(dst_n) / float(src_n)
+    scale = 1.0 / inv_scale
+    idx = np.zeros(dst_n, np.int64)
+    a0 = np.zeros(dst_n, np.int64)
+    a1 = np.zeros(dst_n, np.int64)
+    for d in range(dst_n):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if clamp:
+            if s < 0:
+                s, f = 0, np.float32(0)
+            if s >= src_n - 1:
+                s, f = src_n - 1, np.float32(0)
+        idx[d] = s
+        a0[d] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+        a1[d] = int(np.rint(np.float32(f * np.float32(2048))))
+    return idx, a0, a1
+
+
+def resize_linear_u8(src: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+    sh, sw = src.shape[:2]
+    if (sh, sw) == (dst_h, dst_w):
+        return src.copy()
+    xi, xa0, xa1 = _linear_coeffs(dst_w, sw, True)
+    yi, ya0, ya1 = _linear_coeffs(dst_h, sh, False)
+    s = src.astype(np.int64)
+    x1 = np.minimum(xi + 1, sw - 1)
+    hor = s[:, xi, :] * xa0[None, :, None] + s[:, x1, :] * xa1[None, :, None]
+    y0 = np.clip(yi, 0, sh - 1)
+    y1 = np.clip(yi + 1, 0, sh - 1)
+    b0 = ya0[:, None, None]
+    b1 = ya1[:, None, None]
+    out = (((b0 * (hor[y0] >> 4)) >> 16) + ((b1 * (hor[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def crop_boxes(xyxys: np.ndarray, img: np.ndarray):
+    """uint8 RGB crops (N,256,128,3) exactly as get_crops stages them before the float conversion."""
+    h, w = img.shape[:2]
+    xyxys = np.asarray(xyxys, dtype=np.float32).reshape(-1, 4)
+    out = np.zeros((len(xyxys), INPUT_HW[0], INPUT_HW[1], 3), np.uint8)
+    for i, box in enumerate(xyxys):
+        x1, y1, x2, y2 = box.round().astype("int")
+        cx1, cy1 = max(0, x1), max(0, y1)
+        cx2, cy2 = min(w, x2), min(h, y2)
+        if cx2 > cx1 and cy2 > cy1:
+            crop = resize_linear_u8(img[cy1:cy2, cx1:cx2], INPUT_HW[0], INPUT_HW[1])
+        else:
+            crop = np.zeros((INPUT_HW[0], INPUT_HW[1], 3), np.uint8)
+        out[i] = crop[:, :, ::-1]
+    return out
+
+
+def get_crops(xyxys: np.ndarray, img: np.ndarray) -> torch.Tensor:
+    """float32 NCHW network input (N,3,256,128)."""
+    u8 = crop_boxes(xyxys, img)
+    x = torch.from_numpy(u8).to(torch.float32).permute(0, 3, 1, 2).contiguous()
+    x = x / 255.0
+    mean = torch.tensor(MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(STD).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+# ----------------------------------------------------------------------------------------------------
+# seeded weights (the container has no pretrained files)
+# ----------------------------------------------------------------------------------------------------
+def make_osnet_state(arch: str = "osnet_x0_25", seed: int = 0, feature_dim: int = 512, num_classes: int = 1041):
+    """A state dict with the reference's parameter names, kaiming-ish conv weights and NON-trivial BatchNorm
+    statistics (so that BN folding is exercised)."""
+    ch = OSNET_ARCHS[arch]
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, k, groups=1, gain=1.0):
+        fan_in = (ci // groups) * k * k
+        sd[name + ".weight"] = torch.randn(co, ci // groups, k, k, generator=g) * (gain / fan_in) ** 0.5
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0)
+
+    def light(name, c):
+        conv(name + ".conv1", c, c, 1)
+        conv(name + ".conv2", c, c, 3, groups=c)
+        bn(name + ".bn", c)
+
+    def osblock(name, cin, cout):
+        mid = cout // 4
+        conv(name + ".conv1.conv", mid, cin, 1)
+        bn(name + ".conv1.bn", mid)
+        light(name + ".conv2a", mid)
+        for br, depth in BRANCH_DEPTHS[1:]:
+            for k in range(depth):
+                light(f"{name}.{br}.{k}", mid)
+        hid = mid // 16
+        conv(name + ".gate.fc1", hid, mid, 1)
+        sd[name + ".gate.fc1.bias"] = 0.1 * torch.randn(hid, generator=g)
+        conv(name + ".gate.fc2", mid, hid, 1)
+        sd[name + ".gate.fc2.bias"] = 0.1 * torch.randn(mid, generator=g)
+        conv(name + ".conv3.conv", cout, mid, 1, gain=0.1)
+        bn(name + ".conv3.bn", cout)
+        if cin != cout:
+            conv(name + ".downsample.conv", cout, cin, 1)
+            bn(name + ".downsample.bn", cout)
+
+    conv("conv1.conv", ch[0], 3, 7)
+    bn("conv1.bn", ch[0])
+    for s, (cin, cout) in enumerate(((ch[0], ch[1]), (ch[1], ch[2]), (ch[2], ch[3]))):
+        stage = f"conv{s + 2}"
+        osblock(f"{stage}.0", cin, cout)
+        osblock(f"{stage}.1", cout, cout)
+        if s < 2:
+            conv(f"{stage}.2.0.conv", cout, cout, 1)
+            bn(f"{stage}.2.0.bn", cout)
+    conv("conv5.conv", ch[3], ch[3], 1)
+    bn("conv5.bn", ch[3])
+    sd["fc.0.weight"] = 0.05 * torch.randn(feature_dim, ch[3], generator=g)
+    sd["fc.0.bias"] = 0.05 * torch.randn(feature_dim, generator=g)
+    bn("fc.1", feature_dim)
+    sd["classifier.weight"] = 0.01 * torch.randn(num_classes, feature_dim, generator=g)
+    sd["classifier.bias"] = torch.zeros(num_classes)
+    return sd
+
+
+def detect_osnet_arch(sd) -> str:
+    c0 = sd["conv1.conv.weight"].shape[0]
+    c3 = sd["conv5.conv.weight"].shape[0]
+    for name, ch in OSNET_ARCHS.items():
+        if ch[0] == c0 and ch[3] == c3:
+            return name
+    raise ValueError("state dict is not an OSNet of a known width")
+
+
+# ----------------------------------------------------------------------------------------------------
+# functional forward (eval mode), float32
+# ----------------------------------------------------------------------------------------------------
+def _bn(sd, name, x, eps=1e-5):
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"],
+                        sd[name + ".bias"], training=False, eps=eps)
+
+
+def _light(sd, name, x):
+    c = x.shape[1]
+    x = F.conv2d(x, sd[name + ".conv1.weight"])
+    x = F.conv2d(x, sd[name + ".conv2.weight"], padding=1, groups=c)
+    return F.relu(_bn(sd, name + ".bn", x))
+
+
+def _gate(sd, name, x):
+    g = F.adaptive_avg_pool2d(x, 1)
+    g = F.relu(F.conv2d(g, sd[name + ".fc1.weight"], sd[name + ".fc1.bias"]))
+    g = torch.sigmoid(F.conv2d(g, sd[name + ".fc2.weight"], sd[name + ".fc2.bias"]))
+    return x * g
+
+
+def _osblock(sd, name, x):
+    identity = x
+    x1 = F.relu(_bn(sd, name + ".conv1.bn", F.conv2d(x, sd[name + ".conv1.conv.weight"])))
+    branches = [_light(sd, name + ".conv2a", x1)]
+    for br, depth in BRANCH_DEPTHS[1:]:
+        y = x1
+        for k in range(depth):
+            y = _light(sd, f"{name}.{br}.{k}", y)
+        branches.append(y)
+    x2 = (_gate(sd, name + ".gate", branches[0]) + _gate(sd, name + ".gate", branches[1])
+          + _gate(sd, name + ".gate", branches[2]) + _gate(sd, name + ".gate", branches[3]))
+    x3 = _bn(sd, name + ".conv3.bn", F.conv2d(x2, sd[name + ".conv3.conv.weight"]))
+    if (name + ".downsample.conv.weight") in sd:
+        identity = _bn(sd, name + ".downsample.bn", F.conv2d(identity, sd[name + ".downsample.conv.weight"]))
+    return F.relu(x3 + identity)
+
+
+@torch.no_grad()
+def osnet_forward(sd, x: torch.Tensor, return_stages: bool = False):
+    """x (N,3,256,128) float32 -> (N, feature_dim) un-normalised embedding (fc output, eval mode)."""
+    stages = {}
+    x = F.relu(_bn(sd, "conv1.bn", F.conv2d(x, sd["conv1.conv.weight"], stride=2, padding=3)))
+    stages["stem"] = x
+    x = F.max_pool2d(x, 3, stride=2, padding=1)
+    stages["pool"] = x
+    for s in range(3):
+        stage = f"conv{s + 2}"
+        x = _osblock(sd, f"{stage}.0", x)
+        stages[f"{stage}.0"] = x
+        x = _osblock(sd, f"{stage}.1", x)
+        stages[f"{stage}.1"] = x
+        if s < 2:
+            x = F.relu(_bn(sd, f"{stage}.2.0.bn", F.conv2d(x, sd[f"{stage}.2.0.conv.weight"])))
+            x = F.avg_pool2d(x, 2, stride=2)
+            stages[f"{stage}.2"] = x
+    x = F.relu(_bn(sd, "conv5.bn", F.conv2d(x, sd["conv5.conv.weight"])))
+    v = F.adaptive_avg_pool2d(x, 1).flatten(1)
+    v = F.linear(v, sd["fc.0.weight"], sd["fc.0.bias"])
+    v = F.relu(_bn(sd, "fc.1", v))
+    return (v, stages) if return_stages else v
+
+
+def get_features(sd, xyxys: np.ndarray, img: np.ndarray) -> np.ndarray:
+    """(N, D) float32 L2-normalised embeddings, as BaseModelBackend.get_features returns them."""
+    xyxys = np.asarray(xyxys, dtype=np.float32)
+    if xyxys.size == 0:
+        return np.array([])
+    feats = osnet_forward(sd, get_crops(xyxys, img)).numpy()
+    return feats / np.linalg.norm(feats, axis=-1, keepdims=True)
+
+
+class OracleReID:
+    """Minimal `reid_model` object for the oracle trackers (get_features only)."""
+
+    def __init__(self, sd):
+        self.sd = sd
+
+    def get_features(self, xyxys, img):
+        return get_features(self.sd, xyxys, img)

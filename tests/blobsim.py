@@ -1,0 +1,91 @@
+"""Walk a `.b200reid` blob exactly as csrc/reid_model.cu does and evaluate the folded network with torch ops
+(NHWC, float32).  Test infrastructure: validates boxmot_b200/weights.py (BN folding, layouts, ordering)
+against the oracle without a GPU, and documents the arithmetic each CUDA kernel implements."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from boxmot_b200.weights import read_blob
+
+LIGHTS = (1, 2, 3, 4)  # branch depths
+
+
+class _Cursor:
+    def __init__(self, payload):
+        self.p = torch.from_numpy(payload.copy())
+        self.o = 0
+
+    def take(self, *shape):
+        n = int(np.prod(shape))
+        t = self.p[self.o:self.o + n].view(*shape)
+        self.o += n
+        return t
+
+
+def _pw(x, w, b, relu):
+    y = x @ w + b
+    return F.relu(y) if relu else y
+
+
+def _dw3(x, w9c, b):
+    # x (N,H,W,C); depthwise 3x3, zero padding 1, weights [9][C] (tap = kh*3+kw)
+    n, h, wd, c = x.shape
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+    acc = torch.zeros_like(x)
+    for kh in range(3):
+        for kw in range(3):
+            acc = acc + xp[:, kh:kh + h, kw:kw + wd, :] * w9c[kh * 3 + kw]
+    return F.relu(acc + b)
+
+
+@torch.no_grad()
+def blob_forward(blob_path, x_nhwc: torch.Tensor, return_stages=False):
+    """x_nhwc (N,256,128,3) float32 normalised RGB -> (N, feat) un-normalised embedding."""
+    header, payload = read_blob(blob_path)
+    c = list(header[3:7])
+    feat = header[7]
+    cur = _Cursor(payload)
+    stages = {}
+    w, b = cur.take(147, c[0]), cur.take(c[0])
+    xn = x_nhwc.permute(0, 3, 1, 2)
+    wt = w.view(7, 7, 3, c[0]).permute(3, 2, 0, 1).contiguous()
+    x = F.relu(F.conv2d(xn, wt, b, stride=2, padding=3))
+    x = F.max_pool2d(x, 3, stride=2, padding=1).permute(0, 2, 3, 1).contiguous()
+    stages["pool"] = x
+    for s in range(3):
+        for j in range(2):
+            cin = c[s] if j == 0 else c[s + 1]
+            cout = c[s + 1]
+            mid, hid = cout // 4, cout // 64
+            x1 = _pw(x, cur.take(cin, mid), cur.take(mid), True)
+            branches = []
+            for depth in LIGHTS:
+                y = x1
+                for _ in range(depth):
+                    wpw, wdw, bb = cur.take(mid, mid), cur.take(9, mid), cur.take(mid)
+                    y = _dw3(y @ wpw, wdw, bb)
+                branches.append(y)
+            w1, b1, w2, b2 = cur.take(mid, hid), cur.take(hid), cur.take(hid, mid), cur.take(mid)
+            x2 = 0
+            for y in branches:
+                g = torch.sigmoid(F.relu(y.mean(dim=(1, 2)) @ w1 + b1) @ w2 + b2)
+                x2 = x2 + y * g[:, None, None, :]
+            if cin != cout:
+                wc, bc = cur.take(mid + cin, cout), cur.take(cout)
+                x = F.relu(torch.cat([x2, x], dim=-1) @ wc + bc)
+            else:
+                wc, bc = cur.take(mid, cout), cur.take(cout)
+                x = F.relu(x2 @ wc + bc + x)
+            stages[f"conv{s + 2}.{j}"] = x
+        if s < 2:
+            x = _pw(x, cur.take(c[s + 1], c[s + 1]), cur.take(c[s + 1]), True)
+            n, h, wd, ch = x.shape
+            x = x.view(n, h // 2, 2, wd // 2, 2, ch).mean(dim=(2, 4))
+            stages[f"conv{s + 2}.2"] = x
+    x = _pw(x, cur.take(c[3], c[3]), cur.take(c[3]), True)
+    v = x.mean(dim=(1, 2))
+    v = F.relu(v @ cur.take(c[3], feat) + cur.take(feat))
+    assert cur.o == payload.size
+    return (v, stages) if return_stages else v

@@ -65,6 +65,57 @@ def run(tracker, frames, img, embs=None):
     return dict(rows=np.concatenate(rows, 0), offsets=np.asarray(offsets, np.int64), **snaps)
 
 
+def make_reid_golden():
+    """Crops and embeddings from the reference classes (BaseModelBackend.get_crops / get_features over the
+    reference OSNet) with seeded weights from oracle.reid.make_osnet_state (no pretrained files exist here)."""
+    import hashlib
+
+    import torch
+    from boxmot.reid.backbones.osnet import osnet_x0_25
+    from boxmot.reid.backends.base_backend import BaseModelBackend
+    from boxmot.reid.core.preprocessing import get_preprocess_fn
+
+    from oracle import reid as orid
+
+    class RefBackend(BaseModelBackend):
+        def __init__(self, model):
+            self.device = torch.device("cpu")
+            self.half = False
+            self.input_shape = (256, 128)
+            self.nhwc = False
+            self.preprocess_fn = get_preprocess_fn(None)
+            self.mean_array = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+            self.std_array = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+            self.model = model
+
+        def forward(self, x):
+            return self.model(x)
+
+        def load_model(self, w):
+            pass
+
+    sd = orid.make_osnet_state("osnet_x0_25", seed=7)
+    model = osnet_x0_25(num_classes=1041, pretrained=False)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    img = np.random.default_rng(123).integers(0, 255, size=(720, 1280, 3), dtype=np.uint8)
+    r2 = np.random.default_rng(5)
+    boxes = []
+    for _ in range(12):
+        cx, cy = r2.uniform(0, 1280), r2.uniform(0, 720)
+        w, h = r2.uniform(8, 160), r2.uniform(16, 320)
+        boxes.append([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+    boxes += [[-50, -50, -10, -10], [10.5, 20.5, 11.4, 300.2], [0, 0, 1280, 720], [600, 300, 728, 556]]
+    boxes = np.array(boxes, np.float32)
+    backend = RefBackend(model)
+    crops = backend.get_crops(boxes, img).numpy()
+    feats = backend.get_features(boxes, img)
+    np.savez_compressed(HERE / "reid_osnet_x0_25.npz", boxes=boxes,
+                        crops_sha256=hashlib.sha256(np.ascontiguousarray(crops).tobytes()).hexdigest(),
+                        crops_sample=crops[[0, 13]], crops_sample_index=np.array([0, 13]),
+                        features=feats.astype(np.float32), weight_seed=7, image_seed=123)
+
+
 def main():
     img = np.zeros((360, 640, 3), np.uint8)
 
@@ -99,6 +150,7 @@ def main():
     embs = stress_embeddings(frames, 256, seed=3)
     np.savez_compressed(HERE / "botsort_bench256.npz",
                         **run(BotSort(reid_model=None, use_cmc=False, **BOTSORT_YAML), frames, img, embs))
+    make_reid_golden()
     for p in sorted(HERE.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

@@ -1,0 +1,74 @@
+"""Pin the ReID oracle (oracle/reid.py): the fixed-point resize against cv2.resize bit for bit, crops and the
+functional OSNet against goldens dumped from the reference classes, and the BN-folded blob (weights.py)
+against the oracle forward."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reid as orid
+from tests.common import GOLDEN
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resize_matches_cv2_bit_exact(seed):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(seed)
+    sizes = [(int(rng.integers(1, 500)), int(rng.integers(1, 300))) for _ in range(25)] + [(256, 128), (512, 256), (1, 1), (2, 700)]
+    for h, w in sizes:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(cv2.resize(src, (128, 256), interpolation=cv2.INTER_LINEAR),
+                              orid.resize_linear_u8(src, 256, 128)), (h, w)
+
+
+def _golden():
+    z = np.load(GOLDEN / "reid_osnet_x0_25.npz")
+    return z
+
+
+def test_crops_match_reference_golden():
+    z = _golden()
+    rng = np.random.default_rng(int(z["image_seed"]))
+    img = rng.integers(0, 255, size=(720, 1280, 3), dtype=np.uint8)
+    import hashlib
+
+    crops = orid.get_crops(z["boxes"], img).numpy()
+    assert np.array_equal(crops[z["crops_sample_index"]], z["crops_sample"])
+    assert hashlib.sha256(np.ascontiguousarray(crops).tobytes()).hexdigest() == str(z["crops_sha256"]), \
+        "staged crops must be bit-exact"
+
+
+def test_osnet_matches_reference_golden():
+    z = _golden()
+    sd = orid.make_osnet_state("osnet_x0_25", seed=int(z["weight_seed"]))
+    rng = np.random.default_rng(int(z["image_seed"]))
+    img = rng.integers(0, 255, size=(720, 1280, 3), dtype=np.uint8)
+    feats = orid.get_features(sd, z["boxes"], img)
+    # same torch build -> identical; other BLAS/oneDNN builds may differ in the last ulps
+    np.testing.assert_allclose(feats, z["features"], rtol=0, atol=2e-6)
+    assert abs(np.linalg.norm(feats, axis=1) - 1).max() < 1e-6
+
+
+@pytest.mark.parametrize("arch", ["osnet_x0_25", "osnet_x1_0"])
+def test_folded_blob_equals_oracle(arch, tmp_path):
+    from boxmot_b200.weights import export_blob
+    from tests.blobsim import blob_forward
+
+    sd = orid.make_osnet_state(arch, seed=3)
+    blob = export_blob(sd, tmp_path / f"{arch}.b200reid")
+    x = torch.randn(3, 3, 256, 128)
+    want, st_w = orid.osnet_forward(sd, x, return_stages=True)
+    got, st_g = blob_forward(blob, x.permute(0, 2, 3, 1).contiguous(), return_stages=True)
+    for k in ("pool", "conv2.0", "conv2.2", "conv3.1", "conv4.1"):
+        np.testing.assert_allclose(st_g[k].permute(0, 3, 1, 2).numpy(), st_w[k].numpy(), rtol=1e-4, atol=2e-5)
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 2e-6 * max(scale, 1.0)
+
+
+def test_pt_roundtrip(tmp_path):
+    from boxmot_b200.weights import export_blob, read_blob
+
+    sd = orid.make_osnet_state("osnet_x0_25", seed=4)
+    torch.save({"state_dict": {"module." + k: v for k, v in sd.items()}}, tmp_path / "osnet_x0_25_msmt17.pt")
+    blob = export_blob(tmp_path / "osnet_x0_25_msmt17.pt")
+    header, payload = read_blob(blob)
+    assert header[3:8] == (16, 64, 96, 128, 512) and payload.size == header[8]
