@@ -88,6 +88,8 @@ SYMBOLS = {
     "boxmot_b200_iou_cost": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "boxmot_b200_cosine_cost": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "boxmot_b200_device_count": (c_int, []),
+    "boxmot_b200_reid_debug_stage": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                             c_int, POINTER(c_int)]),
 }
 
 _LIB = None

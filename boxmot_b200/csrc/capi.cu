@@ -381,6 +381,23 @@ int boxmot_reid_capi_preprocess(void* h, const float* boxes, int n, const uint8_
     return guard([&] { reid_stage(as_reid(h), boxes, n, image, rows, cols, ch); });
 }
 int boxmot_reid_capi_process(void* h) { return guard([&] { reid_run(as_reid(h)); }); }
+int boxmot_b200_reid_debug_stage(void* h, const float* boxes, int n, const uint8_t* image, int rows, int cols,
+                                 int stage, float* out, int cap_floats, int* floats_per_crop) {
+    return guard([&] {
+        ReidHandle* r = as_reid(h);
+        reid_stage(r, boxes, n, image, rows, cols, 3);
+        reid_set_debug_stop(r->model, stage);
+        try { reid_run(r); } catch (...) { reid_set_debug_stop(r->model, -1); throw; }
+        reid_set_debug_stop(r->model, -1);
+        size_t per = 0;
+        const float* t = reid_debug_tensor(r->model, &per);
+        if (!t) throw std::runtime_error("stage index out of range");
+        if (floats_per_crop) *floats_per_crop = (int)per;
+        if ((size_t)cap_floats < per * (size_t)n) throw std::runtime_error("out capacity too small");
+        CAPI_CUDA_OK(cudaMemcpy(out, t, sizeof(float) * per * n, cudaMemcpyDeviceToHost));
+        r->staged_n = -1; r->processed = false;
+    });
+}
 int boxmot_reid_capi_postprocess(void* h, float* out, int cap_floats) {
     return guard([&] { reid_collect(as_reid(h), out, cap_floats); });
 }

@@ -32,6 +32,10 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                  cudaStream_t stream);
 // staged access for the reid C ABI / tests: the normalised input blob (N,256,128,3) float32 NHWC
 const float* reid_last_input_blob(const ReidModel* m);
+// diagnostics: stop the next forward after stage `stage` (0 blob, 1 stem, 2 pool, 3.. block / transition outputs,
+// 11 conv5; -1 = run to the end) and expose that NHWC tensor of the first chunk
+void reid_set_debug_stop(ReidModel* m, int stage);
+const float* reid_debug_tensor(const ReidModel* m, size_t* floats_per_crop);
 
 // ---- tracker engine (tracker_engine.cu) -----------------------------------------------------------------
 struct Engine {

@@ -1,11 +1,807 @@
-// placeholder until the ReID kernels land (next commit)
+// reid_model.cu -- ReID appearance-embedding path on the GPU: detection crops -> OSNet -> L2-normalised rows.
+//
+// Replaces (relative to /root/reference/boxmot):
+//   reid/backends/base_backend.py:148-207   get_crops (cv2.resize INTER_LINEAR, BGR2RGB, /255, mean/std) and
+//                                           get_features (forward + row-wise L2 normalisation)
+//   reid/backbones/osnet.py:27-260,380-405  ConvLayer / Conv1x1 / Conv1x1Linear / LightConv3x3 / ChannelGate /
+//                                           OSBlock / OSNet.forward (eval mode, BatchNorm folded offline)
+//   native/cpp/trackers/base/src/reid_onnx.cpp:51-383  (per-crop batch-1 ORT forward of the native path)
+//
+// Data layout: activations are NHWC float32 in HBM, one chunk of crops at a time so that the producer /
+// consumer pairs of consecutive launches stay L2-resident; weights are a BN-folded float32 blob
+// (boxmot_b200/weights.py) uploaded once.  Round-1 kernels are float32 CUDA-core kernels with shared-memory
+// tiling; every 1x1 convolution goes through one GEMM-shaped kernel (k_pointwise) whose prologue can build
+// the gated branch sum on the fly and whose epilogue fuses bias / residual / ReLU.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
 #include <stdexcept>
+#include <string>
+#include <vector>
+
 #include "engine.h"
+
 namespace bmb {
-struct ReidModel { int dim; };
-ReidModel* reid_load(const char*) { throw std::runtime_error("ReID model support not built"); }
-void reid_free(ReidModel* m) { delete m; }
-int reid_feature_dim(const ReidModel* m) { return m->dim; }
-int reid_forward(ReidModel*, const uint8_t*, size_t, int, int, const CropDesc*, const int*, int, float*, int, cudaStream_t) { return 0; }
-const float* reid_last_input_blob(const ReidModel*) { return nullptr; }
+
+#define RCUDA_OK(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+
+constexpr int IN_H = 256, IN_W = 128;
+constexpr uint32_t BLOB_MAGIC = 0x45523242u;
+
+__device__ __forceinline__ int chunk_count(const int* d_n, int off, int cap) {
+    int n = *d_n - off;
+    n = n < 0 ? 0 : n;
+    return n > cap ? cap : n;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// K1: crop + OpenCV-exact bilinear resize + BGR->RGB + /255 + mean/std  ->  (N,256,128,3) float32
+// One CTA per crop.  cv2.resize(INTER_LINEAR) on uint8 is integer arithmetic: 11-bit coefficients derived from a
+// float32 phase, horizontal pass in int32, vertical (((b0*(S0>>4))>>16)+((b1*(S1>>4))>>16)+2)>>2.  x phases are
+// clamped at the borders, y rows are clipped at fetch (pinned against cv2 in tests/test_oracle_reid.py).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void linear_coeff(int d, int src_n, double scale, bool clamp, int& idx, int& a0, int& a1) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f = f - (float)s;
+    if (clamp) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src_n - 1) { s = src_n - 1; f = 0.f; }
+    }
+    idx = s;
+    a0 = (int)rintf((1.0f - f) * 2048.0f);
+    a1 = (int)rintf(f * 2048.0f);
+}
+
+__global__ void __launch_bounds__(256) k_crop_resize_norm(const uint8_t* __restrict__ images, size_t image_stride,
+                                                          int rows, int cols, const CropDesc* __restrict__ crops,
+                                                          const int* __restrict__ d_n, int off, int cap,
+                                                          float* __restrict__ blob) {
+    const int n = blockIdx.x;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    const CropDesc cd = crops[off + n];
+    __shared__ int xi[IN_W], xa0[IN_W], xa1[IN_W];
+    __shared__ int yi[IN_H], ya0[IN_H], ya1[IN_H];
+    // box.round().astype(int): round half to even
+    const int x1 = (int)rintf(cd.x1), y1 = (int)rintf(cd.y1), x2 = (int)rintf(cd.x2), y2 = (int)rintf(cd.y2);
+    const int cx1 = max(0, x1), cy1 = max(0, y1), cx2 = min(cols, x2), cy2 = min(rows, y2);
+    const bool valid = cx2 > cx1 && cy2 > cy1;
+    const int sw = cx2 - cx1, sh = cy2 - cy1;
+    if (valid) {
+        const double sx = 1.0 / ((double)IN_W / (double)sw), sy = 1.0 / ((double)IN_H / (double)sh);
+        for (int d = threadIdx.x; d < IN_W; d += blockDim.x) linear_coeff(d, sw, sx, true, xi[d], xa0[d], xa1[d]);
+        for (int d = threadIdx.x; d < IN_H; d += blockDim.x) linear_coeff(d, sh, sy, false, yi[d], ya0[d], ya1[d]);
+    }
+    __syncthreads();
+    const uint8_t* img = images + (size_t)cd.image * image_stride;
+    float* out = blob + (size_t)n * IN_H * IN_W * 3;
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int p = threadIdx.x; p < IN_H * IN_W; p += blockDim.x) {
+        const int dy = p / IN_W, dx = p - dy * IN_W;
+        int v[3] = {0, 0, 0};
+        if (valid) {
+            const int sx0 = xi[dx], sx1 = min(sx0 + 1, sw - 1);
+            const int r0 = min(max(yi[dy], 0), sh - 1), r1 = min(max(yi[dy] + 1, 0), sh - 1);
+            const uint8_t* p0 = img + ((size_t)(cy1 + r0) * cols + cx1) * 3;
+            const uint8_t* p1 = img + ((size_t)(cy1 + r1) * cols + cx1) * 3;
+            const int a0 = xa0[dx], a1 = xa1[dx], b0 = ya0[dy], b1 = ya1[dy];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int h0 = (int)p0[sx0 * 3 + c] * a0 + (int)p0[sx1 * 3 + c] * a1;
+                const int h1 = (int)p1[sx0 * 3 + c] * a0 + (int)p1[sx1 * 3 + c] * a1;
+                int r = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                v[c] = min(max(r, 0), 255);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {  // output channel c is RGB: source channel 2-c
+            const float f = __fdiv_rn((float)v[2 - c], 255.0f);
+            out[(size_t)p * 3 + c] = __fdiv_rn(f - mean[c], stdv[c]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: stem 7x7 stride-2 conv (3 -> C0) + folded BN + ReLU : (N,256,128,3) -> (N,128,64,C0)
+// CTA = 8 output rows x 64 columns of one crop; the 21 x 134 x 3 input window and the weight chunk live in
+// shared memory; a thread owns two output pixels (x, x+32) x 16 output channels.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ST_R = 8, ST_IR = 2 * ST_R + 5, ST_IC = IN_W + 6;
+__global__ void __launch_bounds__(256) k_stem(const float* __restrict__ blob, const float* __restrict__ w,
+                                              const float* __restrict__ bias, int C0, const int* __restrict__ d_n,
+                                              int off, int cap, float* __restrict__ out) {
+    const int n = blockIdx.y;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    extern __shared__ float smem[];
+    float* sin = smem;                         // [ST_IR][ST_IC][3]
+    float* sw = smem + ST_IR * ST_IC * 3;      // [147][16]
+    const int oy0 = blockIdx.x * ST_R;
+    const int iy0 = oy0 * 2 - 3;
+    const float* src = blob + (size_t)n * IN_H * IN_W * 3;
+    for (int e = threadIdx.x; e < ST_IR * ST_IC * 3; e += blockDim.x) {
+        const int r = e / (ST_IC * 3), rem = e - r * (ST_IC * 3);
+        const int cidx = rem / 3, ch = rem - cidx * 3;
+        const int iy = iy0 + r, ix = cidx - 3;
+        sin[e] = (iy >= 0 && iy < IN_H && ix >= 0 && ix < IN_W) ? src[((size_t)iy * IN_W + ix) * 3 + ch] : 0.f;
+    }
+    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;
+    for (int co0 = 0; co0 < C0; co0 += 16) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 147 * 16; e += blockDim.x) {
+            const int k = e >> 4, c = e & 15;
+            sw[e] = w[(size_t)k * C0 + co0 + c];
+        }
+        __syncthreads();
+        float acc0[16], acc1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+        for (int kh = 0; kh < 7; ++kh) {
+            const float* row = sin + (size_t)(ty * 2 + kh) * ST_IC * 3;
+            for (int kw = 0; kw < 7; ++kw) {
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float a0 = row[(tx * 2 + kw) * 3 + ci];
+                    const float a1 = row[((tx + 32) * 2 + kw) * 3 + ci];
+                    const float4* wp = reinterpret_cast<const float4*>(sw + ((kh * 7 + kw) * 3 + ci) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 wv = wp[q];
+                        acc0[q * 4 + 0] = fmaf(a0, wv.x, acc0[q * 4 + 0]);
+                        acc0[q * 4 + 1] = fmaf(a0, wv.y, acc0[q * 4 + 1]);
+                        acc0[q * 4 + 2] = fmaf(a0, wv.z, acc0[q * 4 + 2]);
+                        acc0[q * 4 + 3] = fmaf(a0, wv.w, acc0[q * 4 + 3]);
+                        acc1[q * 4 + 0] = fmaf(a1, wv.x, acc1[q * 4 + 0]);
+                        acc1[q * 4 + 1] = fmaf(a1, wv.y, acc1[q * 4 + 1]);
+                        acc1[q * 4 + 2] = fmaf(a1, wv.z, acc1[q * 4 + 2]);
+                        acc1[q * 4 + 3] = fmaf(a1, wv.w, acc1[q * 4 + 3]);
+                    }
+                }
+            }
+        }
+        float* o0 = out + (((size_t)n * 128 + oy0 + ty) * 64 + tx) * C0 + co0;
+        float* o1 = o0 + (size_t)32 * C0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + co0 + q * 4);
+            float4 r0 = make_float4(fmaxf(acc0[q * 4] + b.x, 0.f), fmaxf(acc0[q * 4 + 1] + b.y, 0.f),
+                                    fmaxf(acc0[q * 4 + 2] + b.z, 0.f), fmaxf(acc0[q * 4 + 3] + b.w, 0.f));
+            float4 r1 = make_float4(fmaxf(acc1[q * 4] + b.x, 0.f), fmaxf(acc1[q * 4 + 1] + b.y, 0.f),
+                                    fmaxf(acc1[q * 4 + 2] + b.z, 0.f), fmaxf(acc1[q * 4 + 3] + b.w, 0.f));
+            reinterpret_cast<float4*>(o0)[q] = r0;
+            reinterpret_cast<float4*>(o1)[q] = r1;
+        }
+    }
+}
+
+// K3: max pool 3x3 stride 2 pad 1 : (N,H,W,C) -> (N,H/2,W/2,C)
+__global__ void k_maxpool3s2(const float* __restrict__ in, int H, int W, int C, const int* __restrict__ d_n, int off,
+                             int cap, float* __restrict__ out) {
+    const int n_crops = chunk_count(d_n, off, cap);
+    const int OH = H / 2, OW = W / 2, C4 = C / 4;
+    const size_t total = (size_t)n_crops * OH * OW * C4;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(e % C4);
+        size_t r = e / C4;
+        const int ox = (int)(r % OW); r /= OW;
+        const int oy = (int)(r % OH);
+        const int n = (int)(r / OH);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + iy) * W + ix) * C + c4 * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        *reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox) * C + c4 * 4) = m;
+    }
+}
+
+// K4: average pool 2x2 stride 2
+__global__ void k_avgpool2(const float* __restrict__ in, int H, int W, int C, const int* __restrict__ d_n, int off,
+                           int cap, float* __restrict__ out) {
+    const int n_crops = chunk_count(d_n, off, cap);
+    const int OH = H / 2, OW = W / 2, C4 = C / 4;
+    const size_t total = (size_t)n_crops * OH * OW * C4;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(e % C4);
+        size_t r = e / C4;
+        const int ox = (int)(r % OW); r /= OW;
+        const int oy = (int)(r % OH);
+        const int n = (int)(r / OH);
+        const float* p = in + (((size_t)n * H + oy * 2) * W + ox * 2) * C + c4 * 4;
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + C);
+        const float4 c = *reinterpret_cast<const float4*>(p + (size_t)W * C);
+        const float4 d = *reinterpret_cast<const float4*>(p + (size_t)W * C + C);
+        float4 o;
+        o.x = (a.x + b.x + c.x + d.x) * 0.25f; o.y = (a.y + b.y + c.y + d.y) * 0.25f;
+        o.z = (a.z + b.z + c.z + d.z) * 0.25f; o.w = (a.w + b.w + c.w + d.w) * 0.25f;
+        *reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox) * C + c4 * 4) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: pointwise (1x1) convolution as a GEMM:  out[M][N] = act( A[M][K] * W[K][N] + bias (+ residual) )
+//   prologue PLAIN : A = in[M][K]
+//   prologue GATED : A[m][k] = sum_b gates[crop(m)][b][k] * branch_b[m][k]      for k <  mid
+//                            = x[m][k - mid]                                      for k >= mid  (downsample rows)
+// CTA: 256 threads, BN output channels (16/32/64), BM = 2048/BN*4 rows; thread = 8 rows x 4 channels;
+// K is streamed through shared memory in chunks of 16.
+// ---------------------------------------------------------------------------------------------------
+struct PwArgs {
+    const float* in;          // PLAIN: [M][K];  GATED: x [M][K - mid] (may be null when K == mid)
+    const float* branch[4];   // GATED: four [M][mid] tensors
+    const float* gates;       // GATED: [crops][4][mid]
+    const float* w;           // [K][N]
+    const float* bias;        // [N]
+    const float* residual;    // [M][N] or null
+    float* out;               // [M][N]
+    int K, N, mid, HW, relu;
+};
+
+template <int BN, bool GATED>
+__global__ void __launch_bounds__(256) k_pointwise(const PwArgs a, const int* __restrict__ d_n, int off, int cap) {
+    constexpr int NTN = BN / 4, NTM = 256 / NTN, BM = NTM * 8, BK = 16, LDA = BM + 4;
+    const int M = chunk_count(d_n, off, cap) * a.HW;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (m0 >= M) return;
+    __shared__ float As[BK * LDA];
+    __shared__ float Bs[BK * BN];
+    const int tn = threadIdx.x % NTN, tm = threadIdx.x / NTN;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int K = a.K, N = a.N;
+    const int KX = GATED ? K - a.mid : 0;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // A chunk: BM rows x 16 k, loaded as float4 along k, stored k-major
+        for (int e = threadIdx.x; e < BM * 4; e += 256) {
+            const int r = e >> 2, kq = (e & 3) * 4;
+            const int m = m0 + r, k = k0 + kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && k < K) {
+                if (!GATED) {
+                    v = *reinterpret_cast<const float4*>(a.in + (size_t)m * K + k);
+                } else if (k < a.mid) {
+                    const float* g = a.gates + (size_t)(m / a.HW) * 4 * a.mid + k;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float4 x = *reinterpret_cast<const float4*>(a.branch[b] + (size_t)m * a.mid + k);
+                        const float4 gg = *reinterpret_cast<const float4*>(g + b * a.mid);
+                        v.x = fmaf(x.x, gg.x, v.x); v.y = fmaf(x.y, gg.y, v.y);
+                        v.z = fmaf(x.z, gg.z, v.z); v.w = fmaf(x.w, gg.w, v.w);
+                    }
+                } else {
+                    v = *reinterpret_cast<const float4*>(a.in + (size_t)m * KX + (k - a.mid));
+                }
+            }
+            As[(kq + 0) * LDA + r] = v.x; As[(kq + 1) * LDA + r] = v.y;
+            As[(kq + 2) * LDA + r] = v.z; As[(kq + 3) * LDA + r] = v.w;
+        }
+        for (int e = threadIdx.x; e < BK * BN / 4; e += 256) {
+            const int kk = e / (BN / 4), c = (e % (BN / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + kk < K && n0 + c < N) v = *reinterpret_cast<const float4*>(a.w + (size_t)(k0 + kk) * N + n0 + c);
+            *reinterpret_cast<float4*>(Bs + kk * BN + c) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(As + kk * LDA + tm * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(As + kk * LDA + tm * 8 + 4);
+            const float4 b = *reinterpret_cast<const float4*>(Bs + kk * BN + tn * 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc[i][0] = fmaf(av[i], b.x, acc[i][0]); acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+            }
+        }
+        __syncthreads();
+    }
+    const int c = n0 + tn * 4;
+    if (c >= N) return;
+    const float4 bv = *reinterpret_cast<const float4*>(a.bias + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + tm * 8 + i;
+        if (m >= M) break;
+        float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+        if (a.residual) {
+            const float4 r = *reinterpret_cast<const float4*>(a.residual + (size_t)m * N + c);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        *reinterpret_cast<float4*>(a.out + (size_t)m * N + c) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6: LightConv3x3 = 1x1 (linear) -> depthwise 3x3 -> folded BN -> ReLU, fused per spatial tile.
+// grid = (row tiles, branches of this level, crops).  Phase A computes T = pw(in) for the tile plus a one-pixel
+// halo into shared memory (two pixels x 16 channels per thread per pass, weights broadcast from shared memory);
+// phase B applies the depthwise taps from shared memory, writes the activation and, for the last layer of a
+// branch, per-tile channel sums for the ChannelGate's global average pool (summed in fixed order later).
+// ---------------------------------------------------------------------------------------------------
+struct LightArgs {
+    const float* in[4];
+    float* out[4];
+    const float* wpw[4];
+    const float* wdw[4];
+    const float* bias[4];
+    float* sums[4];   // [crops][tiles][C] or null
+    int H, W, C, R;   // R = tile rows
+};
+
+__global__ void k_lightconv(const LightArgs a, const int* __restrict__ d_n, int off, int cap) {
+    const int n = blockIdx.z;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    const int br = blockIdx.y, tile = blockIdx.x;
+    const int H = a.H, W = a.W, C = a.C, R = a.R;
+    const int TW = W + 2, TR = R + 2;
+    extern __shared__ float smem[];
+    float* sT = smem;                       // [TR][TW][C]
+    float* sW = sT + (size_t)TR * TW * C;   // [C][C]
+    float* sD = sW + (size_t)C * C;         // [9][C]
+    float* sP = sD + 9 * C;                 // partial sums [groups][C]
+    const int y0 = tile * R;
+    const float* in = a.in[br] + (size_t)n * H * W * C;
+    for (int e = threadIdx.x; e < C * C; e += blockDim.x) sW[e] = a.wpw[br][e];
+    for (int e = threadIdx.x; e < 9 * C; e += blockDim.x) sD[e] = a.wdw[br][e];
+    __syncthreads();
+    // ---- phase A: T = in * Wpw on the haloed tile ----
+    const int n_px = TR * TW;
+    const int n_pairs = (n_px + 1) / 2;
+    const int n_cchunks = C / 8;  // 8 output channels per pass keeps 16 accumulators for two pixels
+    for (int item = threadIdx.x; item < n_pairs * n_cchunks; item += blockDim.x) {
+        const int pair = item / n_cchunks, cc = (item - pair * n_cchunks) * 8;
+        const int p0 = pair * 2, p1 = p0 + 1;
+        const int ty0 = p0 / TW, tx0 = p0 - ty0 * TW;
+        const int ty1 = p1 / TW, tx1 = p1 - ty1 * TW;
+        const int gy0 = y0 + ty0 - 1, gx0 = tx0 - 1, gy1 = y0 + ty1 - 1, gx1 = tx1 - 1;
+        const bool v0 = gy0 >= 0 && gy0 < H && gx0 >= 0 && gx0 < W;
+        const bool v1 = p1 < n_px && gy1 >= 0 && gy1 < H && gx1 >= 0 && gx1 < W;
+        float acc0[8], acc1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+        if (v0 || v1) {
+            const float* q0 = in + ((size_t)gy0 * W + gx0) * C;
+            const float* q1 = in + ((size_t)gy1 * W + gx1) * C;
+            for (int k = 0; k < C; k += 4) {
+                const float4 x0 = v0 ? *reinterpret_cast<const float4*>(q0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 x1 = v1 ? *reinterpret_cast<const float4*>(q1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float xa[4] = {x0.x, x0.y, x0.z, x0.w};
+                const float xb[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sW + (size_t)(k + kk) * C + cc);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sW + (size_t)(k + kk) * C + cc + 4);
+                    acc0[0] = fmaf(xa[kk], w0.x, acc0[0]); acc0[1] = fmaf(xa[kk], w0.y, acc0[1]);
+                    acc0[2] = fmaf(xa[kk], w0.z, acc0[2]); acc0[3] = fmaf(xa[kk], w0.w, acc0[3]);
+                    acc0[4] = fmaf(xa[kk], w1.x, acc0[4]); acc0[5] = fmaf(xa[kk], w1.y, acc0[5]);
+                    acc0[6] = fmaf(xa[kk], w1.z, acc0[6]); acc0[7] = fmaf(xa[kk], w1.w, acc0[7]);
+                    acc1[0] = fmaf(xb[kk], w0.x, acc1[0]); acc1[1] = fmaf(xb[kk], w0.y, acc1[1]);
+                    acc1[2] = fmaf(xb[kk], w0.z, acc1[2]); acc1[3] = fmaf(xb[kk], w0.w, acc1[3]);
+                    acc1[4] = fmaf(xb[kk], w1.x, acc1[4]); acc1[5] = fmaf(xb[kk], w1.y, acc1[5]);
+                    acc1[6] = fmaf(xb[kk], w1.z, acc1[6]); acc1[7] = fmaf(xb[kk], w1.w, acc1[7]);
+                }
+            }
+        }
+        float4* t0 = reinterpret_cast<float4*>(sT + (size_t)p0 * C + cc);
+        t0[0] = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+        t0[1] = make_float4(acc0[4], acc0[5], acc0[6], acc0[7]);
+        if (p1 < n_px) {
+            float4* t1 = reinterpret_cast<float4*>(sT + (size_t)p1 * C + cc);
+            t1[0] = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+            t1[1] = make_float4(acc1[4], acc1[5], acc1[6], acc1[7]);
+        }
+    }
+    __syncthreads();
+    // ---- phase B: depthwise 3x3 + bias + ReLU ----
+    const int C4 = C / 4;
+    const int rows_here = min(R, H - y0);
+    const int c4 = threadIdx.x % C4, grp = threadIdx.x / C4, n_grp = blockDim.x / C4;
+    float4 wv[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const float4*>(sD + t * C + c4 * 4);
+    const float4 bv = *reinterpret_cast<const float4*>(a.bias[br] + c4 * 4);
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* outp = a.out[br] + (size_t)n * H * W * C;
+    for (int p = grp; p < rows_here * W; p += n_grp) {
+        const int y = p / W, x = p - y * W;
+        float4 acc = bv;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4 t = *reinterpret_cast<const float4*>(sT + ((size_t)(y + ky) * TW + x + kx) * C + c4 * 4);
+                const float4 w = wv[ky * 3 + kx];
+                acc.x = fmaf(t.x, w.x, acc.x); acc.y = fmaf(t.y, w.y, acc.y);
+                acc.z = fmaf(t.z, w.z, acc.z); acc.w = fmaf(t.w, w.w, acc.w);
+            }
+        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+        *reinterpret_cast<float4*>(outp + ((size_t)(y0 + y) * W + x) * C + c4 * 4) = acc;
+        psum.x += acc.x; psum.y += acc.y; psum.z += acc.z; psum.w += acc.w;
+    }
+    if (a.sums[br]) {
+        *reinterpret_cast<float4*>(sP + (size_t)grp * C + c4 * 4) = psum;
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int g = 0; g < n_grp; ++g) s += sP[(size_t)g * C + c];
+            a.sums[br][((size_t)n * gridDim.x + tile) * C + c] = s;
+        }
+    }
+}
+
+// K7: ChannelGate (osnet.py:161-210): mean -> fc1 -> ReLU -> fc2 -> sigmoid, for the four branches of a block.
+struct GateArgs {
+    const float* sums[4];  // [crops][tiles][C]
+    const float* w1; const float* b1; const float* w2; const float* b2;  // [C][hid], [hid], [hid][C], [C]
+    float* gates;          // [crops][4][C]
+    int C, hid, tiles, HW;
+};
+__global__ void k_gates(const GateArgs a, const int* __restrict__ d_n, int off, int cap) {
+    const int n = blockIdx.x;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    extern __shared__ float smem[];
+    float* mean = smem;            // [4][C]
+    float* hid = smem + 4 * a.C;   // [4][hid]
+    const int C = a.C;
+    for (int e = threadIdx.x; e < 4 * C; e += blockDim.x) {
+        const int b = e / C, c = e - b * C;
+        float s = 0.f;
+        for (int t = 0; t < a.tiles; ++t) s += a.sums[b][((size_t)n * a.tiles + t) * C + c];
+        mean[e] = s / (float)a.HW;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * a.hid; e += blockDim.x) {
+        const int b = e / a.hid, h = e - b * a.hid;
+        float s = a.b1[h];
+        for (int c = 0; c < C; ++c) s = fmaf(mean[b * C + c], a.w1[(size_t)c * a.hid + h], s);
+        hid[e] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * C; e += blockDim.x) {
+        const int b = e / C, c = e - b * C;
+        float s = a.b2[c];
+        for (int h = 0; h < a.hid; ++h) s = fmaf(hid[b * a.hid + h], a.w2[(size_t)h * C + c], s);
+        a.gates[(size_t)n * 4 * C + e] = 1.0f / (1.0f + expf(-s));
+    }
+}
+
+// K8: head: global average pool over HW, fc (+ folded BatchNorm1d) + ReLU, row-wise L2 normalisation, scatter
+// to the caller's row (base_backend.py:197-207).  One CTA per crop.
+__global__ void k_head(const float* __restrict__ x, int HW, int C, const float* __restrict__ wfc,
+                       const float* __restrict__ bfc, int FEAT, const CropDesc* __restrict__ crops,
+                       const int* __restrict__ d_n, int off, int cap, float* __restrict__ out, int out_ld) {
+    const int n = blockIdx.x;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    extern __shared__ float smem[];
+    float* pooled = smem;       // [C]
+    float* red = smem + C;      // [32]
+    const float* xp = x + (size_t)n * HW * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < HW; ++p) s += xp[(size_t)p * C + c];
+        pooled[c] = s / (float)HW;
+    }
+    __syncthreads();
+    float* dst = out + (size_t)crops[off + n].out_row * out_ld;
+    float sq = 0.f;
+    for (int f = threadIdx.x; f < FEAT; f += blockDim.x) {
+        float s = bfc[f];
+        for (int c = 0; c < C; ++c) s = fmaf(pooled[c], wfc[(size_t)c * FEAT + f], s);
+        s = fmaxf(s, 0.f);
+        dst[f] = s;
+        sq = fmaf(s, s, sq);
+    }
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    const float nrm = sqrtf(tot);
+    for (int f = threadIdx.x; f < FEAT; f += blockDim.x) dst[f] = dst[f] / nrm;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct LightW { size_t pw, dw, b; };
+struct BlockW {
+    int cin, cout, mid, hid, has_ds;
+    size_t c1w, c1b;
+    LightW light[10];
+    size_t g1w, g1b, g2w, g2b;
+    size_t cw, cb;
+};
+
+struct ReidModel {
+    int c[4] = {0, 0, 0, 0};
+    int feat = 0;
+    float* d_w = nullptr;
+    size_t stem_w = 0, stem_b = 0;
+    BlockW blocks[6];
+    size_t trans_w[2] = {0, 0}, trans_b[2] = {0, 0};
+    size_t c5w = 0, c5b = 0, fcw = 0, fcb = 0;
+    // workspace for one chunk of crops
+    int chunk = 128;
+    float* blob = nullptr;
+    float* bufA = nullptr;
+    float* bufB = nullptr;
+    float* x1 = nullptr;
+    float* Y[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    float* sums[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* gates = nullptr;
+    int debug_stop = -1;       // stop after this stage index and leave the tensor in debug_ptr
+    const float* debug_ptr = nullptr;
+    size_t debug_floats_per_crop = 0;
+};
+
+static const int kBranchOfLight[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
+static const int kLevelOfLight[10] = {1, 1, 2, 1, 2, 3, 1, 2, 3, 4};
+static const int kDepth[4] = {1, 2, 3, 4};
+
+ReidModel* reid_load(const char* path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error(std::string("cannot open ReID blob: ") + path);
+    int32_t hdr[16];
+    f.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
+    if (!f || (uint32_t)hdr[0] != BLOB_MAGIC || hdr[1] != 1 || hdr[2] != 1)
+        throw std::runtime_error("not a version-1 OSNet .b200reid blob (export it with boxmot_b200.weights.export_blob)");
+    ReidModel* m = new ReidModel();
+    try {
+        for (int i = 0; i < 4; ++i) m->c[i] = hdr[3 + i];
+        m->feat = hdr[7];
+        const size_t n_floats = (size_t)hdr[8];
+        if (m->c[0] % 16 != 0 || m->feat < 1) throw std::runtime_error("unsupported OSNet width (stem channels)");
+        std::vector<float> host(n_floats);
+        f.read(reinterpret_cast<char*>(host.data()), sizeof(float) * n_floats);
+        if (!f) throw std::runtime_error("truncated ReID blob");
+        size_t o = 0;
+        auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+        m->stem_w = take((size_t)147 * m->c[0]);
+        m->stem_b = take(m->c[0]);
+        for (int s = 0; s < 3; ++s) {
+            for (int j = 0; j < 2; ++j) {
+                BlockW& b = m->blocks[s * 2 + j];
+                b.cin = j == 0 ? m->c[s] : m->c[s + 1];
+                b.cout = m->c[s + 1];
+                b.mid = b.cout / 4;
+                b.hid = b.mid / 16;
+                b.has_ds = b.cin != b.cout;
+                if (b.mid % 8 != 0 || b.hid < 1) throw std::runtime_error("unsupported OSNet width (mid channels)");
+                b.c1w = take((size_t)b.cin * b.mid);
+                b.c1b = take(b.mid);
+                for (int l = 0; l < 10; ++l) {
+                    b.light[l].pw = take((size_t)b.mid * b.mid);
+                    b.light[l].dw = take((size_t)9 * b.mid);
+                    b.light[l].b = take(b.mid);
+                }
+                b.g1w = take((size_t)b.mid * b.hid);
+                b.g1b = take(b.hid);
+                b.g2w = take((size_t)b.hid * b.mid);
+                b.g2b = take(b.mid);
+                b.cw = take((size_t)(b.mid + (b.has_ds ? b.cin : 0)) * b.cout);
+                b.cb = take(b.cout);
+            }
+            if (s < 2) {
+                m->trans_w[s] = take((size_t)m->c[s + 1] * m->c[s + 1]);
+                m->trans_b[s] = take(m->c[s + 1]);
+            }
+        }
+        m->c5w = take((size_t)m->c[3] * m->c[3]);
+        m->c5b = take(m->c[3]);
+        m->fcw = take((size_t)m->c[3] * m->feat);
+        m->fcb = take(m->feat);
+        if (o != n_floats) throw std::runtime_error("ReID blob size does not match its header");
+        RCUDA_OK(cudaMalloc(&m->d_w, sizeof(float) * n_floats));
+        RCUDA_OK(cudaMemcpy(m->d_w, host.data(), sizeof(float) * n_floats, cudaMemcpyHostToDevice));
+        // workspace
+        const size_t CH = m->chunk;
+        const size_t big = (size_t)8192 * m->c[0] > (size_t)2048 * m->c[1] ? (size_t)8192 * m->c[0] : (size_t)2048 * m->c[1];
+        const size_t mid_max = (size_t)2048 * (m->c[1] / 4);
+        RCUDA_OK(cudaMalloc(&m->blob, sizeof(float) * CH * IN_H * IN_W * 3));
+        RCUDA_OK(cudaMalloc(&m->bufA, sizeof(float) * CH * big));
+        RCUDA_OK(cudaMalloc(&m->bufB, sizeof(float) * CH * big));
+        RCUDA_OK(cudaMalloc(&m->x1, sizeof(float) * CH * mid_max));
+        for (int b = 0; b < 4; ++b) {
+            for (int k = 0; k < 2; ++k) RCUDA_OK(cudaMalloc(&m->Y[b][k], sizeof(float) * CH * mid_max));
+            RCUDA_OK(cudaMalloc(&m->sums[b], sizeof(float) * CH * 64 * (m->c[3] / 4)));
+        }
+        RCUDA_OK(cudaMalloc(&m->gates, sizeof(float) * CH * 4 * (m->c[3] / 4)));
+    } catch (...) {
+        reid_free(m);
+        throw;
+    }
+    return m;
+}
+
+void reid_free(ReidModel* m) {
+    if (!m) return;
+    cudaFree(m->d_w); cudaFree(m->blob); cudaFree(m->bufA); cudaFree(m->bufB); cudaFree(m->x1);
+    for (int b = 0; b < 4; ++b) { cudaFree(m->Y[b][0]); cudaFree(m->Y[b][1]); cudaFree(m->sums[b]); }
+    cudaFree(m->gates);
+    delete m;
+}
+
+int reid_feature_dim(const ReidModel* m) { return m->feat; }
+const float* reid_last_input_blob(const ReidModel* m) { return m->blob; }
+void reid_set_debug_stop(ReidModel* m, int stage) { m->debug_stop = stage; }
+const float* reid_debug_tensor(const ReidModel* m, size_t* floats_per_crop) {
+    if (floats_per_crop) *floats_per_crop = m->debug_floats_per_crop;
+    return m->debug_ptr;
+}
+
+namespace {
+struct Launcher {
+    ReidModel* m;
+    const int* d_n;
+    int off, cap, upper;  // upper = host-side bound on crops in this chunk (grid sizing)
+    cudaStream_t st;
+    int launches = 0;
+
+    void pointwise(const PwArgs& a) {
+        const int N = a.N;
+        const size_t Mmax = (size_t)upper * a.HW;
+        if (N % 64 == 0) launch_pw<64>(a, Mmax);
+        else if (N % 32 == 0 || N > 16) launch_pw<32>(a, Mmax);
+        else launch_pw<16>(a, Mmax);
+    }
+    template <int BN>
+    void launch_pw(const PwArgs& a, size_t Mmax) {
+        constexpr int BM = (256 / (BN / 4)) * 8;
+        dim3 grid((unsigned)((Mmax + BM - 1) / BM), (unsigned)((a.N + BN - 1) / BN));
+        if (a.gates) k_pointwise<BN, true><<<grid, 256, 0, st>>>(a, d_n, off, cap);
+        else k_pointwise<BN, false><<<grid, 256, 0, st>>>(a, d_n, off, cap);
+        ++launches;
+    }
+    void light(const LightArgs& a, int n_branches, int threads) {
+        const int tiles = (a.H + a.R - 1) / a.R;
+        const int n_grp = threads / (a.C / 4);
+        const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) * a.C + (size_t)a.C * a.C + 9 * a.C +
+                                             (size_t)n_grp * a.C);
+        if (smem > 48 * 1024)
+            RCUDA_OK(cudaFuncSetAttribute(k_lightconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_lightconv<<<dim3(tiles, n_branches, upper), threads, smem, st>>>(a, d_n, off, cap);
+        ++launches;
+    }
+};
+
+int pick_tile_rows(int H, int W, int C) {
+    // largest divisor of H whose haloed tile (+ weights) stays under ~96 KB
+    for (int R = H; R >= 1; --R) {
+        if (H % R) continue;
+        const size_t bytes = sizeof(float) * ((size_t)(R + 2) * (W + 2) * C + (size_t)C * C + 9 * C + 64 * C);
+        if (bytes <= 96 * 1024 && R <= 16) return R;
+    }
+    return 1;
+}
+}  // namespace
+
+int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int rows, int cols,
+                 const CropDesc* d_crops, const int* d_ncrops, int max_crops, float* d_out, int out_ld,
+                 cudaStream_t st) {
+    int launches = 0;
+    const float* W = m->d_w;
+    m->debug_ptr = nullptr;
+    for (int off = 0; off < max_crops; off += m->chunk) {
+        const int upper = (max_crops - off) < m->chunk ? (max_crops - off) : m->chunk;
+        Launcher L{m, d_ncrops, off, m->chunk, upper, st};
+        int stage_idx = 0;
+        auto stop_here = [&](const float* ptr, size_t per_crop) {
+            if (m->debug_stop == stage_idx) { m->debug_ptr = ptr; m->debug_floats_per_crop = per_crop; ++stage_idx; return true; }
+            ++stage_idx;
+            return false;
+        };
+        k_crop_resize_norm<<<upper, 256, 0, st>>>(d_images, image_stride, rows, cols, d_crops, d_ncrops, off, m->chunk,
+                                                  m->blob);
+        ++L.launches;
+        if (stop_here(m->blob, (size_t)IN_H * IN_W * 3)) { launches += L.launches; continue; }
+        {
+            const size_t smem = sizeof(float) * ((size_t)ST_IR * ST_IC * 3 + 147 * 16);
+            RCUDA_OK(cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_stem<<<dim3(128 / ST_R, upper), 256, smem, st>>>(m->blob, W + m->stem_w, W + m->stem_b, m->c[0], d_ncrops,
+                                                                off, m->chunk, m->bufA);
+            ++L.launches;
+        }
+        if (stop_here(m->bufA, (size_t)8192 * m->c[0])) { launches += L.launches; continue; }
+        k_maxpool3s2<<<148 * 8, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_ncrops, off, m->chunk, m->bufB);
+        ++L.launches;
+        if (stop_here(m->bufB, (size_t)2048 * m->c[0])) { launches += L.launches; continue; }
+        float* X = m->bufB;
+        float* Xo = m->bufA;
+        int H = 64, Wd = 32;
+        bool stopped = false;
+        for (int s = 0; s < 3 && !stopped; ++s) {
+            for (int j = 0; j < 2 && !stopped; ++j) {
+                const BlockW& b = m->blocks[s * 2 + j];
+                const int HW = H * Wd;
+                PwArgs p{};
+                p.in = X; p.w = W + b.c1w; p.bias = W + b.c1b; p.out = m->x1;
+                p.K = b.cin; p.N = b.mid; p.HW = HW; p.relu = 1;
+                L.pointwise(p);
+                const int R = pick_tile_rows(H, Wd, b.mid);
+                const int tiles = H / R;
+                const int threads = (256 / (b.mid / 4)) * (b.mid / 4);  // a multiple of the channel groups
+                for (int level = 1; level <= 4; ++level) {
+                    LightArgs la{};
+                    la.H = H; la.W = Wd; la.C = b.mid; la.R = R;
+                    int nb = 0;
+                    for (int l = 0; l < 10; ++l) {
+                        if (kLevelOfLight[l] != level) continue;
+                        const int br = kBranchOfLight[l];
+                        la.in[nb] = level == 1 ? m->x1 : m->Y[br][(level - 1) & 1];
+                        la.out[nb] = m->Y[br][level & 1];
+                        la.wpw[nb] = W + b.light[l].pw;
+                        la.wdw[nb] = W + b.light[l].dw;
+                        la.bias[nb] = W + b.light[l].b;
+                        la.sums[nb] = kDepth[br] == level ? m->sums[br] : nullptr;
+                        ++nb;
+                    }
+                    L.light(la, nb, threads);
+                }
+                GateArgs ga{};
+                for (int br = 0; br < 4; ++br) ga.sums[br] = m->sums[br];
+                ga.w1 = W + b.g1w; ga.b1 = W + b.g1b; ga.w2 = W + b.g2w; ga.b2 = W + b.g2b;
+                ga.gates = m->gates; ga.C = b.mid; ga.hid = b.hid; ga.tiles = tiles; ga.HW = HW;
+                k_gates<<<upper, 128, sizeof(float) * (4 * b.mid + 4 * b.hid), st>>>(ga, d_ncrops, off, m->chunk);
+                ++L.launches;
+                PwArgs c{};
+                for (int br = 0; br < 4; ++br) c.branch[br] = m->Y[br][kDepth[br] & 1];
+                c.gates = m->gates; c.mid = b.mid;
+                c.in = b.has_ds ? X : nullptr;
+                c.residual = b.has_ds ? nullptr : X;
+                c.w = W + b.cw; c.bias = W + b.cb; c.out = Xo;
+                c.K = b.mid + (b.has_ds ? b.cin : 0); c.N = b.cout; c.HW = HW; c.relu = 1;
+                L.pointwise(c);
+                float* t = X; X = Xo; Xo = t;
+                if (stop_here(X, (size_t)HW * b.cout)) { stopped = true; break; }
+            }
+            if (stopped) break;
+            if (s < 2) {
+                const int C = m->c[s + 1];
+                PwArgs p{};
+                p.in = X; p.w = W + m->trans_w[s]; p.bias = W + m->trans_b[s]; p.out = Xo;
+                p.K = C; p.N = C; p.HW = H * Wd; p.relu = 1;
+                L.pointwise(p);
+                k_avgpool2<<<148 * 4, 256, 0, st>>>(Xo, H, Wd, C, d_ncrops, off, m->chunk, X);
+                ++L.launches;
+                H /= 2; Wd /= 2;
+                if (stop_here(X, (size_t)H * Wd * C)) { stopped = true; break; }
+            }
+        }
+        if (!stopped) {
+            const int C = m->c[3];
+            PwArgs p{};
+            p.in = X; p.w = W + m->c5w; p.bias = W + m->c5b; p.out = Xo;
+            p.K = C; p.N = C; p.HW = H * Wd; p.relu = 1;
+            L.pointwise(p);
+            if (!stop_here(Xo, (size_t)H * Wd * C)) {
+                k_head<<<upper, 256, sizeof(float) * (C + 32), st>>>(Xo, H * Wd, C, W + m->fcw, W + m->fcb, m->feat,
+                                                                     d_crops, d_ncrops, off, m->chunk, d_out, out_ld);
+                ++L.launches;
+            }
+        }
+        launches += L.launches;
+    }
+    RCUDA_OK(cudaGetLastError());
+    return launches;
+}
+
+}  // namespace bmb

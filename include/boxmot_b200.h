@@ -189,6 +189,12 @@ BOXMOT_B200_API int boxmot_b200_iou_cost(const double* track_xyxy, int rows, con
 /* max(0, cosine distance) of float32 rows a (T,F) x b (D,F) -> (T,D) float64. */
 BOXMOT_B200_API int boxmot_b200_cosine_cost(const float* a, int rows, const float* b, int cols, int dim, double* out);
 BOXMOT_B200_API int boxmot_b200_device_count(void);
+/* Diagnostics for the ReID kernels: run the forward up to `stage` (0 input blob, 1 stem, 2 max-pool, 3..10 the
+ * six OSBlocks and two transitions in order, 11 conv5) and copy that NHWC float32 tensor of the n crops out. */
+BOXMOT_B200_API int boxmot_b200_reid_debug_stage(void* reid_handle, const float* boxes_xyxy, int n_boxes,
+                                                 const uint8_t* image_data, int image_rows, int image_cols,
+                                                 int stage, float* out, int out_capacity_floats,
+                                                 int* out_floats_per_crop);
 
 #if defined(__cplusplus)
 }
