@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ blob, co
                                               int off, int cap, float* __restrict__ out) {
     const int n = blockIdx.y;
     if (n >= chunk_count(d_n, off, cap)) return;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* sin = smem;                         // [ST_IR][ST_IC][3]
-    float* sw = smem + ST_IR * ST_IC * 3;      // [147][16]
+    float* sw = smem + ((ST_IR * ST_IC * 3 + 3) & ~3);  // [147][16], 16-byte aligned for float4 reads
     const int oy0 = blockIdx.x * ST_R;
     const int iy0 = oy0 * 2 - 3;
     const float* src = blob + (size_t)n * IN_H * IN_W * 3;
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(256) k_pointwise(const PwArgs a, const int* __
     const int M = chunk_count(d_n, off, cap) * a.HW;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     if (m0 >= M) return;
-    __shared__ float As[BK * LDA];
-    __shared__ float Bs[BK * BN];
+    __shared__ __align__(16) float As[BK * LDA];
+    __shared__ __align__(16) float Bs[BK * BN];
     const int tn = threadIdx.x % NTN, tm = threadIdx.x / NTN;
     float acc[8][4];
 #pragma unroll
@@ -353,7 +353,7 @@ __global__ void k_lightconv(const LightArgs a, const int* __restrict__ d_n, int 
     const int br = blockIdx.y, tile = blockIdx.x;
     const int H = a.H, W = a.W, C = a.C, R = a.R;
     const int TW = W + 2, TR = R + 2;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* sT = smem;                       // [TR][TW][C]
     float* sW = sT + (size_t)TR * TW * C;   // [C][C]
     float* sD = sW + (size_t)C * C;         // [9][C]
@@ -458,7 +458,7 @@ struct GateArgs {
 __global__ void k_gates(const GateArgs a, const int* __restrict__ d_n, int off, int cap) {
     const int n = blockIdx.x;
     if (n >= chunk_count(d_n, off, cap)) return;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* mean = smem;            // [4][C]
     float* hid = smem + 4 * a.C;   // [4][hid]
     const int C = a.C;
@@ -491,7 +491,7 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
                        const int* __restrict__ d_n, int off, int cap, float* __restrict__ out, int out_ld) {
     const int n = blockIdx.x;
     if (n >= chunk_count(d_n, off, cap)) return;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* pooled = smem;       // [C]
     float* red = smem + C;      // [32]
     const float* xp = x + (size_t)n * HW * C;
@@ -574,7 +574,7 @@ ReidModel* reid_load(const char* path) {
         f.read(reinterpret_cast<char*>(host.data()), sizeof(float) * n_floats);
         if (!f) throw std::runtime_error("truncated ReID blob");
         size_t o = 0;
-        auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+        auto take = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };  // 16-byte aligned tensors
         m->stem_w = take((size_t)147 * m->c[0]);
         m->stem_b = take(m->c[0]);
         for (int s = 0; s < 3; ++s) {
@@ -714,7 +714,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
         ++L.launches;
         if (stop_here(m->blob, (size_t)IN_H * IN_W * 3)) { launches += L.launches; continue; }
         {
-            const size_t smem = sizeof(float) * ((size_t)ST_IR * ST_IC * 3 + 147 * 16);
+            const size_t smem = sizeof(float) * ((size_t)((ST_IR * ST_IC * 3 + 3) & ~3) + 147 * 16);
             RCUDA_OK(cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_stem<<<dim3(128 / ST_R, upper), 256, smem, st>>>(m->blob, W + m->stem_w, W + m->stem_b, m->c[0], d_ncrops,
                                                                 off, m->chunk, m->bufA);

@@ -17,7 +17,7 @@ followed by float32 parameters in the exact order csrc/reid_model.cu walks them:
     conv5     W[c3][c3], b[c3]
     fc        W[c3][feat] (BatchNorm1d folded), b[feat]
 All 1x1 weights are stored K-major ([cin][cout]) so a thread owning consecutive output channels loads
-consecutive floats.
+consecutive floats; every tensor is zero-padded to a multiple of 4 floats (16-byte aligned float4 loads).
 """
 from __future__ import annotations
 
@@ -131,7 +131,12 @@ def export_blob(weights, out_path=None) -> Path:
     if "conv1.conv.weight" not in sd or "conv5.conv.weight" not in sd:
         raise ValueError("only the OSNet family is implemented on the B200 ReID path so far")
     dims, arrays = fold_osnet(sd)
-    payload = np.concatenate([np.asarray(a, dtype=np.float32).ravel() for a in arrays])
+    # every tensor starts on a 16-byte boundary (the kernels read weights as float4)
+    padded = []
+    for a in arrays:
+        flat = np.asarray(a, dtype=np.float32).ravel()
+        padded.append(np.pad(flat, (0, (-flat.size) % 4)))
+    payload = np.concatenate(padded)
     header = [MAGIC, VERSION, ARCH_OSNET, *dims, int(payload.size)] + [0] * (16 - 9)
     out_path = Path(out_path)
     tmp = out_path.with_suffix(out_path.suffix + ".tmp")
