@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- tracker.update() frames/sec at 256 dets/frame (BASELINE.json metric), B200 arm and CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- BoT-SORT + OSNet_x0_25 ReID inside update(), one
+1280x720 stream of 256 detections per frame per GPU, reference bench generator (benchmark_fps.py:60-94),
+YAML-default parameters with CMC off, float32 kernels.  N GPUs = N independent streams, one process per GPU
+(weak scaling, no collective on the frame path; NCCL only for the barrier and the max-over-ranks gather).
+
+One "step" = one frame through the whole hot path (crop staging, ReID CNN, appearance cost, Kalman
+predict/update, three assignment rounds, lifecycle, output rows).
+  value : frames/s with frames and detections resident in HBM (ring of distinct frames larger than L2),
+          timed with CUDA events on the engine's stream, max over ranks.
+  e2e   : same metric through the public API `MultiStreamTracker.update(dets, imgs)` with HOST numpy buffers:
+          every step copies the frame + detections host->device and reads the result rows back.
+  roofline : the dominant kernel class by device time, from a CUDA-event profiling pass inside this script.
+  cpu_baseline : the oracle port of the reference path (numpy/scipy/torch-CPU restatement pinned to the reference
+          by tests/golden) on this box's host cores, on a bounded sample of the same workload.
+`--impl reference` runs that CPU arm alone and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+LOCAL_RANK = int(os.environ.get("LOCAL_RANK", "0"))
+RANK = int(os.environ.get("RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+if WORLD > 1 and "BENCH_KEEP_VISIBLE" not in os.environ:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    ids = vis.split(",") if vis else [str(i) for i in range(64)]
+    os.environ["CUDA_VISIBLE_DEVICES"] = ids[LOCAL_RANK % len(ids)]  # one GPU per process, device 0 inside it
+
+import numpy as np  # noqa: E402
+
+N_DETS = 256
+IMG_HW = (720, 1280)
+RING = 64  # distinct frames in the input ring: 64 x 2.76 MB = 177 MB > 126 MB of L2
+BOTSORT = dict(
+    track_high_thresh=0.6296854875023994, track_low_thresh=0.1014392537025336,
+    new_track_thresh=0.6246494191492591, track_buffer=40, match_thresh=0.7722224024589055,
+    proximity_thresh=0.6084297894561342, appearance_thresh=0.6188818853936099,
+    unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
+    unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329, fuse_first_associate=True,
+    frame_rate=30, with_reid=True)
+METRIC = "tracker.update() frames/sec at 256 dets/frame"
+WORKLOAD = "BoT-SORT + OSNet_x0_25 ReID in update(), 1 stream x 256 dets/frame per GPU, 1280x720, CMC off"
+CLASSES = ["crop_resize_norm", "stem_conv7x7", "maxpool", "pointwise_gemm", "lightconv", "gates", "avgpool", "head",
+           "association"]
+
+
+# ------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm_gbs=float(d["hbm_gbs"]), tensor_tflops=float(d["bf16_tflops_sustained"]), source="measured")
+    return dict(hbm_gbs=6650.0, tensor_tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        gpu = os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", gpu], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def osnet_class_costs(ch=(16, 64, 96, 128), feat=512):
+    """Algorithmic MACs and compulsory float32 bytes PER CROP for each kernel class of csrc/reid_model.cu."""
+    mac = {c: 0.0 for c in CLASSES}
+    byt = {c: 0.0 for c in CLASSES}
+    mac["stem_conv7x7"] = 128 * 64 * 147 * ch[0]
+    byt["stem_conv7x7"] = 4 * (256 * 128 * 3 + 128 * 64 * ch[0])
+    byt["crop_resize_norm"] = 70 * 140 * 3 + 4 * 256 * 128 * 3
+    byt["maxpool"] = 4 * (128 * 64 * ch[0] + 64 * 32 * ch[0])
+    hw = 64 * 32
+    for s in range(3):
+        for j in range(2):
+            cin = ch[s] if j == 0 else ch[s + 1]
+            cout = ch[s + 1]
+            mid = cout // 4
+            mac["pointwise_gemm"] += hw * cin * mid
+            byt["pointwise_gemm"] += 4 * hw * (cin + mid)
+            mac["lightconv"] += 10 * hw * (mid * mid + 9 * mid)
+            byt["lightconv"] += 10 * 4 * hw * 2 * mid
+            k = mid + (cin if cin != cout else 0)
+            mac["pointwise_gemm"] += hw * k * cout + 4 * hw * mid
+            byt["pointwise_gemm"] += 4 * hw * (4 * mid + cin + cout)
+            byt["gates"] += 4 * 4 * mid * 2
+        if s < 2:
+            c = ch[s + 1]
+            mac["pointwise_gemm"] += hw * c * c
+            byt["pointwise_gemm"] += 4 * hw * 2 * c
+            byt["avgpool"] += 4 * hw * c * 1.25
+            hw //= 4
+    mac["pointwise_gemm"] += hw * ch[3] * ch[3]
+    byt["pointwise_gemm"] += 4 * hw * 2 * ch[3]
+    mac["head"] = ch[3] * feat
+    byt["head"] = 4 * (hw * ch[3] + feat)
+    return mac, byt
+
+
+def make_inputs(stream_index: int, frames: int):
+    from boxmot_b200.synthetic import bench_stream
+
+    _, dets = bench_stream(N_DETS, frames, hw=IMG_HW, stream=stream_index)
+    rng = np.random.default_rng(9000 + stream_index)
+    imgs = rng.integers(0, 255, size=(RING, IMG_HW[0], IMG_HW[1], 3), dtype=np.uint8)
+    return imgs, dets
+
+
+def make_blob(tmpdir: Path) -> Path:
+    from boxmot_b200.synthetic import make_osnet_state
+    from boxmot_b200.weights import export_blob
+
+    return export_blob(make_osnet_state("osnet_x0_25", seed=0), tmpdir / "osnet_x0_25_synthetic.b200reid")
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_arm(sample_frames: int, warm: int):
+    import torch
+
+    from boxmot_b200.synthetic import make_osnet_state
+    from oracle import reid as orid
+    from oracle.trackers import BotSortOracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_osnet_state("osnet_x0_25", seed=0)
+    imgs, dets = make_inputs(0, warm + sample_frames)
+    trk = BotSortOracle(reid_model=orid.OracleReID(sd), **BOTSORT)
+    for f in range(warm):
+        trk.update(dets[f], imgs[f % RING])
+    t0 = time.perf_counter()
+    for f in range(warm, warm + sample_frames):
+        trk.update(dets[f], imgs[f % RING])
+    dt = time.perf_counter() - t0
+    return {"value": sample_frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_frames} frames of the same 256-det stream after {warm} warm-up frames, "
+                      f"oracle port (numpy/scipy/lapjv-C + torch-CPU OSNet fp32, {cores} threads)",
+            "ms_per_frame": 1e3 * dt / sample_frames}
+
+
+def run_reference(args):
+    if RANK != 0:
+        return
+    steps = max(1, min(args.steps, 12))
+    base = cpu_arm(steps, max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_frame"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "single stream on the host cores; steps bounded to keep the run short"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    import boxmot_b200 as bb
+    from boxmot_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: boxmot_b200 has no CPU fallback")
+    torch.cuda.set_device(0)
+    dist = None
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda:0"))
+    lib = _lib.require_device()
+    K, Wm = args.steps, max(3, args.warmup)
+    tmp = Path(tempfile.mkdtemp(prefix="b200bench_"))
+    blob = make_blob(tmp)
+    S = 1
+    imgs, dets = make_inputs(RANK, Wm + K + 8)
+    n_first = float(np.mean([(d[:, 4].astype(np.float64) > BOTSORT["track_high_thresh"]).sum() for d in dets]))
+
+    def new_tracker():
+        return bb.MultiStreamTracker("botsort", n_streams=S, cap_tracks=1024, cap_dets=N_DETS, feat_dim=512,
+                                     reid_blob=str(blob), **BOTSORT)
+
+    # ---------------- value: inputs resident in HBM ----------------
+    trk = new_tracker()
+    d_imgs = torch.from_numpy(imgs).cuda()                          # [RING][H][W][3] u8
+    # frame f uses dets[f] (the stream is a sequence); frames cycle through the ring of distinct images
+    d_dets = torch.from_numpy(np.stack([np.pad(d, ((0, N_DETS - len(d)), (0, 0))) for d in dets])[:, None].astype(np.float32)).cuda()
+    rows = (ctypes.c_int * S)(N_DETS)
+    torch.cuda.synchronize()
+    H, Wd = IMG_HW
+    img_bytes = H * Wd * 3
+
+    def dev_step(f, sync=0):
+        ok = lib.boxmot_b200_tracker_update_device(trk.handle, d_dets[f].data_ptr(), rows, None,
+                                                   d_imgs[f % RING].data_ptr(), H, Wd, sync)
+        if not ok:
+            raise RuntimeError(_lib.last_error(lib))
+
+    for f in range(Wm):
+        dev_step(f, 1)
+    launches_per_step = trk.last_launches()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = ClockSampler()
+    clocks.start()
+    lib.boxmot_b200_tracker_mark(trk.handle, 0)
+    for f in range(Wm, Wm + K):
+        dev_step(f, 0)
+    lib.boxmot_b200_tracker_mark(trk.handle, 1)
+    ms = ctypes.c_double(0)
+    if not lib.boxmot_b200_tracker_elapsed_ms(trk.handle, ctypes.byref(ms)):
+        raise RuntimeError(_lib.last_error(lib))
+    torch.cuda.synchronize()
+    out_rows = (ctypes.c_int * S)()
+    if not lib.boxmot_b200_tracker_fetch(trk.handle, None, None, out_rows):   # surfaces device-side errors
+        raise RuntimeError(_lib.last_error(lib))
+    value_ms = ms.value
+
+    # ---------------- roofline: profiling pass (events around every launch) ----------------
+    lib.boxmot_b200_tracker_profile(trk.handle, 1)
+    P = 16
+    for f in range(Wm + K - P, Wm + K):
+        dev_step(f % (Wm + K), 1)
+    cls_ms = (ctypes.c_double * 9)()
+    cls_n = (ctypes.c_int * 9)()
+    lib.boxmot_b200_tracker_profile_read(trk.handle, cls_ms, cls_n)
+    lib.boxmot_b200_tracker_profile(trk.handle, 0)
+    clock_info = clocks.stop()
+    prof = {CLASSES[i]: {"ms_per_step": cls_ms[i] / P, "launches_per_step": cls_n[i] / P} for i in range(9)}
+    trk.close()
+
+    # ---------------- e2e: public API, host buffers ----------------
+    trk = new_tracker()
+    for f in range(Wm):
+        trk.update([dets[f]], [imgs[f % RING]])
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    last = None
+    for f in range(Wm, Wm + K):
+        last = trk.update([dets[f]], [imgs[f % RING]])
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    n_out = int(len(last[0]))
+    trk.close()
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([value_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value_ms, e2e_ms = float(t[0]), float(t[1])
+    if RANK != 0:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    mac, byt = osnet_class_costs()
+    dom = max((c for c in CLASSES if c != "association"), key=lambda c: prof[c]["ms_per_step"])
+    crops = n_first
+    dom_bytes = byt[dom] * crops
+    dom_s = prof[dom]["ms_per_step"] * 1e-3
+    reid_ms = sum(prof[c]["ms_per_step"] for c in CLASSES if c != "association")
+    fps = WORLD * S * K / (value_ms * 1e-3)
+    e2e_fps = WORLD * S * K / (e2e_ms * 1e-3)
+    total_flop = 2 * sum(mac.values()) * crops
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": WORLD, "steps": K, "warmup": Wm,
+        "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": S, "dets_per_frame": N_DETS,
+                   "first_round_crops_per_frame": crops, "reid": "osnet_x0_25 random-init (seed 0), fp32 kernels",
+                   "l2": f"input ring of {RING} distinct frames ({RING * img_bytes / 1e6:.0f} MB) and a per-chunk "
+                         f"activation workspace larger than L2; no explicit flush", "parallelism": f"streams x{WORLD}"},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "ms_per_step": e2e_ms / K,
+                "h2d_bytes_per_step": S * (img_bytes + N_DETS * 6 * 4 + 4),
+                "d2h_bytes_per_step": S * (N_DETS * 8 * 4 + 16 * 4), "rows_last_frame": n_out},
+        "gpu_launches": launches_per_step * K,
+        "launches_per_step": launches_per_step,
+        "clocks": clock_info,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": dom_bytes / dom_s / 1e9, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                     "peak_source": peaks["source"], "algorithmic_bytes_per_step": dom_bytes,
+                     "ms_per_step": prof[dom]["ms_per_step"], "share_of_reid": prof[dom]["ms_per_step"] / max(reid_ms, 1e-9)},
+        "reid_conv_roofline": {"achieved_tflops": total_flop / (reid_ms * 1e-3) / 1e12, "peak_tflops": peaks["tensor_tflops"],
+                               "frac_of_tensor_peak": total_flop / (reid_ms * 1e-3) / 1e12 / peaks["tensor_tflops"],
+                               "flop_per_crop": 2 * sum(mac.values()), "reid_ms_per_step": reid_ms},
+        "kernel_classes": prof,
+    }
+    if WORLD == 1:
+        line["cpu_baseline"] = cpu_arm(args.cpu_frames, 2)
+        line["speedup_e2e_vs_cpu"] = e2e_fps / line["cpu_baseline"]["value"]
+    print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,19 @@ int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* h, double* reid_ms, do
     });
 }
 
+int boxmot_b200_tracker_mark(BoxMOTB200Tracker* h, int which) {
+    return guard([&] { as_engine(h)->mark_event(which); });
+}
+int boxmot_b200_tracker_elapsed_ms(BoxMOTB200Tracker* h, double* out_ms) {
+    return guard([&] { *out_ms = as_engine(h)->marks_elapsed_ms(); });
+}
+int boxmot_b200_tracker_profile(BoxMOTB200Tracker* h, int enable) {
+    return guard([&] { as_engine(h)->set_profile(enable != 0); });
+}
+int boxmot_b200_tracker_profile_read(BoxMOTB200Tracker* h, double* ms, int* launches) {
+    return guard([&] { as_engine(h)->profile_read(ms, launches); });
+}
+
 // ---- ByteTrack (reference ABI) ----------------------------------------------------------------------------
 BoxMOTByteTrackHandle* boxmot_bytetrack_create(const BoxMOTByteTrackConfig* c) {
     Engine* e = nullptr;

@@ -32,6 +32,10 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                  cudaStream_t stream);
 // staged access for the reid C ABI / tests: the normalised input blob (N,256,128,3) float32 NHWC
 const float* reid_last_input_blob(const ReidModel* m);
+// per-kernel-class device timing: crop, stem, maxpool, pointwise, lightconv, gates, avgpool, head
+constexpr int REID_N_CLASSES = 8;
+void reid_set_profile(ReidModel* m, bool on);
+void reid_profile_collect(ReidModel* m, double* ms, int* launches);
 // diagnostics: stop the next forward after stage `stage` (0 blob, 1 stem, 2 pool, 3.. block / transition outputs,
 // 11 conv5; -1 = run to the end) and expose that NHWC tensor of the first chunk
 void reid_set_debug_stop(ReidModel* m, int stage);
@@ -63,6 +67,13 @@ struct Engine {
     float* h_embs = nullptr;
     uint8_t* h_images = nullptr;
     cudaEvent_t ev[3]{};
+    cudaEvent_t mark[2]{};
+    int* h_ndets_ring = nullptr;   // pinned ring so that queued frames keep their own det counts
+    int ring_pos = 0;
+    static constexpr int NDETS_RING = 256;
+    double assoc_ms_accum = 0.0;
+    int assoc_frames = 0;
+    bool profile = false;
     int launches = 0;
     double last_reid_ms = 0.0, last_assoc_ms = 0.0;
 
@@ -79,6 +90,10 @@ struct Engine {
                        const uint8_t* images_dev, int rows, int cols, bool sync);
     void fetch(float* const* out, const int* out_cap, int* out_rows);
     int snapshot(int stream_index, int* ids, double* means, double* covs, int cap);
+    void set_profile(bool on);
+    void profile_read(double* ms, int* launch_counts);  // REID_N_CLASSES + 1 entries (last = association)
+    void mark_event(int which);
+    double marks_elapsed_ms();
 
    private:
     void ensure_images(int rows, int cols, bool host_too);

@@ -522,6 +522,7 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+enum { CLS_CROP = 0, CLS_STEM, CLS_MAXPOOL, CLS_POINTWISE, CLS_LIGHTCONV, CLS_GATES, CLS_AVGPOOL, CLS_HEAD };
 struct LightW { size_t pw, dw, b; };
 struct BlockW {
     int cin, cout, mid, hid, has_ds;
@@ -548,6 +549,12 @@ struct ReidModel {
     float* Y[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     float* sums[4] = {nullptr, nullptr, nullptr, nullptr};
     float* gates = nullptr;
+    // per-kernel-class device timing (bench / profiles): events around every launch when enabled
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_cls;
+    double prof_ms[REID_N_CLASSES] = {0};
+    int prof_launches[REID_N_CLASSES] = {0};
     int debug_stop = -1;       // stop after this stage index and leave the tensor in debug_ptr
     const float* debug_ptr = nullptr;
     size_t debug_floats_per_crop = 0;
@@ -642,6 +649,26 @@ void reid_free(ReidModel* m) {
 
 int reid_feature_dim(const ReidModel* m) { return m->feat; }
 const float* reid_last_input_blob(const ReidModel* m) { return m->blob; }
+void reid_set_profile(ReidModel* m, bool on) { m->profile = on; }
+// Fold the events recorded since the last call into per-class totals (the stream must be idle).
+void reid_profile_collect(ReidModel* m, double* ms, int* launches) {
+    for (size_t i = 0; i < m->prof_cls.size(); ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]);
+        m->prof_ms[m->prof_cls[i]] += t;
+        m->prof_launches[m->prof_cls[i]] += 1;
+        cudaEventDestroy(m->prof_ev[2 * i]);
+        cudaEventDestroy(m->prof_ev[2 * i + 1]);
+    }
+    m->prof_ev.clear();
+    m->prof_cls.clear();
+    for (int c = 0; c < REID_N_CLASSES; ++c) {
+        if (ms) ms[c] = m->prof_ms[c];
+        if (launches) launches[c] = m->prof_launches[c];
+        m->prof_ms[c] = 0;
+        m->prof_launches[c] = 0;
+    }
+}
 void reid_set_debug_stop(ReidModel* m, int stage) { m->debug_stop = stage; }
 const float* reid_debug_tensor(const ReidModel* m, size_t* floats_per_crop) {
     if (floats_per_crop) *floats_per_crop = m->debug_floats_per_crop;
@@ -656,6 +683,21 @@ struct Launcher {
     cudaStream_t st;
     int launches = 0;
 
+    void begin(int cls) {
+        if (!m->profile) return;
+        cudaEvent_t e0, e1;
+        RCUDA_OK(cudaEventCreate(&e0));
+        RCUDA_OK(cudaEventCreate(&e1));
+        m->prof_ev.push_back(e0);
+        m->prof_ev.push_back(e1);
+        m->prof_cls.push_back(cls);
+        RCUDA_OK(cudaEventRecord(e0, st));
+    }
+    void end() {
+        if (!m->profile) return;
+        RCUDA_OK(cudaEventRecord(m->prof_ev.back(), st));
+    }
+
     void pointwise(const PwArgs& a) {
         const int N = a.N;
         const size_t Mmax = (size_t)upper * a.HW;
@@ -667,8 +709,10 @@ struct Launcher {
     void launch_pw(const PwArgs& a, size_t Mmax) {
         constexpr int BM = (256 / (BN / 4)) * 8;
         dim3 grid((unsigned)((Mmax + BM - 1) / BM), (unsigned)((a.N + BN - 1) / BN));
+        begin(CLS_POINTWISE);
         if (a.gates) k_pointwise<BN, true><<<grid, 256, 0, st>>>(a, d_n, off, cap);
         else k_pointwise<BN, false><<<grid, 256, 0, st>>>(a, d_n, off, cap);
+        end();
         ++launches;
     }
     void light(const LightArgs& a, int n_branches, int threads) {
@@ -678,7 +722,9 @@ struct Launcher {
                                              (size_t)n_grp * a.C);
         if (smem > 48 * 1024)
             RCUDA_OK(cudaFuncSetAttribute(k_lightconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        begin(CLS_LIGHTCONV);
         k_lightconv<<<dim3(tiles, n_branches, upper), threads, smem, st>>>(a, d_n, off, cap);
+        end();
         ++launches;
     }
 };
@@ -709,19 +755,25 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             ++stage_idx;
             return false;
         };
+        L.begin(CLS_CROP);
         k_crop_resize_norm<<<upper, 256, 0, st>>>(d_images, image_stride, rows, cols, d_crops, d_ncrops, off, m->chunk,
                                                   m->blob);
+        L.end();
         ++L.launches;
         if (stop_here(m->blob, (size_t)IN_H * IN_W * 3)) { launches += L.launches; continue; }
         {
             const size_t smem = sizeof(float) * ((size_t)((ST_IR * ST_IC * 3 + 3) & ~3) + 147 * 16);
             RCUDA_OK(cudaFuncSetAttribute(k_stem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            L.begin(CLS_STEM);
             k_stem<<<dim3(128 / ST_R, upper), 256, smem, st>>>(m->blob, W + m->stem_w, W + m->stem_b, m->c[0], d_ncrops,
                                                                 off, m->chunk, m->bufA);
+            L.end();
             ++L.launches;
         }
         if (stop_here(m->bufA, (size_t)8192 * m->c[0])) { launches += L.launches; continue; }
+        L.begin(CLS_MAXPOOL);
         k_maxpool3s2<<<148 * 8, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_ncrops, off, m->chunk, m->bufB);
+        L.end();
         ++L.launches;
         if (stop_here(m->bufB, (size_t)2048 * m->c[0])) { launches += L.launches; continue; }
         float* X = m->bufB;
@@ -760,7 +812,9 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 for (int br = 0; br < 4; ++br) ga.sums[br] = m->sums[br];
                 ga.w1 = W + b.g1w; ga.b1 = W + b.g1b; ga.w2 = W + b.g2w; ga.b2 = W + b.g2b;
                 ga.gates = m->gates; ga.C = b.mid; ga.hid = b.hid; ga.tiles = tiles; ga.HW = HW;
+                L.begin(CLS_GATES);
                 k_gates<<<upper, 128, sizeof(float) * (4 * b.mid + 4 * b.hid), st>>>(ga, d_ncrops, off, m->chunk);
+                L.end();
                 ++L.launches;
                 PwArgs c{};
                 for (int br = 0; br < 4; ++br) c.branch[br] = m->Y[br][kDepth[br] & 1];
@@ -780,7 +834,9 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 p.in = X; p.w = W + m->trans_w[s]; p.bias = W + m->trans_b[s]; p.out = Xo;
                 p.K = C; p.N = C; p.HW = H * Wd; p.relu = 1;
                 L.pointwise(p);
+                L.begin(CLS_AVGPOOL);
                 k_avgpool2<<<148 * 4, 256, 0, st>>>(Xo, H, Wd, C, d_ncrops, off, m->chunk, X);
+                L.end();
                 ++L.launches;
                 H /= 2; Wd /= 2;
                 if (stop_here(X, (size_t)H * Wd * C)) { stopped = true; break; }
@@ -793,8 +849,10 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             p.K = C; p.N = C; p.HW = H * Wd; p.relu = 1;
             L.pointwise(p);
             if (!stop_here(Xo, (size_t)H * Wd * C)) {
+                L.begin(CLS_HEAD);
                 k_head<<<upper, 256, sizeof(float) * (C + 32), st>>>(Xo, H * Wd, C, W + m->fcw, W + m->fcb, m->feat,
                                                                      d_crops, d_ncrops, off, m->chunk, d_out, out_ld);
+                L.end();
                 ++L.launches;
             }
         }

@@ -207,6 +207,9 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
         CUDA_OK(cudaMalloc(&d_crops, sizeof(CropDesc) * CD * S));
         CUDA_OK(cudaMalloc(&d_ncrops, sizeof(int)));
     }
+    CUDA_OK(cudaMallocHost(&h_ndets_ring, sizeof(int) * S * NDETS_RING));
+    CUDA_OK(cudaEventCreate(&mark[0]));
+    CUDA_OK(cudaEventCreate(&mark[1]));
     CUDA_OK(cudaEventCreate(&ev[0]));
     CUDA_OK(cudaEventCreate(&ev[1]));
     CUDA_OK(cudaEventCreate(&ev[2]));
@@ -219,7 +222,8 @@ Engine::~Engine() {
     cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
     cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
     cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
-    cudaFreeHost(h_embs); cudaFreeHost(h_images);
+    cudaFreeHost(h_embs); cudaFreeHost(h_images); cudaFreeHost(h_ndets_ring);
+    cudaEventDestroy(mark[0]); cudaEventDestroy(mark[1]);
     for (auto& e : ev) cudaEventDestroy(e);
     cudaStreamDestroy(stream);
 }
@@ -269,6 +273,44 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
     ++launches;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(ev[2], stream));
+    if (profile) {  // profiling pass: serialise and attribute device time per kernel class
+        CUDA_OK(cudaStreamSynchronize(stream));
+        float b = 0.f;
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        assoc_ms_accum += b;
+        assoc_frames += 1;
+    }
+}
+
+void Engine::set_profile(bool on) {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    profile = on;
+    if (reid) reid_set_profile(reid, on);
+    assoc_ms_accum = 0.0;
+    assoc_frames = 0;
+    if (reid) reid_profile_collect(reid, nullptr, nullptr);
+}
+
+void Engine::profile_read(double* ms, int* launch_counts) {
+    CUDA_OK(cudaStreamSynchronize(stream));
+    for (int c = 0; c < REID_N_CLASSES + 1; ++c) { ms[c] = 0.0; launch_counts[c] = 0; }
+    if (reid) reid_profile_collect(reid, ms, launch_counts);
+    ms[REID_N_CLASSES] = assoc_ms_accum;
+    launch_counts[REID_N_CLASSES] = assoc_frames * (cfg.with_reid ? 3 : 1);
+    assoc_ms_accum = 0.0;
+    assoc_frames = 0;
+}
+
+void Engine::mark_event(int which) {
+    if (which < 0 || which > 1) throw std::runtime_error("mark index must be 0 or 1");
+    CUDA_OK(cudaEventRecord(mark[which], stream));
+}
+
+double Engine::marks_elapsed_ms() {
+    CUDA_OK(cudaEventSynchronize(mark[1]));
+    float t = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&t, mark[0], mark[1]));
+    return (double)t;
 }
 
 void Engine::enqueue_fetch() {
@@ -359,12 +401,13 @@ void Engine::update_device(const float* dets_dev, const int* det_rows, const flo
                            const uint8_t* images_dev, int rows, int cols, bool sync) {
     const size_t CD = cfg.cap_dets;
     int total = 0;
+    int* slot = h_ndets_ring + (size_t)(ring_pos++ % NDETS_RING) * S;
     for (int i = 0; i < S; ++i) {
         if (det_rows[i] < 0 || det_rows[i] > (int)CD) throw std::runtime_error("det_rows exceeds cap_dets");
-        h_ndets[i] = det_rows[i];
+        slot[i] = det_rows[i];
         total += det_rows[i];
     }
-    CUDA_OK(cudaMemcpyAsync(d_ndets, h_ndets, sizeof(int) * S, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(d_ndets, slot, sizeof(int) * S, cudaMemcpyHostToDevice, stream));
     if (dets_dev != d_dets)
         CUDA_OK(cudaMemcpyAsync(d_dets, dets_dev, sizeof(float) * 6 * CD * S, cudaMemcpyDeviceToDevice, stream));
     enqueue_frame(cfg.with_reid ? embs_dev : nullptr, images_dev, rows, cols, total);

@@ -1,0 +1,116 @@
+"""Seeded synthetic inputs for benchmarks and tests: the reference's own throughput-sweep detection
+generator and random-init OSNet weights.  Data generators only -- no arithmetic of the tracked path.
+
+`bench_stream` restates /root/reference/tests/performance/benchmark_fps.py:60-94 (`_make_random_dets` +
+`_jitter_dets`, seed 42 + n_dets (+ 1000 * stream), fixed random uint8 frame) -- SURVEY.md section 8(d).
+`make_osnet_state` builds a state dict with the reference's parameter names (reid/backbones/osnet.py) because the
+container has no pretrained checkpoints; BatchNorm statistics are randomised so folding is
+exercised, and gains are chosen so activations stay O(1-10) through the network.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+OSNET_ARCHS = {
+    "osnet_x0_25": (16, 64, 96, 128),
+    "osnet_x0_5": (32, 128, 192, 256),
+    "osnet_x0_75": (48, 192, 288, 384),
+    "osnet_x1_0": (64, 256, 384, 512),
+}
+BRANCH_DEPTHS = (("conv2a", 1), ("conv2b", 2), ("conv2c", 3), ("conv2d", 4))
+
+
+def bench_image(hw=(720, 1280), seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 255, size=(hw[0], hw[1], 3), dtype=np.uint8)
+
+
+def bench_stream(n_dets: int, n_frames: int, hw=(720, 1280), stream: int = 0):
+    """Returns (image, [dets_f32 (n,6)] * n_frames) exactly as the reference benchmark would feed them."""
+    h, w = hw
+    rng = np.random.default_rng(42 + n_dets + 1000 * stream)
+    img = rng.integers(0, 255, size=(h, w, 3), dtype=np.uint8)
+    cx = rng.uniform(80, w - 80, size=n_dets)
+    cy = rng.uniform(80, h - 80, size=n_dets)
+    bw = rng.uniform(40, 100, size=n_dets)
+    bh = rng.uniform(80, 200, size=n_dets)
+    x1 = np.clip(cx - bw / 2, 0, w - 1)
+    y1 = np.clip(cy - bh / 2, 0, h - 1)
+    x2 = np.clip(cx + bw / 2, 1, w)
+    y2 = np.clip(cy + bh / 2, 1, h)
+    conf = rng.uniform(0.55, 0.95, size=n_dets)
+    cls = np.zeros(n_dets, dtype=np.float32)
+    base = np.stack([x1, y1, x2, y2, conf, cls], axis=1).astype(np.float32)
+    frames = []
+    for _ in range(n_frames):
+        out = base.copy()
+        dx = rng.normal(0.0, 4.0, size=n_dets).astype(np.float32)
+        dy = rng.normal(0.0, 4.0, size=n_dets).astype(np.float32)
+        out[:, 0] = np.clip(out[:, 0] + dx, 0, w - 1)
+        out[:, 2] = np.clip(out[:, 2] + dx, 1, w)
+        out[:, 1] = np.clip(out[:, 1] + dy, 0, h - 1)
+        out[:, 3] = np.clip(out[:, 3] + dy, 1, h)
+        frames.append(out)
+    return img, frames
+
+
+
+def make_osnet_state(arch: str = "osnet_x0_25", seed: int = 0, feature_dim: int = 512, num_classes: int = 1041):
+    import torch
+
+    ch = OSNET_ARCHS[arch]
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, k, groups=1, gain=1.0):
+        fan_in = (ci // groups) * k * k
+        sd[name + ".weight"] = torch.randn(co, ci // groups, k, k, generator=g) * (gain / fan_in) ** 0.5
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0)
+
+    def light(name, c):
+        conv(name + ".conv1", c, c, 1)
+        conv(name + ".conv2", c, c, 3, groups=c)
+        bn(name + ".bn", c)
+
+    def osblock(name, cin, cout):
+        mid = cout // 4
+        conv(name + ".conv1.conv", mid, cin, 1)
+        bn(name + ".conv1.bn", mid)
+        light(name + ".conv2a", mid)
+        for br, depth in BRANCH_DEPTHS[1:]:
+            for k in range(depth):
+                light(f"{name}.{br}.{k}", mid)
+        hid = mid // 16
+        conv(name + ".gate.fc1", hid, mid, 1)
+        sd[name + ".gate.fc1.bias"] = 0.1 * torch.randn(hid, generator=g)
+        conv(name + ".gate.fc2", mid, hid, 1)
+        sd[name + ".gate.fc2.bias"] = 0.1 * torch.randn(mid, generator=g)
+        conv(name + ".conv3.conv", cout, mid, 1, gain=0.1)
+        bn(name + ".conv3.bn", cout)
+        if cin != cout:
+            conv(name + ".downsample.conv", cout, cin, 1)
+            bn(name + ".downsample.bn", cout)
+
+    conv("conv1.conv", ch[0], 3, 7)
+    bn("conv1.bn", ch[0])
+    for s, (cin, cout) in enumerate(((ch[0], ch[1]), (ch[1], ch[2]), (ch[2], ch[3]))):
+        stage = f"conv{s + 2}"
+        osblock(f"{stage}.0", cin, cout)
+        osblock(f"{stage}.1", cout, cout)
+        if s < 2:
+            conv(f"{stage}.2.0.conv", cout, cout, 1)
+            bn(f"{stage}.2.0.bn", cout)
+    conv("conv5.conv", ch[3], ch[3], 1)
+    bn("conv5.bn", ch[3])
+    sd["fc.0.weight"] = 0.05 * torch.randn(feature_dim, ch[3], generator=g)
+    sd["fc.0.bias"] = 0.05 * torch.randn(feature_dim, generator=g)
+    bn("fc.1", feature_dim)
+    sd["classifier.weight"] = 0.01 * torch.randn(num_classes, feature_dim, generator=g)
+    sd["classifier.bias"] = torch.zeros(num_classes)
+    return sd

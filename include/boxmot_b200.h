@@ -174,6 +174,15 @@ BOXMOT_B200_API int boxmot_b200_tracker_snapshot(BoxMOTB200Tracker* handle, int 
 /* Kernel launches issued by the last update call, and CUDA stream / device-time accessors for benchmarks. */
 BOXMOT_B200_API int boxmot_b200_tracker_last_launches(BoxMOTB200Tracker* handle, int* out_launches);
 BOXMOT_B200_API int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* handle, double* reid_ms, double* assoc_ms);
+/* Device timing on the handle's own CUDA stream: record mark 0 / mark 1 around a region, then read the elapsed
+ * milliseconds (synchronises on mark 1). */
+BOXMOT_B200_API int boxmot_b200_tracker_mark(BoxMOTB200Tracker* handle, int which);
+BOXMOT_B200_API int boxmot_b200_tracker_elapsed_ms(BoxMOTB200Tracker* handle, double* out_ms);
+/* Profiling pass: when enabled every kernel launch is bracketed by CUDA events (frames are serialised).
+ * profile_read returns accumulated milliseconds and launch counts for 9 classes:
+ * crop, stem, maxpool, pointwise, lightconv, gates, avgpool, head, association (3 kernels) - and resets them. */
+BOXMOT_B200_API int boxmot_b200_tracker_profile(BoxMOTB200Tracker* handle, int enable);
+BOXMOT_B200_API int boxmot_b200_tracker_profile_read(BoxMOTB200Tracker* handle, double* ms, int* launches);
 BOXMOT_B200_API const char* boxmot_b200_last_error(void);
 
 /* Standalone hot-path kernels (parity tests and micro-benchmarks call these through the same library). */

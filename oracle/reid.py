@@ -23,13 +23,7 @@ MEAN = (0.485, 0.456, 0.406)
 STD = (0.229, 0.224, 0.225)
 INPUT_HW = (256, 128)
 
-OSNET_ARCHS = {
-    "osnet_x0_25": (16, 64, 96, 128),
-    "osnet_x0_5": (32, 128, 192, 256),
-    "osnet_x0_75": (48, 192, 288, 384),
-    "osnet_x1_0": (64, 256, 384, 512),
-}
-BRANCH_DEPTHS = (("conv2a", 1), ("conv2b", 2), ("conv2c", 3), ("conv2d", 4))
+from boxmot_b200.synthetic import BRANCH_DEPTHS, OSNET_ARCHS  # noqa: E402
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -100,68 +94,7 @@ def get_crops(xyxys: np.ndarray, img: np.ndarray) -> torch.Tensor:
     return (x - mean) / std
 
 
-# ----------------------------------------------------------------------------------------------------
-# seeded weights (the container has no pretrained files)
-# ----------------------------------------------------------------------------------------------------
-def make_osnet_state(arch: str = "osnet_x0_25", seed: int = 0, feature_dim: int = 512, num_classes: int = 1041):
-    """A state dict with the reference's parameter names, kaiming-ish conv weights and NON-trivial BatchNorm
-    statistics (so that BN folding is exercised)."""
-    ch = OSNET_ARCHS[arch]
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-
-    def conv(name, co, ci, k, groups=1, gain=1.0):
-        fan_in = (ci // groups) * k * k
-        sd[name + ".weight"] = torch.randn(co, ci // groups, k, k, generator=g) * (gain / fan_in) ** 0.5
-
-    def bn(name, c):
-        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
-        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
-        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
-        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
-        sd[name + ".num_batches_tracked"] = torch.tensor(0)
-
-    def light(name, c):
-        conv(name + ".conv1", c, c, 1)
-        conv(name + ".conv2", c, c, 3, groups=c)
-        bn(name + ".bn", c)
-
-    def osblock(name, cin, cout):
-        mid = cout // 4
-        conv(name + ".conv1.conv", mid, cin, 1)
-        bn(name + ".conv1.bn", mid)
-        light(name + ".conv2a", mid)
-        for br, depth in BRANCH_DEPTHS[1:]:
-            for k in range(depth):
-                light(f"{name}.{br}.{k}", mid)
-        hid = mid // 16
-        conv(name + ".gate.fc1", hid, mid, 1)
-        sd[name + ".gate.fc1.bias"] = 0.1 * torch.randn(hid, generator=g)
-        conv(name + ".gate.fc2", mid, hid, 1)
-        sd[name + ".gate.fc2.bias"] = 0.1 * torch.randn(mid, generator=g)
-        conv(name + ".conv3.conv", cout, mid, 1, gain=0.1)
-        bn(name + ".conv3.bn", cout)
-        if cin != cout:
-            conv(name + ".downsample.conv", cout, cin, 1)
-            bn(name + ".downsample.bn", cout)
-
-    conv("conv1.conv", ch[0], 3, 7)
-    bn("conv1.bn", ch[0])
-    for s, (cin, cout) in enumerate(((ch[0], ch[1]), (ch[1], ch[2]), (ch[2], ch[3]))):
-        stage = f"conv{s + 2}"
-        osblock(f"{stage}.0", cin, cout)
-        osblock(f"{stage}.1", cout, cout)
-        if s < 2:
-            conv(f"{stage}.2.0.conv", cout, cout, 1)
-            bn(f"{stage}.2.0.bn", cout)
-    conv("conv5.conv", ch[3], ch[3], 1)
-    bn("conv5.bn", ch[3])
-    sd["fc.0.weight"] = 0.05 * torch.randn(feature_dim, ch[3], generator=g)
-    sd["fc.0.bias"] = 0.05 * torch.randn(feature_dim, generator=g)
-    bn("fc.1", feature_dim)
-    sd["classifier.weight"] = 0.01 * torch.randn(num_classes, feature_dim, generator=g)
-    sd["classifier.bias"] = torch.zeros(num_classes)
-    return sd
+from boxmot_b200.synthetic import make_osnet_state  # noqa: E402,F401  (seeded weights; no arithmetic of the path)
 
 
 def detect_osnet_arch(sd) -> str:

@@ -11,38 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 
-def bench_image(hw=(720, 1280), seed=0):
-    rng = np.random.default_rng(seed)
-    return rng.integers(0, 255, size=(hw[0], hw[1], 3), dtype=np.uint8)
-
-
-def bench_stream(n_dets: int, n_frames: int, hw=(720, 1280), stream: int = 0):
-    """Returns (image, [dets_f32 (n,6)] * n_frames) exactly as the reference benchmark would feed them."""
-    h, w = hw
-    rng = np.random.default_rng(42 + n_dets + 1000 * stream)
-    img = rng.integers(0, 255, size=(h, w, 3), dtype=np.uint8)
-    cx = rng.uniform(80, w - 80, size=n_dets)
-    cy = rng.uniform(80, h - 80, size=n_dets)
-    bw = rng.uniform(40, 100, size=n_dets)
-    bh = rng.uniform(80, 200, size=n_dets)
-    x1 = np.clip(cx - bw / 2, 0, w - 1)
-    y1 = np.clip(cy - bh / 2, 0, h - 1)
-    x2 = np.clip(cx + bw / 2, 1, w)
-    y2 = np.clip(cy + bh / 2, 1, h)
-    conf = rng.uniform(0.55, 0.95, size=n_dets)
-    cls = np.zeros(n_dets, dtype=np.float32)
-    base = np.stack([x1, y1, x2, y2, conf, cls], axis=1).astype(np.float32)
-    frames = []
-    for _ in range(n_frames):
-        out = base.copy()
-        dx = rng.normal(0.0, 4.0, size=n_dets).astype(np.float32)
-        dy = rng.normal(0.0, 4.0, size=n_dets).astype(np.float32)
-        out[:, 0] = np.clip(out[:, 0] + dx, 0, w - 1)
-        out[:, 2] = np.clip(out[:, 2] + dx, 1, w)
-        out[:, 1] = np.clip(out[:, 1] + dy, 0, h - 1)
-        out[:, 3] = np.clip(out[:, 3] + dy, 1, h)
-        frames.append(out)
-    return img, frames
+from boxmot_b200.synthetic import bench_image, bench_stream  # noqa: E402,F401
 
 
 def stress_stream(n_objects: int, n_frames: int, hw=(360, 640), seed: int = 7, dropout: float = 0.2,
