@@ -82,6 +82,7 @@ SYMBOLS = {
     "boxmot_b200_tracker_last_device_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "boxmot_b200_tracker_mark": (c_int, [c_void_p, c_int]),
     "boxmot_b200_tracker_elapsed_ms": (c_int, [c_void_p, POINTER(c_double)]),
+    "boxmot_b200_tracker_phase_clocks": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "boxmot_b200_tracker_profile": (c_int, [c_void_p, c_int]),
     "boxmot_b200_tracker_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "boxmot_b200_last_error": (c_char_p, []),

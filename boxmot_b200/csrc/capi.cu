@@ -146,6 +146,9 @@ int boxmot_b200_tracker_mark(BoxMOTB200Tracker* h, int which) {
 int boxmot_b200_tracker_elapsed_ms(BoxMOTB200Tracker* h, double* out_ms) {
     return guard([&] { *out_ms = as_engine(h)->marks_elapsed_ms(); });
 }
+int boxmot_b200_tracker_phase_clocks(BoxMOTB200Tracker* h, int stream, long long* out16, int reset) {
+    return guard([&] { as_engine(h)->read_timers(stream, out16, reset != 0); });
+}
 int boxmot_b200_tracker_profile(BoxMOTB200Tracker* h, int enable) {
     return guard([&] { as_engine(h)->set_profile(enable != 0); });
 }

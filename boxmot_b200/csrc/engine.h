@@ -90,6 +90,7 @@ struct Engine {
                        const uint8_t* images_dev, int rows, int cols, bool sync);
     void fetch(float* const* out, const int* out_cap, int* out_rows);
     int snapshot(int stream_index, int* ids, double* means, double* covs, int cap);
+    void read_timers(int stream_index, long long* out16, bool reset);
     void set_profile(bool on);
     void profile_read(double* ms, int* launch_counts);  // REID_N_CLASSES + 1 entries (last = association)
     void mark_event(int which);

@@ -38,7 +38,9 @@
 #define BMB_SHFL_I(v, l) __shfl_sync(0xffffffffu, (v), (l))
 #define BMB_SHFL_XOR_F(v, o) __shfl_xor_sync(0xffffffffu, (v), (o))
 #define BMB_DEVICE 1
+#define BMB_CLOCK() clock64()
 #else
+#define BMB_CLOCK() 0ll
 #define BMB_FN static inline
 #define BMB_TID 0
 #define BMB_NT 1
@@ -65,7 +67,12 @@ enum { KIND_XYAH = 0, KIND_XYWH = 1 };
 enum { HIST_CAP = 8 };  // distinct classes remembered per track by the BoT-SORT class vote
 enum {
     SC_N_ACTIVE = 0, SC_N_LOST, SC_FRAME, SC_NEXT_ID, SC_RING_HEAD, SC_RING_COUNT, SC_ERROR, SC_N_OUT,
-    SC_LAP_STEPS, SC_COUNT = 16
+    SC_LAP_STEPS, SC_N_EMA, SC_COUNT = 16
+};
+// mailbox slots (first MB_COUNT ints of free_l): counts produced by one thread, read by the whole CTA after a sync
+enum {
+    MB_N_FIRST = 0, MB_N_SECOND, MB_N_UNC, MB_N_POOL0, MB_N_POOL, MB_N_ACT, MB_N_REFIND, MB_N_EMA, MB_N_RT,
+    MB_N_REST, MB_N_LOSTNOW, MB_N_REMNOW, MB_N_BIRTH, MB_M1, MB_M2, MB_M3, MB_Q1, MB_Q2, MB_COUNT = 32
 };
 enum { ERR_NONE = 0, ERR_TRACK_CAPACITY = 1, ERR_CLS_HIST = 2, ERR_DET_CAPACITY = 3 };
 
@@ -108,6 +115,7 @@ struct TrkStream {
     int* active;       // [CT] ordered slot list
     int* lost;         // [CT] ordered slot list
     int* scalars;      // [SC_COUNT]
+    long long* timers; // [16] accumulated clock64() ticks per phase (diagnostics)
     // per-frame inputs
     const float* dets;  // [CD][6]
     const int* n_dets;  // [1]
@@ -132,7 +140,9 @@ struct TrkStream {
     int* tmp_a;     // [CT]
     int* tmp_b;     // [CT]
     int* mark;      // [CT]
-    int* free_l;    // [CT]
+    int* free_l;    // [MB_COUNT + CT]  mailbox + free-slot list
+    int* ema_slot;  // [CD] matched (slot, detection) pairs whose appearance EMA is applied after the frame
+    int* ema_det;   // [CD]
     // linear assignment scratch
     int* lap_x;       // [CT]
     int* lap_y;       // [CD]
@@ -425,13 +435,35 @@ BMB_FN double cosine_cost_f64(const float* a, const float* b, int n) {
 // float64) on CSR candidate lists; one warp runs the search, lanes relax candidates and reduce the frontier.
 // Unique optimum  =>  same matches as lapjv (ties have measure zero on continuous costs).
 // ---------------------------------------------------------------------------------------------------
+// Ordered append by ONE warp: for every i in [0,n) with pred(i), in ascending i, out[base++] = val(i).
+template <typename Pred, typename Val>
+BMB_FN int warp_append(int n, int* out, int base, Pred pred, Val val) {
+    for (int i0 = 0; i0 < n; i0 += BMB_NL) {
+        const int i = i0 + BMB_LANE;
+        const bool p = i < n && pred(i);
+        const unsigned m = BMB_BALLOT(p);
+        if (p) {
+#if BMB_DEVICE
+            out[base + __popc(m & ((1u << BMB_LANE) - 1u))] = val(i);
+#else
+            out[base] = val(i);
+#endif
+        }
+        base += BMB_POPC(m);
+    }
+    return base;
+}
+
 BMB_FN void lap_build_csr(TrkStream& s, int T, int D, int ld, double thresh) {
-    // count (parallel over rows), prefix (thread 0), fill (parallel over rows)
-    for (int i = BMB_TID; i < T; i += BMB_NT) {
+    // candidate count per row (one warp per row, coalesced), prefix (thread 0), ordered fill
+    for (int i = BMB_WARP; i < T; i += BMB_NW) {
         const double* ci = s.cost + (size_t)i * ld;
         int n = 0;
-        for (int j = 0; j < D; ++j) n += (ci[j] < thresh) ? 1 : 0;
-        s.lap_x[i] = n;  // temporarily the row count
+        for (int j0 = 0; j0 < D; j0 += BMB_NL) {
+            const int j = j0 + BMB_LANE;
+            n += BMB_POPC(BMB_BALLOT(j < D && ci[j] < thresh));
+        }
+        if (BMB_LANE == 0) s.lap_x[i] = n;  // temporarily the row count
     }
     BMB_SYNC();
     if (BMB_TID == 0) {
@@ -440,11 +472,9 @@ BMB_FN void lap_build_csr(TrkStream& s, int T, int D, int ld, double thresh) {
         s.csr_ptr[T] = acc;
     }
     BMB_SYNC();
-    for (int i = BMB_TID; i < T; i += BMB_NT) {
+    for (int i = BMB_WARP; i < T; i += BMB_NW) {
         const double* ci = s.cost + (size_t)i * ld;
-        int p = s.csr_ptr[i];
-        for (int j = 0; j < D; ++j)
-            if (ci[j] < thresh) s.csr_col[p++] = j;
+        warp_append(D, s.csr_col, s.csr_ptr[i], [&](int j) { return ci[j] < thresh; }, [&](int j) { return j; });
     }
     BMB_SYNC();
 }
@@ -588,55 +618,50 @@ BMB_FN void lap_solve(TrkStream& s, int T, int D, int ld, double thresh) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// match application: Kalman update (thread per match), appearance EMA (warp per match), bookkeeping
+// match application: Kalman update + per-slot bookkeeping (thread per match), ordered list appends (warp 0).
+// The appearance EMA of matched tracks is only consumed by the NEXT frame's appearance cost, so the pairs are
+// recorded here and applied by a wide kernel after this one (one warp per pair across the whole GPU).
 // ---------------------------------------------------------------------------------------------------
-// rows[i] = slot of LAP row i, cols[j] = detection index of LAP column j.
+// rows[i] = slot of LAP row i, cols[j] = detection index of LAP column j.  Counts live in the mailbox `mb`.
 BMB_FN void apply_matches(const TrkCfg& c, TrkStream& s, int T, const int* rows, const int* cols, int frame,
-                          int force_update_branch, int use_feat, int* n_act, int* n_refind) {
-    // 1) Kalman update, one thread per matched row
+                          int force_update_branch, int use_feat, int* mb) {
     for (int i = BMB_TID; i < T; i += BMB_NT) {
-        int j = s.lap_x[i];
-        if (j < 0) continue;
-        int slot = rows[i];
-        int det = cols[j];
+        const int j = s.lap_x[i];
+        if (j < 0) { s.tmp_b[i] = 0; continue; }
+        const int slot = rows[i];
+        const int det = cols[j];
         kf_update(c, s.dmeas + det * 4, s.mean + slot * 8, s.cov + slot * 64);
-    }
-    // 2) appearance EMA, one warp per matched row
-    if (use_feat) {
-        for (int i = BMB_WARP; i < T; i += BMB_NW) {
-            int j = s.lap_x[i];
-            if (j < 0) continue;
-            feat_ema(s.smooth + (size_t)rows[i] * c.feat_dim, s.dfeat + (size_t)cols[j] * c.feat_dim, c.feat_dim);
+        const float* d = s.dets + det * 6;
+        const int tracked = force_update_branch || s.state[slot] == ST_TRACKED;
+        if (tracked) {
+            s.frame_id[slot] = frame;
+            s.tracklet_len[slot] += 1;
+        } else {
+            s.tracklet_len[slot] = 0;
+            s.frame_id[slot] = frame;
         }
+        s.state[slot] = ST_TRACKED;
+        s.activated[slot] = 1;
+        s.conf[slot] = d[4];
+        s.cls[slot] = d[5];
+        s.det_ind[slot] = (float)det;
+        if (c.vote_cls) vote_cls(c, s, slot, d[5], d[4]);
+        s.tmp_b[i] = tracked ? 1 : 2;
     }
     BMB_SYNC();
-    // 3) bookkeeping in ascending row order (list order is output order)
-    if (BMB_TID == 0) {
-        int na = *n_act, nr = *n_refind;
-        for (int i = 0; i < T; ++i) {
-            int j = s.lap_x[i];
-            if (j < 0) continue;
-            int slot = rows[i];
-            int det = cols[j];
-            const float* d = s.dets + det * 6;
-            if (force_update_branch || s.state[slot] == ST_TRACKED) {
-                s.frame_id[slot] = frame;
-                s.tracklet_len[slot] += 1;
-                s.act_l[na++] = slot;
-            } else {
-                s.tracklet_len[slot] = 0;
-                s.frame_id[slot] = frame;
-                s.refind_l[nr++] = slot;
-            }
-            s.state[slot] = ST_TRACKED;
-            s.activated[slot] = 1;
-            s.conf[slot] = d[4];
-            s.cls[slot] = d[5];
-            s.det_ind[slot] = (float)det;
-            if (c.vote_cls) vote_cls(c, s, slot, d[5], d[4]);
+    if (BMB_WARP == 0) {
+        const int na = warp_append(T, s.act_l, mb[MB_N_ACT], [&](int i) { return s.tmp_b[i] == 1; },
+                                   [&](int i) { return rows[i]; });
+        const int nr = warp_append(T, s.refind_l, mb[MB_N_REFIND], [&](int i) { return s.tmp_b[i] == 2; },
+                                   [&](int i) { return rows[i]; });
+        int ne = mb[MB_N_EMA];
+        if (use_feat) {
+            warp_append(T, s.ema_slot, ne, [&](int i) { return s.tmp_b[i] != 0; }, [&](int i) { return rows[i]; });
+            ne = warp_append(T, s.ema_det, ne, [&](int i) { return s.tmp_b[i] != 0; },
+                             [&](int i) { return cols[s.lap_x[i]]; });
         }
-        *n_act = na;
-        *n_refind = nr;
+        BMB_SYNCWARP();
+        if (BMB_LANE == 0) { mb[MB_N_ACT] = na; mb[MB_N_REFIND] = nr; mb[MB_N_EMA] = ne; }
     }
     BMB_SYNC();
 }
@@ -644,8 +669,8 @@ BMB_FN void apply_matches(const TrkCfg& c, TrkStream& s, int T, const int* rows,
 // removed-set membership of a live track (ByteTrack: unbounded list -> slot flag; BoT-SORT: deque of ids)
 BMB_FN int in_removed_set(const TrkCfg& c, const TrkStream& s, int slot) {
     if (c.removed_cap == 0) return s.in_removed[slot];
-    int id = s.id[slot];
-    int n = s.scalars[SC_RING_COUNT];
+    const int id = s.id[slot];
+    const int n = s.scalars[SC_RING_COUNT];
     for (int k = 0; k < n; ++k)
         if (s.removed_ring[k] == id) return 1;
     return 0;
@@ -653,7 +678,7 @@ BMB_FN int in_removed_set(const TrkCfg& c, const TrkStream& s, int slot) {
 
 BMB_FN void push_removed(const TrkCfg& c, TrkStream& s, int slot) {
     if (c.removed_cap == 0) { s.in_removed[slot] = 1; return; }
-    int head = s.scalars[SC_RING_HEAD], n = s.scalars[SC_RING_COUNT];
+    const int head = s.scalars[SC_RING_HEAD], n = s.scalars[SC_RING_COUNT];
     if (n < c.removed_cap) {
         s.removed_ring[(head + n) % c.removed_cap] = s.id[slot];
         s.scalars[SC_RING_COUNT] = n + 1;
@@ -663,81 +688,97 @@ BMB_FN void push_removed(const TrkCfg& c, TrkStream& s, int slot) {
     }
 }
 
+// cost rows, one warp per track row: the track box is loaded once, detections stream through the lanes
+template <typename CostFn>
+BMB_FN void build_cost(TrkStream& s, int T, int D, int ld, const int* rows, CostFn fn) {
+    for (int i = BMB_WARP; i < T; i += BMB_NW) {
+        const int t = rows[i];
+        const double tb[4] = {s.txyxy[t * 4], s.txyxy[t * 4 + 1], s.txyxy[t * 4 + 2], s.txyxy[t * 4 + 3]};
+        double* ci = s.cost + (size_t)i * ld;
+        for (int j = BMB_LANE; j < D; j += BMB_NL) ci[j] = fn(t, tb, j);
+    }
+    BMB_SYNC();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // the frame
 // ---------------------------------------------------------------------------------------------------
+// phase timers: thread 0 accumulates elapsed SM clocks since the previous boundary into timers[phase]
+#define BMB_PHASE(idx)                                                        \
+    do {                                                                      \
+        if (BMB_TID == 0) {                                                   \
+            long long _now = BMB_CLOCK();                                     \
+            s.timers[idx] += _now - _t_prev;                                  \
+            _t_prev = _now;                                                   \
+        }                                                                     \
+    } while (0)
+
 BMB_FN void tracker_frame(const TrkCfg& c, TrkStream& s) {
     const int CT = c.cap_tracks, CD = c.cap_dets, F = c.feat_dim;
+    long long _t_prev = BMB_CLOCK();
+    int* mb = s.free_l;                  // mailbox: MB_COUNT ints written by one thread, read by all after a sync
+    int* free_slots = s.free_l + MB_COUNT;
     int D = *s.n_dets;
     if (D > CD) {
         if (BMB_TID == 0) s.scalars[SC_ERROR] = ERR_DET_CAPACITY;
         D = CD;
     }
     const int frame = s.scalars[SC_FRAME] + 1;
+    const int n_active0 = s.scalars[SC_N_ACTIVE], n_lost0 = s.scalars[SC_N_LOST];
     BMB_SYNC();
 
-    // ---- S0: detection geometry + confidence split (botsort.py:251-261, bytetrack.py:273-282) ----
+    // ---- S0/S1: detection geometry + confidence split; unconfirmed / pool lists ----
     for (int d = BMB_TID; d < D; d += BMB_NT)
         det_geometry(c, s.dets + d * 6, s.dxywh + d * 4, s.dmeas + d * 4, s.dxyxy + d * 4);
-    // counts produced by thread 0 are broadcast through the first 8 ints of free_l (a mailbox)
-    int n_first = 0, n_second = 0;
-    if (BMB_TID == 0) {
-        for (int d = 0; d < D; ++d) {
-            double cf = (double)s.dets[d * 6 + 4];
-            if (cf > c.high_thresh) s.first[n_first++] = d;
-            else if (cf > c.low_thresh && cf < c.high_thresh) s.second[n_second++] = d;
+    for (int k = BMB_TID; k < CT; k += BMB_NT) s.mark[k] = 0;
+    if (BMB_WARP == 0) {
+        const int nf = warp_append(D, s.first, 0, [&](int d) { return (double)s.dets[d * 6 + 4] > c.high_thresh; },
+                                   [&](int d) { return d; });
+        const int ns = warp_append(D, s.second, 0, [&](int d) {
+            const double cf = (double)s.dets[d * 6 + 4];
+            return !(cf > c.high_thresh) && cf > c.low_thresh && cf < c.high_thresh; }, [&](int d) { return d; });
+        const int nu = warp_append(n_active0, s.unconf, 0, [&](int k) { return !s.activated[s.active[k]]; },
+                                   [&](int k) { return s.active[k]; });
+        const int np = warp_append(n_active0, s.pool, 0, [&](int k) { return s.activated[s.active[k]] != 0; },
+                                   [&](int k) { return s.active[k]; });
+        if (BMB_LANE == 0) {
+            mb[MB_N_FIRST] = nf; mb[MB_N_SECOND] = ns; mb[MB_N_UNC] = nu; mb[MB_N_POOL0] = np;
+            mb[MB_N_ACT] = 0; mb[MB_N_REFIND] = 0; mb[MB_N_EMA] = 0;
         }
-        s.free_l[0] = n_first;
-        s.free_l[1] = n_second;
     }
     BMB_SYNC();
-    n_first = s.free_l[0];
-    n_second = s.free_l[1];
+    const int n_first = mb[MB_N_FIRST], n_second = mb[MB_N_SECOND], n_unc = mb[MB_N_UNC];
+    for (int k = BMB_TID; k < mb[MB_N_POOL0]; k += BMB_NT) s.mark[s.pool[k]] = 1;
     BMB_SYNC();
-
-    // ---- S1: unconfirmed / tracked split, pool = tracked ++ lost (joint by identity) ----
-    int n_pool = 0, n_unc = 0;
-    if (BMB_TID == 0) {
-        int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
-        for (int k = 0; k < CT; ++k) s.mark[k] = 0;
-        for (int k = 0; k < na; ++k) {
-            int t = s.active[k];
-            if (!s.activated[t]) s.unconf[n_unc++] = t;
-            else { s.pool[n_pool++] = t; s.mark[t] = 1; }
-        }
-        for (int k = 0; k < nl; ++k) {
-            int t = s.lost[k];
-            if (!s.mark[t]) { s.pool[n_pool++] = t; s.mark[t] = 1; }
-        }
-        s.free_l[0] = n_pool;
-        s.free_l[1] = n_unc;
+    if (BMB_WARP == 0) {  // joint(tracked, lost): a lost entry that is already in the pool is skipped
+        const int np = warp_append(n_lost0, s.pool, mb[MB_N_POOL0], [&](int k) { return !s.mark[s.lost[k]]; },
+                                   [&](int k) { return s.lost[k]; });
+        if (BMB_LANE == 0) mb[MB_N_POOL] = np;
     }
     BMB_SYNC();
-    n_pool = s.free_l[0];
-    n_unc = s.free_l[1];
-    BMB_SYNC();
+    const int n_pool = mb[MB_N_POOL];
 
     // ---- S2: Kalman predict over the pool (state is updated in place, as the reference does) ----
     for (int k = BMB_TID; k < n_pool; k += BMB_NT) {
-        int t = s.pool[k];
+        const int t = s.pool[k];
         kf_predict(c, s.state[t] == ST_TRACKED, s.mean + t * 8, s.cov + t * 64);
         track_xyxy(c, s.mean + t * 8, s.txyxy + t * 4);
     }
     for (int k = BMB_TID; k < n_unc; k += BMB_NT) {
-        int t = s.unconf[k];
+        const int t = s.unconf[k];
         track_xyxy(c, s.mean + t * 8, s.txyxy + t * 4);
     }
     BMB_SYNC();
+    BMB_PHASE(0);  // split + pool + predict
 
     // ---- S3: first-association cost (botsort.py:306-317 / bytetrack.py:303-305) ----
-    for (int e = BMB_TID; e < n_pool * n_first; e += BMB_NT) {
-        int i = e / n_first, j = e - i * n_first;
-        int t = s.pool[i], d = s.first[j];
-        double iou_d = iou_dist_td(s.txyxy + t * 4, s.dxyxy + d * 4);
-        int far = iou_d > c.proximity;
+    build_cost(s, n_pool, n_first, CD, s.pool, [&](int t, const double* tb, int j) {
+        const int d = s.first[j];
+        double iou_d = iou_dist_td(tb, s.dxyxy + d * 4);
+        const int far = iou_d > c.proximity;
         if (c.fuse_first) {
-            double sim = 1.0 - iou_d;
-            double fs = sim * (double)s.dets[d * 6 + 4];
+            const double sim = 1.0 - iou_d;
+            const double fs = sim * (double)s.dets[d * 6 + 4];
             iou_d = 1.0 - fs;
         }
         double v = iou_d;
@@ -745,59 +786,56 @@ BMB_FN void tracker_frame(const TrkCfg& c, TrkStream& s) {
             double em = s.embd[(size_t)t * CD + d];
             if (em > c.appearance) em = 1.0;
             if (c.proximity_mask && far) em = 1.0;
-            v = (iou_d != iou_d || em != em) ? NAN : (iou_d < em ? iou_d : em);
+            v = (iou_d != iou_d || em != em) ? (double)NAN : (iou_d < em ? iou_d : em);
         }
-        s.cost[(size_t)i * CD + j] = v;
-    }
-    BMB_SYNC();
+        return v;
+    });
+    BMB_PHASE(1);  // cost build round 1
     lap_solve(s, n_pool, n_first, CD, c.match1);
-
-    int n_act = 0, n_refind = 0, n_lostnow = 0, n_remnow = 0;
-    // scalars that thread 0 accumulates are mirrored through free_l[] after each sequential section
-    if (BMB_TID == 0) { s.free_l[2] = 0; s.free_l[3] = 0; }
-    BMB_SYNC();
-    apply_matches(c, s, n_pool, s.pool, s.first, frame, 0, c.with_reid, &s.free_l[2], &s.free_l[3]);
+    BMB_PHASE(2);  // assignment round 1
+    apply_matches(c, s, n_pool, s.pool, s.first, frame, 0, c.with_reid, mb);
+    BMB_PHASE(3);  // Kalman update + bookkeeping round 1
 
     // ---- S6: second association: remaining Tracked pool rows x low-confidence detections ----
-    int n_rt = 0, n_rest = 0;
-    if (BMB_TID == 0) {
-        for (int i = 0; i < n_pool; ++i)
-            if (s.lap_x[i] < 0 && s.state[s.pool[i]] == ST_TRACKED) s.rtracked[n_rt++] = s.pool[i];
-        for (int j = 0; j < n_first; ++j)
-            if (s.lap_y[j] < 0) s.rest[n_rest++] = s.first[j];
-        s.free_l[0] = n_rt;
-        s.free_l[1] = n_rest;
+    if (BMB_WARP == 0) {
+        const int nrt = warp_append(n_pool, s.rtracked, 0,
+                                    [&](int i) { return s.lap_x[i] < 0 && s.state[s.pool[i]] == ST_TRACKED; },
+                                    [&](int i) { return s.pool[i]; });
+        const int nrest = warp_append(n_first, s.rest, 0, [&](int j) { return s.lap_y[j] < 0; },
+                                      [&](int j) { return s.first[j]; });
+        if (BMB_LANE == 0) { mb[MB_N_RT] = nrt; mb[MB_N_REST] = nrest; }
     }
     BMB_SYNC();
-    n_rt = s.free_l[0];
-    n_rest = s.free_l[1];
-    BMB_SYNC();
-    for (int e = BMB_TID; e < n_rt * n_second; e += BMB_NT) {
-        int i = e / n_second, j = e - i * n_second;
-        s.cost[(size_t)i * CD + j] = iou_dist_td(s.txyxy + s.rtracked[i] * 4, s.dxyxy + s.second[j] * 4);
-    }
-    BMB_SYNC();
+    const int n_rt = mb[MB_N_RT], n_rest = mb[MB_N_REST];
+    build_cost(s, n_rt, n_second, CD, s.rtracked,
+               [&](int t, const double* tb, int j) { return iou_dist_td(tb, s.dxyxy + s.second[j] * 4); });
     lap_solve(s, n_rt, n_second, CD, c.match2);
-    apply_matches(c, s, n_rt, s.rtracked, s.second, frame, 0, 0, &s.free_l[2], &s.free_l[3]);
-    if (BMB_TID == 0) {
-        for (int i = 0; i < n_rt; ++i) {
-            if (s.lap_x[i] >= 0) continue;
-            int t = s.rtracked[i];
-            if (s.state[t] != ST_LOST) { s.state[t] = ST_LOST; s.lostnow_l[n_lostnow++] = t; }
+    apply_matches(c, s, n_rt, s.rtracked, s.second, frame, 0, 0, mb);
+    for (int i = BMB_TID; i < n_rt; i += BMB_NT) {
+        int flag = 0;
+        if (s.lap_x[i] < 0) {
+            const int t = s.rtracked[i];
+            if (s.state[t] != ST_LOST) { s.state[t] = ST_LOST; flag = 1; }
         }
-        s.free_l[4] = n_lostnow;
+        s.tmp_b[i] = flag;
     }
     BMB_SYNC();
+    if (BMB_WARP == 0) {
+        const int nl = warp_append(n_rt, s.lostnow_l, 0, [&](int i) { return s.tmp_b[i] != 0; },
+                                   [&](int i) { return s.rtracked[i]; });
+        if (BMB_LANE == 0) mb[MB_N_LOSTNOW] = nl;
+    }
+    BMB_SYNC();
+    BMB_PHASE(4);  // second association
 
     // ---- S7: unconfirmed tracks x detections left over from round 1 ----
-    for (int e = BMB_TID; e < n_unc * n_rest; e += BMB_NT) {
-        int i = e / n_rest, j = e - i * n_rest;
-        int t = s.unconf[i], d = s.rest[j];
-        double iou_d = iou_dist_td(s.txyxy + t * 4, s.dxyxy + d * 4);
-        int far = iou_d > c.proximity;
+    build_cost(s, n_unc, n_rest, CD, s.unconf, [&](int t, const double* tb, int j) {
+        const int d = s.rest[j];
+        double iou_d = iou_dist_td(tb, s.dxyxy + d * 4);
+        const int far = iou_d > c.proximity;
         {
-            double sim = 1.0 - iou_d;
-            double fs = sim * (double)s.dets[d * 6 + 4];
+            const double sim = 1.0 - iou_d;
+            const double fs = sim * (double)s.dets[d * 6 + 4];
             iou_d = 1.0 - fs;
         }
         double v = iou_d;
@@ -805,41 +843,57 @@ BMB_FN void tracker_frame(const TrkCfg& c, TrkStream& s) {
             double em = s.embd[(size_t)t * CD + d] / c.unc_emb_scale;
             if (em > c.appearance) em = 1.0;
             if (c.proximity_mask && far) em = 1.0;
-            v = (iou_d != iou_d || em != em) ? NAN : (iou_d < em ? iou_d : em);
+            v = (iou_d != iou_d || em != em) ? (double)NAN : (iou_d < em ? iou_d : em);
         }
-        s.cost[(size_t)i * CD + j] = v;
+        return v;
+    });
+    lap_solve(s, n_unc, n_rest, CD, c.match3);
+    apply_matches(c, s, n_unc, s.unconf, s.rest, frame, 1, c.with_reid, mb);
+    BMB_PHASE(5);  // unconfirmed round
+
+    // ---- S8: removals of unmatched unconfirmed tracks, births (botsort.py:425-440 / bytetrack.py:362-373) ----
+    for (int i = BMB_TID; i < n_unc; i += BMB_NT)
+        if (s.lap_x[i] < 0) s.state[s.unconf[i]] = ST_REMOVED;
+    for (int k = BMB_TID; k < CT; k += BMB_NT) s.mark[k] = 0;
+    BMB_SYNC();
+    for (int k = BMB_TID; k < n_active0; k += BMB_NT) s.mark[s.active[k]] = 1;
+    for (int k = BMB_TID; k < n_lost0; k += BMB_NT) s.mark[s.lost[k]] = 1;
+    BMB_SYNC();
+    if (BMB_WARP == 0) {
+        const int nrem = warp_append(n_unc, s.remnow_l, 0, [&](int i) { return s.lap_x[i] < 0; },
+                                     [&](int i) { return s.unconf[i]; });
+        // birth candidates: rest[j] unmatched in round 3 whose confidence passes the float32 gate
+        int nb = warp_append(n_rest, s.tmp_a, 0,
+                             [&](int j) { return s.lap_y[j] < 0 && !(s.dets[s.rest[j] * 6 + 4] < c.new_thresh_f32); },
+                             [&](int j) { return s.rest[j]; });
+        // that many free slots (anything not referenced by the active / lost lists)
+        int nfree = 0;
+        for (int k0 = 0; k0 < CT && nfree < nb; k0 += BMB_NL) {
+            const int k = k0 + BMB_LANE;
+            const bool p = k < CT && !s.mark[k];
+            const unsigned m = BMB_BALLOT(p);
+#if BMB_DEVICE
+            const int pos = nfree + __popc(m & ((1u << BMB_LANE) - 1u));
+#else
+            const int pos = nfree;
+#endif
+            if (p && pos < nb) free_slots[pos] = k;
+            nfree += BMB_POPC(m);
+        }
+        if (nfree < nb) {
+            if (BMB_LANE == 0) s.scalars[SC_ERROR] = ERR_TRACK_CAPACITY;
+            nb = nfree;
+        }
+        if (BMB_LANE == 0) { mb[MB_N_REMNOW] = nrem; mb[MB_N_BIRTH] = nb; }
     }
     BMB_SYNC();
-    lap_solve(s, n_unc, n_rest, CD, c.match3);
-    apply_matches(c, s, n_unc, s.unconf, s.rest, frame, 1, c.with_reid, &s.free_l[2], &s.free_l[3]);
-
-    // ---- S8..S10: removals, births, list algebra, duplicate suppression (sequential bookkeeping) ----
-    if (BMB_TID == 0) {
-        n_act = s.free_l[2];
-        n_refind = s.free_l[3];
-        n_lostnow = s.free_l[4];
-        for (int i = 0; i < n_unc; ++i)
-            if (s.lap_x[i] < 0) { int t = s.unconf[i]; s.state[t] = ST_REMOVED; s.remnow_l[n_remnow++] = t; }
-        // free slots: everything not referenced by the active / lost lists
-        int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
-        for (int k = 0; k < CT; ++k) s.mark[k] = 0;
-        for (int k = 0; k < na; ++k) s.mark[s.active[k]] = 1;
-        for (int k = 0; k < nl; ++k) s.mark[s.lost[k]] = 1;
-        int n_free = 0;
-        for (int k = 0; k < CT; ++k)
-            if (!s.mark[k]) s.free_l[8 + n_free++] = k;  // free_l has CT + 8 entries
-        // births (botsort.py:433-440 / bytetrack.py:368-373); rest[j] with lap_y[j] < 0, ascending
-        int used = 0;
-        int next_id = s.scalars[SC_NEXT_ID];
-        for (int j = 0; j < n_rest; ++j) {
-            if (s.lap_y[j] >= 0) continue;
-            int d = s.rest[j];
-            float cf = s.dets[d * 6 + 4];
-            if (cf < c.new_thresh_f32) continue;
-            if (used >= n_free) { s.scalars[SC_ERROR] = ERR_TRACK_CAPACITY; break; }
-            int t = s.free_l[8 + used++];
-            s.id[t] = ++next_id;
-            s.tmp_a[used - 1] = d;  // remember the detection for the parallel initiation below
+    const int n_birth = mb[MB_N_BIRTH];
+    {
+        const int id0 = s.scalars[SC_NEXT_ID];
+        for (int k = BMB_TID; k < n_birth; k += BMB_NT) {
+            const int t = free_slots[k], d = s.tmp_a[k];
+            const float cf = s.dets[d * 6 + 4];
+            s.id[t] = id0 + 1 + k;
             s.tracklet_len[t] = 0;
             s.state[t] = ST_TRACKED;
             s.activated[t] = (frame == 1) ? 1 : 0;
@@ -852,120 +906,137 @@ BMB_FN void tracker_frame(const TrkCfg& c, TrkStream& s) {
             s.hist_n[t] = 1;
             s.hist_cls[t * HIST_CAP] = s.dets[d * 6 + 5];
             s.hist_sum[t * HIST_CAP] = cf;
-            s.act_l[n_act++] = t;
-        }
-        s.scalars[SC_NEXT_ID] = next_id;
-        s.free_l[5] = used;
-        s.free_l[2] = n_act;
-    }
-    BMB_SYNC();
-    {
-        int n_new = s.free_l[5];
-        for (int k = BMB_TID; k < n_new; k += BMB_NT) {
-            int t = s.free_l[8 + k], d = s.tmp_a[k];
             kf_initiate(c, s.dmeas + d * 4, s.mean + t * 8, s.cov + t * 64);
         }
         if (c.with_reid) {
-            for (int k = BMB_WARP; k < n_new; k += BMB_NW) {
-                int t = s.free_l[8 + k], d = s.tmp_a[k];
+            for (int k = BMB_WARP; k < n_birth; k += BMB_NW) {
+                const int t = free_slots[k], d = s.tmp_a[k];
                 for (int q = BMB_LANE; q < F; q += BMB_NL) s.smooth[(size_t)t * F + q] = s.dfeat[(size_t)d * F + q];
             }
         }
     }
-    BMB_SYNC();
-    if (BMB_TID == 0) {
-        n_act = s.free_l[2];
-        int na = s.scalars[SC_N_ACTIVE], nl = s.scalars[SC_N_LOST];
-        // lost tracks that timed out (botsort.py:472-476)
-        for (int k = 0; k < nl; ++k) {
-            int t = s.lost[k];
-            if (frame - s.frame_id[t] > c.max_time_lost) { s.state[t] = ST_REMOVED; s.remnow_l[n_remnow++] = t; }
-        }
-        // active' = [Tracked in active] ++ activated ++ refind (joint by identity)
-        for (int k = 0; k < CT; ++k) s.mark[k] = 0;
-        int m = 0;
-        for (int k = 0; k < na; ++k) {
-            int t = s.active[k];
-            if (s.state[t] == ST_TRACKED) { s.tmp_a[m++] = t; s.mark[t] = 1; }
-        }
-        for (int k = 0; k < n_act; ++k) {
-            int t = s.act_l[k];
-            if (!s.mark[t]) { s.tmp_a[m++] = t; s.mark[t] = 1; }
-        }
-        for (int k = 0; k < n_refind; ++k) {
-            int t = s.refind_l[k];
-            if (!s.mark[t]) { s.tmp_a[m++] = t; s.mark[t] = 1; }
-        }
-        // lost' = (lost - active') ++ lost_now, minus everything in the removed set
-        int q = 0;
-        for (int k = 0; k < nl; ++k) {
-            int t = s.lost[k];
-            if (!s.mark[t]) s.tmp_b[q++] = t;
-        }
-        for (int k = 0; k < n_lostnow; ++k) s.tmp_b[q++] = s.lostnow_l[k];
-        int q2 = 0;
-        for (int k = 0; k < q; ++k) {
-            int t = s.tmp_b[k];
-            if (!in_removed_set(c, s, t)) s.tmp_b[q2++] = t;
-        }
-        for (int k = 0; k < n_remnow; ++k) push_removed(c, s, s.remnow_l[k]);
-        s.free_l[0] = m;
-        s.free_l[1] = q2;
+    // lost tracks that timed out (botsort.py:472-476): flags first, ordered append below
+    for (int k = BMB_TID; k < n_lost0; k += BMB_NT) {
+        const int t = s.lost[k];
+        int flag = 0;
+        if (frame - s.frame_id[t] > c.max_time_lost) { s.state[t] = ST_REMOVED; flag = 1; }
+        s.tmp_b[k] = flag;
     }
+    for (int k = BMB_TID; k < CT; k += BMB_NT) s.mark[k] = 0;
     BMB_SYNC();
-    // duplicate suppression (botsort_utils.py:53-82): IoU distance active' x lost' < 0.15
-    {
-        int m = s.free_l[0], q = s.free_l[1];
-        for (int k = BMB_TID; k < m; k += BMB_NT) track_xyxy(c, s.mean + s.tmp_a[k] * 8, s.txyxy + s.tmp_a[k] * 4);
-        for (int k = BMB_TID; k < q; k += BMB_NT) track_xyxy(c, s.mean + s.tmp_b[k] * 8, s.txyxy + s.tmp_b[k] * 4);
-        BMB_SYNC();
-        // duplicate flags go into `mark` (1 = member of active'): 2 = drop from lost', 3 = drop from active'
-        for (int e = BMB_TID; e < m * q; e += BMB_NT) {
-            int p = e / q, r = e - p * q;
-            int ta = s.tmp_a[p], tb = s.tmp_b[r];
-            double dist = iou_dist_tt(s.txyxy + ta * 4, s.txyxy + tb * 4);
-            if (dist < 0.15) {
-                int tp = s.frame_id[ta] - s.start_frame[ta];
-                int tq = s.frame_id[tb] - s.start_frame[tb];
-                if (tp > tq) s.mark[tb] = 2; else s.mark[ta] = 3;
-            }
+    if (BMB_WARP == 0) {
+        const int na = warp_append(n_birth, s.act_l, mb[MB_N_ACT], [&](int) { return true; },
+                                   [&](int k) { return free_slots[k]; });
+        const int nrem = warp_append(n_lost0, s.remnow_l, mb[MB_N_REMNOW], [&](int k) { return s.tmp_b[k] != 0; },
+                                     [&](int k) { return s.lost[k]; });
+        // active' part 1: still-Tracked members of the old active list
+        const int m1 = warp_append(n_active0, s.pool, 0, [&](int k) { return s.state[s.active[k]] == ST_TRACKED; },
+                                   [&](int k) { return s.active[k]; });
+        if (BMB_LANE == 0) {
+            mb[MB_N_ACT] = na; mb[MB_N_REMNOW] = nrem; mb[MB_M1] = m1;
+            s.scalars[SC_NEXT_ID] += n_birth;
         }
     }
     BMB_SYNC();
-    if (BMB_TID == 0) {
-        int m = s.free_l[0], q = s.free_l[1];
-        int na = 0, nl = 0, n_out = 0;
-        for (int k = 0; k < m; ++k) {
-            int t = s.tmp_a[k];
-            if (s.mark[t] == 3) continue;
-            s.active[na++] = t;
-        }
-        for (int k = 0; k < q; ++k) {
-            int t = s.tmp_b[k];
-            if (s.mark[t] == 2) continue;
-            s.lost[nl++] = t;
-        }
-        s.scalars[SC_N_ACTIVE] = na;
-        s.scalars[SC_N_LOST] = nl;
-        s.scalars[SC_FRAME] = frame;
-        // output rows (botsort.py:494-500)
-        for (int k = 0; k < na; ++k) {
-            int t = s.active[k];
-            if (!s.activated[t]) continue;
-            if (n_out >= CD) { s.scalars[SC_ERROR] = ERR_DET_CAPACITY; break; }
-            double b[4];
-            track_xyxy(c, s.mean + t * 8, b);
-            float* o = s.out + n_out * 8;
-            o[0] = (float)b[0]; o[1] = (float)b[1]; o[2] = (float)b[2]; o[3] = (float)b[3];
-            o[4] = (float)s.id[t];
-            o[5] = s.conf[t];
-            o[6] = s.cls[t];
-            o[7] = s.det_ind[t];
-            ++n_out;
-        }
-        s.scalars[SC_N_OUT] = n_out;
+    for (int k = BMB_TID; k < mb[MB_M1]; k += BMB_NT) s.mark[s.pool[k]] = 1;
+    BMB_SYNC();
+    if (BMB_WARP == 0) {  // joint with the activated list
+        const int m2 = warp_append(mb[MB_N_ACT], s.pool, mb[MB_M1], [&](int k) { return !s.mark[s.act_l[k]]; },
+                                   [&](int k) { return s.act_l[k]; });
+        if (BMB_LANE == 0) mb[MB_M2] = m2;
     }
     BMB_SYNC();
+    for (int k = mb[MB_M1] + BMB_TID; k < mb[MB_M2]; k += BMB_NT) s.mark[s.pool[k]] = 1;
+    BMB_SYNC();
+    if (BMB_WARP == 0) {  // joint with the refind list; lost' = (lost - active') ++ lost_now
+        const int m3 = warp_append(mb[MB_N_REFIND], s.pool, mb[MB_M2], [&](int k) { return !s.mark[s.refind_l[k]]; },
+                                   [&](int k) { return s.refind_l[k]; });
+        if (BMB_LANE == 0) mb[MB_M3] = m3;
+    }
+    BMB_SYNC();
+    for (int k = mb[MB_M2] + BMB_TID; k < mb[MB_M3]; k += BMB_NT) s.mark[s.pool[k]] = 1;
+    BMB_SYNC();
+    if (BMB_WARP == 0) {
+        int q = warp_append(n_lost0, s.rtracked, 0, [&](int k) { return !s.mark[s.lost[k]]; },
+                            [&](int k) { return s.lost[k]; });
+        q = warp_append(mb[MB_N_LOSTNOW], s.rtracked, q, [&](int) { return true; },
+                        [&](int k) { return s.lostnow_l[k]; });
+        if (BMB_LANE == 0) mb[MB_Q1] = q;
+    }
+    BMB_SYNC();
+    // ... minus everything in the removed set (evaluated BEFORE this frame's removals are pushed)
+    for (int k = BMB_TID; k < mb[MB_Q1]; k += BMB_NT) s.tmp_b[k] = in_removed_set(c, s, s.rtracked[k]);
+    BMB_SYNC();
+    if (BMB_WARP == 0) {
+        const int q2 = warp_append(mb[MB_Q1], s.tmp_a, 0, [&](int k) { return !s.tmp_b[k]; },
+                                   [&](int k) { return s.rtracked[k]; });
+        if (BMB_LANE == 0) {
+            mb[MB_Q2] = q2;
+            const int nrem = mb[MB_N_REMNOW];
+            for (int k = 0; k < nrem; ++k) push_removed(c, s, s.remnow_l[k]);
+        }
+    }
+    BMB_SYNC();
+    BMB_PHASE(6);  // births + list algebra
+
+    // ---- duplicate suppression (botsort_utils.py:53-82): IoU distance active' x lost' < 0.15 ----
+    const int m = mb[MB_M3], q = mb[MB_Q2];
+    for (int k = BMB_TID; k < m; k += BMB_NT) track_xyxy(c, s.mean + s.pool[k] * 8, s.txyxy + s.pool[k] * 4);
+    for (int k = BMB_TID; k < q; k += BMB_NT) track_xyxy(c, s.mean + s.tmp_a[k] * 8, s.txyxy + s.tmp_a[k] * 4);
+    BMB_SYNC();
+    // duplicate flags go into `mark` (1 = member of active'): 2 = drop from lost', 3 = drop from active'
+    for (int e = BMB_TID; e < m * q; e += BMB_NT) {
+        const int pi = e / q, r = e - pi * q;
+        const int ta = s.pool[pi], tb = s.tmp_a[r];
+        const double dist = iou_dist_tt(s.txyxy + ta * 4, s.txyxy + tb * 4);
+        if (dist < 0.15) {
+            const int tp = s.frame_id[ta] - s.start_frame[ta];
+            const int tq = s.frame_id[tb] - s.start_frame[tb];
+            if (tp > tq) s.mark[tb] = 2; else s.mark[ta] = 3;
+        }
+    }
+    BMB_SYNC();
+    if (BMB_WARP == 0) {
+        const int na = warp_append(m, s.active, 0, [&](int k) { return s.mark[s.pool[k]] != 3; },
+                                   [&](int k) { return s.pool[k]; });
+        const int nl = warp_append(q, s.lost, 0, [&](int k) { return s.mark[s.tmp_a[k]] != 2; },
+                                   [&](int k) { return s.tmp_a[k]; });
+        BMB_SYNCWARP();
+        int n_out = warp_append(na, s.tmp_b, 0, [&](int k) { return s.activated[s.active[k]] != 0; },
+                                [&](int k) { return s.active[k]; });
+        if (n_out > CD) {
+            if (BMB_LANE == 0) s.scalars[SC_ERROR] = ERR_DET_CAPACITY;
+            n_out = CD;
+        }
+        if (BMB_LANE == 0) {
+            s.scalars[SC_N_ACTIVE] = na;
+            s.scalars[SC_N_LOST] = nl;
+            s.scalars[SC_FRAME] = frame;
+            s.scalars[SC_N_OUT] = n_out;
+            s.scalars[SC_N_EMA] = mb[MB_N_EMA];
+        }
+    }
+    BMB_SYNC();
+    // output rows (botsort.py:494-500)
+    for (int k = BMB_TID; k < s.scalars[SC_N_OUT]; k += BMB_NT) {
+        const int t = s.tmp_b[k];
+        double b[4];
+        track_xyxy(c, s.mean + t * 8, b);
+        float* o = s.out + k * 8;
+        o[0] = (float)b[0]; o[1] = (float)b[1]; o[2] = (float)b[2]; o[3] = (float)b[3];
+        o[4] = (float)s.id[t];
+        o[5] = s.conf[t];
+        o[6] = s.cls[t];
+        o[7] = s.det_ind[t];
+    }
+    BMB_SYNC();
+    BMB_PHASE(7);  // duplicate suppression + output rows
+}
+
+// Deferred appearance EMA of this frame's matches (botsort_track.py:58-67 via update()/re_activate()).
+// Warp-cooperative; `pair` indexes the list recorded by tracker_frame.
+BMB_FN void apply_feature_ema(const TrkCfg& c, TrkStream& s, int pair) {
+    feat_ema(s.smooth + (size_t)s.ema_slot[pair] * c.feat_dim, s.dfeat + (size_t)s.ema_det[pair] * c.feat_dim, c.feat_dim);
 }
 
 }  // namespace bmb

@@ -30,9 +30,39 @@ namespace bmb {
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tracker_frame(const TrkCfg cfg, TrkStream* streams) {
+// Shared-memory residency for the assignment's dual prices / frontier arrays (they are touched on every step of
+// the augmenting-path search); falls back to the HBM scratch of the slab when the capacities are too large.
+__host__ __device__ inline size_t lap_smem_bytes(int CT, int CD) {
+    return sizeof(double) * ((size_t)CT + 2 * (size_t)CD) + sizeof(int) * (2 * (size_t)CT + 1 + 5 * (size_t)CD) + 16;
+}
+
+__global__ void __launch_bounds__(256) k_tracker_frame(const TrkCfg cfg, TrkStream* streams, int lap_in_smem) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     TrkStream s = streams[blockIdx.x];
+    if (lap_in_smem) {
+        const int CT = cfg.cap_tracks, CD = cfg.cap_dets;
+        double* pd = reinterpret_cast<double*>(dyn_smem);
+        s.lap_u = pd; pd += CT;
+        s.lap_v = pd; pd += CD;
+        s.lap_spc = pd; pd += CD;
+        int* pi = reinterpret_cast<int*>(pd);
+        s.lap_x = pi; pi += CT;
+        s.csr_ptr = pi; pi += CT + 1;
+        s.lap_y = pi; pi += CD;
+        s.lap_path = pi; pi += CD;
+        s.lap_insc = pi; pi += CD;
+        s.lap_tl = pi; pi += CD;
+        s.lap_sc = pi;
+    }
     tracker_frame(cfg, s);
+}
+
+// the appearance EMA of this frame's matched (track, detection) pairs, one warp per pair
+__global__ void __launch_bounds__(256) k_feat_ema(const TrkCfg cfg, TrkStream* streams) {
+    TrkStream s = streams[blockIdx.y];
+    const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= s.scalars[SC_N_EMA]) return;
+    apply_feature_ema(cfg, s, pair);
 }
 
 // detection appearance: the reference normalises each high-confidence row twice in place
@@ -269,8 +299,18 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
     } else {
         CUDA_OK(cudaEventRecord(ev[1], stream));
     }
-    k_tracker_frame<<<S, 256, 0, stream>>>(cfg, d_streams);
-    ++launches;
+    {
+        const size_t lb = lap_smem_bytes(cfg.cap_tracks, cfg.cap_dets);
+        const bool in_smem = lb <= 160 * 1024;
+        if (in_smem && lb > 48 * 1024)
+            CUDA_OK(cudaFuncSetAttribute(k_tracker_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb));
+        k_tracker_frame<<<S, 256, in_smem ? lb : 0, stream>>>(cfg, d_streams, in_smem ? 1 : 0);
+        ++launches;
+        if (cfg.with_reid) {
+            k_feat_ema<<<dim3((cfg.cap_dets + 7) / 8, S), 256, 0, stream>>>(cfg, d_streams);
+            ++launches;
+        }
+    }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(ev[2], stream));
     if (profile) {  // profiling pass: serialise and attribute device time per kernel class
@@ -280,6 +320,13 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         assoc_ms_accum += b;
         assoc_frames += 1;
     }
+}
+
+void Engine::read_timers(int sidx, long long* out16, bool reset) {
+    if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(out16, h_streams[sidx].timers, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_OK(cudaMemset(h_streams[sidx].timers, 0, sizeof(long long) * 16));
 }
 
 void Engine::set_profile(bool on) {
@@ -296,7 +343,7 @@ void Engine::profile_read(double* ms, int* launch_counts) {
     for (int c = 0; c < REID_N_CLASSES + 1; ++c) { ms[c] = 0.0; launch_counts[c] = 0; }
     if (reid) reid_profile_collect(reid, ms, launch_counts);
     ms[REID_N_CLASSES] = assoc_ms_accum;
-    launch_counts[REID_N_CLASSES] = assoc_frames * (cfg.with_reid ? 3 : 1);
+    launch_counts[REID_N_CLASSES] = assoc_frames * (cfg.with_reid ? 4 : 1);
     assoc_ms_accum = 0.0;
     assoc_frames = 0;
 }

@@ -27,6 +27,7 @@ inline size_t carve_stream(const TrkCfg& c, uint8_t* base, TrkStream* s, size_t*
     Carver k{base, 0};
     TrkStream t{};
     t.scalars = k.take<int>(SC_COUNT);
+    t.timers = k.take<long long>(16);
     t.state = k.take<int>(CT);
     t.activated = k.take<int>(CT);
     t.id = k.take<int>(CT);
@@ -68,7 +69,9 @@ inline size_t carve_stream(const TrkCfg& c, uint8_t* base, TrkStream* s, size_t*
     t.tmp_a = k.take<int>(CT);
     t.tmp_b = k.take<int>(CT);
     t.mark = k.take<int>(CT);
-    t.free_l = k.take<int>(CT + 8);
+    t.free_l = k.take<int>(CT + MB_COUNT);
+    t.ema_slot = k.take<int>(CD);
+    t.ema_det = k.take<int>(CD);
     t.lap_x = k.take<int>(CT);
     t.lap_y = k.take<int>(CD);
     t.lap_u = k.take<double>(CT);

@@ -181,6 +181,11 @@ BOXMOT_B200_API int boxmot_b200_tracker_elapsed_ms(BoxMOTB200Tracker* handle, do
 /* Profiling pass: when enabled every kernel launch is bracketed by CUDA events (frames are serialised).
  * profile_read returns accumulated milliseconds and launch counts for 9 classes:
  * crop, stem, maxpool, pointwise, lightconv, gates, avgpool, head, association (3 kernels) - and resets them. */
+/* SM-clock ticks the association kernel spent per phase since the last reset (16 slots; 0 split+predict,
+ * 1 cost build, 2 assignment, 3 Kalman update + bookkeeping, 4 second round, 5 unconfirmed round, 6 births +
+ * list algebra, 7 duplicate suppression + output). */
+BOXMOT_B200_API int boxmot_b200_tracker_phase_clocks(BoxMOTB200Tracker* handle, int stream, long long* out16,
+                                                     int reset);
 BOXMOT_B200_API int boxmot_b200_tracker_profile(BoxMOTB200Tracker* handle, int enable);
 BOXMOT_B200_API int boxmot_b200_tracker_profile_read(BoxMOTB200Tracker* handle, double* ms, int* launches);
 BOXMOT_B200_API const char* boxmot_b200_last_error(void);

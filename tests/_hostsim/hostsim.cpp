@@ -62,6 +62,8 @@ int hostsim_update(HostSim* h, const float* dets, int n, const float* embs, floa
     }
     h->s.scalars[SC_LAP_STEPS] = 0;
     tracker_frame(c, h->s);
+    if (c.with_reid)
+        for (int k = 0; k < h->s.scalars[SC_N_EMA]; ++k) apply_feature_ema(c, h->s, k);
     if (lap_steps) *lap_steps = h->s.scalars[SC_LAP_STEPS];
     if (h->s.scalars[SC_ERROR]) return -h->s.scalars[SC_ERROR];
     int m = h->s.scalars[SC_N_OUT];
