@@ -92,6 +92,8 @@ SYMBOLS = {
     "boxmot_b200_kalman_initiate": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),
     "boxmot_b200_iou_cost": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "boxmot_b200_cosine_cost": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "boxmot_b200_pointwise_gemm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                           c_void_p, POINTER(c_float)]),
     "boxmot_b200_device_count": (c_int, []),
     "boxmot_b200_reid_debug_stage": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                              c_int, POINTER(c_int)]),

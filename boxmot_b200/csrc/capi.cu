@@ -258,6 +258,10 @@ int boxmot_b200_kalman_initiate(int kind, const float* meas, double* mean, doubl
 int boxmot_b200_iou_cost(const double* t, int rows, const float* d, int cols, double* out) {
     return guard([&] { standalone_iou(t, rows, d, cols, out); });
 }
+int boxmot_b200_pointwise_gemm(const float* a, int m, int k, const float* w, int n, const float* bias,
+                               const float* residual, int relu, int use_tensor_cores, float* out, float* elapsed_ms) {
+    return guard([&] { standalone_pointwise(a, m, k, w, n, bias, residual, relu, use_tensor_cores, out, elapsed_ms); });
+}
 int boxmot_b200_cosine_cost(const float* a, int rows, const float* b, int cols, int dim, double* out) {
     return guard([&] { standalone_cosine(a, rows, b, cols, dim, out); });
 }

@@ -107,5 +107,7 @@ void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int
 void standalone_kf(int op, int kind, double* mean, double* cov, const int* tracked, const float* meas, int n);
 void standalone_iou(const double* t, int T, const float* d, int D, double* out);
 void standalone_cosine(const float* a, int T, const float* b, int D, int F, double* out);
+void standalone_pointwise(const float* A, int M, int K, const float* W, int N, const float* bias, const float* residual,
+                          int relu, int use_tc, float* out, float* elapsed_ms);
 
 }  // namespace bmb

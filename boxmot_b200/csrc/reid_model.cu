@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "pointwise_tc.cuh"
 
 namespace bmb {
 
@@ -249,6 +250,8 @@ struct PwArgs {
     const float* residual;    // [M][N] or null
     float* out;               // [M][N]
     int K, N, mid, HW, relu;
+    const float* w_tc;        // canonical hi/lo weight blocks for the tcgen05 path (null: CUDA-core kernel)
+    int Kpad, Npad;
 };
 
 template <int BN, bool GATED>
@@ -524,12 +527,14 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
 // ---------------------------------------------------------------------------------------------------
 enum { CLS_CROP = 0, CLS_STEM, CLS_MAXPOOL, CLS_POINTWISE, CLS_LIGHTCONV, CLS_GATES, CLS_AVGPOOL, CLS_HEAD };
 struct LightW { size_t pw, dw, b; };
+struct TcW { const float* w = nullptr; int Kpad = 0, Npad = 0; };  // packed weights of one pointwise layer
 struct BlockW {
     int cin, cout, mid, hid, has_ds;
     size_t c1w, c1b;
     LightW light[10];
     size_t g1w, g1b, g2w, g2b;
     size_t cw, cb;
+    TcW tc_c1, tc_c;
 };
 
 struct ReidModel {
@@ -540,6 +545,9 @@ struct ReidModel {
     BlockW blocks[6];
     size_t trans_w[2] = {0, 0}, trans_b[2] = {0, 0};
     size_t c5w = 0, c5b = 0, fcw = 0, fcb = 0;
+    TcW tc_trans[2], tc_c5;
+    float* d_wtc = nullptr;    // all packed tensor-core weights
+    bool use_tc = false;
     // workspace for one chunk of crops
     int chunk = 128;
     float* blob = nullptr;
@@ -619,6 +627,36 @@ ReidModel* reid_load(const char* path) {
         if (o != n_floats) throw std::runtime_error("ReID blob size does not match its header");
         RCUDA_OK(cudaMalloc(&m->d_w, sizeof(float) * n_floats));
         RCUDA_OK(cudaMemcpy(m->d_w, host.data(), sizeof(float) * n_floats, cudaMemcpyHostToDevice));
+        {   // tensor-core copies of every 1x1 weight that fits the tcgen05 kernel's shared-memory budget
+            const char* env = getenv("BOXMOT_B200_REID_TC");
+            // Measured in round 1 (profiles/r1_tcgen05_pointwise.md): at OSNet_x0_25's K,N <= 128 every 1x1 layer is
+            // bandwidth-bound and the float32 CUDA-core GEMM is 1.2-1.8x faster than this first (unpipelined)
+            // tcgen05 kernel, so the tensor-core path is opt-in until it is pipelined / fused.
+            m->use_tc = env && env[0] == '1';
+            std::vector<float> packed;
+            struct Todo { TcW* dst; size_t w; int K, N; size_t at; };
+            std::vector<Todo> todo;
+            auto add = [&](TcW* dst, size_t w, int K, int N) {
+                const int Kpad = (K + 7) / 8 * 8, Npad = (N + 15) / 16 * 16;
+                if (Npad > 256 || tc::smem_bytes(Kpad, Npad) > 200 * 1024) return;
+                dst->Kpad = Kpad; dst->Npad = Npad;
+                todo.push_back({dst, w, K, N, packed.size()});
+                packed.resize(packed.size() + 2 * (size_t)Npad * Kpad);
+            };
+            for (int bi = 0; bi < 6; ++bi) {
+                BlockW& b = m->blocks[bi];
+                add(&b.tc_c1, b.c1w, b.cin, b.mid);
+                add(&b.tc_c, b.cw, b.mid + (b.has_ds ? b.cin : 0), b.cout);
+            }
+            for (int s = 0; s < 2; ++s) add(&m->tc_trans[s], m->trans_w[s], m->c[s + 1], m->c[s + 1]);
+            add(&m->tc_c5, m->c5w, m->c[3], m->c[3]);
+            for (auto& t : todo) tc::pack_weights(host.data() + t.w, t.K, t.N, t.dst->Kpad, t.dst->Npad, packed.data() + t.at);
+            if (!packed.empty()) {
+                RCUDA_OK(cudaMalloc(&m->d_wtc, sizeof(float) * packed.size()));
+                RCUDA_OK(cudaMemcpy(m->d_wtc, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice));
+                for (auto& t : todo) t.dst->w = m->d_wtc + t.at;
+            }
+        }
         // workspace
         const size_t CH = m->chunk;
         const size_t big = (size_t)8192 * m->c[0] > (size_t)2048 * m->c[1] ? (size_t)8192 * m->c[0] : (size_t)2048 * m->c[1];
@@ -641,7 +679,7 @@ ReidModel* reid_load(const char* path) {
 
 void reid_free(ReidModel* m) {
     if (!m) return;
-    cudaFree(m->d_w); cudaFree(m->blob); cudaFree(m->bufA); cudaFree(m->bufB); cudaFree(m->x1);
+    cudaFree(m->d_w); cudaFree(m->d_wtc); cudaFree(m->blob); cudaFree(m->bufA); cudaFree(m->bufB); cudaFree(m->x1);
     for (int b = 0; b < 4; ++b) { cudaFree(m->Y[b][0]); cudaFree(m->Y[b][1]); cudaFree(m->sums[b]); }
     cudaFree(m->gates);
     delete m;
@@ -698,7 +736,32 @@ struct Launcher {
         RCUDA_OK(cudaEventRecord(m->prof_ev.back(), st));
     }
 
+    void pointwise_tc(const PwArgs& a) {
+        tc::Args t{};
+        t.in = a.in;
+        for (int b = 0; b < 4; ++b) t.branch[b] = a.branch[b];
+        t.gates = a.gates; t.w_tc = a.w_tc; t.bias = a.bias; t.residual = a.residual; t.out = a.out;
+        t.K = a.K; t.N = a.N; t.Kpad = a.Kpad; t.Npad = a.Npad; t.mid = a.mid; t.HW = a.HW; t.relu = a.relu;
+        const size_t smem = tc::smem_bytes(a.Kpad, a.Npad);
+        const int tmem_cols = a.Npad <= 32 ? 32 : (a.Npad <= 64 ? 64 : (a.Npad <= 128 ? 128 : 256));
+        int per_sm = (int)((220 * 1024) / (smem + 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 512 / tmem_cols ? 512 / tmem_cols : per_sm);
+        per_sm = per_sm > 8 ? 8 : per_sm;
+        const int tiles = (int)(((size_t)upper * a.HW) / tc::TILE_M);
+        const int grid = tiles < 148 * per_sm ? tiles : 148 * per_sm;
+        begin(CLS_POINTWISE);
+        if (a.gates) {
+            RCUDA_OK(cudaFuncSetAttribute(tc::k_pointwise_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc::k_pointwise_tc<true><<<grid, tc::THREADS, smem, st>>>(t, d_n, off, cap);
+        } else {
+            RCUDA_OK(cudaFuncSetAttribute(tc::k_pointwise_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tc::k_pointwise_tc<false><<<grid, tc::THREADS, smem, st>>>(t, d_n, off, cap);
+        }
+        end();
+        ++launches;
+    }
     void pointwise(const PwArgs& a) {
+        if (m->use_tc && a.w_tc && a.HW % tc::TILE_M == 0) { pointwise_tc(a); return; }
         const int N = a.N;
         const size_t Mmax = (size_t)upper * a.HW;
         if (N % 64 == 0) launch_pw<64>(a, Mmax);
@@ -787,6 +850,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 PwArgs p{};
                 p.in = X; p.w = W + b.c1w; p.bias = W + b.c1b; p.out = m->x1;
                 p.K = b.cin; p.N = b.mid; p.HW = HW; p.relu = 1;
+                p.w_tc = b.tc_c1.w; p.Kpad = b.tc_c1.Kpad; p.Npad = b.tc_c1.Npad;
                 L.pointwise(p);
                 const int R = pick_tile_rows(H, Wd, b.mid);
                 const int tiles = H / R;
@@ -823,6 +887,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 c.residual = b.has_ds ? nullptr : X;
                 c.w = W + b.cw; c.bias = W + b.cb; c.out = Xo;
                 c.K = b.mid + (b.has_ds ? b.cin : 0); c.N = b.cout; c.HW = HW; c.relu = 1;
+                c.w_tc = b.tc_c.w; c.Kpad = b.tc_c.Kpad; c.Npad = b.tc_c.Npad;
                 L.pointwise(c);
                 float* t = X; X = Xo; Xo = t;
                 if (stop_here(X, (size_t)HW * b.cout)) { stopped = true; break; }
@@ -833,6 +898,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 PwArgs p{};
                 p.in = X; p.w = W + m->trans_w[s]; p.bias = W + m->trans_b[s]; p.out = Xo;
                 p.K = C; p.N = C; p.HW = H * Wd; p.relu = 1;
+                p.w_tc = m->tc_trans[s].w; p.Kpad = m->tc_trans[s].Kpad; p.Npad = m->tc_trans[s].Npad;
                 L.pointwise(p);
                 L.begin(CLS_AVGPOOL);
                 k_avgpool2<<<148 * 4, 256, 0, st>>>(Xo, H, Wd, C, d_ncrops, off, m->chunk, X);
@@ -847,6 +913,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             PwArgs p{};
             p.in = X; p.w = W + m->c5w; p.bias = W + m->c5b; p.out = Xo;
             p.K = C; p.N = C; p.HW = H * Wd; p.relu = 1;
+            p.w_tc = m->tc_c5.w; p.Kpad = m->tc_c5.Kpad; p.Npad = m->tc_c5.Npad;
             L.pointwise(p);
             if (!stop_here(Xo, (size_t)H * Wd * C)) {
                 L.begin(CLS_HEAD);
@@ -860,6 +927,65 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
     }
     RCUDA_OK(cudaGetLastError());
     return launches;
+}
+
+
+// Standalone 1x1-convolution GEMM on host arrays (parity tests / micro-benchmarks): out = act(A W + bias (+ res)).
+void standalone_pointwise(const float* A, int M, int K, const float* W, int N, const float* bias, const float* residual,
+                          int relu, int use_tc, float* out, float* elapsed_ms) {
+    if (M <= 0 || K <= 0 || N <= 0 || K % 4 || N % 4) throw std::runtime_error("M,K,N > 0 and K,N multiples of 4 required");
+    float *dA = nullptr, *dW = nullptr, *dB = nullptr, *dR = nullptr, *dO = nullptr, *dWtc = nullptr;
+    int* dn = nullptr;
+    auto cleanup = [&] { cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dR); cudaFree(dO); cudaFree(dWtc); cudaFree(dn); };
+    try {
+        RCUDA_OK(cudaMalloc(&dA, sizeof(float) * (size_t)M * K));
+        RCUDA_OK(cudaMalloc(&dW, sizeof(float) * (size_t)K * N));
+        RCUDA_OK(cudaMalloc(&dB, sizeof(float) * N));
+        RCUDA_OK(cudaMalloc(&dO, sizeof(float) * (size_t)M * N));
+        RCUDA_OK(cudaMalloc(&dn, sizeof(int)));
+        RCUDA_OK(cudaMemcpy(dA, A, sizeof(float) * (size_t)M * K, cudaMemcpyHostToDevice));
+        RCUDA_OK(cudaMemcpy(dW, W, sizeof(float) * (size_t)K * N, cudaMemcpyHostToDevice));
+        RCUDA_OK(cudaMemcpy(dB, bias, sizeof(float) * N, cudaMemcpyHostToDevice));
+        if (residual) {
+            RCUDA_OK(cudaMalloc(&dR, sizeof(float) * (size_t)M * N));
+            RCUDA_OK(cudaMemcpy(dR, residual, sizeof(float) * (size_t)M * N, cudaMemcpyHostToDevice));
+        }
+        const int one = 1;
+        RCUDA_OK(cudaMemcpy(dn, &one, sizeof(int), cudaMemcpyHostToDevice));
+        ReidModel fake;
+        fake.use_tc = use_tc != 0;
+        PwArgs p{};
+        p.in = dA; p.w = dW; p.bias = dB; p.residual = dR; p.out = dO; p.K = K; p.N = N; p.HW = M; p.relu = relu;
+        if (use_tc) {
+            if (M % tc::TILE_M) throw std::runtime_error("tensor-core path needs M % 128 == 0");
+            const int Kpad = (K + 7) / 8 * 8, Npad = (N + 15) / 16 * 16;
+            if (Npad > 256 || tc::smem_bytes(Kpad, Npad) > 200 * 1024) throw std::runtime_error("shape exceeds the tcgen05 kernel's shared-memory budget");
+            std::vector<float> packed(2 * (size_t)Npad * Kpad);
+            tc::pack_weights(W, K, N, Kpad, Npad, packed.data());
+            RCUDA_OK(cudaMalloc(&dWtc, sizeof(float) * packed.size()));
+            RCUDA_OK(cudaMemcpy(dWtc, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice));
+            p.w_tc = dWtc; p.Kpad = Kpad; p.Npad = Npad;
+        }
+        cudaEvent_t e0, e1;
+        RCUDA_OK(cudaEventCreate(&e0));
+        RCUDA_OK(cudaEventCreate(&e1));
+        Launcher L{&fake, dn, 0, 1, 1, nullptr};
+        L.pointwise(p);  // warm-up
+        RCUDA_OK(cudaDeviceSynchronize());
+        RCUDA_OK(cudaEventRecord(e0));
+        for (int r = 0; r < 10; ++r) L.pointwise(p);
+        RCUDA_OK(cudaEventRecord(e1));
+        RCUDA_OK(cudaDeviceSynchronize());
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (elapsed_ms) *elapsed_ms = ms / 10.f;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        RCUDA_OK(cudaMemcpy(out, dO, sizeof(float) * (size_t)M * N, cudaMemcpyDeviceToHost));
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
 }
 
 }  // namespace bmb

@@ -454,22 +454,52 @@ BMB_FN int warp_append(int n, int* out, int base, Pred pred, Val val) {
     return base;
 }
 
+// Candidate lists (CSR) plus a parallel start for the augmenting-path solver: every row takes its cheapest
+// candidate as dual price u[i] (v = 0 keeps all reduced costs >= 0) and claims that column; a column claimed by
+// several rows goes to the lowest row.  The claimed pairs are tight edges of a feasible dual, i.e. a valid partial
+// matching for the exact search below, which then only has to place the rows that lost a claim.
 BMB_FN void lap_build_csr(TrkStream& s, int T, int D, int ld, double thresh) {
-    // candidate count per row (one warp per row, coalesced), prefix (thread 0), ordered fill
+    for (int j = BMB_TID; j < D; j += BMB_NT) s.lap_tl[j] = 0x7fffffff;  // column claims (lap_tl is free here)
     for (int i = BMB_WARP; i < T; i += BMB_NW) {
         const double* ci = s.cost + (size_t)i * ld;
         int n = 0;
+        double best = INFINITY;
+        int bj = -1;
         for (int j0 = 0; j0 < D; j0 += BMB_NL) {
             const int j = j0 + BMB_LANE;
-            n += BMB_POPC(BMB_BALLOT(j < D && ci[j] < thresh));
+            const double v = j < D ? ci[j] : INFINITY;
+            const bool cand = j < D && v < thresh;
+            n += BMB_POPC(BMB_BALLOT(cand));
+            if (cand && v < best) { best = v; bj = j; }
         }
-        if (BMB_LANE == 0) s.lap_x[i] = n;  // temporarily the row count
+#if BMB_DEVICE
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = BMB_SHFL_DOWN_D(best, o);
+            const int oj = BMB_SHFL_DOWN_I(bj, o);
+            if (oj >= 0 && (bj < 0 || ov < best || (ov == best && oj < bj))) { best = ov; bj = oj; }
+        }
+#endif
+        if (BMB_LANE == 0) {
+            s.lap_x[i] = n;  // temporarily the row count
+            s.lap_u[i] = bj >= 0 ? best : 0.0;
+            s.tmp_b[i] = bj;
+        }
     }
     BMB_SYNC();
     if (BMB_TID == 0) {
         int acc = 0;
         for (int i = 0; i < T; ++i) { s.csr_ptr[i] = acc; acc += s.lap_x[i]; }
         s.csr_ptr[T] = acc;
+    }
+    for (int i = BMB_TID; i < T; i += BMB_NT) {
+        const int bj = s.tmp_b[i];
+        if (bj >= 0) {
+#if BMB_DEVICE
+            atomicMin(&s.lap_tl[bj], i);
+#else
+            if (i < s.lap_tl[bj]) s.lap_tl[bj] = i;
+#endif
+        }
     }
     BMB_SYNC();
     for (int i = BMB_WARP; i < T; i += BMB_NW) {
@@ -488,9 +518,14 @@ BMB_FN void lap_solve(TrkStream& s, int T, int D, int ld, double thresh) {
         return;
     }
     lap_build_csr(s, T, D, ld, thresh);
-    for (int i = BMB_TID; i < T; i += BMB_NT) { s.lap_x[i] = -1; s.lap_u[i] = 0.0; }
     for (int j = BMB_TID; j < D; j += BMB_NT) {
         s.lap_y[j] = -1; s.lap_v[j] = 0.0; s.lap_spc[j] = INFINITY; s.lap_insc[j] = 0;
+    }
+    BMB_SYNC();
+    for (int i = BMB_TID; i < T; i += BMB_NT) {  // uncontested claims become the initial matching
+        const int bj = s.tmp_b[i];
+        if (bj >= 0 && s.lap_tl[bj] == i) { s.lap_x[i] = bj; s.lap_y[bj] = i; }
+        else s.lap_x[i] = -1;
     }
     BMB_SYNC();
     if (BMB_WARP == 0) {
@@ -498,6 +533,7 @@ BMB_FN void lap_solve(TrkStream& s, int T, int D, int ld, double thresh) {
         const double INF = INFINITY;
         int steps = 0;
         for (int cur = 0; cur < T; ++cur) {
+            if (s.lap_x[cur] >= 0) continue;                        // placed by the parallel start
             if (s.csr_ptr[cur + 1] == s.csr_ptr[cur]) continue;  // no candidate: stays unmatched
             double minval = 0.0;
             int i = cur;
@@ -695,7 +731,20 @@ BMB_FN void build_cost(TrkStream& s, int T, int D, int ld, const int* rows, Cost
         const int t = rows[i];
         const double tb[4] = {s.txyxy[t * 4], s.txyxy[t * 4 + 1], s.txyxy[t * 4 + 2], s.txyxy[t * 4 + 3]};
         double* ci = s.cost + (size_t)i * ld;
-        for (int j = BMB_LANE; j < D; j += BMB_NL) ci[j] = fn(t, tb, j);
+        // four independent evaluations in flight per lane: the loads (L2 latency) and the float64 divide overlap
+        for (int j0 = BMB_LANE; j0 < D; j0 += 4 * BMB_NL) {
+            double v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + q * BMB_NL;
+                v[q] = j < D ? fn(t, tb, j) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + q * BMB_NL;
+                if (j < D) ci[j] = v[q];
+            }
+        }
     }
     BMB_SYNC();
 }

@@ -202,6 +202,12 @@ BOXMOT_B200_API int boxmot_b200_iou_cost(const double* track_xyxy, int rows, con
                                          double* out);
 /* max(0, cosine distance) of float32 rows a (T,F) x b (D,F) -> (T,D) float64. */
 BOXMOT_B200_API int boxmot_b200_cosine_cost(const float* a, int rows, const float* b, int cols, int dim, double* out);
+/* 1x1 convolution as a GEMM on host arrays: out (M,N) = act(A (M,K) * W (K,N) + bias (+ residual)); K, N multiples
+ * of 4.  use_tensor_cores = 1 runs the tcgen05 tf32x3 kernel (M % 128 == 0), 0 the CUDA-core kernel.  elapsed_ms
+ * (optional) receives the average device time of 10 back-to-back launches. */
+BOXMOT_B200_API int boxmot_b200_pointwise_gemm(const float* a, int m, int k, const float* w, int n, const float* bias,
+                                               const float* residual, int relu, int use_tensor_cores, float* out,
+                                               float* elapsed_ms);
 BOXMOT_B200_API int boxmot_b200_device_count(void);
 /* Diagnostics for the ReID kernels: run the forward up to `stage` (0 input blob, 1 stem, 2 max-pool, 3..10 the
  * six OSBlocks and two transitions in order, 11 conv5) and copy that NHWC float32 tensor of the n crops out. */
