@@ -200,7 +200,8 @@ def cpu_arm(sample_frames: int, warm: int):
     for f in range(warm, warm + sample_frames):
         trk.update(dets[f], imgs[f % RING])
     dt = time.perf_counter() - t0
-    return {"value": sample_frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+    return {"value": sample_frames / dt, "unit": "frames/s", "cores": cores, "kind": "port", "frames": sample_frames,
+            "warm": warm,
             "sample": f"{sample_frames} frames of the same 256-det stream after {warm} warm-up frames, "
                       f"oracle port (numpy/scipy/lapjv-C + torch-CPU OSNet fp32, {cores} of {avail} usable threads, "
                       f"fastest of a thread-count probe)",
@@ -213,7 +214,7 @@ def run_reference(args):
     steps = max(2, min(args.steps, 12))
     base = cpu_arm(steps, max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_frame"],
+            "steps": base["frames"], "warmup": base["warm"], "ms_per_step": base["ms_per_frame"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "single stream on the host cores; steps bounded to keep the run short"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -321,10 +322,10 @@ def run_b200(args):
     trk.close()
 
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([value_ms, e2e_ms], device="cuda", dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value_ms, e2e_ms = float(t[0]), float(t[1])
+    from boxmot_b200 import sharding
+
+    value_ms, e2e_ms = sharding.reduce_max([value_ms, e2e_ms], dist, device="cuda")  # slowest rank defines the job
+    frames_per_rank = sharding.gather_counts(S * K, dist, device="cuda")
     if RANK != 0:
         if dist:
             dist.barrier()
@@ -337,8 +338,8 @@ def run_b200(args):
     dom_bytes = byt[dom] * crops
     dom_s = prof[dom]["ms_per_step"] * 1e-3
     reid_ms = sum(prof[c]["ms_per_step"] for c in CLASSES if c != "association")
-    fps = WORLD * S * K / (value_ms * 1e-3)
-    e2e_fps = WORLD * S * K / (e2e_ms * 1e-3)
+    fps = sum(frames_per_rank) / (value_ms * 1e-3)
+    e2e_fps = sum(frames_per_rank) / (e2e_ms * 1e-3)
     total_flop = 2 * sum(mac.values()) * crops
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": WORLD, "steps": K, "warmup": Wm,

@@ -498,9 +498,24 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
     float* pooled = smem;       // [C]
     float* red = smem + C;      // [32]
     const float* xp = x + (size_t)n * HW * C;
+    // global average pool: consecutive threads read consecutive channels of one pixel (coalesced); the pixel
+    // stripes of the thread groups are combined in a fixed order so the result is run-to-run deterministic
+    float* part = red + 32;  // [groups][C]
+    const int groups = blockDim.x / C > 0 ? blockDim.x / C : 1;
+    if ((int)threadIdx.x < groups * C) {
+        const int c = threadIdx.x % C, g = threadIdx.x / C;
+        float s = 0.f;
+        for (int p = g; p < HW; p += groups) s += xp[(size_t)p * C + c];
+        part[g * C + c] = s;
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
-        for (int p = 0; p < HW; ++p) s += xp[(size_t)p * C + c];
+        if (blockDim.x >= (unsigned)C) {
+            for (int g = 0; g < groups; ++g) s += part[g * C + c];
+        } else {
+            for (int p = 0; p < HW; ++p) s += xp[(size_t)p * C + c];
+        }
         pooled[c] = s / (float)HW;
     }
     __syncthreads();
@@ -658,6 +673,10 @@ ReidModel* reid_load(const char* path) {
             }
         }
         // workspace
+        if (const char* ce = getenv("BOXMOT_B200_REID_CHUNK")) {
+            const int v = atoi(ce);
+            if (v >= 8 && v <= 1024) m->chunk = v;
+        }
         const size_t CH = m->chunk;
         const size_t big = (size_t)8192 * m->c[0] > (size_t)2048 * m->c[1] ? (size_t)8192 * m->c[0] : (size_t)2048 * m->c[1];
         const size_t mid_max = (size_t)2048 * (m->c[1] / 4);
@@ -917,7 +936,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             L.pointwise(p);
             if (!stop_here(Xo, (size_t)H * Wd * C)) {
                 L.begin(CLS_HEAD);
-                k_head<<<upper, 256, sizeof(float) * (C + 32), st>>>(Xo, H * Wd, C, W + m->fcw, W + m->fcb, m->feat,
+                k_head<<<upper, 256, sizeof(float) * (C + 32 + (256 / C > 0 ? 256 / C : 1) * C), st>>>(Xo, H * Wd, C, W + m->fcw, W + m->fcb, m->feat,
                                                                      d_crops, d_ncrops, off, m->chunk, d_out, out_ld);
                 L.end();
                 ++L.launches;

@@ -117,3 +117,19 @@ def test_reid_abi_errors(tmp_path):
     assert lib.boxmot_reid_capi_compute_features(reid.handle, box.ctypes.data, 1, img.ctypes.data, 32, 32, 4,
                                                  out.ctypes.data, 512) == 0
     assert lib.boxmot_reid_capi_postprocess(reid.handle, out.ctypes.data, 512) == 0  # nothing staged
+
+
+@pytest.mark.parametrize("env", [{"BOXMOT_B200_REID_TC": "1"}, {"BOXMOT_B200_REID_CHUNK": "32"},
+                                 {"BOXMOT_B200_REID_CHUNK": "256", "BOXMOT_B200_REID_TC": "1"}])
+def test_alternative_kernel_paths_keep_parity(tmp_path, monkeypatch, env):
+    """tcgen05 (tf32 x3) pointwise path and other chunk sizes: same embeddings within the bound."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sd, reid = _model(tmp_path, seed=9)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 255, size=(480, 640, 3), dtype=np.uint8)
+    n = 70
+    cx, cy = rng.uniform(0, 640, n), rng.uniform(0, 480, n)
+    w, h = rng.uniform(20, 120, n), rng.uniform(40, 240, n)
+    boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+    _emb_ok(reid.get_features(boxes, img), orid.get_features(sd, boxes, img))
