@@ -140,6 +140,12 @@ int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* h, double* reid_ms, do
     });
 }
 
+int boxmot_b200_tracker_set_warp(BoxMOTB200Tracker* h, int stream, const double* warp2x3) {
+    return guard([&] {
+        if (!warp2x3) throw std::runtime_error("warp is NULL");
+        as_engine(h)->set_warp(stream, warp2x3);
+    });
+}
 int boxmot_b200_tracker_mark(BoxMOTB200Tracker* h, int which) {
     return guard([&] { as_engine(h)->mark_event(which); });
 }

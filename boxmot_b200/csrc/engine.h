@@ -54,6 +54,8 @@ struct Engine {
     float* d_dets = nullptr;
     int* d_ndets = nullptr;
     float* d_embs = nullptr;
+    double* d_warp = nullptr;      // [S][8] pending camera-motion warps (slot 6 = pending flag)
+    bool warp_dirty = false;
     float* d_out = nullptr;
     int* d_scalars_out = nullptr;
     CropDesc* d_crops = nullptr;
@@ -90,6 +92,7 @@ struct Engine {
                        const uint8_t* images_dev, int rows, int cols, bool sync);
     void fetch(float* const* out, const int* out_cap, int* out_rows);
     int snapshot(int stream_index, int* ids, double* means, double* covs, int cap);
+    void set_warp(int stream_index, const double* warp6);
     void read_timers(int stream_index, long long* out16, bool reset);
     void set_profile(bool on);
     void profile_read(double* ms, int* launch_counts);  // REID_N_CLASSES + 1 entries (last = association)

@@ -119,6 +119,7 @@ struct TrkStream {
     // per-frame inputs
     const float* dets;  // [CD][6]
     const int* n_dets;  // [1]
+    const double* warp; // [8]: warp[0..5] = 2x3 camera-motion matrix (row major), warp[6] != 0 when one is pending
     // per-frame scratch
     float* dxywh;   // [CD][4]
     float* dmeas;   // [CD][4]
@@ -343,6 +344,32 @@ BMB_FN void kf_update(const TrkCfg& c, const float* meas32, double* mean, double
         }
     if (mean[2] < 1e-4) mean[2] = 1e-4;
     if (mean[3] < 1e-4) mean[3] = 1e-4;
+}
+
+// STrack.multi_gmc (botsort_track.py:117-132): x <- kron(I4, R) x, x[:2] += t, P <- R8 P R8^T for a given 2x3 warp.
+// The warp ESTIMATION (motion/cmc/*) is outside this path; applying a supplied warp is part of the Kalman kernel.
+BMB_FN void kf_apply_warp(const double* H, double* mean, double* cov) {
+    const double r00 = H[0], r01 = H[1], tx = H[2], r10 = H[3], r11 = H[4], ty = H[5];
+    for (int b = 0; b < 4; ++b) {
+        const double x = mean[2 * b], y = mean[2 * b + 1];
+        mean[2 * b] = r00 * x + r01 * y;
+        mean[2 * b + 1] = r10 * x + r11 * y;
+    }
+    mean[0] += tx;
+    mean[1] += ty;
+    double tmp[64];
+    for (int b = 0; b < 4; ++b)       // tmp = R8 P
+        for (int j = 0; j < 8; ++j) {
+            const double p0 = cov[(2 * b) * 8 + j], p1 = cov[(2 * b + 1) * 8 + j];
+            tmp[(2 * b) * 8 + j] = r00 * p0 + r01 * p1;
+            tmp[(2 * b + 1) * 8 + j] = r10 * p0 + r11 * p1;
+        }
+    for (int i = 0; i < 8; ++i)       // P' = tmp R8^T
+        for (int b = 0; b < 4; ++b) {
+            const double q0 = tmp[i * 8 + 2 * b], q1 = tmp[i * 8 + 2 * b + 1];
+            cov[i * 8 + 2 * b] = q0 * r00 + q1 * r01;
+            cov[i * 8 + 2 * b + 1] = q0 * r10 + q1 * r11;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -808,13 +835,16 @@ BMB_FN void tracker_frame(const TrkCfg& c, TrkStream& s) {
     const int n_pool = mb[MB_N_POOL];
 
     // ---- S2: Kalman predict over the pool (state is updated in place, as the reference does) ----
+    const bool warp_pending = c.kind == KIND_XYWH && s.warp[6] != 0.0;  // BoT-SORT only (botsort.py:301)
     for (int k = BMB_TID; k < n_pool; k += BMB_NT) {
         const int t = s.pool[k];
         kf_predict(c, s.state[t] == ST_TRACKED, s.mean + t * 8, s.cov + t * 64);
+        if (warp_pending) kf_apply_warp(s.warp, s.mean + t * 8, s.cov + t * 64);
         track_xyxy(c, s.mean + t * 8, s.txyxy + t * 4);
     }
     for (int k = BMB_TID; k < n_unc; k += BMB_NT) {
         const int t = s.unconf[k];
+        if (warp_pending) kf_apply_warp(s.warp, s.mean + t * 8, s.cov + t * 64);
         track_xyxy(c, s.mean + t * 8, s.txyxy + t * 4);
     }
     BMB_SYNC();

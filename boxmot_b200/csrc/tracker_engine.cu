@@ -212,6 +212,8 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     CUDA_OK(cudaMemset(d_mem, 0, stream_bytes * S));
     const size_t CD = cfg.cap_dets, F = cfg.feat_dim > 0 ? cfg.feat_dim : 1;
     CUDA_OK(cudaMalloc(&d_dets, sizeof(float) * 6 * CD * S));
+    CUDA_OK(cudaMalloc(&d_warp, sizeof(double) * 8 * S));
+    CUDA_OK(cudaMemset(d_warp, 0, sizeof(double) * 8 * S));
     CUDA_OK(cudaMalloc(&d_ndets, sizeof(int) * S));
     CUDA_OK(cudaMemset(d_ndets, 0, sizeof(int) * S));
     if (cfg.with_reid) {
@@ -230,6 +232,7 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
         carve_stream(cfg, d_mem + stream_bytes * i, &h_streams[i], nullptr);
         h_streams[i].dets = d_dets + (size_t)i * CD * 6;
         h_streams[i].n_dets = d_ndets + i;
+        h_streams[i].warp = d_warp + (size_t)i * 8;
     }
     CUDA_OK(cudaMalloc(&d_streams, sizeof(TrkStream) * S));
     CUDA_OK(cudaMemcpy(d_streams, h_streams.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
@@ -249,7 +252,7 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
 Engine::~Engine() {
     cudaStreamSynchronize(stream);
     if (reid) reid_free(reid);
-    cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
+    cudaFree(d_warp); cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
     cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
     cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
     cudaFreeHost(h_embs); cudaFreeHost(h_images); cudaFreeHost(h_ndets_ring);
@@ -310,6 +313,10 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
             k_feat_ema<<<dim3((cfg.cap_dets + 7) / 8, S), 256, 0, stream>>>(cfg, d_streams);
             ++launches;
         }
+        if (warp_dirty) {  // a supplied camera-motion warp applies to exactly one frame
+            CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
+            warp_dirty = false;
+        }
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(ev[2], stream));
@@ -320,6 +327,15 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         assoc_ms_accum += b;
         assoc_frames += 1;
     }
+}
+
+void Engine::set_warp(int sidx, const double* warp6) {
+    if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
+    if (cfg.kind != KIND_XYWH) throw std::runtime_error("camera-motion warps apply to BoT-SORT only");
+    double w[8] = {warp6[0], warp6[1], warp6[2], warp6[3], warp6[4], warp6[5], 1.0, 0.0};
+    CUDA_OK(cudaStreamSynchronize(stream));
+    CUDA_OK(cudaMemcpy(d_warp + (size_t)sidx * 8, w, sizeof(w), cudaMemcpyHostToDevice));
+    warp_dirty = true;
 }
 
 void Engine::read_timers(int sidx, long long* out16, bool reset) {

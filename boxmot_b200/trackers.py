@@ -162,6 +162,12 @@ class MultiStreamTracker:
             raise B200Error(_lib.last_error(self.lib))
         self.frame_count = 0
 
+    def set_warp(self, stream: int, warp) -> None:
+        """Camera-motion warp (2x3) to apply on the next update of `stream` (BoT-SORT multi_gmc)."""
+        w = np.ascontiguousarray(warp, dtype=np.float64).reshape(6)
+        if not self.lib.boxmot_b200_tracker_set_warp(self.handle, int(stream), w.ctypes.data):
+            raise B200Error(_lib.last_error(self.lib))
+
     def update(self, dets: Sequence[np.ndarray], imgs: Optional[Sequence[np.ndarray]] = None,
                embs: Optional[Sequence[Optional[np.ndarray]]] = None):
         S = self.n_streams
@@ -269,7 +275,11 @@ class _SingleStreamTracker:
         self._engine.reset()
         self.frame_count = 0
 
-    def update(self, dets, img=None, embs=None, masks=None) -> TrackResults:
+    def update(self, dets, img=None, embs=None, masks=None, warp=None) -> TrackResults:
+        """`warp`: optional 2x3 camera-motion matrix for this frame (BoT-SORT); the reference estimates it with
+        OpenCV inside update() (botsort.py:142-144), here the caller supplies it."""
+        if warp is not None:
+            self._engine.set_warp(0, warp)
         if hasattr(dets, "data") and not isinstance(dets, np.ndarray):
             dets = dets.data
         if isinstance(dets, memoryview):

@@ -174,6 +174,10 @@ BOXMOT_B200_API int boxmot_b200_tracker_snapshot(BoxMOTB200Tracker* handle, int 
 /* Kernel launches issued by the last update call, and CUDA stream / device-time accessors for benchmarks. */
 BOXMOT_B200_API int boxmot_b200_tracker_last_launches(BoxMOTB200Tracker* handle, int* out_launches);
 BOXMOT_B200_API int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* handle, double* reid_ms, double* assoc_ms);
+/* BoT-SORT camera-motion compensation with a SUPPLIED 2x3 warp (row major, float64): applied once, on the next
+ * update, to the predicted pool and the unconfirmed tracks exactly as STrack.multi_gmc does
+ * (trackers/bbox/botsort/botsort_track.py:117-132).  Estimating the warp (motion/cmc/*) is out of scope. */
+BOXMOT_B200_API int boxmot_b200_tracker_set_warp(BoxMOTB200Tracker* handle, int stream, const double* warp2x3);
 /* Device timing on the handle's own CUDA stream: record mark 0 / mark 1 around a region, then read the elapsed
  * milliseconds (synchronises on mark 1). */
 BOXMOT_B200_API int boxmot_b200_tracker_mark(BoxMOTB200Tracker* handle, int which);

@@ -55,6 +55,17 @@ def stress_stream(n_objects: int, n_frames: int, hw=(360, 640), seed: int = 7, d
     return frames
 
 
+def warp_sequence(n_frames: int, seed: int = 17):
+    """Small seeded affine camera motions (2x3, float64), one per frame."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_frames):
+        a = rng.normal(0.0, 0.003, size=(2, 2))
+        t = rng.normal(0.0, 2.0, size=2)
+        out.append(np.hstack([np.eye(2) + a, t[:, None]]))
+    return out
+
+
 def stress_embeddings(frames, n_objects_hint: int, dim: int = 512, seed: int = 11, noise: float = 0.35):
     """Per-detection appearance vectors for `stress_stream` frames (same seed => same vectors).
 

@@ -376,7 +376,21 @@ class BotSortOracle(_TrackerBase):
             t.vote_cls(det.cls, det.conf)
             refind.append(t)
 
-    def update(self, dets, img=None, embs=None):
+    @staticmethod
+    def _gmc(tracks, H):
+        """STrack.multi_gmc (botsort_track.py:117-132) for a supplied 2x3 warp."""
+        if not tracks:
+            return
+        H = np.asarray(H, dtype=float)
+        R8 = np.kron(np.eye(4), H[:2, :2])
+        t = H[:2, 2]
+        for st in tracks:
+            mean = R8.dot(st.mean)
+            mean[:2] += t
+            st.mean = mean
+            st.cov = R8.dot(st.cov).dot(R8.T)
+
+    def update(self, dets, img=None, embs=None, warp=None):
         if embs is not None:
             assert len(dets) == len(embs), "Missmatch between detections and embeddings sizes"
         dets = self._with_ind(dets)
@@ -409,6 +423,9 @@ class BotSortOracle(_TrackerBase):
 
         # first association ---------------------------------------------------------------------
         self._predict(pool)
+        if warp is not None:  # camera-motion compensation with a supplied warp (botsort.py:301)
+            self._gmc(pool, warp)
+            self._gmc(unconfirmed, warp)
         iou_d = iou_cost([t.xyxy() for t in pool], [d.xyxy() for d in detections])
         far = iou_d > self.proximity_thresh
         if self.fuse_first_associate:

@@ -19,6 +19,7 @@ struct HostSim {
     std::vector<float> dets;
     std::vector<float> embs;
     int n_dets;
+    double warp[8];
 };
 
 extern "C" {
@@ -33,12 +34,19 @@ HostSim* hostsim_create(const TrkCfg* cfg) {
     h->embs.assign((size_t)cfg->cap_dets * (cfg->feat_dim > 0 ? cfg->feat_dim : 1), 0.f);
     h->s.dets = h->dets.data();
     h->s.n_dets = &h->n_dets;
+    for (double& w : h->warp) w = 0.0;
+    h->s.warp = h->warp;
     return h;
 }
 
 void hostsim_destroy(HostSim* h) { delete h; }
 
 int hostsim_cfg_size() { return (int)sizeof(TrkCfg); }
+
+void hostsim_set_warp(HostSim* h, const double* w6) {
+    for (int i = 0; i < 6; ++i) h->warp[i] = w6[i];
+    h->warp[6] = 1.0;
+}
 
 // returns number of output rows, or -(error code)
 int hostsim_update(HostSim* h, const float* dets, int n, const float* embs, float* out, int* lap_steps) {
@@ -62,6 +70,7 @@ int hostsim_update(HostSim* h, const float* dets, int n, const float* embs, floa
     }
     h->s.scalars[SC_LAP_STEPS] = 0;
     tracker_frame(c, h->s);
+    h->warp[6] = 0.0;  // a warp applies to one frame
     if (c.with_reid)
         for (int k = 0; k < h->s.scalars[SC_N_EMA]; ++k) apply_feature_ema(c, h->s, k);
     if (lap_steps) *lap_steps = h->s.scalars[SC_LAP_STEPS];

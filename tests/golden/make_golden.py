@@ -49,6 +49,18 @@ def _snapshot(tracker):
     return (np.asarray(ids, dtype=np.int64), np.asarray(means).reshape(-1, 8), np.asarray(covs).reshape(-1, 8, 8))
 
 
+class _GivenWarps:
+    """Stands in for the reference's CMC estimator (motion/cmc/*, OpenCV): returns the supplied warp."""
+
+    def __init__(self, warps):
+        self.warps, self.i = warps, 0
+
+    def apply(self, img, dets):
+        w = self.warps[self.i]
+        self.i += 1
+        return w
+
+
 def run(tracker, frames, img, embs=None):
     rows, offsets, snaps = [], [0], {}
     for f, dets in enumerate(frames):
@@ -145,6 +157,13 @@ def main():
     frames = stress_stream(64, 200, seed=23)
     np.savez_compressed(HERE / "botsort_noreid_stress64.npz",
                         **run(BotSort(reid_model=None, use_cmc=False, with_reid=False), frames, img))
+
+    from oracle.streams import warp_sequence
+    frames = stress_stream(64, 150, seed=29)
+    embs = stress_embeddings(frames, 64, seed=31)
+    trk = BotSort(reid_model=None, use_cmc=False, **BOTSORT_YAML)
+    trk.cmc = _GivenWarps(warp_sequence(150))
+    np.savez_compressed(HERE / "botsort_warp_stress64.npz", **run(trk, frames, img, embs))
 
     _, frames = bench_stream(256, 40)
     embs = stress_embeddings(frames, 256, seed=3)
