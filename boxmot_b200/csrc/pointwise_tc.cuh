@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(THREADS) k_pointwise_tc(const Args a, const in
                         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                     }
                     if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (a.relu == 2) { o.x = fminf(o.x, 6.f); o.y = fminf(o.y, 6.f); o.z = fminf(o.z, 6.f); o.w = fminf(o.w, 6.f); }
                     *reinterpret_cast<float4*>(orow + c) = o;
                 }
             }

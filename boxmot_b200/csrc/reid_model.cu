@@ -16,6 +16,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <fstream>
 #include <stdexcept>
 #include <string>
@@ -329,6 +330,7 @@ __global__ void __launch_bounds__(256) k_pointwise(const PwArgs a, const int* __
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
         if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (a.relu == 2) { v.x = fminf(v.x, 6.f); v.y = fminf(v.y, 6.f); v.z = fminf(v.z, 6.f); v.w = fminf(v.w, 6.f); }  // ReLU6
         *reinterpret_cast<float4*>(a.out + (size_t)m * N + c) = v;
     }
 }
@@ -451,6 +453,73 @@ __global__ void k_lightconv(const LightArgs a, const int* __restrict__ d_n, int 
     }
 }
 
+// K6b (MobileNetV2): 3x3 stride-2 stem (3 -> C0) + folded BN + ReLU6 : (N,256,128,3) -> (N,128,64,C0)
+__global__ void k_stem3(const float* __restrict__ blob, const float* __restrict__ w, const float* __restrict__ bias,
+                        int C0, const int* __restrict__ d_n, int off, int cap, float* __restrict__ out) {
+    const int n_crops = chunk_count(d_n, off, cap);
+    const int C4 = C0 / 4;
+    const size_t total = (size_t)n_crops * 128 * 64 * C4;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(e % C4);
+        size_t r = e / C4;
+        const int ox = (int)(r % 64); r /= 64;
+        const int oy = (int)(r % 128);
+        const int n = (int)(r / 128);
+        float4 acc = *reinterpret_cast<const float4*>(bias + c4 * 4);
+        const float* src = blob + (size_t)n * IN_H * IN_W * 3;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - 1 + ky;
+            if (iy < 0 || iy >= IN_H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 - 1 + kx;
+                if (ix < 0 || ix >= IN_W) continue;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float a = src[((size_t)iy * IN_W + ix) * 3 + ci];
+                    const float4 wv = *reinterpret_cast<const float4*>(w + (size_t)((ky * 3 + kx) * 3 + ci) * C0 + c4 * 4);
+                    acc.x = fmaf(a, wv.x, acc.x); acc.y = fmaf(a, wv.y, acc.y);
+                    acc.z = fmaf(a, wv.z, acc.z); acc.w = fmaf(a, wv.w, acc.w);
+                }
+            }
+        }
+        acc.x = fminf(fmaxf(acc.x, 0.f), 6.f); acc.y = fminf(fmaxf(acc.y, 0.f), 6.f);
+        acc.z = fminf(fmaxf(acc.z, 0.f), 6.f); acc.w = fminf(fmaxf(acc.w, 0.f), 6.f);
+        *reinterpret_cast<float4*>(out + (((size_t)n * 128 + oy) * 64 + ox) * C0 + c4 * 4) = acc;
+    }
+}
+
+// K6c (MobileNetV2): depthwise 3x3, stride 1 or 2, pad 1, + folded BN + ReLU6, NHWC float4 channels
+__global__ void k_dwconv3(const float* __restrict__ in, int H, int W, int C, int stride, const float* __restrict__ w9c,
+                          const float* __restrict__ bias, const int* __restrict__ d_n, int off, int cap,
+                          float* __restrict__ out) {
+    const int n_crops = chunk_count(d_n, off, cap);
+    const int OH = H / stride, OW = W / stride, C4 = C / 4;
+    const size_t total = (size_t)n_crops * OH * OW * C4;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(e % C4);
+        size_t r = e / C4;
+        const int ox = (int)(r % OW); r /= OW;
+        const int oy = (int)(r % OH);
+        const int n = (int)(r / OH);
+        float4 acc = *reinterpret_cast<const float4*>(bias + c4 * 4);
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * stride - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * stride - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(in + (((size_t)n * H + iy) * W + ix) * C + c4 * 4);
+                const float4 wv = *reinterpret_cast<const float4*>(w9c + (size_t)(ky * 3 + kx) * C + c4 * 4);
+                acc.x = fmaf(v.x, wv.x, acc.x); acc.y = fmaf(v.y, wv.y, acc.y);
+                acc.z = fmaf(v.z, wv.z, acc.z); acc.w = fmaf(v.w, wv.w, acc.w);
+            }
+        }
+        acc.x = fminf(fmaxf(acc.x, 0.f), 6.f); acc.y = fminf(fmaxf(acc.y, 0.f), 6.f);
+        acc.z = fminf(fmaxf(acc.z, 0.f), 6.f); acc.w = fminf(fmaxf(acc.w, 0.f), 6.f);
+        *reinterpret_cast<float4*>(out + (((size_t)n * OH + oy) * OW + ox) * C + c4 * 4) = acc;
+    }
+}
+
 // K7: ChannelGate (osnet.py:161-210): mean -> fc1 -> ReLU -> fc2 -> sigmoid, for the four branches of a block.
 struct GateArgs {
     const float* sums[4];  // [crops][tiles][C]
@@ -522,9 +591,14 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
     float* dst = out + (size_t)crops[off + n].out_row * out_ld;
     float sq = 0.f;
     for (int f = threadIdx.x; f < FEAT; f += blockDim.x) {
-        float s = bfc[f];
-        for (int c = 0; c < C; ++c) s = fmaf(pooled[c], wfc[(size_t)c * FEAT + f], s);
-        s = fmaxf(s, 0.f);
+        float s;
+        if (wfc) {
+            s = bfc[f];
+            for (int c = 0; c < C; ++c) s = fmaf(pooled[c], wfc[(size_t)c * FEAT + f], s);
+            s = fmaxf(s, 0.f);
+        } else {
+            s = pooled[f];  // MobileNetV2: the pooled conv9 map is the embedding (mobilenetv2.py:186-193)
+        }
         dst[f] = s;
         sq = fmaf(s, s, sq);
     }
@@ -552,7 +626,16 @@ struct BlockW {
     TcW tc_c1, tc_c;
 };
 
+struct MbBlock {
+    int cin, cout, t, stride, cinp, midp, coutp;
+    size_t we, be, wd, bd, wp, bp;
+};
+
 struct ReidModel {
+    int arch = 1;                 // 1 OSNet, 2 MobileNetV2
+    std::vector<MbBlock> mb;      // MobileNetV2 bottlenecks
+    int mb_stem = 0, mb_stemp = 0, mb_last = 0;
+    size_t mb_stem_w = 0, mb_stem_b = 0, mb_c9w = 0, mb_c9b = 0;
     int c[4] = {0, 0, 0, 0};
     int feat = 0;
     float* d_w = nullptr;
@@ -592,9 +675,70 @@ ReidModel* reid_load(const char* path) {
     if (!f) throw std::runtime_error(std::string("cannot open ReID blob: ") + path);
     int32_t hdr[16];
     f.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
-    if (!f || (uint32_t)hdr[0] != BLOB_MAGIC || hdr[1] != 1 || hdr[2] != 1)
-        throw std::runtime_error("not a version-1 OSNet .b200reid blob (export it with boxmot_b200.weights.export_blob)");
+    if (!f || (uint32_t)hdr[0] != BLOB_MAGIC || hdr[1] != 1 || (hdr[2] != 1 && hdr[2] != 2))
+        throw std::runtime_error("not a version-1 .b200reid blob (export it with boxmot_b200.weights.export_blob)");
     ReidModel* m = new ReidModel();
+    if (hdr[2] == 2) {
+        // ---- MobileNetV2 (reid/backbones/mobilenetv2.py): stem, 17 inverted-residual blocks, conv9, GAP ----
+        try {
+            m->arch = 2;
+            m->mb_stem = hdr[3];
+            m->mb_stemp = (hdr[3] + 3) / 4 * 4;
+            const int n_blocks = hdr[4];
+            m->feat = hdr[7];
+            const size_t n_floats = (size_t)hdr[8];
+            if (n_blocks < 1 || n_blocks > 64 || m->feat < 1) throw std::runtime_error("bad MobileNetV2 blob header");
+            std::vector<int32_t> table((size_t)n_blocks * 4);
+            f.read(reinterpret_cast<char*>(table.data()), sizeof(int32_t) * table.size());
+            std::vector<float> host(n_floats);
+            f.read(reinterpret_cast<char*>(host.data()), sizeof(float) * n_floats);
+            if (!f) throw std::runtime_error("truncated ReID blob");
+            size_t o = 0;
+            auto take = [&](size_t n) { size_t r = o; o += (n + 3) / 4 * 4; return r; };
+            auto p4 = [](int n) { return (n + 3) / 4 * 4; };
+            m->mb_stem_w = take((size_t)27 * m->mb_stemp);
+            m->mb_stem_b = take(m->mb_stemp);
+            int H = 128, Wd = 64;
+            size_t max_x = (size_t)H * Wd * m->mb_stemp, max_e = 0, max_d = 0;
+            for (int i = 0; i < n_blocks; ++i) {
+                MbBlock b{};
+                b.cin = table[i * 4]; b.cout = table[i * 4 + 1]; b.t = table[i * 4 + 2]; b.stride = table[i * 4 + 3];
+                if (b.stride != 1 && b.stride != 2) throw std::runtime_error("bad MobileNetV2 stride");
+                b.cinp = p4(b.cin); b.midp = p4(b.cin * b.t); b.coutp = p4(b.cout);
+                b.we = take((size_t)b.cinp * b.midp); b.be = take(b.midp);
+                b.wd = take((size_t)9 * b.midp); b.bd = take(b.midp);
+                b.wp = take((size_t)b.midp * b.coutp); b.bp = take(b.coutp);
+                max_e = std::max(max_e, (size_t)H * Wd * b.midp);
+                H /= b.stride; Wd /= b.stride;
+                max_d = std::max(max_d, (size_t)H * Wd * b.midp);
+                max_x = std::max(max_x, (size_t)H * Wd * b.coutp);
+                m->mb.push_back(b);
+            }
+            m->mb_last = m->mb.back().coutp;
+            const int featp = p4(m->feat);
+            m->mb_c9w = take((size_t)m->mb_last * featp);
+            m->mb_c9b = take(featp);
+            if (o != n_floats || featp != m->feat) throw std::runtime_error("ReID blob size does not match its header");
+            max_x = std::max(max_x, (size_t)H * Wd * featp);
+            RCUDA_OK(cudaMalloc(&m->d_w, sizeof(float) * n_floats));
+            RCUDA_OK(cudaMemcpy(m->d_w, host.data(), sizeof(float) * n_floats, cudaMemcpyHostToDevice));
+            m->chunk = 64;
+            if (const char* ce = getenv("BOXMOT_B200_REID_CHUNK")) {
+                const int v = atoi(ce);
+                if (v >= 8 && v <= 1024) m->chunk = v;
+            }
+            const size_t CH = m->chunk;
+            RCUDA_OK(cudaMalloc(&m->blob, sizeof(float) * CH * IN_H * IN_W * 3));
+            RCUDA_OK(cudaMalloc(&m->bufA, sizeof(float) * CH * max_x));
+            RCUDA_OK(cudaMalloc(&m->bufB, sizeof(float) * CH * max_x));
+            RCUDA_OK(cudaMalloc(&m->x1, sizeof(float) * CH * max_e));
+            RCUDA_OK(cudaMalloc(&m->Y[0][0], sizeof(float) * CH * max_d));
+        } catch (...) {
+            reid_free(m);
+            throw;
+        }
+        return m;
+    }
     try {
         for (int i = 0; i < 4; ++i) m->c[i] = hdr[3 + i];
         m->feat = hdr[7];
@@ -828,6 +972,56 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
     int launches = 0;
     const float* W = m->d_w;
     m->debug_ptr = nullptr;
+    if (m->arch == 2) {
+        // MobileNetV2: stem -> [expand 1x1 + ReLU6 -> depthwise 3x3 + ReLU6 -> project 1x1 (+ residual)] x 17 -> conv9 -> GAP
+        for (int off = 0; off < max_crops; off += m->chunk) {
+            const int upper = (max_crops - off) < m->chunk ? (max_crops - off) : m->chunk;
+            Launcher L{m, d_ncrops, off, m->chunk, upper, st};
+            L.begin(CLS_CROP);
+            k_crop_resize_norm<<<upper, 256, 0, st>>>(d_images, image_stride, rows, cols, d_crops, d_ncrops, off, m->chunk,
+                                                      m->blob);
+            L.end();
+            ++L.launches;
+            float* X = m->bufA;
+            float* Xo = m->bufB;
+            L.begin(CLS_STEM);
+            k_stem3<<<148 * 8, 256, 0, st>>>(m->blob, W + m->mb_stem_w, W + m->mb_stem_b, m->mb_stemp, d_ncrops, off,
+                                              m->chunk, X);
+            L.end();
+            ++L.launches;
+            int H = 128, Wd = 64;
+            for (const MbBlock& b : m->mb) {
+                PwArgs e{};
+                e.in = X; e.w = W + b.we; e.bias = W + b.be; e.out = m->x1;
+                e.K = b.cinp; e.N = b.midp; e.HW = H * Wd; e.relu = 2;
+                L.pointwise(e);
+                L.begin(CLS_LIGHTCONV);
+                k_dwconv3<<<148 * 8, 256, 0, st>>>(m->x1, H, Wd, b.midp, b.stride, W + b.wd, W + b.bd, d_ncrops, off,
+                                                    m->chunk, m->Y[0][0]);
+                L.end();
+                ++L.launches;
+                H /= b.stride; Wd /= b.stride;
+                PwArgs p{};
+                p.in = m->Y[0][0]; p.w = W + b.wp; p.bias = W + b.bp; p.out = Xo;
+                p.residual = (b.stride == 1 && b.cin == b.cout) ? X : nullptr;
+                p.K = b.midp; p.N = b.coutp; p.HW = H * Wd; p.relu = 0;
+                L.pointwise(p);
+                float* t = X; X = Xo; Xo = t;
+            }
+            PwArgs c9{};
+            c9.in = X; c9.w = W + m->mb_c9w; c9.bias = W + m->mb_c9b; c9.out = Xo;
+            c9.K = m->mb_last; c9.N = m->feat; c9.HW = H * Wd; c9.relu = 2;
+            L.pointwise(c9);
+            L.begin(CLS_HEAD);
+            k_head<<<upper, 256, sizeof(float) * (2 * m->feat + 32), st>>>(Xo, H * Wd, m->feat, nullptr, nullptr, m->feat,
+                                                                           d_crops, d_ncrops, off, m->chunk, d_out, out_ld);
+            L.end();
+            ++L.launches;
+            launches += L.launches;
+        }
+        RCUDA_OK(cudaGetLastError());
+        return launches;
+    }
     for (int off = 0; off < max_crops; off += m->chunk) {
         const int upper = (max_crops - off) < m->chunk ? (max_crops - off) : m->chunk;
         Launcher L{m, d_ncrops, off, m->chunk, upper, st};

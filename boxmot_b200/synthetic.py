@@ -114,3 +114,64 @@ def make_osnet_state(arch: str = "osnet_x0_25", seed: int = 0, feature_dim: int 
     sd["classifier.weight"] = 0.01 * torch.randn(num_classes, feature_dim, generator=g)
     sd["classifier.bias"] = torch.zeros(num_classes)
     return sd
+
+
+MOBILENETV2_LAYERS = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+                      (6, 320, 1, 1))  # (expansion t, base channels c, repeats n, first stride s), mobilenetv2.py:91-99
+
+
+def mobilenetv2_blocks(width_mult: float = 1.4):
+    """[(cin, cout, t, stride)] for every Bottleneck, plus stem channels and feature dim (mobilenetv2.py:86-102)."""
+    cin = int(32 * width_mult)
+    stem = cin
+    blocks = []
+    for t, c, n, s in MOBILENETV2_LAYERS:
+        cout = int(c * width_mult)
+        for i in range(n):
+            blocks.append((cin, cout, t, s if i == 0 else 1))
+            cin = cout
+    feat = int(1280 * width_mult) if width_mult > 1 else 1280
+    return stem, blocks, feat
+
+
+def make_mobilenetv2_state(width_mult: float = 1.4, seed: int = 0, num_classes: int = 1041):
+    """Seeded state dict with the reference's MobileNetV2 parameter names (reid/backbones/mobilenetv2.py)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, k, groups=1, gain=1.0):
+        fan_in = (ci // groups) * k * k
+        sd[name + ".weight"] = torch.randn(co, ci // groups, k, k, generator=g) * (gain / fan_in) ** 0.5
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0)
+
+    stem, blocks, feat = mobilenetv2_blocks(width_mult)
+    conv("conv1.conv", stem, 3, 3, gain=2.0)
+    bn("conv1.bn", stem)
+    stage, idx, prev = 2, 0, None
+    layer_of = []
+    for t, c, n, s in MOBILENETV2_LAYERS:
+        for i in range(n):
+            layer_of.append((stage, i))
+        stage += 1
+    for (cin, cout, t, stride), (st, i) in zip(blocks, layer_of):
+        name = f"conv{st}.{i}"
+        mid = cin * t
+        conv(name + ".conv1.conv", mid, cin, 1, gain=2.0)
+        bn(name + ".conv1.bn", mid)
+        conv(name + ".dwconv2.conv", mid, mid, 3, groups=mid, gain=2.0)
+        bn(name + ".dwconv2.bn", mid)
+        conv(name + ".conv3.0", cout, mid, 1, gain=0.5)
+        bn(name + ".conv3.1", cout)
+    conv("conv9.conv", feat, blocks[-1][1], 1, gain=2.0)
+    bn("conv9.bn", feat)
+    sd["classifier.weight"] = 0.01 * torch.randn(num_classes, feat, generator=g)
+    sd["classifier.bias"] = torch.zeros(num_classes)
+    return sd

@@ -31,6 +31,7 @@ import numpy as np
 MAGIC = 0x45523242  # 'B2RE'
 VERSION = 1
 ARCH_OSNET = 1
+ARCH_MOBILENETV2 = 2
 BRANCHES = (("conv2a", 1), ("conv2b", 2), ("conv2c", 3), ("conv2d", 4))
 EPS = 1e-5
 
@@ -115,6 +116,62 @@ def fold_osnet(sd) -> Tuple[List[int], List[np.ndarray]]:
     return chans + [feat], out
 
 
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _pad_mat(w: np.ndarray, rows: int, cols: int) -> np.ndarray:
+    out = np.zeros((rows, cols))
+    out[: w.shape[0], : w.shape[1]] = w
+    return out
+
+
+def _pad_vec(b: np.ndarray, n: int) -> np.ndarray:
+    out = np.zeros(n)
+    out[: b.shape[0]] = b
+    return out
+
+
+def fold_mobilenetv2(sd):
+    """MobileNetV2 (reid/backbones/mobilenetv2.py) -> (stem_c, feat, block table, arrays).  Channel counts such as
+    22, 33, 89, 134 are zero-padded to multiples of 4 (padded lanes stay exactly 0 through ReLU6 and feed zero
+    weight rows), so the float4 kernels apply unchanged.  Blob (arch 2): header, int32 table [n_blocks][4] =
+    (cin, cout, t, stride), then  stem W[27][C0p], b | per block: expand W[cinp][midp], b; dw W[9][midp], b;
+    project W[midp][coutp], b | conv9 W[clastp][featp], b."""
+    from .synthetic import MOBILENETV2_LAYERS
+
+    stem_c = sd["conv1.conv.weight"].shape[0]
+    arrays, table = [], []
+    w = _np(sd["conv1.conv.weight"])  # [c0][3][3][3]
+    sc, sh = _bn_fold(sd, "conv1.bn")
+    w = (w * sc[:, None, None, None]).transpose(2, 3, 1, 0).reshape(27, stem_c)
+    arrays += [_pad_mat(w, 27, _pad4(stem_c)), _pad_vec(sh, _pad4(stem_c))]
+    stage = 2
+    while f"conv{stage}.0.conv1.conv.weight" in sd:
+        i = 0
+        while f"conv{stage}.{i}.conv1.conv.weight" in sd:
+            name = f"conv{stage}.{i}"
+            mid, cin = sd[name + ".conv1.conv.weight"].shape[:2]
+            cout = sd[name + ".conv3.0.weight"].shape[0]
+            stride = MOBILENETV2_LAYERS[stage - 2][3] if i == 0 else 1
+            table.append((cin, cout, mid // cin, stride))
+            we, be = _pw(sd, name + ".conv1.conv", name + ".conv1.bn")
+            arrays += [_pad_mat(we, _pad4(cin), _pad4(mid)), _pad_vec(be, _pad4(mid))]
+            sc, sh = _bn_fold(sd, name + ".dwconv2.bn")
+            wd = (_np(sd[name + ".dwconv2.conv.weight"])[:, 0] * sc[:, None, None]).reshape(mid, 9).T
+            arrays += [_pad_mat(wd, 9, _pad4(mid)), _pad_vec(sh, _pad4(mid))]
+            # conv3 is nn.Sequential(Conv2d, BatchNorm2d): keys conv3.0 / conv3.1
+            w3 = _np(sd[name + ".conv3.0.weight"])[:, :, 0, 0]
+            sc, sh = _bn_fold(sd, name + ".conv3.1")
+            arrays += [_pad_mat((w3 * sc[:, None]).T, _pad4(mid), _pad4(cout)), _pad_vec(sh, _pad4(cout))]
+            i += 1
+        stage += 1
+    w9, b9 = _pw(sd, "conv9.conv", "conv9.bn")
+    feat = w9.shape[1]
+    arrays += [_pad_mat(w9, _pad4(w9.shape[0]), _pad4(feat)), _pad_vec(b9, _pad4(feat))]
+    return stem_c, feat, table, arrays
+
+
 def export_blob(weights, out_path=None) -> Path:
     """`weights`: path to a .pt checkpoint or an in-memory state dict.  Returns the blob path."""
     if isinstance(weights, (str, Path)):
@@ -128,20 +185,28 @@ def export_blob(weights, out_path=None) -> Path:
         sd = weights
         if out_path is None:
             raise ValueError("out_path is required when exporting an in-memory state dict")
-    if "conv1.conv.weight" not in sd or "conv5.conv.weight" not in sd:
-        raise ValueError("only the OSNet family is implemented on the B200 ReID path so far")
-    dims, arrays = fold_osnet(sd)
+    table = []
+    if "conv9.conv.weight" in sd:
+        stem_c, feat, table, arrays = fold_mobilenetv2(sd)
+        arch, dims = ARCH_MOBILENETV2, [stem_c, len(table), 0, 0, feat]
+    elif "conv1.conv.weight" in sd and "conv5.conv.weight" in sd and "fc.0.weight" in sd:
+        dims, arrays = fold_osnet(sd)
+        arch = ARCH_OSNET
+    else:
+        raise ValueError("only OSNet and MobileNetV2 state dicts are implemented on the B200 ReID path")
     # every tensor starts on a 16-byte boundary (the kernels read weights as float4)
     padded = []
     for a in arrays:
         flat = np.asarray(a, dtype=np.float32).ravel()
         padded.append(np.pad(flat, (0, (-flat.size) % 4)))
     payload = np.concatenate(padded)
-    header = [MAGIC, VERSION, ARCH_OSNET, *dims, int(payload.size)] + [0] * (16 - 9)
+    header = [MAGIC, VERSION, arch, *dims, int(payload.size)] + [0] * (16 - 9)
     out_path = Path(out_path)
     tmp = out_path.with_suffix(out_path.suffix + ".tmp")
     with open(tmp, "wb") as f:
         f.write(struct.pack("<16i", *header))
+        for row in table:
+            f.write(struct.pack("<4i", *row))
         f.write(payload.tobytes())
     tmp.replace(out_path)
     return out_path
@@ -152,9 +217,20 @@ def read_blob(path):
     header = struct.unpack("<16i", raw[:64])
     if header[0] != MAGIC or header[1] != VERSION:
         raise ValueError("not a .b200reid blob")
-    payload = np.frombuffer(raw[64:], dtype=np.float32)
+    off = 64
+    if header[2] == ARCH_MOBILENETV2:
+        off += 16 * header[4]
+    payload = np.frombuffer(raw[off:], dtype=np.float32)
     assert payload.size == header[8]
     return header, payload
+
+
+def read_block_table(path):
+    raw = Path(path).read_bytes()
+    header = struct.unpack("<16i", raw[:64])
+    if header[2] != ARCH_MOBILENETV2:
+        return []
+    return [struct.unpack("<4i", raw[64 + 16 * i: 80 + 16 * i]) for i in range(header[4])]
 
 
 def blob_digest(path) -> str:

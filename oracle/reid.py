@@ -170,12 +170,54 @@ def osnet_forward(sd, x: torch.Tensor, return_stages: bool = False):
     return (v, stages) if return_stages else v
 
 
+def is_mobilenetv2(sd) -> bool:
+    return "conv9.conv.weight" in sd
+
+
+@torch.no_grad()
+def mobilenetv2_forward(sd, x: torch.Tensor, return_stages: bool = False):
+    """reid/backbones/mobilenetv2.py:19-41 (ConvBlock = conv + BN + ReLU6), :43-77 (Bottleneck), :168-198 (forward):
+    x (N,3,256,128) -> (N, feature_dim) global-average-pooled conv9 map (eval mode, no fc)."""
+    stages = {}
+
+    def block(name, y, k, s=1, p=0, g=1):
+        return F.relu6(_bn(sd, name + ".bn", F.conv2d(y, sd[name + ".conv.weight"], stride=s, padding=p, groups=g)))
+
+    x = block("conv1", x, 3, s=2, p=1)
+    stages["conv1"] = x
+    stage = 2
+    while f"conv{stage}.0.conv1.conv.weight" in sd:
+        i = 0
+        while f"conv{stage}.{i}.conv1.conv.weight" in sd:
+            name = f"conv{stage}.{i}"
+            mid = sd[name + ".conv1.conv.weight"].shape[0]
+            cin = sd[name + ".conv1.conv.weight"].shape[1]
+            cout = sd[name + ".conv3.0.weight"].shape[0]
+            # the first Bottleneck of a stage carries the stage stride (mobilenetv2.py:104-110)
+            from boxmot_b200.synthetic import MOBILENETV2_LAYERS
+            stride = MOBILENETV2_LAYERS[stage - 2][3] if i == 0 else 1
+            m = block(name + ".conv1", x, 1)
+            m = block(name + ".dwconv2", m, 3, s=stride, p=1, g=mid)
+            m = _bn(sd, name + ".conv3.1", F.conv2d(m, sd[name + ".conv3.0.weight"]))
+            x = x + m if (stride == 1 and cin == cout) else m
+            stages[name] = x
+            i += 1
+        stage += 1
+    x = block("conv9", x, 1)
+    v = F.adaptive_avg_pool2d(x, 1).flatten(1)
+    return (v, stages) if return_stages else v
+
+
+def backbone_forward(sd, x):
+    return mobilenetv2_forward(sd, x) if is_mobilenetv2(sd) else osnet_forward(sd, x)
+
+
 def get_features(sd, xyxys: np.ndarray, img: np.ndarray) -> np.ndarray:
     """(N, D) float32 L2-normalised embeddings, as BaseModelBackend.get_features returns them."""
     xyxys = np.asarray(xyxys, dtype=np.float32)
     if xyxys.size == 0:
         return np.array([])
-    feats = osnet_forward(sd, get_crops(xyxys, img)).numpy()
+    feats = backbone_forward(sd, get_crops(xyxys, img)).numpy()
     return feats / np.linalg.norm(feats, axis=-1, keepdims=True)
 
 

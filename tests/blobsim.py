@@ -40,10 +40,42 @@ def _dw3(x, w9c, b):
     return F.relu(acc + b)
 
 
+def _dw3s(x, w9c, b, stride):
+    n, h, wd, c = x.shape
+    y = F.conv2d(x.permute(0, 3, 1, 2), w9c.t().reshape(c, 1, 3, 3).contiguous(), b, stride=stride, padding=1, groups=c)
+    return F.relu6(y).permute(0, 2, 3, 1).contiguous()
+
+
+@torch.no_grad()
+def blob_forward_mobilenetv2(blob_path, x_nhwc):
+    from boxmot_b200.weights import read_block_table
+
+    header, payload = read_blob(blob_path)
+    table = read_block_table(blob_path)
+    stem_c, feat = header[3], header[7]
+    p4 = lambda n: (n + 3) // 4 * 4
+    cur = _Cursor(payload)
+    w, b = cur.take(27, p4(stem_c)), cur.take(p4(stem_c))
+    wt = w.view(3, 3, 3, p4(stem_c)).permute(3, 2, 0, 1).contiguous()
+    x = F.relu6(F.conv2d(x_nhwc.permute(0, 3, 1, 2), wt, b, stride=2, padding=1)).permute(0, 2, 3, 1).contiguous()
+    for cin, cout, t, stride in table:
+        mid = cin * t
+        e = F.relu6(x @ cur.take(p4(cin), p4(mid)) + cur.take(p4(mid)))
+        d = _dw3s(e, cur.take(9, p4(mid)), cur.take(p4(mid)), stride)
+        y = d @ cur.take(p4(mid), p4(cout)) + cur.take(p4(cout))
+        x = x + y if (stride == 1 and cin == cout) else y
+    last = table[-1][1]
+    x = F.relu6(x @ cur.take(p4(last), p4(feat)) + cur.take(p4(feat)))
+    assert cur.o == payload.size
+    return x.mean(dim=(1, 2))[:, :feat]
+
+
 @torch.no_grad()
 def blob_forward(blob_path, x_nhwc: torch.Tensor, return_stages=False):
     """x_nhwc (N,256,128,3) float32 normalised RGB -> (N, feat) un-normalised embedding."""
     header, payload = read_blob(blob_path)
+    if header[2] == 2:
+        return blob_forward_mobilenetv2(blob_path, x_nhwc)
     c = list(header[3:7])
     feat = header[7]
     cur = _Cursor(payload)

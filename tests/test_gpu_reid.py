@@ -133,3 +133,24 @@ def test_alternative_kernel_paths_keep_parity(tmp_path, monkeypatch, env):
     w, h = rng.uniform(20, 120, n), rng.uniform(40, 240, n)
     boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
     _emb_ok(reid.get_features(boxes, img), orid.get_features(sd, boxes, img))
+
+
+def test_mobilenetv2_x1_4_embeddings_match_oracle(tmp_path):
+    """Row a4: MobileNetV2_x1_4 (1792-d), channel counts 22/33/89/134 padded to multiples of 4."""
+    from boxmot_b200.reid import B200ReID
+    from boxmot_b200.synthetic import make_mobilenetv2_state
+    from boxmot_b200.weights import export_blob
+
+    sd = make_mobilenetv2_state(1.4, seed=6)
+    reid = B200ReID(export_blob(sd, tmp_path / "mobilenetv2_x1_4.b200reid"))
+    assert reid.feature_dim == 1792
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 255, size=(540, 960, 3), dtype=np.uint8)
+    n = 70
+    cx, cy = rng.uniform(0, 960, n), rng.uniform(0, 540, n)
+    w, h = rng.uniform(20, 120, n), rng.uniform(40, 240, n)
+    boxes = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1).astype(np.float32)
+    got = reid.get_features(boxes, img)
+    want = orid.get_features(sd, boxes, img)
+    assert got.shape == (n, 1792)
+    _emb_ok(got, want)

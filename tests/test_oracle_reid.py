@@ -72,3 +72,18 @@ def test_pt_roundtrip(tmp_path):
     blob = export_blob(tmp_path / "osnet_x0_25_msmt17.pt")
     header, payload = read_blob(blob)
     assert header[3:8] == (16, 64, 96, 128, 512) and payload.size == header[8]
+
+
+def test_mobilenetv2_folded_blob_equals_oracle(tmp_path):
+    from boxmot_b200.synthetic import make_mobilenetv2_state
+    from boxmot_b200.weights import export_blob, read_blob, read_block_table
+    from tests.blobsim import blob_forward
+
+    sd = make_mobilenetv2_state(1.4, seed=2)
+    blob = export_blob(sd, tmp_path / "mobilenetv2_x1_4.b200reid")
+    header, _ = read_blob(blob)
+    assert header[2] == 2 and header[3] == 44 and header[7] == 1792 and len(read_block_table(blob)) == 17
+    x = torch.randn(2, 3, 256, 128)
+    want = orid.mobilenetv2_forward(sd, x)
+    got = blob_forward(blob, x.permute(0, 2, 3, 1).contiguous())
+    assert float((got - want).abs().max()) < 5e-6 * float(want.abs().max())
