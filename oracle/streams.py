@@ -66,6 +66,15 @@ def warp_sequence(n_frames: int, seed: int = 17):
     return out
 
 
+def unit_embeddings(frames, n_objects_hint: int, dim: int = 512, seed: int = 11):
+    """`stress_embeddings` rows L2-normalised in float32, as a ReID backend's get_features returns them."""
+    out = []
+    for e in stress_embeddings(frames, n_objects_hint, dim=dim, seed=seed):
+        e = np.asarray(e, np.float32)
+        out.append(e / np.linalg.norm(e, axis=1, keepdims=True) if len(e) else e)
+    return out
+
+
 def stress_embeddings(frames, n_objects_hint: int, dim: int = 512, seed: int = 11, noise: float = 0.35):
     """Per-detection appearance vectors for `stress_stream` frames (same seed => same vectors).
 

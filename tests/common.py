@@ -5,7 +5,7 @@ from pathlib import Path
 
 import numpy as np
 
-from oracle.streams import bench_stream, stress_embeddings, stress_stream
+from oracle.streams import bench_stream, stress_embeddings, stress_stream, unit_embeddings
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -30,6 +30,11 @@ CASES = {
                               lambda: stress_stream(48, 200, seed=19, n_classes=3, empty_every=37),
                               lambda fr: stress_embeddings(fr, 48, seed=5)),
     "botsort_noreid_stress64": ("botsort", dict(with_reid=False), lambda: stress_stream(64, 200, seed=23), None),
+    "deepocsort_stress96": ("deepocsort", {}, lambda: stress_stream(96, 300), lambda fr: unit_embeddings(fr, 96, seed=5)),
+    "deepocsort_stress48_gaps": ("deepocsort", {}, lambda: stress_stream(48, 200, seed=19, n_classes=3, empty_every=37),
+                                 lambda fr: unit_embeddings(fr, 96, seed=5)),
+    "deepocsort_bench128": ("deepocsort", {}, lambda: bench_stream(128, 60, hw=(360, 640))[1],
+                            lambda fr: unit_embeddings(fr, 96, seed=5)),
     "botsort_bench256": ("botsort", BOTSORT_YAML, lambda: bench_stream(256, 40)[1],
                          lambda fr: stress_embeddings(fr, 256, seed=3)),
 }

@@ -40,6 +40,17 @@ BOTSORT_YAML = dict(
 SNAP_FRAMES = (1, 2, 10, 50, 150, 299)
 
 
+def _snapshot_docs(tracker):
+    ids, means, covs = [], [], []
+    for t in tracker.active_tracks:
+        ids.append(t.id)
+        means.append(np.r_[np.asarray(t.kf.x, dtype=np.float64).reshape(-1), 0.0])
+        c = np.zeros((8, 8))
+        c[:7, :7] = t.kf.P
+        covs.append(c)
+    return (np.asarray(ids, dtype=np.int64), np.asarray(means).reshape(-1, 8), np.asarray(covs).reshape(-1, 8, 8))
+
+
 def _snapshot(tracker):
     ids, means, covs = [], [], []
     for t in list(tracker.active_tracks) + list(tracker.lost_stracks):
@@ -65,12 +76,14 @@ def run(tracker, frames, img, embs=None):
     rows, offsets, snaps = [], [0], {}
     for f, dets in enumerate(frames):
         e = None if embs is None else embs[f].copy()
+        if e is not None and len(dets) == 0:
+            e = np.empty((0, e.shape[1] if e.ndim == 2 else 512), np.float32)
         out = np.asarray(tracker.update(dets.copy(), img, e) if e is not None else tracker.update(dets.copy(), img))
         out = out.reshape(-1, 8) if out.size else np.empty((0, 8), np.float32)
         rows.append(out.astype(np.float32))
         offsets.append(offsets[-1] + len(out))
         if (f + 1) in SNAP_FRAMES:
-            ids, m, c = _snapshot(tracker)
+            ids, m, c = _snapshot_docs(tracker) if tracker.__class__.__name__ == "DeepOcSort" else _snapshot(tracker)
             snaps[f"snap{f + 1}_ids"] = ids
             snaps[f"snap{f + 1}_mean"] = m
             snaps[f"snap{f + 1}_cov"] = c
@@ -169,6 +182,13 @@ def main():
     embs = stress_embeddings(frames, 256, seed=3)
     np.savez_compressed(HERE / "botsort_bench256.npz",
                         **run(BotSort(reid_model=None, use_cmc=False, **BOTSORT_YAML), frames, img, embs))
+    from boxmot.trackers.bbox.deepocsort.deepocsort import DeepOcSort
+    from oracle.streams import unit_embeddings
+    for name, frames in (("deepocsort_stress96", stress_stream(96, 300)),
+                         ("deepocsort_stress48_gaps", stress_stream(48, 200, seed=19, n_classes=3, empty_every=37)),
+                         ("deepocsort_bench128", bench_stream(128, 60, hw=(360, 640))[1])):
+        embs = unit_embeddings(frames, 96, seed=5)
+        np.savez_compressed(HERE / f"{name}.npz", **run(DeepOcSort(reid_model=None, cmc_off=True), frames, img, embs))
     make_reid_golden()
     for p in sorted(HERE.glob("*.npz")):
         print(p.name, p.stat().st_size)
