@@ -1,0 +1,229 @@
+// jv_dense.cuh -- dense Jonker-Volgenant linear assignment with the SAME tie-breaking as lap.lapjv
+// (restated for the oracle in oracle/lapjv.c): column reduction + reduction transfer, two passes of augmenting row
+// reduction, shortest-augmenting-path augmentation with lapjv's column-list bookkeeping.
+//
+// DeepOCSORT's association (association/association.py:20-24, 105-123; deepocsort.py:433) calls
+// lapjv(extend_cost=True) WITHOUT a cost limit on matrices full of exact zeros (no overlap, no velocity, gated
+// appearance): many optima tie, lapjv's choice among them decides the ORDER in which unmatched detections become
+// tracks and therefore the track ids.  Bit-exact ids need the same algorithm, not just an exact optimum.
+//
+// One warp runs the solver.  Control flow is lapjv's sequential control flow; the O(n) inner scans are spread
+// over the lanes with reductions that reproduce the sequential result exactly: minima are combined as
+// (value, lowest index), the two-smallest search of the row reduction as lexicographic (value, index) pairs, and
+// the relaxation loop of the path search updates all columns in parallel and then replays the rare
+// "distance equals the band minimum" events in ascending position order.
+#pragma once
+#include "tracker_core.cuh"
+
+namespace bmb {
+
+// S provides: cost (n x n, leading dimension ld), lap_x, lap_y, lap_v, lap_spc (d), lap_path (pred),
+// lap_tl (cols), lap_sc (free rows), lap_insc (once flags).  Called by the whole CTA.
+template <typename S>
+BMB_FN void jv_dense_solve(S& s, int n, int ld) {
+    if (n <= 0) return;
+    const double BIG = 1.7976931348623157e308;
+    int* x = s.lap_x; int* y = s.lap_y; double* v = s.lap_v; double* d = s.lap_spc;
+    int* pred = s.lap_path; int* cols = s.lap_tl; int* free_rows = s.lap_sc; int* once = s.lap_insc;
+    const double* c = s.cost;
+    // ---- column reduction: every column elects its cheapest row (first minimal row) ----
+    for (int i = BMB_TID; i < n; i += BMB_NT) { x[i] = -1; once[i] = 1; }
+    for (int j = BMB_TID; j < n; j += BMB_NT) {
+        double vj = BIG; int yj = 0;
+        for (int i = 0; i < n; ++i) {
+            const double cij = c[(size_t)i * ld + j];
+            if (cij < vj) { vj = cij; yj = i; }
+        }
+        v[j] = vj; y[j] = yj;
+    }
+    BMB_SYNC();
+    if (BMB_WARP == 0) {
+        const int lane = BMB_LANE;
+        if (lane == 0) {
+            for (int j = n - 1; j >= 0; --j) {
+                const int i = y[j];
+                if (x[i] < 0) x[i] = j;
+                else { once[i] = 0; y[j] = -1; }
+            }
+        }
+        BMB_SYNCWARP();
+        // reduction transfer (sequential over rows: prices change as we go), free rows collected in order
+        int n_free = 0;
+        for (int i = 0; i < n; ++i) {
+            const int xi = x[i];
+            if (xi < 0) { if (lane == 0) free_rows[n_free] = i; ++n_free; continue; }
+            if (!once[i]) continue;
+            const double* ci = c + (size_t)i * ld;
+            double m = BIG;
+            for (int k = lane; k < n; k += BMB_NL)
+                if (k != xi) { const double r = ci[k] - v[k]; if (r < m) m = r; }
+#if BMB_DEVICE
+            for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (t < m) m = t; }
+#endif
+            if (lane == 0) v[xi] -= m;
+            BMB_SYNCWARP();
+        }
+        // ---- augmenting row reduction, two passes ----
+        for (int pass = 0; pass < 2 && n_free > 0; ++pass) {
+            int cur = 0, kept = 0;
+            long long rounds = 0;
+            while (cur < n_free) {
+                ++rounds;
+                const int fi = free_rows[cur++];
+                const double* ci = c + (size_t)fi * ld;
+                // lexicographic (value, index) minimum and the minimum over the remaining indices
+                double a1 = BIG, a2 = BIG; int i1 = -1, i2 = -1;
+                for (int j = lane; j < n; j += BMB_NL) {
+                    const double r = ci[j] - v[j];
+                    if (i1 < 0 || r < a1) { a2 = a1; i2 = i1; a1 = r; i1 = j; }
+                    else if (i2 < 0 || r < a2) { a2 = r; i2 = j; }
+                }
+#if BMB_DEVICE
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+                    const int k1 = __shfl_xor_sync(0xffffffffu, i1, o), k2 = __shfl_xor_sync(0xffffffffu, i2, o);
+                    // merge two sorted pairs {(a1,i1),(a2,i2)} and {(b1,k1),(b2,k2)}; missing entries have index -1
+                    auto less = [](double va, int ia, double vb, int ib) {
+                        if (ib < 0) return ia >= 0;
+                        if (ia < 0) return false;
+                        return va < vb || (va == vb && ia < ib);
+                    };
+                    double n1, n2; int m1, m2;
+                    if (less(a1, i1, b1, k1)) {
+                        n1 = a1; m1 = i1;
+                        if (less(a2, i2, b1, k1)) { n2 = a2; m2 = i2; } else { n2 = b1; m2 = k1; }
+                    } else {
+                        n1 = b1; m1 = k1;
+                        if (less(b2, k2, a1, i1)) { n2 = b2; m2 = k2; } else { n2 = a1; m2 = i1; }
+                    }
+                    a1 = n1; i1 = m1; a2 = n2; i2 = m2;
+                }
+#endif
+                int j1 = i1, j2 = i2;
+                const double v1 = a1, v2 = (i2 >= 0) ? a2 : BIG;
+                int i0 = y[j1];
+                const double lowered = v[j1] - (v2 - v1);
+                const int moves = lowered < v[j1];
+                BMB_SYNCWARP();
+                if (rounds < (long long)cur * n) {
+                    if (moves) { if (lane == 0) v[j1] = lowered; }
+                    else if (i0 >= 0 && j2 >= 0) { j1 = j2; i0 = y[j2]; }
+                    if (i0 >= 0) {
+                        if (moves) { --cur; if (lane == 0) free_rows[cur] = i0; }
+                        else { if (lane == 0) free_rows[kept] = i0; ++kept; }
+                    }
+                } else {
+                    if (i0 >= 0) { if (lane == 0) free_rows[kept] = i0; ++kept; }
+                }
+                if (lane == 0) { x[fi] = j1; y[j1] = fi; }
+                BMB_SYNCWARP();
+            }
+            n_free = kept;
+        }
+        // ---- augmentation ----
+        for (int f = 0; f < n_free; ++f) {
+            const int start = free_rows[f];
+            int lo = 0, hi = 0, n_ready = 0, band = 0, final_j = -1;
+            {
+                const double* cs = c + (size_t)start * ld;
+                for (int j = lane; j < n; j += BMB_NL) { cols[j] = j; pred[j] = start; d[j] = cs[j] - v[j]; }
+            }
+            BMB_SYNCWARP();
+            while (final_j == -1) {
+                if (lo == hi) {
+                    // _find_dense: sequential (its swaps define the scan order of ties)
+                    if (lane == 0) {
+                        int h2 = lo + 1;
+                        double mind = d[cols[lo]];
+                        for (int k = lo + 1; k < n; ++k) {
+                            const int j = cols[k];
+                            const double dj = d[j];
+                            if (dj <= mind) {
+                                if (dj < mind) { h2 = lo; mind = dj; }
+                                cols[k] = cols[h2];
+                                cols[h2++] = j;
+                            }
+                        }
+                        int fj = -1;
+                        for (int k = lo; k < h2; ++k)
+                            if (y[cols[k]] < 0) fj = cols[k];
+                        s.free_l[MB_COUNT - 1] = h2;
+                        s.free_l[MB_COUNT - 2] = fj;
+                    }
+                    BMB_SYNCWARP();
+                    n_ready = lo;
+                    band = lo;
+                    hi = s.free_l[MB_COUNT - 1];
+                    final_j = s.free_l[MB_COUNT - 2];
+                    BMB_SYNCWARP();
+                }
+                if (final_j == -1) {
+                    // _scan_dense over the ready band
+                    while (lo != hi && final_j == -1) {
+                        const int j = cols[lo++];
+                        const int i = y[j];
+                        const double mind = d[j];
+                        const double* ci = c + (size_t)i * ld;
+                        const double h = ci[j] - v[j] - mind;
+                        const int hi0 = hi;
+                        for (int k0 = hi0; k0 < n && final_j == -1; k0 += BMB_NL) {
+                            const int k = k0 + lane;
+                            int jj = -1;
+                            bool hit = false;
+                            if (k < n) {
+                                jj = cols[k];
+                                const double r = ci[jj] - v[jj] - h;
+                                if (r < d[jj]) {
+                                    d[jj] = r;
+                                    pred[jj] = i;
+                                    hit = (r == mind);
+                                }
+                            }
+                            unsigned m = BMB_BALLOT(hit);
+                            // replay the "equals the band minimum" events in ascending position order
+                            while (m) {
+#if BMB_DEVICE
+                                const int src = __ffs(m) - 1;
+                                const int kq = k0 + src;
+                                const int jq = __shfl_sync(0xffffffffu, jj, src);
+#else
+                                const int src = 0;
+                                const int kq = k0;
+                                const int jq = jj;
+#endif
+                                m &= m - 1;
+                                if (y[jq] < 0) { final_j = jq; break; }
+                                if (lane == 0) { cols[kq] = cols[hi]; cols[hi] = jq; }
+                                ++hi;
+                                BMB_SYNCWARP();
+                                (void)src;
+                            }
+                            BMB_SYNCWARP();
+                        }
+                    }
+                }
+            }
+            // price update for the columns scanned before the last band, then augment along the path
+            {
+                const double mind = d[cols[band]];
+                BMB_SYNCWARP();
+                for (int k = lane; k < n_ready; k += BMB_NL) { const int j = cols[k]; v[j] += d[j] - mind; }
+            }
+            BMB_SYNCWARP();
+            if (lane == 0) {
+                int j = final_j, i = -1;
+                while (i != start) {
+                    i = pred[j];
+                    y[j] = i;
+                    const int prev = x[i];
+                    x[i] = j;
+                    j = prev;
+                }
+            }
+            BMB_SYNCWARP();
+        }
+    }
+    BMB_SYNC();
+}
+
+}  // namespace bmb

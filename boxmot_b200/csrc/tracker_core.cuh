@@ -39,7 +39,9 @@
 #define BMB_SHFL_XOR_F(v, o) __shfl_xor_sync(0xffffffffu, (v), (o))
 #define BMB_DEVICE 1
 #define BMB_CLOCK() clock64()
+#define BMB_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #else
+#define BMB_ATOMIC_MAX(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
 #define BMB_CLOCK() 0ll
 #define BMB_FN static inline
 #define BMB_TID 0
@@ -485,7 +487,8 @@ BMB_FN int warp_append(int n, int* out, int base, Pred pred, Val val) {
 // candidate as dual price u[i] (v = 0 keeps all reduced costs >= 0) and claims that column; a column claimed by
 // several rows goes to the lowest row.  The claimed pairs are tight edges of a feasible dual, i.e. a valid partial
 // matching for the exact search below, which then only has to place the rows that lost a claim.
-BMB_FN void lap_build_csr(TrkStream& s, int T, int D, int ld, double thresh) {
+template <typename S>
+BMB_FN void lap_build_csr(S& s, int T, int D, int ld, double thresh) {
     for (int j = BMB_TID; j < D; j += BMB_NT) s.lap_tl[j] = 0x7fffffff;  // column claims (lap_tl is free here)
     for (int i = BMB_WARP; i < T; i += BMB_NW) {
         const double* ci = s.cost + (size_t)i * ld;
@@ -537,7 +540,8 @@ BMB_FN void lap_build_csr(TrkStream& s, int T, int D, int ld, double thresh) {
 }
 
 // Called by the whole CTA; result in lap_x[0..T) (column or -1) and lap_y[0..D) (row or -1).
-BMB_FN void lap_solve(TrkStream& s, int T, int D, int ld, double thresh) {
+template <typename S>
+BMB_FN void lap_solve(S& s, int T, int D, int ld, double thresh) {
     if (T == 0 || D == 0) {
         for (int i = BMB_TID; i < T; i += BMB_NT) s.lap_x[i] = -1;
         for (int j = BMB_TID; j < D; j += BMB_NT) s.lap_y[j] = -1;

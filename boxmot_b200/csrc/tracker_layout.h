@@ -89,3 +89,54 @@ inline size_t carve_stream(const TrkCfg& c, uint8_t* base, TrkStream* s, size_t*
 }
 
 }  // namespace bmb
+
+#include "docs_core.cuh"
+
+namespace bmb {
+
+inline size_t carve_docs(const DocsCfg& c, uint8_t* base, DocsStream* s, size_t* persistent_bytes) {
+    const size_t CT = (size_t)c.cap_tracks, CD = (size_t)c.cap_dets, F = (size_t)(c.feat_dim > 0 ? c.feat_dim : 1);
+    const size_t MX = CT > CD ? CT : CD;
+    Carver k{base, 0};
+    DocsStream t{};
+    t.scalars = k.take<int>(SC_COUNT);
+    t.timers = k.take<long long>(16);
+    t.gap = k.take<int>(CT); t.has_saved = k.take<int>(CT); t.observed = k.take<int>(CT);
+    t.age = k.take<int>(CT); t.hits = k.take<int>(CT); t.hit_streak = k.take<int>(CT); t.tsu = k.take<int>(CT);
+    t.id = k.take<int>(CT); t.obs_age = k.take<int>(CT * DOCS_RING); t.obs_n = k.take<int>(CT);
+    t.has_vel = k.take<int>(CT); t.tracks = k.take<int>(CT);
+    t.x = k.take<double>(CT * 8); t.P = k.take<double>(CT * 56);
+    t.xs = k.take<double>(CT * 8); t.Ps = k.take<double>(CT * 56);
+    t.zlast = k.take<double>(CT * 4);
+    t.conf = k.take<double>(CT); t.cls = k.take<double>(CT); t.det_ind = k.take<double>(CT);
+    t.last_obs = k.take<double>(CT * 5); t.obs_box = k.take<double>(CT * DOCS_RING * 5);
+    t.vel = k.take<double>(CT * 2);
+    t.emb = k.take<double>(CT * F);
+    if (persistent_bytes) *persistent_bytes = k.off;
+    t.kdet = k.take<int>(CD);
+    t.dbox = k.take<double>(CD * 5);
+    t.dalpha = k.take<double>(CD);
+    t.tbox = k.take<double>(CT * 4);
+    t.kobs = k.take<double>(CT * 5);
+    t.iou = k.take<double>(CD * CT);
+    t.embc = k.take<double>(CD * CT);
+    t.cost = k.take<double>(MX * MX);   // lapjv's zero-padded square problem
+    t.top = k.take<double>(2 * (CD + CT));
+    t.mrow = k.take<int>(CD);
+    t.und = k.take<int>(CD);
+    t.unt = k.take<int>(CT);
+    t.tmp_a = k.take<int>(CT + CD);
+    t.tmp_b = k.take<int>(MX);
+    t.mark = k.take<int>(CT);
+    t.free_l = k.take<int>(CT + MB_COUNT);
+    t.lap_x = k.take<int>(MX); t.lap_y = k.take<int>(MX);
+    t.lap_u = k.take<double>(MX); t.lap_v = k.take<double>(MX); t.lap_spc = k.take<double>(MX);
+    t.lap_path = k.take<int>(MX); t.lap_insc = k.take<int>(MX); t.lap_tl = k.take<int>(MX); t.lap_sc = k.take<int>(MX);
+    t.csr_ptr = k.take<int>(MX + 1);
+    t.csr_col = k.take<int>(CT * CD);
+    t.out = k.take<float>(CD * 8);
+    if (s) *s = t;
+    return (k.off + 255) & ~(size_t)255;
+}
+
+}  // namespace bmb

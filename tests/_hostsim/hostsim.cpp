@@ -96,6 +96,60 @@ int hostsim_snapshot(HostSim* h, int* ids, double* means, double* covs, int cap)
     return n;
 }
 
+// ---- DeepOCSORT host simulation -------------------------------------------------------------------------------
+struct DocsSim {
+    DocsCfg cfg;
+    DocsStream s;
+    std::vector<uint8_t> mem;
+    std::vector<float> dets, embs;
+    int n_dets;
+};
+
+DocsSim* docs_create(const DocsCfg* cfg) {
+    DocsSim* h = new DocsSim();
+    h->cfg = *cfg;
+    size_t bytes = carve_docs(h->cfg, nullptr, nullptr, nullptr);
+    h->mem.assign(bytes, 0);
+    carve_docs(h->cfg, h->mem.data(), &h->s, nullptr);
+    h->dets.assign((size_t)cfg->cap_dets * 6, 0.f);
+    h->embs.assign((size_t)cfg->cap_dets * (cfg->feat_dim > 0 ? cfg->feat_dim : 1), 0.f);
+    h->s.dets = h->dets.data();
+    h->s.n_dets = &h->n_dets;
+    h->s.embs = nullptr;
+    return h;
+}
+void docs_destroy(DocsSim* h) { delete h; }
+int docs_cfg_size() { return (int)sizeof(DocsCfg); }
+
+int docs_update(DocsSim* h, const float* dets, int n, const float* embs, float* out) {
+    const DocsCfg& c = h->cfg;
+    if (n > c.cap_dets) return -ERR_DET_CAPACITY;
+    h->n_dets = n;
+    if (n) memcpy(h->dets.data(), dets, sizeof(float) * 6 * n);
+    if (embs && n) {
+        memcpy(h->embs.data(), embs, sizeof(float) * (size_t)c.feat_dim * n);
+        h->s.embs = h->embs.data();
+    } else {
+        h->s.embs = embs ? h->embs.data() : nullptr;
+    }
+    docs_frame(c, h->s);
+    if (h->s.scalars[SC_ERROR]) return -h->s.scalars[SC_ERROR];
+    const int m = h->s.scalars[SC_N_OUT];
+    memcpy(out, h->s.out, sizeof(float) * 8 * m);
+    return m;
+}
+
+int docs_snapshot(DocsSim* h, int* ids, double* xs, double* Ps, int cap) {
+    int n = 0;
+    for (int k = 0; k < h->s.scalars[SC_N_ACTIVE] && n < cap; ++k, ++n) {
+        const int t = h->s.tracks[k];
+        ids[n] = h->s.id[t];
+        memcpy(xs + (size_t)n * 7, h->s.x + (size_t)t * 8, sizeof(double) * 7);
+        memcpy(Ps + (size_t)n * 49, h->s.P + (size_t)t * 56, sizeof(double) * 49);
+    }
+    return n;
+}
+
 // standalone LAP entry for solver tests: cost is (T, D) row-major
 int hostsim_lap(HostSim* h, const double* cost, int T, int D, double thresh, int* x, int* y) {
     const TrkCfg& c = h->cfg;

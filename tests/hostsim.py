@@ -129,3 +129,62 @@ class HostSimTracker:
         y = np.empty(D, np.int32)
         assert self.lib.hostsim_lap(self.h, cost.ctypes.data, T, D, thresh, x.ctypes.data, y.ctypes.data) == 0
         return x, y
+
+
+class DocsCfg(ctypes.Structure):
+    _fields_ = [("cap_tracks", ctypes.c_int), ("cap_dets", ctypes.c_int), ("feat_dim", ctypes.c_int),
+                ("delta_t", ctypes.c_int), ("max_age", ctypes.c_int), ("min_hits", ctypes.c_int),
+                ("embedding_off", ctypes.c_int), ("aw_off", ctypes.c_int), ("det_thresh_f32", ctypes.c_float),
+                ("det_thresh", ctypes.c_double), ("iou_threshold", ctypes.c_double), ("inertia", ctypes.c_double),
+                ("w_emb", ctypes.c_double), ("alpha_fixed", ctypes.c_double), ("aw_param", ctypes.c_double),
+                ("q_xy", ctypes.c_double), ("q_s", ctypes.c_double)]
+
+
+def deepocsort_cfg(delta_t=3, inertia=0.2, w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5,
+                   embedding_off=False, aw_off=False, Q_xy_scaling=0.01, Q_s_scaling=0.0001, det_thresh=0.3,
+                   max_age=30, min_hits=3, iou_threshold=0.3, feat_dim=512, cap_tracks=512, cap_dets=256):
+    c = DocsCfg()
+    c.cap_tracks, c.cap_dets, c.feat_dim, c.delta_t = cap_tracks, cap_dets, feat_dim, delta_t
+    c.max_age, c.min_hits, c.embedding_off, c.aw_off = max_age, min_hits, int(embedding_off), int(aw_off)
+    c.det_thresh_f32 = np.float32(det_thresh)
+    c.det_thresh, c.iou_threshold, c.inertia, c.w_emb = det_thresh, iou_threshold, inertia, w_association_emb
+    c.alpha_fixed, c.aw_param, c.q_xy, c.q_s = alpha_fixed_emb, aw_param, Q_xy_scaling, Q_s_scaling
+    return c
+
+
+class HostSimDeepOcSort:
+    def __init__(self, cfg: DocsCfg):
+        self.lib = ctypes.CDLL(str(build()))
+        assert self.lib.docs_cfg_size() == ctypes.sizeof(DocsCfg)
+        self.lib.docs_create.restype = ctypes.c_void_p
+        self.lib.docs_create.argtypes = [ctypes.POINTER(DocsCfg)]
+        self.lib.docs_update.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.docs_snapshot.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        self.lib.docs_destroy.argtypes = [ctypes.c_void_p]
+        self.cfg = cfg
+        self.h = self.lib.docs_create(ctypes.byref(cfg))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.docs_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, img=None, embs=None):
+        dets = np.ascontiguousarray(dets, dtype=np.float32).reshape(-1, 6)
+        n = len(dets)
+        out = np.empty((max(n, 1), 8), np.float32)
+        e = None
+        if embs is not None:
+            e = np.ascontiguousarray(embs, dtype=np.float32).reshape(n, -1) if n else np.zeros((1, self.cfg.feat_dim), np.float32)
+        m = self.lib.docs_update(self.h, dets.ctypes.data, n, e.ctypes.data if e is not None else None, out.ctypes.data)
+        if m < 0:
+            raise RuntimeError(f"hostsim error {-m}")
+        return out[:m].copy()
+
+    def state_snapshot(self):
+        cap = self.cfg.cap_tracks
+        ids = np.empty(cap, np.int32)
+        xs = np.empty((cap, 7))
+        ps = np.empty((cap, 7, 7))
+        n = self.lib.docs_snapshot(self.h, ids.ctypes.data, xs.ctypes.data, ps.ctypes.data, cap)
+        return {int(ids[i]): (xs[i].copy(), ps[i].copy()) for i in range(n)}
