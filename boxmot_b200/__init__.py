@@ -9,7 +9,7 @@ Public surface mirrors the reference seams for this path only (SURVEY.md section
 Nothing here falls back to the CPU; the CUDA library must be present and a GPU visible.
 """
 from ._lib import B200Error, load_library, require_device  # noqa: F401
-from .trackers import BotSort, ByteTrack, MultiStreamTracker, TrackResults, create_tracker  # noqa: F401
+from .trackers import BotSort, ByteTrack, DeepOcSort, MultiStreamTracker, TrackResults, create_tracker  # noqa: F401
 
-__all__ = ["ByteTrack", "BotSort", "MultiStreamTracker", "TrackResults", "create_tracker", "B200Error",
+__all__ = ["ByteTrack", "BotSort", "DeepOcSort", "MultiStreamTracker", "TrackResults", "create_tracker", "B200Error",
            "load_library", "require_device"]

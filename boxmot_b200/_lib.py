@@ -14,6 +14,7 @@ LIB_PATH = PKG / "libboxmot_b200.so"
 
 TRACKER_BYTETRACK = 0
 TRACKER_BOTSORT = 1
+TRACKER_DEEPOCSORT = 2
 
 
 class BoxMOTByteTrackConfig(ctypes.Structure):
@@ -37,7 +38,11 @@ class BoxMOTB200TrackerConfig(ctypes.Structure):
                 ("match_thresh", c_double), ("second_match_thresh", c_double),
                 ("unconfirmed_match_thresh", c_double), ("proximity_thresh", c_double),
                 ("appearance_thresh", c_double), ("unconfirmed_emb_scale", c_double),
-                ("reid_model_path", c_char_p)]
+                ("reid_model_path", c_char_p),
+                ("delta_t", c_int), ("max_age", c_int), ("min_hits", c_int), ("embedding_off", c_int),
+                ("aw_off", c_int), ("det_thresh", c_double), ("iou_threshold", c_double), ("inertia", c_double),
+                ("w_association_emb", c_double), ("alpha_fixed_emb", c_double), ("aw_param", c_double),
+                ("q_xy_scaling", c_double), ("q_s_scaling", c_double)]
 
 
 # every symbol include/boxmot_b200.h declares: name -> (restype, argtypes)
@@ -87,6 +92,7 @@ SYMBOLS = {
     "boxmot_b200_tracker_profile": (c_int, [c_void_p, c_int]),
     "boxmot_b200_tracker_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "boxmot_b200_last_error": (c_char_p, []),
+    "boxmot_b200_jv_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "boxmot_b200_lap_solve": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "boxmot_b200_kalman_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),
     "boxmot_b200_kalman_update": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),

@@ -249,6 +249,9 @@ int boxmot_botsort_last_reid_postprocess_time_ms(BoxMOTBotSortHandle* h, double*
 }
 
 // ---- standalone kernels ----------------------------------------------------------------------------------------
+int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y) {
+    return guard([&] { standalone_jv(cost, rows, cols, x, y); });
+}
 int boxmot_b200_lap_solve(const double* cost, int rows, int cols, double cost_limit, int* x, int* y) {
     return guard([&] { standalone_lap(cost, rows, cols, cost_limit, x, y); });
 }

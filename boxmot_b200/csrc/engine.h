@@ -9,6 +9,7 @@
 
 #include "../../include/boxmot_b200.h"
 #include "tracker_core.cuh"
+#include "docs_core.cuh"
 
 namespace bmb {
 
@@ -51,6 +52,13 @@ struct Engine {
     size_t stream_bytes = 0, persistent_bytes = 0;
     TrkStream* d_streams = nullptr;
     std::vector<TrkStream> h_streams;
+    bool is_docs = false;              // DeepOCSORT engine (docs_core.cuh) instead of the STrack family
+    DocsCfg dcfg{};
+    DocsStream* d_docs = nullptr;
+    std::vector<DocsStream> h_docs;
+    std::vector<float*> out_ptr;       // per-stream output rows / scalars / timers (either family)
+    std::vector<int*> scalars_ptr;
+    std::vector<long long*> timers_ptr;
     float* d_dets = nullptr;
     int* d_ndets = nullptr;
     float* d_embs = nullptr;
@@ -106,6 +114,7 @@ struct Engine {
     void finish_fetch(float* const* out, const int* out_cap, int* out_rows);
 };
 
+void standalone_jv(const double* cost, int R, int C, int* x, int* y);
 void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int* y);
 void standalone_kf(int op, int kind, double* mean, double* cov, const int* tracked, const float* meas, int n);
 void standalone_iou(const double* t, int T, const float* d, int D, double* out);

@@ -129,6 +129,32 @@ __global__ void __launch_bounds__(256) k_embedding_cost(const TrkCfg cfg, TrkStr
     }
 }
 
+__global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStream* streams) {
+    DocsStream s = streams[blockIdx.x];
+    docs_frame(cfg, s);
+}
+
+// DeepOCSORT embeds every detection above det_thresh (deepocsort.py:333-343)
+__global__ void k_build_crops_docs(const DocsCfg cfg, DocsStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    for (int sidx = 0; sidx < n_streams; ++sidx) {
+        const DocsStream& s = streams[sidx];
+        const int D = min(*s.n_dets, cfg.cap_dets);
+        for (int d = 0; d < D; ++d) {
+            const float* r = s.dets + d * 6;
+            if (r[4] > cfg.det_thresh_f32) {
+                CropDesc c;
+                c.x1 = r[0]; c.y1 = r[1]; c.x2 = r[2]; c.y2 = r[3];
+                c.image = sidx;
+                c.out_row = sidx * cfg.cap_dets + d;
+                crops[n++] = c;
+            }
+        }
+    }
+    *n_crops = n;
+}
+
 // crop list for on-device ReID: one entry per first-round detection, ordered by (stream, detection).
 __global__ void k_build_crops(const TrkCfg cfg, TrkStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -189,14 +215,30 @@ static TrkCfg make_core_cfg(const BoxMOTB200TrackerConfig& p) {
 Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     if (p.n_streams < 1) throw std::runtime_error("n_streams must be >= 1");
     if (p.cap_tracks < 8 || p.cap_dets < 1) throw std::runtime_error("cap_tracks >= 8 and cap_dets >= 1 required");
-    if (p.tracker != BOXMOT_B200_TRACKER_BOTSORT && p.tracker != BOXMOT_B200_TRACKER_BYTETRACK)
+    if (p.tracker != BOXMOT_B200_TRACKER_BOTSORT && p.tracker != BOXMOT_B200_TRACKER_BYTETRACK &&
+        p.tracker != BOXMOT_B200_TRACKER_DEEPOCSORT)
         throw std::runtime_error("unknown tracker kind");
+    is_docs = p.tracker == BOXMOT_B200_TRACKER_DEEPOCSORT;
     if (p.tracker == BOXMOT_B200_TRACKER_BOTSORT && p.removed_stracks_buffer < 1)
         throw std::runtime_error("removed_stracks_buffer must be >= 1");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         throw std::runtime_error("no CUDA device: boxmot_b200 has no CPU fallback");
     cfg = make_core_cfg(p);
+    if (is_docs) {
+        if (p.delta_t < 1 || p.delta_t >= DOCS_RING) throw std::runtime_error("delta_t must be in [1, 7]");
+        if (p.max_age < 1 || p.max_age > 46) throw std::runtime_error("max_age must be in [1, 46] (reference history window)");
+        dcfg.cap_tracks = p.cap_tracks; dcfg.cap_dets = p.cap_dets; dcfg.feat_dim = p.feat_dim;
+        dcfg.delta_t = p.delta_t; dcfg.max_age = p.max_age; dcfg.min_hits = p.min_hits;
+        dcfg.embedding_off = p.embedding_off ? 1 : 0; dcfg.aw_off = p.aw_off ? 1 : 0;
+        dcfg.det_thresh_f32 = (float)p.det_thresh; dcfg.det_thresh = p.det_thresh;
+        dcfg.iou_threshold = p.iou_threshold; dcfg.inertia = p.inertia; dcfg.w_emb = p.w_association_emb;
+        dcfg.alpha_fixed = p.alpha_fixed_emb; dcfg.aw_param = p.aw_param; dcfg.q_xy = p.q_xy_scaling; dcfg.q_s = p.q_s_scaling;
+        // the shared staging code below reads these from the STrack-family config
+        cfg.with_reid = dcfg.embedding_off ? 0 : 1;
+        cfg.feat_dim = cfg.with_reid ? p.feat_dim : 0;
+        cfg.cap_tracks = p.cap_tracks; cfg.cap_dets = p.cap_dets;
+    }
     if (cfg.with_reid && cfg.feat_dim < 1) throw std::runtime_error("feat_dim must be set when with_reid");
     S = p.n_streams;
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -206,7 +248,9 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
             cfg.feat_dim = reid_feature_dim(reid);
         }
     }
-    stream_bytes = carve_stream(cfg, nullptr, nullptr, &persistent_bytes);
+    if (is_docs) dcfg.feat_dim = cfg.feat_dim;
+    stream_bytes = is_docs ? carve_docs(dcfg, nullptr, nullptr, &persistent_bytes)
+                           : carve_stream(cfg, nullptr, nullptr, &persistent_bytes);
     persistent_bytes = (persistent_bytes + 15) & ~(size_t)15;
     CUDA_OK(cudaMalloc(&d_mem, stream_bytes * S));
     CUDA_OK(cudaMemset(d_mem, 0, stream_bytes * S));
@@ -227,15 +271,31 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     if (cfg.with_reid) CUDA_OK(cudaMallocHost(&h_embs, sizeof(float) * F * CD * S));
     CUDA_OK(cudaMalloc(&d_out, sizeof(float) * 8 * CD * S));
     CUDA_OK(cudaMalloc(&d_scalars_out, sizeof(int) * SC_COUNT * S));
-    h_streams.resize(S);
-    for (int i = 0; i < S; ++i) {
-        carve_stream(cfg, d_mem + stream_bytes * i, &h_streams[i], nullptr);
-        h_streams[i].dets = d_dets + (size_t)i * CD * 6;
-        h_streams[i].n_dets = d_ndets + i;
-        h_streams[i].warp = d_warp + (size_t)i * 8;
+    out_ptr.resize(S); scalars_ptr.resize(S); timers_ptr.resize(S);
+    if (is_docs) {
+        h_docs.resize(S);
+        for (int i = 0; i < S; ++i) {
+            carve_docs(dcfg, d_mem + stream_bytes * i, &h_docs[i], nullptr);
+            h_docs[i].dets = d_dets + (size_t)i * CD * 6;
+            h_docs[i].n_dets = d_ndets + i;
+            h_docs[i].embs = cfg.with_reid ? d_embs + (size_t)i * CD * F : nullptr;
+            out_ptr[i] = h_docs[i].out; scalars_ptr[i] = h_docs[i].scalars; timers_ptr[i] = h_docs[i].timers;
+        }
+        CUDA_OK(cudaMalloc(&d_docs, sizeof(DocsStream) * S));
+        CUDA_OK(cudaMemcpy(d_docs, h_docs.data(), sizeof(DocsStream) * S, cudaMemcpyHostToDevice));
+        // ids start at 1 (KalmanBoxTracker.count = 1 in DeepOcSort.__init__); SC_NEXT_ID holds the last id used
+    } else {
+        h_streams.resize(S);
+        for (int i = 0; i < S; ++i) {
+            carve_stream(cfg, d_mem + stream_bytes * i, &h_streams[i], nullptr);
+            h_streams[i].dets = d_dets + (size_t)i * CD * 6;
+            h_streams[i].n_dets = d_ndets + i;
+            h_streams[i].warp = d_warp + (size_t)i * 8;
+            out_ptr[i] = h_streams[i].out; scalars_ptr[i] = h_streams[i].scalars; timers_ptr[i] = h_streams[i].timers;
+        }
+        CUDA_OK(cudaMalloc(&d_streams, sizeof(TrkStream) * S));
+        CUDA_OK(cudaMemcpy(d_streams, h_streams.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
     }
-    CUDA_OK(cudaMalloc(&d_streams, sizeof(TrkStream) * S));
-    CUDA_OK(cudaMemcpy(d_streams, h_streams.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
     if (reid) {
         CUDA_OK(cudaMalloc(&d_crops, sizeof(CropDesc) * CD * S));
         CUDA_OK(cudaMalloc(&d_ncrops, sizeof(int)));
@@ -253,7 +313,7 @@ Engine::~Engine() {
     cudaStreamSynchronize(stream);
     if (reid) reid_free(reid);
     cudaFree(d_warp); cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
-    cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
+    cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_docs); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
     cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
     cudaFreeHost(h_embs); cudaFreeHost(h_images); cudaFreeHost(h_ndets_ring);
     cudaEventDestroy(mark[0]); cudaEventDestroy(mark[1]);
@@ -262,6 +322,12 @@ Engine::~Engine() {
 }
 
 void Engine::reset() {
+    if (is_docs) {
+        CUDA_OK(cudaStreamSynchronize(stream));
+        for (int i = 0; i < S; ++i) CUDA_OK(cudaMemsetAsync(d_mem + stream_bytes * i, 0, persistent_bytes, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        return;
+    }
     k_reset_streams<<<S, 256, 0, stream>>>(d_streams, persistent_bytes);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -282,6 +348,29 @@ void Engine::ensure_images(int rows, int cols, bool host_too) {
 void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total) {
     launches = 0;
     CUDA_OK(cudaEventRecord(ev[0], stream));
+    if (is_docs) {
+        if (cfg.with_reid && !embs_dev) {
+            if (!reid) throw std::runtime_error("DeepOCSORT needs embeddings, a ReID model, or embedding_off");
+            if (!images_dev) throw std::runtime_error("ReID inside update() needs an image");
+            k_build_crops_docs<<<1, 32, 0, stream>>>(dcfg, d_docs, S, d_crops, d_ncrops);
+            ++launches;
+            launches += reid_forward(reid, images_dev, (size_t)rows * cols * 3, rows, cols, d_crops, d_ncrops,
+                                     max_dets_total, d_embs, cfg.feat_dim, stream);
+        }
+        CUDA_OK(cudaEventRecord(ev[1], stream));
+        k_docs_frame<<<S, 256, 0, stream>>>(dcfg, d_docs);
+        ++launches;
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaEventRecord(ev[2], stream));
+        if (profile) {
+            CUDA_OK(cudaStreamSynchronize(stream));
+            float b = 0.f;
+            cudaEventElapsedTime(&b, ev[1], ev[2]);
+            assoc_ms_accum += b;
+            assoc_frames += 1;
+        }
+        return;
+    }
     if (cfg.with_reid) {
         const float* src = embs_dev;
         if (!src) {
@@ -331,7 +420,7 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
 
 void Engine::set_warp(int sidx, const double* warp6) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
-    if (cfg.kind != KIND_XYWH) throw std::runtime_error("camera-motion warps apply to BoT-SORT only");
+    if (is_docs || cfg.kind != KIND_XYWH) throw std::runtime_error("camera-motion warps apply to BoT-SORT only");
     double w[8] = {warp6[0], warp6[1], warp6[2], warp6[3], warp6[4], warp6[5], 1.0, 0.0};
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaMemcpy(d_warp + (size_t)sidx * 8, w, sizeof(w), cudaMemcpyHostToDevice));
@@ -341,8 +430,8 @@ void Engine::set_warp(int sidx, const double* warp6) {
 void Engine::read_timers(int sidx, long long* out16, bool reset) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
     CUDA_OK(cudaStreamSynchronize(stream));
-    CUDA_OK(cudaMemcpy(out16, h_streams[sidx].timers, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
-    if (reset) CUDA_OK(cudaMemset(h_streams[sidx].timers, 0, sizeof(long long) * 16));
+    CUDA_OK(cudaMemcpy(out16, timers_ptr[sidx], sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+    if (reset) CUDA_OK(cudaMemset(timers_ptr[sidx], 0, sizeof(long long) * 16));
 }
 
 void Engine::set_profile(bool on) {
@@ -378,9 +467,9 @@ double Engine::marks_elapsed_ms() {
 
 void Engine::enqueue_fetch() {
     // gather every stream's rows + scalars into pinned memory (two strided copies)
-    CUDA_OK(cudaMemcpy2DAsync(h_out, sizeof(float) * 8 * cfg.cap_dets, h_streams[0].out, stream_bytes,
+    CUDA_OK(cudaMemcpy2DAsync(h_out, sizeof(float) * 8 * cfg.cap_dets, out_ptr[0], stream_bytes,
                               sizeof(float) * 8 * cfg.cap_dets, S, cudaMemcpyDeviceToHost, stream));
-    CUDA_OK(cudaMemcpy2DAsync(h_scalars, sizeof(int) * SC_COUNT, h_streams[0].scalars, stream_bytes,
+    CUDA_OK(cudaMemcpy2DAsync(h_scalars, sizeof(int) * SC_COUNT, scalars_ptr[0], stream_bytes,
                               sizeof(int) * SC_COUNT, S, cudaMemcpyDeviceToHost, stream));
 }
 
@@ -485,6 +574,27 @@ void Engine::fetch(float* const* out, const int* out_cap, int* out_rows) {
 int Engine::snapshot(int sidx, int* ids, double* means, double* covs, int cap) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
     CUDA_OK(cudaStreamSynchronize(stream));
+    if (is_docs) {
+        const DocsStream& s = h_docs[sidx];
+        const int CT = cfg.cap_tracks;
+        std::vector<int> sc(SC_COUNT), lst(CT), idv(CT);
+        std::vector<double> xs((size_t)CT * 8), ps((size_t)CT * 56);
+        CUDA_OK(cudaMemcpy(sc.data(), s.scalars, sizeof(int) * SC_COUNT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(lst.data(), s.tracks, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(idv.data(), s.id, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(xs.data(), s.x, sizeof(double) * 8 * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(ps.data(), s.P, sizeof(double) * 56 * CT, cudaMemcpyDeviceToHost));
+        int n = 0;
+        for (int k = 0; k < sc[SC_N_ACTIVE] && n < cap; ++k, ++n) {
+            const int t = lst[k];
+            ids[n] = idv[t];
+            for (int i = 0; i < 8; ++i) means[(size_t)n * 8 + i] = i < 7 ? xs[(size_t)t * 8 + i] : 0.0;
+            for (int i = 0; i < 64; ++i) covs[(size_t)n * 64 + i] = 0.0;
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 7; ++j) covs[(size_t)n * 64 + i * 8 + j] = ps[(size_t)t * 56 + i * 7 + j];
+        }
+        return n;
+    }
     const TrkStream& s = h_streams[sidx];
     const int CT = cfg.cap_tracks;
     std::vector<int> sc(SC_COUNT), act(CT), lost(CT), idv(CT);
@@ -515,6 +625,45 @@ int Engine::snapshot(int sidx, int* ids, double* means, double* covs, int cap) {
 __global__ void __launch_bounds__(256) k_lap_only(const TrkCfg cfg, TrkStream* streams, int T, int D, double thresh) {
     TrkStream s = streams[blockIdx.x];
     lap_solve(s, T, D, cfg.cap_dets, thresh);
+}
+
+__global__ void __launch_bounds__(256) k_jv_only(DocsStream* streams, int n, int ld) {
+    DocsStream s = streams[blockIdx.x];
+    jv_dense_solve(s, n, ld);
+}
+
+// lapjv(cost, extend_cost=True) on an (R, C) float64 host matrix with lapjv's own tie-breaking
+void standalone_jv(const double* cost, int R, int C, int* x, int* y) {
+    if (R < 0 || C < 0) throw std::runtime_error("negative shape");
+    const int n = R > C ? R : C;
+    if (n == 0) return;
+    DocsCfg c{};
+    c.cap_tracks = n < 8 ? 8 : n;
+    c.cap_dets = n < 8 ? 8 : n;
+    c.feat_dim = 0;
+    const int ld = c.cap_tracks;
+    size_t bytes = carve_docs(c, nullptr, nullptr, nullptr);
+    uint8_t* mem = nullptr;
+    DocsStream hs, *ds = nullptr;
+    CUDA_OK(cudaMalloc(&mem, bytes));
+    CUDA_OK(cudaMemset(mem, 0, bytes));
+    carve_docs(c, mem, &hs, nullptr);
+    std::vector<double> sq((size_t)n * ld, 0.0);
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < C; ++j) sq[(size_t)i * ld + j] = cost[(size_t)i * C + j];
+    CUDA_OK(cudaMalloc(&ds, sizeof(DocsStream)));
+    CUDA_OK(cudaMemcpy(ds, &hs, sizeof(DocsStream), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(hs.cost, sq.data(), sizeof(double) * sq.size(), cudaMemcpyHostToDevice));
+    k_jv_only<<<1, 256>>>(ds, n, ld);
+    std::vector<int> hx(n), hy(n);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(hx.data(), hs.lap_x, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(hy.data(), hs.lap_y, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    cudaFree(mem);
+    cudaFree(ds);
+    CUDA_OK(e);
+    for (int i = 0; i < R; ++i) x[i] = hx[i] < C ? hx[i] : -1;
+    for (int j = 0; j < C; ++j) y[j] = hy[j] < R ? hy[j] : -1;
 }
 
 void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int* y) {

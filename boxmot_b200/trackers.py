@@ -123,8 +123,26 @@ class MultiStreamTracker:
             cfg.removed_stracks_buffer = int(p["removed_stracks_buffer"])
             cfg.with_reid = int(bool(p["with_reid"]))
             cfg.fuse_first_associate = int(bool(p["fuse_first_associate"]))
+        elif kind == "deepocsort":
+            p = dict(delta_t=3, inertia=0.2, w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5,
+                     embedding_off=False, aw_off=False, Q_xy_scaling=0.01, Q_s_scaling=0.0001, det_thresh=0.3,
+                     max_age=30, min_hits=3, iou_threshold=0.3)
+            unknown = set(params) - set(p)
+            if unknown:
+                raise TypeError(f"unknown DeepOcSort parameters: {sorted(unknown)}")
+            p.update(params)
+            cfg.tracker = _lib.TRACKER_DEEPOCSORT
+            cfg.delta_t, cfg.max_age, cfg.min_hits = int(p["delta_t"]), int(p["max_age"]), int(p["min_hits"])
+            cfg.embedding_off, cfg.aw_off = int(bool(p["embedding_off"])), int(bool(p["aw_off"]))
+            cfg.det_thresh, cfg.iou_threshold, cfg.inertia = p["det_thresh"], p["iou_threshold"], p["inertia"]
+            cfg.w_association_emb, cfg.alpha_fixed_emb, cfg.aw_param = p["w_association_emb"], p["alpha_fixed_emb"], p["aw_param"]
+            cfg.q_xy_scaling, cfg.q_s_scaling = p["Q_xy_scaling"], p["Q_s_scaling"]
+            cfg.with_reid = int(not p["embedding_off"])
+            p.setdefault("track_buffer", 0)
+            p.setdefault("frame_rate", 30)
+            p["track_high_thresh"] = p["det_thresh"]  # detections above det_thresh are embedded
         else:
-            raise ValueError(f"tracker '{tracker}' is not part of the B200 hot path (bytetrack, botsort)")
+            raise ValueError(f"tracker '{tracker}' is not part of the B200 hot path (bytetrack, botsort, deepocsort)")
         cfg.n_streams = int(n_streams)
         cfg.cap_tracks = int(cap_tracks)
         cfg.cap_dets = int(cap_dets)
@@ -266,6 +284,8 @@ class _SingleStreamTracker:
         blob = getattr(reid_model, "blob_path", None)
         if reid_model is not None and blob is not None:
             feat_dim = int(getattr(reid_model, "feature_dim", feat_dim))
+        if self._kind == "deepocsort":  # BaseTracker settings that DeepOCSORT's update actually reads
+            params = dict(params, det_thresh=det_thresh, max_age=max_age, min_hits=min_hits, iou_threshold=iou_threshold)
         self._engine = MultiStreamTracker(self._kind, 1, cap_tracks, cap_dets, feat_dim, reid_blob=blob, **params)
         self.provides_reid = blob is not None
         self.with_reid = self._engine.with_reid
@@ -343,6 +363,26 @@ class BotSort(_SingleStreamTracker):
                          unconfirmed_match_thresh=unconfirmed_match_thresh,
                          unconfirmed_emb_scale=unconfirmed_emb_scale,
                          removed_stracks_buffer=removed_stracks_buffer, **kwargs)
+
+
+class DeepOcSort(_SingleStreamTracker):
+    """DeepOCSORT on the GPU; arguments as boxmot/trackers/bbox/deepocsort/deepocsort.py:263-300.  `cmc_off` must be
+    True (camera-motion estimation is outside this hot path)."""
+
+    _kind = "deepocsort"
+
+    def __init__(self, reid_model: Any = None, delta_t: int = 3, inertia: float = 0.2, w_association_emb: float = 0.5,
+                 alpha_fixed_emb: float = 0.95, aw_param: float = 0.5, embedding_off: bool = False,
+                 cmc_off: bool = True, aw_off: bool = False, Q_xy_scaling: float = 0.01, Q_s_scaling: float = 0.0001,
+                 det_thresh: float = 0.3, max_age: int = 30, min_hits: int = 3, iou_threshold: float = 0.3,
+                 **kwargs: Any):
+        if not cmc_off:
+            raise NotImplementedError("cmc_off=False: camera-motion compensation is out of scope (pass cmc_off=True)")
+        super().__init__(reid_model=None if embedding_off else reid_model, delta_t=delta_t, inertia=inertia,
+                         w_association_emb=w_association_emb, alpha_fixed_emb=alpha_fixed_emb, aw_param=aw_param,
+                         embedding_off=embedding_off, aw_off=aw_off, Q_xy_scaling=Q_xy_scaling,
+                         Q_s_scaling=Q_s_scaling, det_thresh=det_thresh, max_age=max_age, min_hits=min_hits,
+                         iou_threshold=iou_threshold, **kwargs)
 
 
 def create_tracker(tracker_type: str, reid_weights=None, device=None, half: bool = False, per_class: bool = False,

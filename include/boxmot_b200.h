@@ -112,6 +112,7 @@ BOXMOT_B200_API const char* boxmot_botsort_last_error(void);
 /* ------------------------------------------------------------------------------------------------ */
 #define BOXMOT_B200_TRACKER_BYTETRACK 0
 #define BOXMOT_B200_TRACKER_BOTSORT 1
+#define BOXMOT_B200_TRACKER_DEEPOCSORT 2
 
 /* Every parameter of the reference Python constructors (bytetrack.py:226-257, botsort.py:66-118), in
  * double precision so thresholds compare exactly as python floats do. */
@@ -136,6 +137,21 @@ typedef struct BoxMOTB200TrackerConfig {
     double appearance_thresh;
     double unconfirmed_emb_scale;
     const char* reid_model_path; /* optional .b200reid blob: ReID runs on-device inside update() */
+    /* DeepOCSORT (trackers/bbox/deepocsort/deepocsort.py:263-300 + BaseTracker det_thresh / max_age / min_hits /
+     * iou_threshold); ignored by the other trackers */
+    int delta_t;
+    int max_age;
+    int min_hits;
+    int embedding_off;
+    int aw_off;
+    double det_thresh;
+    double iou_threshold;
+    double inertia;
+    double w_association_emb;
+    double alpha_fixed_emb;
+    double aw_param;
+    double q_xy_scaling;
+    double q_s_scaling;
 } BoxMOTB200TrackerConfig;
 
 typedef struct BoxMOTB200Tracker BoxMOTB200Tracker;
@@ -197,6 +213,9 @@ BOXMOT_B200_API const char* boxmot_b200_last_error(void);
 /* Standalone hot-path kernels (parity tests and micro-benchmarks call these through the same library). */
 /* lapjv(extend_cost=True, cost_limit=thresh): cost (T,D) float64 host -> x (T), y (D) int32. */
 BOXMOT_B200_API int boxmot_b200_lap_solve(const double* cost, int rows, int cols, double cost_limit, int* x, int* y);
+/* lapjv(cost, extend_cost=True) (no cost limit, zero-padded to square) with lapjv's own tie-breaking -- the dense
+ * Jonker-Volgenant solver DeepOCSORT's association needs for bit-exact ids. cost (rows, cols) float64 host. */
+BOXMOT_B200_API int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y);
 /* batched Kalman steps on host arrays: kind 0 = XYAH, 1 = XYWH; mean (n,8), cov (n,8,8) float64 in place. */
 BOXMOT_B200_API int boxmot_b200_kalman_predict(int kind, double* mean, double* cov, const int* tracked, int n);
 BOXMOT_B200_API int boxmot_b200_kalman_update(int kind, double* mean, double* cov, const float* meas, int n);

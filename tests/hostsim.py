@@ -181,6 +181,15 @@ class HostSimDeepOcSort:
             raise RuntimeError(f"hostsim error {-m}")
         return out[:m].copy()
 
+    def jv(self, cost):
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        r, c = cost.shape
+        x = np.empty(max(r, 1), np.int32)
+        y = np.empty(max(c, 1), np.int32)
+        self.lib.docs_jv.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        assert self.lib.docs_jv(self.h, cost.ctypes.data, r, c, x.ctypes.data, y.ctypes.data) == 0
+        return x[:r], y[:c]
+
     def state_snapshot(self):
         cap = self.cfg.cap_tracks
         ids = np.empty(cap, np.int32)

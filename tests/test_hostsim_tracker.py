@@ -58,3 +58,23 @@ def test_hostsim_empty_and_capacity():
     assert trk.update(np.zeros((0, 6), np.float32)).shape == (0, 8)
     with pytest.raises(RuntimeError):
         trk.update(np.zeros((5, 6), np.float32))
+
+
+def _tie_heavy(rng, r, c):
+    """DeepOCSORT-shaped costs: mostly exact zeros, a few negative entries, some exact duplicates."""
+    cost = np.zeros((r, c))
+    k = rng.integers(0, r * c // 2 + 1)
+    cost.flat[rng.choice(r * c, size=k, replace=False)] = -np.round(rng.random(k), 2)  # rounded -> value ties
+    return cost
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_hostsim_dense_jv_reproduces_lapjv_ties(seed):
+    """The dense JV restatement must pick the SAME optimum as the oracle's lapjv among ties (ids depend on it)."""
+    rng = np.random.default_rng(seed)
+    r, c = rng.integers(1, 40, 2)
+    cost = _tie_heavy(rng, r, c)
+    sim = HostSimDeepOcSort(deepocsort_cfg(cap_tracks=64, cap_dets=64, feat_dim=0))
+    x, y = sim.jv(cost)
+    _, xo, yo = lapjv(cost, extend_cost=True)
+    assert np.array_equal(x, xo) and np.array_equal(y, yo)
