@@ -129,8 +129,27 @@ __global__ void __launch_bounds__(256) k_embedding_cost(const TrkCfg cfg, TrkStr
     }
 }
 
-__global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStream* streams) {
+// shared-memory residency of the dense JV solver's per-column / per-row state (prices, distances, column list, ...)
+__host__ __device__ inline size_t jv_smem_bytes(int MX) {
+    return (size_t)MX * (2 * sizeof(double) + 6 * sizeof(int)) + 16;
+}
+
+__global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStream* streams, int jv_in_smem) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     DocsStream s = streams[blockIdx.x];
+    if (jv_in_smem) {
+        const int MX = cfg.cap_tracks > cfg.cap_dets ? cfg.cap_tracks : cfg.cap_dets;
+        double* pd = reinterpret_cast<double*>(dyn_smem);
+        s.lap_v = pd; pd += MX;
+        s.lap_spc = pd; pd += MX;
+        int* pi = reinterpret_cast<int*>(pd);
+        s.lap_x = pi; pi += MX;
+        s.lap_y = pi; pi += MX;
+        s.lap_path = pi; pi += MX;
+        s.lap_tl = pi; pi += MX;
+        s.lap_sc = pi; pi += MX;
+        s.lap_insc = pi;
+    }
     docs_frame(cfg, s);
 }
 
@@ -358,7 +377,14 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
                                      max_dets_total, d_embs, cfg.feat_dim, stream);
         }
         CUDA_OK(cudaEventRecord(ev[1], stream));
-        k_docs_frame<<<S, 256, 0, stream>>>(dcfg, d_docs);
+        {
+            const int MX = dcfg.cap_tracks > dcfg.cap_dets ? dcfg.cap_tracks : dcfg.cap_dets;
+            const size_t jb = jv_smem_bytes(MX);
+            const bool in_smem = jb <= 200 * 1024;
+            if (in_smem && jb > 48 * 1024)
+                CUDA_OK(cudaFuncSetAttribute(k_docs_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb));
+            k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, d_docs, in_smem ? 1 : 0);
+        }
         ++launches;
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaEventRecord(ev[2], stream));
