@@ -154,45 +154,50 @@ __global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStrea
 }
 
 // DeepOCSORT embeds every detection above det_thresh (deepocsort.py:333-343)
+// ordered (stream, detection) crop list built by one warp with ballot compaction
+template <typename Keep>
+__device__ __forceinline__ int append_crops(const float* dets, int D, int sidx, int cap_dets, CropDesc* crops, int n, Keep keep) {
+    const int lane = threadIdx.x & 31;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        const int d = d0 + lane;
+        const bool p = d < D && keep(dets + d * 6);
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (p) {
+            const float* r = dets + d * 6;
+            CropDesc c;
+            c.x1 = r[0]; c.y1 = r[1]; c.x2 = r[2]; c.y2 = r[3];
+            c.image = sidx;
+            c.out_row = sidx * cap_dets + d;
+            crops[n + __popc(m & ((1u << lane) - 1u))] = c;
+        }
+        n += __popc(m);
+    }
+    return n;
+}
+
 __global__ void k_build_crops_docs(const DocsCfg cfg, DocsStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x >= 32 || blockIdx.x != 0) return;
     int n = 0;
     for (int sidx = 0; sidx < n_streams; ++sidx) {
         const DocsStream& s = streams[sidx];
-        const int D = min(*s.n_dets, cfg.cap_dets);
-        for (int d = 0; d < D; ++d) {
-            const float* r = s.dets + d * 6;
-            if (r[4] > cfg.det_thresh_f32) {
-                CropDesc c;
-                c.x1 = r[0]; c.y1 = r[1]; c.x2 = r[2]; c.y2 = r[3];
-                c.image = sidx;
-                c.out_row = sidx * cfg.cap_dets + d;
-                crops[n++] = c;
-            }
-        }
+        const float thr = cfg.det_thresh_f32;
+        n = append_crops(s.dets, min(*s.n_dets, cfg.cap_dets), sidx, cfg.cap_dets, crops, n,
+                         [thr](const float* r) { return r[4] > thr; });
     }
-    *n_crops = n;
+    if (threadIdx.x == 0) *n_crops = n;
 }
 
 // crop list for on-device ReID: one entry per first-round detection, ordered by (stream, detection).
 __global__ void k_build_crops(const TrkCfg cfg, TrkStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x >= 32 || blockIdx.x != 0) return;
     int n = 0;
     for (int sidx = 0; sidx < n_streams; ++sidx) {
         const TrkStream& s = streams[sidx];
-        const int D = min(*s.n_dets, cfg.cap_dets);
-        for (int d = 0; d < D; ++d) {
-            const float* r = s.dets + d * 6;
-            if ((double)r[4] > cfg.high_thresh) {
-                CropDesc c;
-                c.x1 = r[0]; c.y1 = r[1]; c.x2 = r[2]; c.y2 = r[3];
-                c.image = sidx;
-                c.out_row = sidx * cfg.cap_dets + d;
-                crops[n++] = c;
-            }
-        }
+        const double thr = cfg.high_thresh;
+        n = append_crops(s.dets, min(*s.n_dets, cfg.cap_dets), sidx, cfg.cap_dets, crops, n,
+                         [thr](const float* r) { return (double)r[4] > thr; });
     }
-    *n_crops = n;
+    if (threadIdx.x == 0) *n_crops = n;
 }
 
 __global__ void k_reset_streams(TrkStream* streams, size_t persistent_bytes) {
