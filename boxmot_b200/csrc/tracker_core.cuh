@@ -76,7 +76,7 @@ enum {
     MB_N_FIRST = 0, MB_N_SECOND, MB_N_UNC, MB_N_POOL0, MB_N_POOL, MB_N_ACT, MB_N_REFIND, MB_N_EMA, MB_N_RT,
     MB_N_REST, MB_N_LOSTNOW, MB_N_REMNOW, MB_N_BIRTH, MB_M1, MB_M2, MB_M3, MB_Q1, MB_Q2, MB_COUNT = 32
 };
-enum { ERR_NONE = 0, ERR_TRACK_CAPACITY = 1, ERR_CLS_HIST = 2, ERR_DET_CAPACITY = 3 };
+enum { ERR_NONE = 0, ERR_TRACK_CAPACITY = 1, ERR_CLS_HIST = 2, ERR_DET_CAPACITY = 3, ERR_LSA_INFEASIBLE = 4 };
 
 struct TrkCfg {
     int kind;             // KIND_XYAH (ByteTrack) / KIND_XYWH (BoT-SORT)

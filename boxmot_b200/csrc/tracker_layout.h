@@ -140,3 +140,45 @@ inline size_t carve_docs(const DocsCfg& c, uint8_t* base, DocsStream* s, size_t*
 }
 
 }  // namespace bmb
+
+#include "ss_core.cuh"
+
+namespace bmb {
+
+// StrongSORT: the sample gallery ([CT][budget][F] float32) dominates; it sits behind the zero-on-reset region
+// (gal_n = 0 is all a reset needs).
+inline size_t carve_ss(const SsCfg& c, uint8_t* base, SsStream* s, size_t* persistent_bytes) {
+    const size_t CT = (size_t)c.cap_tracks, CD = (size_t)c.cap_dets, F = (size_t)(c.feat_dim > 0 ? c.feat_dim : 1);
+    const size_t B = (size_t)(c.budget > 0 ? c.budget : 1);
+    const size_t MX = CT > CD ? CT : CD;
+    Carver k{base, 0};
+    SsStream t{};
+    t.scalars = k.take<int>(SC_COUNT);
+    t.timers = k.take<long long>(16);
+    t.state = k.take<int>(CT); t.id = k.take<int>(CT); t.hits = k.take<int>(CT); t.age = k.take<int>(CT);
+    t.tsu = k.take<int>(CT); t.gal_n = k.take<int>(CT); t.gal_head = k.take<int>(CT);
+    t.pend_kind = k.take<int>(CT); t.pend_det = k.take<int>(CT); t.tracks = k.take<int>(CT);
+    t.conf = k.take<double>(CT); t.cls = k.take<double>(CT); t.det_ind = k.take<double>(CT);
+    t.mean = k.take<double>(CT * 8); t.cov = k.take<double>(CT * 64);
+    if (persistent_bytes) *persistent_bytes = k.off;
+    t.feat = k.take<float>(CT * F);
+    t.gal = k.take<float>(CT * B * F);
+    t.dfeatn = k.take<float>(CD * F);
+    t.appc = k.take<float>(CT * CD);
+    t.kdet = k.take<int>(CD);
+    t.dtlwh = k.take<double>(CD * 4); t.dxyah = k.take<double>(CD * 4); t.dconf = k.take<double>(CD);
+    t.tproj = k.take<double>(CT * 20);
+    t.cost = k.take<double>(CT * CD);
+    t.conf_pos = k.take<int>(CT); t.cand = k.take<int>(CT); t.unta = k.take<int>(CT); t.mdet = k.take<int>(CT);
+    t.rowcol = k.take<int>(CT); t.colrow = k.take<int>(CD); t.und = k.take<int>(CD); t.und2 = k.take<int>(CD);
+    t.tmp_a = k.take<int>(CT + CD); t.mark = k.take<int>(CT); t.free_l = k.take<int>(CT + MB_COUNT);
+    t.set_buf = k.take<int>(4 * (8 * CT + 16));
+    t.lsa_u = k.take<double>(MX); t.lsa_v = k.take<double>(MX); t.lsa_spc = k.take<double>(MX);
+    t.lsa_path = k.take<int>(MX); t.lsa_row4col = k.take<int>(MX); t.lsa_col4row = k.take<int>(MX);
+    t.lsa_rem = k.take<int>(MX); t.lsa_sr = k.take<int>(MX); t.lsa_sc = k.take<int>(MX);
+    t.out = k.take<float>(CD * 8);
+    if (s) *s = t;
+    return (k.off + 255) & ~(size_t)255;
+}
+
+}  // namespace bmb

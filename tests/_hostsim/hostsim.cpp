@@ -172,4 +172,106 @@ int hostsim_lap(HostSim* h, const double* cost, int T, int D, double thresh, int
     memcpy(y, h->s.lap_y, sizeof(int) * D);
     return 0;
 }
+
+// ---- StrongSORT host simulation ---------------------------------------------------------------------------------
+struct SsSim {
+    SsCfg cfg;
+    SsStream s;
+    std::vector<uint8_t> mem;
+    std::vector<float> dets, embs;
+    int n_dets;
+    double warp[8];
+};
+
+SsSim* ss_create(const SsCfg* cfg) {
+    SsSim* h = new SsSim();
+    h->cfg = *cfg;
+    size_t bytes = carve_ss(h->cfg, nullptr, nullptr, nullptr);
+    h->mem.assign(bytes, 0);
+    carve_ss(h->cfg, h->mem.data(), &h->s, nullptr);
+    h->dets.assign((size_t)cfg->cap_dets * 6, 0.f);
+    h->embs.assign((size_t)cfg->cap_dets * (cfg->feat_dim > 0 ? cfg->feat_dim : 1), 0.f);
+    h->s.dets = h->dets.data();
+    h->s.n_dets = &h->n_dets;
+    h->s.embs = h->embs.data();
+    for (double& w : h->warp) w = 0.0;
+    h->s.warp = h->warp;
+    return h;
+}
+void ss_destroy(SsSim* h) { delete h; }
+int ss_cfg_size() { return (int)sizeof(SsCfg); }
+void ss_set_warp(SsSim* h, const double* w6) {
+    for (int i = 0; i < 6; ++i) h->warp[i] = w6[i];
+    h->warp[6] = 1.0;
+}
+
+int ss_update(SsSim* h, const float* dets, int n, const float* embs, float* out) {
+    const SsCfg& c = h->cfg;
+    if (n > c.cap_dets) return -ERR_DET_CAPACITY;
+    h->n_dets = n;
+    if (n) memcpy(h->dets.data(), dets, sizeof(float) * 6 * n);
+    if (n) memcpy(h->embs.data(), embs, sizeof(float) * (size_t)c.feat_dim * n);
+    for (int d = 0; d < n; ++d) ss_prepare_row(c, h->s, d);
+    for (int k = 0; k < h->s.scalars[SC_N_ACTIVE]; ++k) {
+        const int t = h->s.tracks[k];
+        if (h->s.state[t] != SS_CONFIRMED) continue;
+        for (int d = 0; d < n; ++d) h->s.appc[(size_t)t * c.cap_dets + d] = ss_nn_cosine(c, h->s, t, d);
+    }
+    ss_frame(c, h->s);
+    h->warp[6] = 0.0;
+    for (int k = 0; k < h->s.scalars[SC_N_ACTIVE]; ++k) ss_features_pos(c, h->s, k);
+    if (h->s.scalars[SC_ERROR]) return -h->s.scalars[SC_ERROR];
+    const int m = h->s.scalars[SC_N_OUT];
+    memcpy(out, h->s.out, sizeof(float) * 8 * m);
+    return m;
+}
+
+int ss_snapshot(SsSim* h, int* ids, double* means, double* covs, int cap) {
+    int n = 0;
+    for (int k = 0; k < h->s.scalars[SC_N_ACTIVE] && n < cap; ++k, ++n) {
+        const int t = h->s.tracks[k];
+        ids[n] = h->s.id[t];
+        memcpy(means + (size_t)n * 8, h->s.mean + (size_t)t * 8, sizeof(double) * 8);
+        memcpy(covs + (size_t)n * 64, h->s.cov + (size_t)t * 64, sizeof(double) * 64);
+    }
+    return n;
+}
+
+// scipy.optimize.linear_sum_assignment(cost (R, C)) -> row_ind, col_ind (min(R, C) pairs, rows ascending)
+int ss_lsa(SsSim* h, const double* cost, int R, int C, int* row_ind, int* col_ind) {
+    const SsCfg& c = h->cfg;
+    if ((size_t)R * C > (size_t)c.cap_tracks * c.cap_dets) return -1;
+    const int MX = c.cap_tracks > c.cap_dets ? c.cap_tracks : c.cap_dets;
+    if (R > MX || C > MX) return -1;
+    const bool tr = C < R;
+    const int nr = tr ? C : R, nc = tr ? R : C;
+    for (int r = 0; r < R; ++r)
+        for (int q = 0; q < C; ++q) h->s.cost[tr ? (size_t)q * nc + r : (size_t)r * nc + q] = cost[(size_t)r * C + q];
+    lsa_solve(h->s, h->s.cost, nr, nc, nc);
+    if (h->s.scalars[SC_ERROR]) { h->s.scalars[SC_ERROR] = 0; return -2; }
+    int n = 0;
+    if (!tr) {
+        for (int i = 0; i < nr; ++i) { row_ind[n] = i; col_ind[n] = h->s.lsa_col4row[i]; ++n; }
+    } else {
+        for (int r = 0; r < R; ++r)
+            if (h->s.lsa_row4col[r] >= 0) { row_ind[n] = r; col_ind[n] = h->s.lsa_row4col[r]; ++n; }
+    }
+    return n;
+}
+
+// list(set(a) - set(b)): a ascending, in_b[k] flags the members of b; returns the count
+int ss_pyset_difference(SsSim* h, const int* a, int na, const unsigned char* in_b, int* out) {
+    const SsCfg& c = h->cfg;
+    if (na > c.cap_tracks) return -1;
+    std::vector<unsigned char> flag(na ? a[na - 1] + 1 : 1, 0);
+    int nb = 0, n = 0, umax = -1;
+    for (int k = 0; k < na; ++k) {
+        if (in_b[k]) { flag[a[k]] = 1; ++nb; }
+        else { out[n++] = a[k]; umax = a[k]; }
+    }
+    if (na == 0 || pyset_difference_is_ascending(na, a[na - 1], nb, umax)) return n;
+    const size_t stride = (size_t)8 * c.cap_tracks + 16;
+    return pyset_difference(a, na, nb, [&](int key) { return flag[key] != 0; }, out, h->s.tmp_a, h->s.set_buf,
+                            h->s.set_buf + stride, h->s.set_buf + 2 * stride, h->s.set_buf + 3 * stride);
+}
 }

@@ -33,7 +33,7 @@ class TrkCfg(ctypes.Structure):
 
 
 def build():
-    deps = [SRC, CSRC / "tracker_core.cuh", CSRC / "tracker_layout.h"]
+    deps = [SRC] + sorted(CSRC.glob("*.cuh")) + [CSRC / "tracker_layout.h"]
     if OUT.exists() and all(OUT.stat().st_mtime >= d.stat().st_mtime for d in deps):
         return OUT
     tmp = OUT.with_suffix(f".{os.getpid()}.tmp.so")
@@ -197,3 +197,77 @@ class HostSimDeepOcSort:
         ps = np.empty((cap, 7, 7))
         n = self.lib.docs_snapshot(self.h, ids.ctypes.data, xs.ctypes.data, ps.ctypes.data, cap)
         return {int(ids[i]): (xs[i].copy(), ps[i].copy()) for i in range(n)}
+
+
+class SsCfg(ctypes.Structure):
+    _fields_ = [("cap_tracks", ctypes.c_int), ("cap_dets", ctypes.c_int), ("feat_dim", ctypes.c_int),
+                ("n_init", ctypes.c_int), ("max_age", ctypes.c_int), ("budget", ctypes.c_int),
+                ("min_conf", ctypes.c_double), ("max_cos_dist", ctypes.c_double), ("max_iou_dist", ctypes.c_double),
+                ("mc_lambda", ctypes.c_double), ("ema_alpha", ctypes.c_double)]
+
+
+def strongsort_cfg(min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3, nn_budget=100, mc_lambda=0.98,
+                   ema_alpha=0.9, max_age=30, feat_dim=96, cap_tracks=256, cap_dets=128):
+    c = SsCfg()
+    c.cap_tracks, c.cap_dets, c.feat_dim, c.n_init, c.max_age, c.budget = cap_tracks, cap_dets, feat_dim, n_init, max_age, nn_budget
+    c.min_conf, c.max_cos_dist, c.max_iou_dist, c.mc_lambda, c.ema_alpha = min_conf, max_cos_dist, max_iou_dist, mc_lambda, ema_alpha
+    return c
+
+
+class HostSimStrongSort:
+    def __init__(self, cfg: SsCfg):
+        self.lib = ctypes.CDLL(str(build()))
+        assert self.lib.ss_cfg_size() == ctypes.sizeof(SsCfg)
+        self.lib.ss_create.restype = ctypes.c_void_p
+        self.lib.ss_create.argtypes = [ctypes.POINTER(SsCfg)]
+        self.lib.ss_update.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.ss_snapshot.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int]
+        self.lib.ss_set_warp.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.ss_lsa.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.ss_pyset_difference.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        self.lib.ss_destroy.argtypes = [ctypes.c_void_p]
+        self.cfg = cfg
+        self.h = self.lib.ss_create(ctypes.byref(cfg))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ss_destroy(self.h)
+            self.h = None
+
+    def update(self, dets, img=None, embs=None, warp=None):
+        if warp is not None:
+            w = np.ascontiguousarray(warp, dtype=np.float64).reshape(6)
+            self.lib.ss_set_warp(self.h, w.ctypes.data)
+        dets = np.ascontiguousarray(dets, dtype=np.float32).reshape(-1, 6)
+        n = len(dets)
+        out = np.empty((max(n, 1), 8), np.float32)
+        e = np.ascontiguousarray(embs, dtype=np.float32).reshape(n, -1) if n else np.zeros((1, self.cfg.feat_dim), np.float32)
+        m = self.lib.ss_update(self.h, dets.ctypes.data, n, e.ctypes.data, out.ctypes.data)
+        if m < 0:
+            raise RuntimeError(f"hostsim error {-m}")
+        return out[:m].copy()
+
+    def lsa(self, cost):
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        r, c = cost.shape
+        ri = np.empty(max(min(r, c), 1), np.int32)
+        ci = np.empty(max(min(r, c), 1), np.int32)
+        n = self.lib.ss_lsa(self.h, cost.ctypes.data, r, c, ri.ctypes.data, ci.ctypes.data)
+        assert n >= 0, n
+        return ri[:n].copy(), ci[:n].copy()
+
+    def set_difference(self, a, in_b):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        f = np.ascontiguousarray(in_b, dtype=np.uint8)
+        out = np.empty(max(len(a), 1), np.int32)
+        n = self.lib.ss_pyset_difference(self.h, a.ctypes.data, len(a), f.ctypes.data, out.ctypes.data)
+        assert n >= 0
+        return out[:n].tolist()
+
+    def state_snapshot(self):
+        cap = self.cfg.cap_tracks
+        ids = np.empty(cap, np.int32)
+        means = np.empty((cap, 8))
+        covs = np.empty((cap, 8, 8))
+        n = self.lib.ss_snapshot(self.h, ids.ctypes.data, means.ctypes.data, covs.ctypes.data, cap)
+        return {int(ids[i]): (means[i].copy(), covs[i].copy()) for i in range(n)}
