@@ -15,6 +15,7 @@ LIB_PATH = PKG / "libboxmot_b200.so"
 TRACKER_BYTETRACK = 0
 TRACKER_BOTSORT = 1
 TRACKER_DEEPOCSORT = 2
+TRACKER_STRONGSORT = 3
 
 
 class BoxMOTByteTrackConfig(ctypes.Structure):
@@ -42,7 +43,9 @@ class BoxMOTB200TrackerConfig(ctypes.Structure):
                 ("delta_t", c_int), ("max_age", c_int), ("min_hits", c_int), ("embedding_off", c_int),
                 ("aw_off", c_int), ("det_thresh", c_double), ("iou_threshold", c_double), ("inertia", c_double),
                 ("w_association_emb", c_double), ("alpha_fixed_emb", c_double), ("aw_param", c_double),
-                ("q_xy_scaling", c_double), ("q_s_scaling", c_double)]
+                ("q_xy_scaling", c_double), ("q_s_scaling", c_double),
+                ("n_init", c_int), ("nn_budget", c_int), ("min_conf", c_double), ("max_cos_dist", c_double),
+                ("max_iou_dist", c_double), ("mc_lambda", c_double), ("ema_alpha", c_double)]
 
 
 # every symbol include/boxmot_b200.h declares: name -> (restype, argtypes)
@@ -93,6 +96,7 @@ SYMBOLS = {
     "boxmot_b200_tracker_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "boxmot_b200_last_error": (c_char_p, []),
     "boxmot_b200_jv_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "boxmot_b200_lsa_solve": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int)]),
     "boxmot_b200_lap_solve": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "boxmot_b200_kalman_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),
     "boxmot_b200_kalman_update": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),

@@ -10,6 +10,7 @@
 #include "../../include/boxmot_b200.h"
 #include "tracker_core.cuh"
 #include "docs_core.cuh"
+#include "ss_core.cuh"
 
 namespace bmb {
 
@@ -56,6 +57,10 @@ struct Engine {
     DocsCfg dcfg{};
     DocsStream* d_docs = nullptr;
     std::vector<DocsStream> h_docs;
+    bool is_ss = false;                // StrongSORT engine (ss_core.cuh)
+    SsCfg scfg{};
+    SsStream* d_ss = nullptr;
+    std::vector<SsStream> h_ss;
     std::vector<float*> out_ptr;       // per-stream output rows / scalars / timers (either family)
     std::vector<int*> scalars_ptr;
     std::vector<long long*> timers_ptr;
@@ -113,6 +118,12 @@ struct Engine {
     void enqueue_fetch();
     void finish_fetch(float* const* out, const int* out_cap, int* out_rows);
 };
+
+// ---- StrongSORT kernels (ss_kernels.cu) ---------------------------------------------------------------------
+void ss_build_crops(const SsCfg& cfg, SsStream* d_streams, int S, CropDesc* crops, int* n_crops, cudaStream_t stream);
+// unit detection rows -> gallery distances -> per-stream frame -> appearance / gallery update; returns launches
+int ss_enqueue_frame(const SsCfg& cfg, SsStream* d_streams, int S, cudaStream_t stream);
+int standalone_lsa(const double* cost, int R, int C, int* row_ind, int* col_ind);
 
 void standalone_jv(const double* cost, int R, int C, int* x, int* y);
 void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int* y);

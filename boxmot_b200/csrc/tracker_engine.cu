@@ -240,9 +240,10 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     if (p.n_streams < 1) throw std::runtime_error("n_streams must be >= 1");
     if (p.cap_tracks < 8 || p.cap_dets < 1) throw std::runtime_error("cap_tracks >= 8 and cap_dets >= 1 required");
     if (p.tracker != BOXMOT_B200_TRACKER_BOTSORT && p.tracker != BOXMOT_B200_TRACKER_BYTETRACK &&
-        p.tracker != BOXMOT_B200_TRACKER_DEEPOCSORT)
+        p.tracker != BOXMOT_B200_TRACKER_DEEPOCSORT && p.tracker != BOXMOT_B200_TRACKER_STRONGSORT)
         throw std::runtime_error("unknown tracker kind");
     is_docs = p.tracker == BOXMOT_B200_TRACKER_DEEPOCSORT;
+    is_ss = p.tracker == BOXMOT_B200_TRACKER_STRONGSORT;
     if (p.tracker == BOXMOT_B200_TRACKER_BOTSORT && p.removed_stracks_buffer < 1)
         throw std::runtime_error("removed_stracks_buffer must be >= 1");
     int ndev = 0;
@@ -263,6 +264,18 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
         cfg.feat_dim = cfg.with_reid ? p.feat_dim : 0;
         cfg.cap_tracks = p.cap_tracks; cfg.cap_dets = p.cap_dets;
     }
+    if (is_ss) {
+        if (p.n_init < 1) throw std::runtime_error("n_init must be >= 1");
+        if (p.nn_budget < 1) throw std::runtime_error("nn_budget must be >= 1 (the reference's None = unbounded is not supported)");
+        if (p.max_age < 1) throw std::runtime_error("max_age must be >= 1");
+        scfg.cap_tracks = p.cap_tracks; scfg.cap_dets = p.cap_dets; scfg.feat_dim = p.feat_dim;
+        scfg.n_init = p.n_init; scfg.max_age = p.max_age; scfg.budget = p.nn_budget;
+        scfg.min_conf = p.min_conf; scfg.max_cos_dist = p.max_cos_dist; scfg.max_iou_dist = p.max_iou_dist;
+        scfg.mc_lambda = p.mc_lambda; scfg.ema_alpha = p.ema_alpha;
+        cfg.with_reid = 1;   // StrongSORT always associates on appearance
+        cfg.feat_dim = p.feat_dim;
+        cfg.cap_tracks = p.cap_tracks; cfg.cap_dets = p.cap_dets;
+    }
     if (cfg.with_reid && cfg.feat_dim < 1) throw std::runtime_error("feat_dim must be set when with_reid");
     S = p.n_streams;
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -273,7 +286,12 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
         }
     }
     if (is_docs) dcfg.feat_dim = cfg.feat_dim;
+    if (is_ss) {
+        scfg.feat_dim = cfg.feat_dim;
+        if (scfg.feat_dim % 4) throw std::runtime_error("StrongSORT feat_dim must be a multiple of 4");
+    }
     stream_bytes = is_docs ? carve_docs(dcfg, nullptr, nullptr, &persistent_bytes)
+                 : is_ss   ? carve_ss(scfg, nullptr, nullptr, &persistent_bytes)
                            : carve_stream(cfg, nullptr, nullptr, &persistent_bytes);
     persistent_bytes = (persistent_bytes + 15) & ~(size_t)15;
     CUDA_OK(cudaMalloc(&d_mem, stream_bytes * S));
@@ -296,7 +314,19 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     CUDA_OK(cudaMalloc(&d_out, sizeof(float) * 8 * CD * S));
     CUDA_OK(cudaMalloc(&d_scalars_out, sizeof(int) * SC_COUNT * S));
     out_ptr.resize(S); scalars_ptr.resize(S); timers_ptr.resize(S);
-    if (is_docs) {
+    if (is_ss) {
+        h_ss.resize(S);
+        for (int i = 0; i < S; ++i) {
+            carve_ss(scfg, d_mem + stream_bytes * i, &h_ss[i], nullptr);
+            h_ss[i].dets = d_dets + (size_t)i * CD * 6;
+            h_ss[i].n_dets = d_ndets + i;
+            h_ss[i].embs = d_embs + (size_t)i * CD * F;
+            h_ss[i].warp = d_warp + (size_t)i * 8;
+            out_ptr[i] = h_ss[i].out; scalars_ptr[i] = h_ss[i].scalars; timers_ptr[i] = h_ss[i].timers;
+        }
+        CUDA_OK(cudaMalloc(&d_ss, sizeof(SsStream) * S));
+        CUDA_OK(cudaMemcpy(d_ss, h_ss.data(), sizeof(SsStream) * S, cudaMemcpyHostToDevice));
+    } else if (is_docs) {
         h_docs.resize(S);
         for (int i = 0; i < S; ++i) {
             carve_docs(dcfg, d_mem + stream_bytes * i, &h_docs[i], nullptr);
@@ -337,7 +367,7 @@ Engine::~Engine() {
     cudaStreamSynchronize(stream);
     if (reid) reid_free(reid);
     cudaFree(d_warp); cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
-    cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_docs); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
+    cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_docs); cudaFree(d_ss); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
     cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
     cudaFreeHost(h_embs); cudaFreeHost(h_images); cudaFreeHost(h_ndets_ring);
     cudaEventDestroy(mark[0]); cudaEventDestroy(mark[1]);
@@ -346,7 +376,7 @@ Engine::~Engine() {
 }
 
 void Engine::reset() {
-    if (is_docs) {
+    if (is_docs || is_ss) {
         CUDA_OK(cudaStreamSynchronize(stream));
         for (int i = 0; i < S; ++i) CUDA_OK(cudaMemsetAsync(d_mem + stream_bytes * i, 0, persistent_bytes, stream));
         CUDA_OK(cudaStreamSynchronize(stream));
@@ -372,6 +402,34 @@ void Engine::ensure_images(int rows, int cols, bool host_too) {
 void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total) {
     launches = 0;
     CUDA_OK(cudaEventRecord(ev[0], stream));
+    if (is_ss) {
+        const size_t CD = cfg.cap_dets, F = cfg.feat_dim;
+        if (!embs_dev) {
+            if (!reid) throw std::runtime_error("StrongSORT needs embeddings or a ReID model");
+            if (!images_dev) throw std::runtime_error("ReID inside update() needs an image");
+            ss_build_crops(scfg, d_ss, S, d_crops, d_ncrops, stream);
+            ++launches;
+            launches += reid_forward(reid, images_dev, (size_t)rows * cols * 3, rows, cols, d_crops, d_ncrops,
+                                     max_dets_total, d_embs, cfg.feat_dim, stream);
+        } else if (embs_dev != d_embs) {
+            CUDA_OK(cudaMemcpyAsync(d_embs, embs_dev, sizeof(float) * F * CD * S, cudaMemcpyDeviceToDevice, stream));
+        }
+        CUDA_OK(cudaEventRecord(ev[1], stream));
+        launches += ss_enqueue_frame(scfg, d_ss, S, stream);
+        if (warp_dirty) {
+            CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
+            warp_dirty = false;
+        }
+        CUDA_OK(cudaEventRecord(ev[2], stream));
+        if (profile) {
+            CUDA_OK(cudaStreamSynchronize(stream));
+            float b = 0.f;
+            cudaEventElapsedTime(&b, ev[1], ev[2]);
+            assoc_ms_accum += b;
+            assoc_frames += 1;
+        }
+        return;
+    }
     if (is_docs) {
         if (cfg.with_reid && !embs_dev) {
             if (!reid) throw std::runtime_error("DeepOCSORT needs embeddings, a ReID model, or embedding_off");
@@ -451,7 +509,8 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
 
 void Engine::set_warp(int sidx, const double* warp6) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
-    if (is_docs || cfg.kind != KIND_XYWH) throw std::runtime_error("camera-motion warps apply to BoT-SORT only");
+    if (!is_ss && (is_docs || cfg.kind != KIND_XYWH))
+        throw std::runtime_error("camera-motion warps apply to BoT-SORT and StrongSORT only");
     double w[8] = {warp6[0], warp6[1], warp6[2], warp6[3], warp6[4], warp6[5], 1.0, 0.0};
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaMemcpy(d_warp + (size_t)sidx * 8, w, sizeof(w), cudaMemcpyHostToDevice));
@@ -479,7 +538,7 @@ void Engine::profile_read(double* ms, int* launch_counts) {
     for (int c = 0; c < REID_N_CLASSES + 1; ++c) { ms[c] = 0.0; launch_counts[c] = 0; }
     if (reid) reid_profile_collect(reid, ms, launch_counts);
     ms[REID_N_CLASSES] = assoc_ms_accum;
-    launch_counts[REID_N_CLASSES] = assoc_frames * (cfg.with_reid ? 4 : 1);
+    launch_counts[REID_N_CLASSES] = assoc_frames * (is_docs ? 1 : (cfg.with_reid ? 4 : 1));
     assoc_ms_accum = 0.0;
     assoc_frames = 0;
 }
@@ -511,6 +570,7 @@ void Engine::finish_fetch(float* const* out, const int* out_cap, int* out_rows) 
         if (sc[SC_ERROR] != ERR_NONE) {
             const char* what = sc[SC_ERROR] == ERR_TRACK_CAPACITY ? "track capacity (cap_tracks) exceeded"
                              : sc[SC_ERROR] == ERR_CLS_HIST      ? "more than 8 distinct classes voted on one track"
+                             : sc[SC_ERROR] == ERR_LSA_INFEASIBLE ? "assignment cost matrix has no finite solution (NaN / inf costs)"
                                                                  : "detection capacity (cap_dets) exceeded";
             throw std::runtime_error(std::string("stream ") + std::to_string(i) + ": " + what);
         }
@@ -605,6 +665,25 @@ void Engine::fetch(float* const* out, const int* out_cap, int* out_rows) {
 int Engine::snapshot(int sidx, int* ids, double* means, double* covs, int cap) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
     CUDA_OK(cudaStreamSynchronize(stream));
+    if (is_ss) {
+        const SsStream& s = h_ss[sidx];
+        const int CT = cfg.cap_tracks;
+        std::vector<int> sc(SC_COUNT), lst(CT), idv(CT);
+        std::vector<double> mean((size_t)CT * 8), cov((size_t)CT * 64);
+        CUDA_OK(cudaMemcpy(sc.data(), s.scalars, sizeof(int) * SC_COUNT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(lst.data(), s.tracks, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(idv.data(), s.id, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(mean.data(), s.mean, sizeof(double) * 8 * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(cov.data(), s.cov, sizeof(double) * 64 * CT, cudaMemcpyDeviceToHost));
+        int n = 0;
+        for (int k = 0; k < sc[SC_N_ACTIVE] && n < cap; ++k, ++n) {
+            const int t = lst[k];
+            ids[n] = idv[t];
+            memcpy(means + (size_t)n * 8, mean.data() + (size_t)t * 8, sizeof(double) * 8);
+            memcpy(covs + (size_t)n * 64, cov.data() + (size_t)t * 64, sizeof(double) * 64);
+        }
+        return n;
+    }
     if (is_docs) {
         const DocsStream& s = h_docs[sidx];
         const int CT = cfg.cap_tracks;

@@ -27,6 +27,11 @@ TRACKER_DEFAULTS = {
         proximity_thresh=0.6084297894561342, appearance_thresh=0.6188818853936099,
         unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
         unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329),
+    "deepocsort": dict(det_thresh=0.3, max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2,
+                       w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False,
+                       cmc_off=True, aw_off=False, Q_xy_scaling=0.01, Q_s_scaling=0.0001),
+    "strongsort": dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
+                       mc_lambda=0.98, nn_budget=100),
 }
 
 
@@ -141,8 +146,25 @@ class MultiStreamTracker:
             p.setdefault("track_buffer", 0)
             p.setdefault("frame_rate", 30)
             p["track_high_thresh"] = p["det_thresh"]  # detections above det_thresh are embedded
+        elif kind == "strongsort":
+            p = dict(min_conf=0.1, max_cos_dist=0.2, max_iou_dist=0.7, n_init=3, nn_budget=100, mc_lambda=0.98,
+                     ema_alpha=0.9, max_age=30)
+            unknown = set(params) - set(p)
+            if unknown:
+                raise TypeError(f"unknown StrongSort parameters: {sorted(unknown)}")
+            p.update(params)
+            if p["nn_budget"] is None:
+                raise NotImplementedError("nn_budget=None (unbounded gallery) is not supported; pass a sample budget")
+            cfg.tracker = _lib.TRACKER_STRONGSORT
+            cfg.n_init, cfg.nn_budget, cfg.max_age = int(p["n_init"]), int(p["nn_budget"]), int(p["max_age"])
+            cfg.min_conf, cfg.max_cos_dist, cfg.max_iou_dist = p["min_conf"], p["max_cos_dist"], p["max_iou_dist"]
+            cfg.mc_lambda, cfg.ema_alpha = p["mc_lambda"], p["ema_alpha"]
+            cfg.with_reid = 1
+            p.setdefault("track_buffer", 0)
+            p.setdefault("frame_rate", 30)
         else:
-            raise ValueError(f"tracker '{tracker}' is not part of the B200 hot path (bytetrack, botsort, deepocsort)")
+            raise ValueError(f"tracker '{tracker}' is not part of the B200 hot path "
+                             "(bytetrack, botsort, deepocsort, strongsort)")
         cfg.n_streams = int(n_streams)
         cfg.cap_tracks = int(cap_tracks)
         cfg.cap_dets = int(cap_dets)
@@ -181,7 +203,8 @@ class MultiStreamTracker:
         self.frame_count = 0
 
     def set_warp(self, stream: int, warp) -> None:
-        """Camera-motion warp (2x3) to apply on the next update of `stream` (BoT-SORT multi_gmc)."""
+        """Camera-motion warp (2x3) to apply on the next update of `stream` (BoT-SORT multi_gmc, StrongSORT
+        camera_update)."""
         w = np.ascontiguousarray(warp, dtype=np.float64).reshape(6)
         if not self.lib.boxmot_b200_tracker_set_warp(self.handle, int(stream), w.ctypes.data):
             raise B200Error(_lib.last_error(self.lib))
@@ -286,6 +309,8 @@ class _SingleStreamTracker:
             feat_dim = int(getattr(reid_model, "feature_dim", feat_dim))
         if self._kind == "deepocsort":  # BaseTracker settings that DeepOCSORT's update actually reads
             params = dict(params, det_thresh=det_thresh, max_age=max_age, min_hits=min_hits, iou_threshold=iou_threshold)
+        if self._kind == "strongsort":  # Tracker(max_age=self.max_age) (strongsort.py:56-64)
+            params = dict(params, max_age=max_age)
         self._engine = MultiStreamTracker(self._kind, 1, cap_tracks, cap_dets, feat_dim, reid_blob=blob, **params)
         self.provides_reid = blob is not None
         self.with_reid = self._engine.with_reid
@@ -314,7 +339,8 @@ class _SingleStreamTracker:
             # own device and hand the rows to the tracker, exactly where botsort.py:191-192 calls the model
             if self.model is None:
                 raise B200Error("with_reid=True needs reid_model=, embs=, or with_reid=False")
-            first = dets[:, 4].astype(np.float64) > eng.params["track_high_thresh"]
+            conf = dets[:, 4].astype(np.float64)
+            first = conf >= eng.params["min_conf"] if eng.kind == "strongsort" else conf > eng.params["track_high_thresh"]
             embs = np.zeros((len(dets), eng.feat_dim), np.float32)
             if first.any():
                 embs[first] = np.asarray(self.model.get_features(dets[first][:, :4], img), dtype=np.float32)
@@ -385,9 +411,25 @@ class DeepOcSort(_SingleStreamTracker):
                          iou_threshold=iou_threshold, **kwargs)
 
 
+class StrongSort(_SingleStreamTracker):
+    """StrongSORT on the GPU; arguments as boxmot/trackers/bbox/strongsort/strongsort.py:38-67 (`max_age` is the
+    BaseTracker setting the reference forwards to its Tracker).  The reference estimates a camera warp with ECC on
+    every frame that has tracks; here the warp is an input (`update(..., warp=)`, identity when omitted) and
+    `camera_update` itself always runs, as in the reference."""
+
+    _kind = "strongsort"
+
+    def __init__(self, reid_model: Any = None, min_conf: float = 0.1, max_cos_dist: float = 0.2,
+                 max_iou_dist: float = 0.7, n_init: int = 3, nn_budget: int = 100, mc_lambda: float = 0.98,
+                 ema_alpha: float = 0.9, **kwargs: Any):
+        super().__init__(reid_model=reid_model, min_conf=min_conf, max_cos_dist=max_cos_dist,
+                         max_iou_dist=max_iou_dist, n_init=n_init, nn_budget=nn_budget, mc_lambda=mc_lambda,
+                         ema_alpha=ema_alpha, **kwargs)
+
+
 def create_tracker(tracker_type: str, reid_weights=None, device=None, half: bool = False, per_class: bool = False,
                    reid_model: Any = None, **overrides: Any):
-    """YAML-default construction like boxmot/trackers/tracker_zoo.py:33-147 for the two STrack trackers.
+    """YAML-default construction like boxmot/trackers/tracker_zoo.py:33-147 for the four trackers of the path.
 
     `reid_weights` may be a `.pt` state dict or a `.b200reid` blob; it is converted once and loaded on the GPU.
     CMC defaults to off (see BotSort)."""
@@ -402,8 +444,10 @@ def create_tracker(tracker_type: str, reid_weights=None, device=None, half: bool
     args.update(overrides)
     if kind == "bytetrack":
         return ByteTrack(per_class=per_class, **args)
-    if reid_model is None and reid_weights is not None and args.get("with_reid", True):
+    wants_reid = args.get("with_reid", True) and not args.get("embedding_off", False)
+    if reid_model is None and reid_weights is not None and wants_reid:
         from .reid import B200ReID
 
         reid_model = B200ReID(reid_weights, half=half)
-    return BotSort(reid_model=reid_model, per_class=per_class, **args)
+    cls = {"botsort": BotSort, "deepocsort": DeepOcSort, "strongsort": StrongSort}[kind]
+    return cls(reid_model=reid_model, per_class=per_class, **args)

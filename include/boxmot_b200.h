@@ -113,6 +113,7 @@ BOXMOT_B200_API const char* boxmot_botsort_last_error(void);
 #define BOXMOT_B200_TRACKER_BYTETRACK 0
 #define BOXMOT_B200_TRACKER_BOTSORT 1
 #define BOXMOT_B200_TRACKER_DEEPOCSORT 2
+#define BOXMOT_B200_TRACKER_STRONGSORT 3
 
 /* Every parameter of the reference Python constructors (bytetrack.py:226-257, botsort.py:66-118), in
  * double precision so thresholds compare exactly as python floats do. */
@@ -152,6 +153,14 @@ typedef struct BoxMOTB200TrackerConfig {
     double aw_param;
     double q_xy_scaling;
     double q_s_scaling;
+    /* StrongSORT (trackers/bbox/strongsort/strongsort.py:38-67; max_age above is shared); ignored by the others */
+    int n_init;
+    int nn_budget;               /* samples kept per track (the reference's None = unbounded is not supported) */
+    double min_conf;
+    double max_cos_dist;
+    double max_iou_dist;
+    double mc_lambda;
+    double ema_alpha;
 } BoxMOTB200TrackerConfig;
 
 typedef struct BoxMOTB200Tracker BoxMOTB200Tracker;
@@ -190,9 +199,11 @@ BOXMOT_B200_API int boxmot_b200_tracker_snapshot(BoxMOTB200Tracker* handle, int 
 /* Kernel launches issued by the last update call, and CUDA stream / device-time accessors for benchmarks. */
 BOXMOT_B200_API int boxmot_b200_tracker_last_launches(BoxMOTB200Tracker* handle, int* out_launches);
 BOXMOT_B200_API int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* handle, double* reid_ms, double* assoc_ms);
-/* BoT-SORT camera-motion compensation with a SUPPLIED 2x3 warp (row major, float64): applied once, on the next
- * update, to the predicted pool and the unconfirmed tracks exactly as STrack.multi_gmc does
- * (trackers/bbox/botsort/botsort_track.py:117-132).  Estimating the warp (motion/cmc/*) is out of scope. */
+/* Camera-motion compensation with a SUPPLIED 2x3 warp (row major, float64), applied once, on the next update:
+ * BoT-SORT to the predicted pool and the unconfirmed tracks exactly as STrack.multi_gmc does
+ * (trackers/bbox/botsort/botsort_track.py:117-132); StrongSORT through Track.camera_update
+ * (trackers/bbox/strongsort/sort/track.py:139-148; without a supplied warp it runs with the identity, as the
+ * reference does whenever tracks exist).  Estimating the warp (motion/cmc/*) is out of scope. */
 BOXMOT_B200_API int boxmot_b200_tracker_set_warp(BoxMOTB200Tracker* handle, int stream, const double* warp2x3);
 /* Device timing on the handle's own CUDA stream: record mark 0 / mark 1 around a region, then read the elapsed
  * milliseconds (synchronises on mark 1). */
@@ -216,6 +227,11 @@ BOXMOT_B200_API int boxmot_b200_lap_solve(const double* cost, int rows, int cols
 /* lapjv(cost, extend_cost=True) (no cost limit, zero-padded to square) with lapjv's own tie-breaking -- the dense
  * Jonker-Volgenant solver DeepOCSORT's association needs for bit-exact ids. cost (rows, cols) float64 host. */
 BOXMOT_B200_API int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y);
+/* scipy.optimize.linear_sum_assignment(cost) with scipy's own tie-breaking (StrongSORT's min_cost_matching,
+ * trackers/bbox/strongsort/sort/linear_assignment.py:62): cost (rows, cols) float64 host -> min(rows, cols) pairs
+ * (row_ind ascending, col_ind), count through out_pairs. */
+BOXMOT_B200_API int boxmot_b200_lsa_solve(const double* cost, int rows, int cols, int* row_ind, int* col_ind,
+                                          int* out_pairs);
 /* batched Kalman steps on host arrays: kind 0 = XYAH, 1 = XYWH; mean (n,8), cov (n,8,8) float64 in place. */
 BOXMOT_B200_API int boxmot_b200_kalman_predict(int kind, double* mean, double* cov, const int* tracked, int n);
 BOXMOT_B200_API int boxmot_b200_kalman_update(int kind, double* mean, double* cov, const float* meas, int n);

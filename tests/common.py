@@ -5,7 +5,7 @@ from pathlib import Path
 
 import numpy as np
 
-from oracle.streams import bench_stream, stress_embeddings, stress_stream, unit_embeddings
+from oracle.streams import bench_stream, stress_embeddings, stress_stream, unit_embeddings, warp_sequence
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
 
@@ -17,6 +17,9 @@ BOTSORT_YAML = dict(
     unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
     unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329, fuse_first_associate=True,
     frame_rate=30, with_reid=True)
+
+STRONGSORT_YAML = dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
+                       mc_lambda=0.98, nn_budget=100)
 
 # name -> (tracker kind, kwargs, frames factory, embeddings factory or None)
 CASES = {
@@ -37,7 +40,21 @@ CASES = {
                             lambda fr: unit_embeddings(fr, 96, seed=5)),
     "botsort_bench256": ("botsort", BOTSORT_YAML, lambda: bench_stream(256, 40)[1],
                          lambda fr: stress_embeddings(fr, 256, seed=3)),
+    # StrongSORT: constructor defaults, the YAML defaults (N11), a short-memory variant with gaps and classes,
+    # supplied camera warps, and the bench-shaped stream
+    "strongsort_stress96": ("strongsort", {}, lambda: stress_stream(96, 120), lambda fr: stress_embeddings(fr, 96)),
+    "strongsort_yaml_stress96": ("strongsort", STRONGSORT_YAML, lambda: stress_stream(96, 120, seed=41),
+                                 lambda fr: stress_embeddings(fr, 96, seed=43)),
+    "strongsort_stress48_gaps": ("strongsort", dict(max_age=10, n_init=2),
+                                 lambda: stress_stream(48, 200, seed=19, n_classes=3, empty_every=37),
+                                 lambda fr: stress_embeddings(fr, 48, seed=5)),
+    "strongsort_warp_stress64": ("strongsort", {}, lambda: stress_stream(64, 100, seed=29),
+                                 lambda fr: stress_embeddings(fr, 64, seed=31)),
+    "strongsort_bench128": ("strongsort", {}, lambda: bench_stream(128, 30, hw=(360, 640))[1],
+                            lambda fr: stress_embeddings(fr, 128, seed=3)),
 }
+# per-frame camera warps of the cases that exercise SURVEY row a15 through the golden table
+WARPS = {"strongsort_warp_stress64": lambda: warp_sequence(100)}
 
 
 def load_golden(name):

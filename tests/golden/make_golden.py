@@ -72,9 +72,28 @@ class _GivenWarps:
         return w
 
 
+def _snapshot_ss(tracker):
+    tr = tracker.tracker.tracks
+    return (np.asarray([t.id for t in tr], dtype=np.int64),
+            np.asarray([t.mean for t in tr], dtype=np.float64).reshape(-1, 8),
+            np.asarray([t.covariance for t in tr], dtype=np.float64).reshape(-1, 8, 8))
+
+
+class _FrameWarps:
+    """StrongSORT only asks its CMC for a warp when tracks exist; this stub answers by frame index."""
+
+    def __init__(self, warps):
+        self.warps, self.f = warps, 0
+
+    def apply(self, img, dets):
+        return self.warps[self.f]
+
+
 def run(tracker, frames, img, embs=None):
     rows, offsets, snaps = [], [0], {}
     for f, dets in enumerate(frames):
+        if isinstance(getattr(tracker, "cmc", None), _FrameWarps):
+            tracker.cmc.f = f
         e = None if embs is None else embs[f].copy()
         if e is not None and len(dets) == 0:
             e = np.empty((0, e.shape[1] if e.ndim == 2 else 512), np.float32)
@@ -83,7 +102,9 @@ def run(tracker, frames, img, embs=None):
         rows.append(out.astype(np.float32))
         offsets.append(offsets[-1] + len(out))
         if (f + 1) in SNAP_FRAMES:
-            ids, m, c = _snapshot_docs(tracker) if tracker.__class__.__name__ == "DeepOcSort" else _snapshot(tracker)
+            kind = tracker.__class__.__name__
+            ids, m, c = (_snapshot_docs(tracker) if kind == "DeepOcSort" else
+                         _snapshot_ss(tracker) if kind == "StrongSort" else _snapshot(tracker))
             snaps[f"snap{f + 1}_ids"] = ids
             snaps[f"snap{f + 1}_mean"] = m
             snaps[f"snap{f + 1}_cov"] = c
@@ -141,8 +162,33 @@ def make_reid_golden():
                         features=feats.astype(np.float32), weight_seed=7, image_seed=123)
 
 
+def make_strongsort_goldens():
+    """StrongSORT: GITHUB_ACTIONS unset, the ECC estimator replaced by a given warp (identity unless
+    the case supplies one) while camera_update itself still runs."""
+    from boxmot.trackers.bbox.strongsort.strongsort import StrongSort
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("b200_tests_common", HERE.parent / "common.py")  # the reference
+    common = importlib.util.module_from_spec(spec)                                               # has a `tests` too
+    spec.loader.exec_module(common)
+    CASES, WARPS = common.CASES, common.WARPS
+
+    img = np.zeros((360, 640, 3), np.uint8)
+    for name, (kind, kwargs, make_frames, make_embs) in CASES.items():
+        if kind != "strongsort":
+            continue
+        frames = make_frames()
+        embs = make_embs(frames)
+        trk = StrongSort(reid_model=None, **kwargs)
+        trk.cmc = _FrameWarps(WARPS[name]() if name in WARPS else [np.eye(2, 3)] * len(frames))
+        np.savez_compressed(HERE / f"{name}.npz", **run(trk, frames, img, embs))
+
+
 def main():
     img = np.zeros((360, 640, 3), np.uint8)
+    if len(sys.argv) > 1 and sys.argv[1] == "strongsort":
+        make_strongsort_goldens()
+        return
 
     bt_base.BaseTrack._count = 0
     _, frames = bench_stream(64, 300)
@@ -190,6 +236,7 @@ def main():
         embs = unit_embeddings(frames, 96, seed=5)
         np.savez_compressed(HERE / f"{name}.npz", **run(DeepOcSort(reid_model=None, cmc_off=True), frames, img, embs))
     make_reid_golden()
+    make_strongsort_goldens()
     for p in sorted(HERE.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

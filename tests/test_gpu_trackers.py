@@ -6,7 +6,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from tests.common import BOTSORT_YAML, BYTETRACK_YAML, CASES, assert_rows_match, load_golden
+from tests.common import BOTSORT_YAML, BYTETRACK_YAML, CASES, WARPS, assert_rows_match, load_golden
 
 
 def _make(kind, kwargs, **extra):
@@ -16,6 +16,8 @@ def _make(kind, kwargs, **extra):
         return bb.ByteTrack(cap_tracks=512, cap_dets=256, **kwargs, **extra)
     if kind == "deepocsort":
         return bb.DeepOcSort(cap_tracks=512, cap_dets=256, **kwargs, **extra)
+    if kind == "strongsort":
+        return bb.StrongSort(cap_tracks=512, cap_dets=256, **kwargs, **extra)
     return bb.BotSort(cap_tracks=512, cap_dets=256, **kwargs, **extra)
 
 
@@ -25,10 +27,13 @@ def test_gpu_tracker_matches_reference_golden(name):
     frames = make_frames()
     embs = make_embs(frames) if make_embs else None
     want, snaps = load_golden(name)
-    trk = _make(kind, kwargs)
+    fd = {} if kind != "strongsort" else {"feat_dim": next(e.shape[1] for e in embs if e.ndim == 2 and len(e))}
+    trk = _make(kind, kwargs, **fd)
+    warps = WARPS[name]() if name in WARPS else None
     img = np.zeros((64, 64, 3), np.uint8)
     for f, dets in enumerate(frames):
-        got = trk.update(dets, img, None if embs is None else embs[f])
+        extra = {} if warps is None else {"warp": warps[f]}
+        got = trk.update(dets, img, None if embs is None else embs[f], **extra)
         assert_rows_match(got, want[f], f, box_rtol=1e-4)
         if (f + 1) in snaps:
             ids, mean, cov = snaps[f + 1]

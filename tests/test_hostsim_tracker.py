@@ -5,15 +5,18 @@ import numpy as np
 import pytest
 
 from oracle.lap import lapjv
-from tests.common import CASES, assert_rows_match, load_golden
-from tests.hostsim import HostSimDeepOcSort, HostSimTracker, botsort_cfg, bytetrack_cfg, deepocsort_cfg
+from tests.common import CASES, WARPS, assert_rows_match, load_golden
+from tests.hostsim import (HostSimDeepOcSort, HostSimStrongSort, HostSimTracker, botsort_cfg, bytetrack_cfg,
+                           deepocsort_cfg, strongsort_cfg)
 
 
-def _make(kind, kwargs):
+def _make(kind, kwargs, feat_dim=None):
     if kind == "bytetrack":
         return HostSimTracker(bytetrack_cfg(**kwargs))
     if kind == "deepocsort":
         return HostSimDeepOcSort(deepocsort_cfg(**kwargs))
+    if kind == "strongsort":
+        return HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=feat_dim, **kwargs))
     return HostSimTracker(botsort_cfg(**kwargs))
 
 
@@ -23,10 +26,12 @@ def test_hostsim_matches_reference_golden(name):
     frames = make_frames()
     embs = make_embs(frames) if make_embs else None
     want, snaps = load_golden(name)
-    trk = _make(kind, kwargs)
+    trk = _make(kind, kwargs, None if embs is None else next(e.shape[1] for e in embs if e.ndim == 2 and len(e)))
+    warps = WARPS[name]() if name in WARPS else None
     worst = 0.0
     for f, dets in enumerate(frames):
-        got = trk.update(dets, None, None if embs is None else embs[f])
+        extra = {} if warps is None else {"warp": warps[f]}
+        got = trk.update(dets, None, None if embs is None else embs[f], **extra)
         assert_rows_match(got, want[f], f, box_rtol=1e-4)
         if (f + 1) in snaps:
             ids, mean, cov = snaps[f + 1]
@@ -78,3 +83,47 @@ def test_hostsim_dense_jv_reproduces_lapjv_ties(seed):
     x, y = sim.jv(cost)
     _, xo, yo = lapjv(cost, extend_cost=True)
     assert np.array_equal(x, xo) and np.array_equal(y, yo)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_hostsim_lsa_reproduces_scipy_ties(seed):
+    """lsa_sap.cuh must return scipy.optimize.linear_sum_assignment's own choice among tied optima: StrongSORT's
+    clipped cost matrices tie by construction and the choice orders the births (ids)."""
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.default_rng(seed)
+    sim = HostSimStrongSort(strongsort_cfg(cap_tracks=64, cap_dets=64, feat_dim=4, nn_budget=2))
+    for trial in range(25):
+        r, c = rng.integers(1, 48, 2)
+        mode = (seed + trial) % 4
+        if mode == 0:
+            cost = rng.integers(0, 3, (r, c)).astype(float)
+        elif mode == 1:
+            cost = rng.random((r, c))
+            cost[cost > 0.5] = 0.5 + 1e-5
+        elif mode == 2:
+            cost = np.zeros((r, c))
+        else:
+            cost = rng.random((r, c))
+            cost[cost > 0.3] = 0.7 + 1e-5
+            cost[rng.integers(0, r)] = 0.7 + 1e-5
+        ri, ci = sim.lsa(cost)
+        ro, co = linear_sum_assignment(cost)
+        assert np.array_equal(ri, ro) and np.array_equal(ci, co)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_hostsim_set_order_equals_cpython(seed):
+    """pyset.cuh against the interpreter's own `list(set(a) - set(b))` (linear_assignment.py:108)."""
+    import random
+
+    rnd = random.Random(seed)
+    sim = HostSimStrongSort(strongsort_cfg(cap_tracks=1024, cap_dets=8, feat_dim=4, nn_budget=2))
+    for _ in range(600):
+        T = rnd.choice([5, 20, 60, 200, 1000])
+        n = rnd.randint(0, T)
+        a = sorted(rnd.sample(range(T), n))
+        m = rnd.randint(0, n) if rnd.random() < 0.7 else rnd.randint(0, max(0, n // 6))
+        b = set(rnd.sample(a, m))
+        assert sim.set_difference(a, [k in b for k in a]) == list(set(a) - set(k for k in a if k in b))
+    assert sim.set_difference([3, 17], [False, False]) == [17, 3]

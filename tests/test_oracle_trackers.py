@@ -6,8 +6,9 @@ import numpy as np
 import pytest
 
 from oracle.deepocsort import DeepOcSortOracle
+from oracle.strongsort import StrongSortOracle
 from oracle.trackers import BotSortOracle, ByteTrackOracle
-from tests.common import CASES, assert_rows_match, load_golden
+from tests.common import CASES, WARPS, assert_rows_match, load_golden
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -16,14 +17,19 @@ def test_oracle_matches_reference_golden(name):
     frames = make_frames()
     embs = make_embs(frames) if make_embs else None
     want, snaps = load_golden(name)
-    trk = {"bytetrack": ByteTrackOracle, "botsort": BotSortOracle, "deepocsort": DeepOcSortOracle}[kind](**kwargs)
+    trk = {"bytetrack": ByteTrackOracle, "botsort": BotSortOracle, "deepocsort": DeepOcSortOracle,
+           "strongsort": StrongSortOracle}[kind](**kwargs)
+    warps = WARPS[name]() if name in WARPS else None
     img = np.zeros((360, 640, 3), np.uint8)
     for f, dets in enumerate(frames):
-        got = trk.update(dets.copy(), img, None if embs is None else embs[f].copy())
+        extra = {} if warps is None else {"warp": warps[f]}
+        got = trk.update(dets.copy(), img, None if embs is None else embs[f].copy(), **extra)
         assert_rows_match(got, want[f], f, box_rtol=1e-6)
         if (f + 1) in snaps:
             ids, mean, cov = snaps[f + 1]
             st = trk.state_snapshot()
+            if kind == "strongsort":
+                st = {int(i): (m, c) for i, m, c in zip(*st)}
             assert sorted(st) == sorted(ids.tolist())
             for i, m, c in zip(ids, mean, cov):
                 k = len(st[int(i)][0])  # 8 (STrack filters) or 7 (XYSR)
