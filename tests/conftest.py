@@ -8,6 +8,10 @@ ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 os.environ.pop("GITHUB_ACTIONS", None)
+# The oracles do thousands of 4x4 / 8x8 numpy calls per frame: BLAS worker threads spinning next to torch's OpenMP
+# pool slow them several-fold.  One BLAS thread; torch keeps its own pool for the CNN oracle.
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
 
 
 def pytest_configure(config):
