@@ -371,7 +371,7 @@ def run_b200(args):
         "kernel_classes": prof,
         "association_phase_sm_clocks_per_step": assoc_phases,
     }
-    if WORLD == 1:
+    if WORLD == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_arm(args.cpu_frames, 1)
         line["speedup_e2e_vs_cpu"] = e2e_fps / line["cpu_baseline"]["value"]
     print(json.dumps(line))
@@ -387,6 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--skip-cpu", action="store_true", help="kernel A/B experiments only: omit the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

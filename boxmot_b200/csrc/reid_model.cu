@@ -453,6 +453,280 @@ __global__ void k_lightconv(const LightArgs a, const int* __restrict__ d_n, int 
     }
 }
 
+// K6 v2.  Same contract as k_lightconv, restructured around the two limits ncu showed for v1 (L1/TEX 79 %):
+//   * phase A read each pixel's K-vector with per-thread float4 loads 64 B apart: every warp request touched 16
+//     cache lines.  v2 stages the haloed input tile once with coalesced cp.async into a K-chunk-planar shared
+//     layout sX[C/4][pixels] (zero fill outside the image), so phase A reads consecutive float4s (conflict-free),
+//     one warp = 64 consecutive pixels x 8 output channels with the 1x1 weights broadcast;
+//   * phase B loaded 9 float4 per output from shared memory.  v2 walks columns: a thread owns (x, 4 channels),
+//     slides down its rows keeping a 3x3 window in registers and loads 3 float4 per output.
+// Shared memory: sX + sT (2 x tile) + weights; pick_tile_rows2 keeps two CTAs per SM for the narrow models.
+static inline size_t light2_smem_bytes(int n_px, int C, int threads, int ppl = 4) {
+    const int n_pxp = ((n_px + 32 * ppl - 1) / (32 * ppl)) * (32 * ppl) + 2;
+    return sizeof(float) * (2 * (size_t)n_pxp * C + (size_t)C * C + 9 * C + (size_t)(threads / (C / 4)) * C);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+
+template <int C, int W, int R, int PPL = 4, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) k_lightconv2(const LightArgs a, const int* __restrict__ d_n, int off, int cap) {
+    const int n = blockIdx.z;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    const int br = blockIdx.y, tile = blockIdx.x;
+    const int H = a.H;
+    constexpr int TW = W + 2, TR = R + 2, C4 = C / 4;
+    constexpr int n_px = TR * TW;
+    constexpr int n_pxp = ((n_px + 32 * PPL - 1) / (32 * PPL)) * (32 * PPL) + 2;   // planes 8 banks apart; whole pixel groups in bounds
+    constexpr int NT = 256;
+    extern __shared__ __align__(16) float smem[];
+    float4* sX = reinterpret_cast<float4*>(smem);            // [C4][n_pxp]
+    float4* sT = sX + (size_t)C4 * n_pxp;                    // [C4][n_pxp]  (planar like sX: conflict-free both ways)
+    float* sW = reinterpret_cast<float*>(sT + (size_t)C4 * n_pxp);   // [C][C]
+    float* sD = sW + (size_t)C * C;                          // [9][C]
+    float* sP = sD + 9 * C;                                  // [NT / C4][C]
+    const int y0 = tile * R;
+    const float* in = a.in[br] + (size_t)n * H * W * C;
+    // ---- stage: weights + haloed input tile (compile-time shapes: the index arithmetic folds to mul/shift) ----
+    for (int e = threadIdx.x; e < n_px * C4; e += NT) {
+        const int p = e / C4, ch = e - p * C4;
+        const int ty = p / TW, tx = p - ty * TW;
+        const int gy = y0 + ty - 1, gx = tx - 1;
+        float4* dst = sX + ch * n_pxp + p;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) cp_async16(dst, in + ((size_t)gy * W + gx) * C + ch * 4);
+        else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int e = threadIdx.x; e < (n_pxp - n_px) * C4; e += NT) {
+        const int q = e / C4, ch = e - q * C4;
+        sX[ch * n_pxp + n_px + q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int e = threadIdx.x; e < C * C / 4; e += NT)
+        reinterpret_cast<float4*>(sW)[e] = reinterpret_cast<const float4*>(a.wpw[br])[e];
+    for (int e = threadIdx.x; e < 9 * C; e += NT) sD[e] = a.wdw[br][e];
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();
+    // ---- phase A: T = X * Wpw, warp item = (128-pixel group, 8 output channels), 4 pixels per lane ----
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr int G = 32 * PPL;
+        constexpr int n_pg = (n_px + G - 1) / G, n_cc = C >> 3;
+        for (int item = warp; item < n_pg * n_cc; item += NT / 32) {
+            const int pg = item % n_pg, cc = (item / n_pg) * 8;
+            const int p0 = pg * G + lane;
+            float acc[PPL][8];
+#pragma unroll
+            for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+#pragma unroll 2
+            for (int kc = 0; kc < C4; ++kc) {
+                float xv[PPL][4];
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const float4 x = sX[kc * n_pxp + p0 + 32 * q];
+                    xv[q][0] = x.x; xv[q][1] = x.y; xv[q][2] = x.z; xv[q][3] = x.w;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sW + (kc * 4 + kk) * C + cc);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sW + (kc * 4 + kk) * C + cc + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(xv[q][kk], wv[j], acc[q][j]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PPL; ++q) {
+                const int p = p0 + 32 * q;
+                if (p < n_px) {
+                    sT[(cc / 4) * n_pxp + p] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+                    sT[(cc / 4 + 1) * n_pxp + p] = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase B: depthwise 3x3 + bias + ReLU, column walkers with a register window ----
+    const int rows_here = min(R, H - y0);
+    constexpr int walkers = W * C4;
+    constexpr int n_grp = NT / C4;
+    constexpr int act = n_grp * C4;    // threads that walk: a multiple of C4 so a thread keeps its channel group
+    constexpr int n_split = (act / walkers) < 1 ? 1 : ((act / walkers) > R ? R : (act / walkers));
+    constexpr int rows_per = (R + n_split - 1) / n_split;
+    float* outp = a.out[br] + (size_t)n * H * W * C;
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < act) {
+        for (int wk = threadIdx.x; wk < walkers * n_split; wk += act) {
+            const int c4 = wk % C4, x = (wk / C4) % W, sp = wk / walkers;
+            const int ya = sp * rows_per, yb = min(ya + rows_per, rows_here);
+            float4 wv[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const float4*>(sD + t * C + c4 * 4);
+            const float4 bv = *reinterpret_cast<const float4*>(a.bias[br] + c4 * 4);
+            const float4* tbase = sT + c4 * n_pxp + x;
+            float4 win[3][3];   // rows (y, y+1, y+2) mod 3 live in fixed registers: the row loop is unrolled by 3
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                win[0][kx] = tbase[ya * TW + kx];
+                win[1][kx] = tbase[(ya + 1) * TW + kx];
+            }
+            float* orow = outp + ((size_t)(y0 + ya) * W + x) * C + c4 * 4;
+            for (int y = ya; y < yb; y += 3) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    if (y + u < yb) {
+                        const int i0 = u % 3, i1 = (u + 1) % 3, i2 = (u + 2) % 3;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            win[i2][kx] = tbase[(y + u + 2) * TW + kx];
+                        float4 acc = bv;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float4 w0 = wv[kx], w1 = wv[3 + kx], w2 = wv[6 + kx];
+                            const float4 t0 = win[i0][kx], t1 = win[i1][kx], t2 = win[i2][kx];
+                            acc.x = fmaf(t0.x, w0.x, acc.x); acc.y = fmaf(t0.y, w0.y, acc.y);
+                            acc.z = fmaf(t0.z, w0.z, acc.z); acc.w = fmaf(t0.w, w0.w, acc.w);
+                            acc.x = fmaf(t1.x, w1.x, acc.x); acc.y = fmaf(t1.y, w1.y, acc.y);
+                            acc.z = fmaf(t1.z, w1.z, acc.z); acc.w = fmaf(t1.w, w1.w, acc.w);
+                            acc.x = fmaf(t2.x, w2.x, acc.x); acc.y = fmaf(t2.y, w2.y, acc.y);
+                            acc.z = fmaf(t2.z, w2.z, acc.z); acc.w = fmaf(t2.w, w2.w, acc.w);
+                        }
+                        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+                        acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                        *reinterpret_cast<float4*>(orow + (size_t)u * W * C) = acc;
+                        psum.x += acc.x; psum.y += acc.y; psum.z += acc.z; psum.w += acc.w;
+                    }
+                }
+                orow += (size_t)3 * W * C;
+            }
+        }
+    }
+    if (a.sums[br]) {
+        // every walking thread owns the fixed slot (threadIdx / C4, threadIdx % C4)
+        if (threadIdx.x < act)
+            *reinterpret_cast<float4*>(sP + (threadIdx.x / C4) * C + (threadIdx.x % C4) * 4) = psum;
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += NT) {
+            float s = 0.f;
+            for (int g = 0; g < n_grp; ++g) s += sP[g * C + c];
+            a.sums[br][((size_t)n * gridDim.x + tile) * C + c] = s;
+        }
+    }
+}
+
+// K5 v2.  Same contract as k_pointwise.  ncu on v1: long-scoreboard bound (global loads serialised with the math:
+// load chunk -> sync -> compute -> sync) and 16 scalar shared stores per thread per chunk for the k-major transpose.
+// v2 streams A with cp.async straight into a K-chunk-planar layout As[4][BM] of float4 (rows interleaved over the
+// threads so consecutive lanes read consecutive float4: conflict-free, no transpose) and double-buffers the chunks,
+// so the copy of chunk c+1 overlaps the FMAs of chunk c.  The GATED prologue (gate-weighted branch sum) still goes
+// through registers.
+template <int BN, bool GATED>
+__global__ void __launch_bounds__(256) k_pointwise2(const PwArgs a, const int* __restrict__ d_n, int off, int cap) {
+    constexpr int NTN = BN / 4, NTM = 256 / NTN, BM = NTM * 8, BK = 16, BMP = BM + 2;
+    constexpr int STAGE_F4 = 4 * BMP + BK * BN / 4;   // float4 per stage: A planes + B rows
+    const int M = chunk_count(d_n, off, cap) * a.HW;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (m0 >= M) return;
+    extern __shared__ __align__(16) float4 pw_smem[];
+    const int tn = threadIdx.x % NTN, tm = threadIdx.x / NTN;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int K = a.K, N = a.N;
+    const int KX = GATED ? K - a.mid : 0;
+    const int n_chunks = (K + BK - 1) / BK;
+    auto load_chunk = [&](int c) {
+        float4* As = pw_smem + (size_t)(c & 1) * STAGE_F4;
+        float4* Bs = As + 4 * BMP;
+        const int k0 = c * BK;
+        for (int e = threadIdx.x; e < BM * 4; e += 256) {
+            const int r = e >> 2, kq = e & 3;
+            const int m = m0 + r, k = k0 + kq * 4;
+            float4* dst = As + kq * BMP + r;
+            if (m < M && k < K) {
+                if (!GATED) {
+                    cp_async16(dst, a.in + (size_t)m * K + k);
+                } else if (k < a.mid) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float* g = a.gates + (size_t)(m / a.HW) * 4 * a.mid + k;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const float4 x = *reinterpret_cast<const float4*>(a.branch[b] + (size_t)m * a.mid + k);
+                        const float4 gg = *reinterpret_cast<const float4*>(g + b * a.mid);
+                        v.x = fmaf(x.x, gg.x, v.x); v.y = fmaf(x.y, gg.y, v.y);
+                        v.z = fmaf(x.z, gg.z, v.z); v.w = fmaf(x.w, gg.w, v.w);
+                    }
+                    *dst = v;
+                } else {
+                    cp_async16(dst, a.in + (size_t)m * KX + (k - a.mid));
+                }
+            } else {
+                *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int e = threadIdx.x; e < BK * BN / 4; e += 256) {
+            const int kk = e / (BN / 4), c4 = e % (BN / 4);
+            if (k0 + kk < K && n0 + c4 * 4 < N) cp_async16(Bs + e, a.w + (size_t)(k0 + kk) * N + n0 + c4 * 4);
+            else Bs[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    load_chunk(0);
+    for (int c = 0; c < n_chunks; ++c) {
+        if (c + 1 < n_chunks) {
+            load_chunk(c + 1);
+            asm volatile("cp.async.wait_group 1;");
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
+        const float4* As = pw_smem + (size_t)(c & 1) * STAGE_F4;
+        const float4* Bs = As + 4 * BMP;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            float xv[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 x = As[kc * BMP + tm + NTM * i];
+                xv[i][0] = x.x; xv[i][1] = x.y; xv[i][2] = x.z; xv[i][3] = x.w;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 b = Bs[(kc * 4 + kk) * (BN / 4) + tn];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc[i][0] = fmaf(xv[i][kk], b.x, acc[i][0]); acc[i][1] = fmaf(xv[i][kk], b.y, acc[i][1]);
+                    acc[i][2] = fmaf(xv[i][kk], b.z, acc[i][2]); acc[i][3] = fmaf(xv[i][kk], b.w, acc[i][3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int cn = n0 + tn * 4;
+    if (cn >= N) return;
+    const float4 bv = *reinterpret_cast<const float4*>(a.bias + cn);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + tm + NTM * i;
+        if (m >= M) continue;
+        float4 v = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+        if (a.residual) {
+            const float4 r = *reinterpret_cast<const float4*>(a.residual + (size_t)m * N + cn);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (a.relu == 2) { v.x = fminf(v.x, 6.f); v.y = fminf(v.y, 6.f); v.z = fminf(v.z, 6.f); v.w = fminf(v.w, 6.f); }  // ReLU6
+        *reinterpret_cast<float4*>(a.out + (size_t)m * N + cn) = v;
+    }
+}
+
 // K6b (MobileNetV2): 3x3 stride-2 stem (3 -> C0) + folded BN + ReLU6 : (N,256,128,3) -> (N,128,64,C0)
 __global__ void k_stem3(const float* __restrict__ blob, const float* __restrict__ w, const float* __restrict__ bias,
                         int C0, const int* __restrict__ d_n, int off, int cap, float* __restrict__ out) {
@@ -573,9 +847,17 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
     const int groups = blockDim.x / C > 0 ? blockDim.x / C : 1;
     if ((int)threadIdx.x < groups * C) {
         const int c = threadIdx.x % C, g = threadIdx.x / C;
-        float s = 0.f;
-        for (int p = g; p < HW; p += groups) s += xp[(size_t)p * C + c];
-        part[g * C + c] = s;
+        // four independent partial sums keep several loads in flight (fixed combination order: deterministic)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int p = g;
+        for (; p + 3 * groups < HW; p += 4 * groups) {
+            s0 += xp[(size_t)p * C + c];
+            s1 += xp[(size_t)(p + groups) * C + c];
+            s2 += xp[(size_t)(p + 2 * groups) * C + c];
+            s3 += xp[(size_t)(p + 3 * groups) * C + c];
+        }
+        for (; p < HW; p += groups) s0 += xp[(size_t)p * C + c];
+        part[g * C + c] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -593,8 +875,15 @@ __global__ void k_head(const float* __restrict__ x, int HW, int C, const float* 
     for (int f = threadIdx.x; f < FEAT; f += blockDim.x) {
         float s;
         if (wfc) {
-            s = bfc[f];
-            for (int c = 0; c < C; ++c) s = fmaf(pooled[c], wfc[(size_t)c * FEAT + f], s);
+            // fc + folded BN1d + ReLU; eight independent chains hide the L2 latency of the weight rows
+            float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int c = 0;
+            for (; c + 8 <= C; c += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = fmaf(pooled[c + u], wfc[(size_t)(c + u) * FEAT + f], t[u]);
+            }
+            for (; c < C; ++c) t[0] = fmaf(pooled[c], wfc[(size_t)c * FEAT + f], t[0]);
+            s = bfc[f] + (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
             s = fmaxf(s, 0.f);
         } else {
             s = pooled[f];  // MobileNetV2: the pooled conv9 map is the embedding (mobilenetv2.py:186-193)
@@ -646,6 +935,8 @@ struct ReidModel {
     TcW tc_trans[2], tc_c5;
     float* d_wtc = nullptr;    // all packed tensor-core weights
     bool use_tc = false;
+    bool pw_v2 = true;      // BOXMOT_B200_PW_V1=1 selects the first-generation pointwise GEMM (A/B runs)
+    bool light_v2 = true;   // BOXMOT_B200_LIGHT_V1=1 selects the first-generation LightConv kernel (A/B runs)
     // workspace for one chunk of crops
     int chunk = 128;
     float* blob = nullptr;
@@ -792,6 +1083,10 @@ ReidModel* reid_load(const char* path) {
             // bandwidth-bound and the float32 CUDA-core GEMM is 1.2-1.8x faster than this first (unpipelined)
             // tcgen05 kernel, so the tensor-core path is opt-in until it is pipelined / fused.
             m->use_tc = env && env[0] == '1';
+            const char* lv = getenv("BOXMOT_B200_LIGHT_V1");
+            m->light_v2 = !(lv && lv[0] == '1');
+            const char* pv = getenv("BOXMOT_B200_PW_V1");
+            m->pw_v2 = !(pv && pv[0] == '1');
             std::vector<float> packed;
             struct Todo { TcW* dst; size_t w; int K, N; size_t at; };
             std::vector<Todo> todo;
@@ -935,13 +1230,50 @@ struct Launcher {
     void launch_pw(const PwArgs& a, size_t Mmax) {
         constexpr int BM = (256 / (BN / 4)) * 8;
         dim3 grid((unsigned)((Mmax + BM - 1) / BM), (unsigned)((a.N + BN - 1) / BN));
+        if (m->pw_v2) {
+            constexpr size_t smem = 2 * sizeof(float4) * (4 * (BM + 2) + 16 * BN / 4);
+            begin(CLS_POINTWISE);
+            if (a.gates) {
+                if (smem > 48 * 1024)
+                    RCUDA_OK(cudaFuncSetAttribute(k_pointwise2<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_pointwise2<BN, true><<<grid, 256, smem, st>>>(a, d_n, off, cap);
+            } else {
+                if (smem > 48 * 1024)
+                    RCUDA_OK(cudaFuncSetAttribute(k_pointwise2<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_pointwise2<BN, false><<<grid, 256, smem, st>>>(a, d_n, off, cap);
+            }
+            end();
+            ++launches;
+            return;
+        }
         begin(CLS_POINTWISE);
         if (a.gates) k_pointwise<BN, true><<<grid, 256, 0, st>>>(a, d_n, off, cap);
         else k_pointwise<BN, false><<<grid, 256, 0, st>>>(a, d_n, off, cap);
         end();
         ++launches;
     }
+    template <int C, int W, int R, int PPL = 4, int MINB = 2>
+    void launch_light2(const LightArgs& a, int n_branches) {
+        const int tiles = (a.H + R - 1) / R;
+        const size_t smem = light2_smem_bytes((R + 2) * (W + 2), C, 256, PPL);
+        if (smem > 48 * 1024)
+            RCUDA_OK(cudaFuncSetAttribute(k_lightconv2<C, W, R, PPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        begin(CLS_LIGHTCONV);
+        k_lightconv2<C, W, R, PPL, MINB><<<dim3(tiles, n_branches, upper), 256, smem, st>>>(a, d_n, off, cap);
+        end();
+        ++launches;
+    }
+    // shape-specialised LightConv (the three OSBlock stages of osnet_x0_25 and osnet_x1_0); false = not covered
+    bool light2(const LightArgs& a, int n_branches) {
+#define BMB_LIGHT2(CC, WW, RR) \
+        if (a.C == CC && a.W == WW && a.R == RR) { launch_light2<CC, WW, RR>(a, n_branches); return true; }
+        BMB_LIGHT2(16, 32, 16) BMB_LIGHT2(24, 16, 16) BMB_LIGHT2(32, 8, 16)
+        BMB_LIGHT2(64, 32, 8) BMB_LIGHT2(96, 16, 4) BMB_LIGHT2(128, 8, 8)
+#undef BMB_LIGHT2
+        return false;
+    }
     void light(const LightArgs& a, int n_branches, int threads) {
+        if (m->light_v2 && light2(a, n_branches)) return;
         const int tiles = (a.H + a.R - 1) / a.R;
         const int n_grp = threads / (a.C / 4);
         const size_t smem = sizeof(float) * ((size_t)(a.R + 2) * (a.W + 2) * a.C + (size_t)a.C * a.C + 9 * a.C +
@@ -954,6 +1286,16 @@ struct Launcher {
         ++launches;
     }
 };
+
+// v2 keeps the staged input and the 1x1 result side by side: aim for two CTAs per SM, fall back to one
+int pick_tile_rows2(int H, int W, int C) {
+    for (size_t budget : {(size_t)100 * 1024, (size_t)220 * 1024})
+        for (int R = H; R >= 1; --R) {
+            if (H % R || R > 16) continue;
+            if (light2_smem_bytes((R + 2) * (W + 2), C, 256) <= budget) return R;
+        }
+    return 1;
+}
 
 int pick_tile_rows(int H, int W, int C) {
     // largest divisor of H whose haloed tile (+ weights) stays under ~96 KB
@@ -1065,7 +1407,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 p.K = b.cin; p.N = b.mid; p.HW = HW; p.relu = 1;
                 p.w_tc = b.tc_c1.w; p.Kpad = b.tc_c1.Kpad; p.Npad = b.tc_c1.Npad;
                 L.pointwise(p);
-                const int R = pick_tile_rows(H, Wd, b.mid);
+                const int R = m->light_v2 ? pick_tile_rows2(H, Wd, b.mid) : pick_tile_rows(H, Wd, b.mid);
                 const int tiles = H / R;
                 const int threads = (256 / (b.mid / 4)) * (b.mid / 4);  // a multiple of the channel groups
                 for (int level = 1; level <= 4; ++level) {
