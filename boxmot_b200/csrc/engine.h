@@ -88,6 +88,18 @@ struct Engine {
     static constexpr int NDETS_RING = 256;
     double assoc_ms_accum = 0.0;
     int assoc_frames = 0;
+    // frame pipeline of the device-resident path (update_device): ReID of frame f+1 runs on its own stream while
+    // the single-CTA-per-stream association of frame f runs on `stream`; inputs are double-buffered (BoT-SORT family)
+    cudaStream_t reid_stream = nullptr;
+    float* d_dets_alt = nullptr;
+    int* d_ndets_alt = nullptr;
+    float* d_embs_alt = nullptr;
+    TrkStream* d_streams_alt = nullptr;
+    std::vector<TrkStream> h_streams_alt;
+    cudaEvent_t ev_reid_done[2]{};
+    cudaEvent_t ev_assoc_done[2]{};
+    int pipe_parity = 0;
+    bool ev_recorded = false;
     bool profile = false;
     int launches = 0;
     double last_reid_ms = 0.0, last_assoc_ms = 0.0;
@@ -115,6 +127,8 @@ struct Engine {
    private:
     void ensure_images(int rows, int cols, bool host_too);
     void enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total);
+    bool can_pipeline() const { return reid && cfg.with_reid && !is_docs && !is_ss && !profile; }
+    void enqueue_association(TrkStream* streams_dev, const float* embs_src);
     void enqueue_fetch();
     void finish_fetch(float* const* out, const int* out_cap, int* out_rows);
 };

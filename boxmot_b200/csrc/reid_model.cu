@@ -7,8 +7,9 @@
 //                                           OSBlock / OSNet.forward (eval mode, BatchNorm folded offline)
 //   native/cpp/trackers/base/src/reid_onnx.cpp:51-383  (per-crop batch-1 ORT forward of the native path)
 //
-// Data layout: activations are NHWC float32 in HBM, one chunk of crops at a time so that the producer /
-// consumer pairs of consecutive launches stay L2-resident; weights are a BN-folded float32 blob
+// Data layout: activations are NHWC float32 in HBM, one chunk of crops at a time (256 by default: measured on B200,
+// one full-width chunk beats two L2-resident half chunks -- 415 vs 351 frames/s at 208 crops -- because the small
+// tile kernels are latency-bound and want full waves); weights are a BN-folded float32 blob
 // (boxmot_b200/weights.py) uploaded once.  Round-1 kernels are float32 CUDA-core kernels with shared-memory
 // tiling; every 1x1 convolution goes through one GEMM-shaped kernel (k_pointwise) whose prologue can build
 // the gated branch sum on the fly and whose epilogue fuses bias / residual / ReLU.
@@ -938,7 +939,7 @@ struct ReidModel {
     bool pw_v2 = true;      // BOXMOT_B200_PW_V1=1 selects the first-generation pointwise GEMM (A/B runs)
     bool light_v2 = true;   // BOXMOT_B200_LIGHT_V1=1 selects the first-generation LightConv kernel (A/B runs)
     // workspace for one chunk of crops
-    int chunk = 128;
+    int chunk = 256;
     float* blob = nullptr;
     float* bufA = nullptr;
     float* bufB = nullptr;
@@ -1013,7 +1014,7 @@ ReidModel* reid_load(const char* path) {
             max_x = std::max(max_x, (size_t)H * Wd * featp);
             RCUDA_OK(cudaMalloc(&m->d_w, sizeof(float) * n_floats));
             RCUDA_OK(cudaMemcpy(m->d_w, host.data(), sizeof(float) * n_floats, cudaMemcpyHostToDevice));
-            m->chunk = 64;
+            m->chunk = 256;
             if (const char* ce = getenv("BOXMOT_B200_REID_CHUNK")) {
                 const int v = atoi(ce);
                 if (v >= 8 && v <= 1024) m->chunk = v;

@@ -36,7 +36,10 @@ __host__ __device__ inline size_t lap_smem_bytes(int CT, int CD) {
     return sizeof(double) * ((size_t)CT + 2 * (size_t)CD) + sizeof(int) * (2 * (size_t)CT + 1 + 5 * (size_t)CD) + 16;
 }
 
-__global__ void __launch_bounds__(256) k_tracker_frame(const TrkCfg cfg, TrkStream* streams, int lap_in_smem) {
+#ifndef BMB_FRAME_THREADS
+#define BMB_FRAME_THREADS 256
+#endif
+__global__ void __launch_bounds__(BMB_FRAME_THREADS) k_tracker_frame(const TrkCfg cfg, TrkStream* streams, int lap_in_smem) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     TrkStream s = streams[blockIdx.x];
     if (lap_in_smem) {
@@ -349,6 +352,25 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
         }
         CUDA_OK(cudaMalloc(&d_streams, sizeof(TrkStream) * S));
         CUDA_OK(cudaMemcpy(d_streams, h_streams.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
+        if (reid && cfg.with_reid) {   // second input set for the frame pipeline of update_device
+            CUDA_OK(cudaStreamCreateWithFlags(&reid_stream, cudaStreamNonBlocking));
+            CUDA_OK(cudaMalloc(&d_dets_alt, sizeof(float) * 6 * CD * S));
+            CUDA_OK(cudaMalloc(&d_ndets_alt, sizeof(int) * S));
+            CUDA_OK(cudaMemset(d_ndets_alt, 0, sizeof(int) * S));
+            CUDA_OK(cudaMalloc(&d_embs_alt, sizeof(float) * F * CD * S));
+            CUDA_OK(cudaMemset(d_embs_alt, 0, sizeof(float) * F * CD * S));
+            h_streams_alt = h_streams;
+            for (int i = 0; i < S; ++i) {
+                h_streams_alt[i].dets = d_dets_alt + (size_t)i * CD * 6;
+                h_streams_alt[i].n_dets = d_ndets_alt + i;
+            }
+            CUDA_OK(cudaMalloc(&d_streams_alt, sizeof(TrkStream) * S));
+            CUDA_OK(cudaMemcpy(d_streams_alt, h_streams_alt.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
+            for (int k = 0; k < 2; ++k) {
+                CUDA_OK(cudaEventCreateWithFlags(&ev_reid_done[k], cudaEventDisableTiming));
+                CUDA_OK(cudaEventCreateWithFlags(&ev_assoc_done[k], cudaEventDisableTiming));
+            }
+        }
     }
     if (reid) {
         CUDA_OK(cudaMalloc(&d_crops, sizeof(CropDesc) * CD * S));
@@ -365,6 +387,12 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
 
 Engine::~Engine() {
     cudaStreamSynchronize(stream);
+    if (reid_stream) {
+        cudaStreamSynchronize(reid_stream);
+        cudaStreamDestroy(reid_stream);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(ev_reid_done[k]); cudaEventDestroy(ev_assoc_done[k]); }
+        cudaFree(d_dets_alt); cudaFree(d_ndets_alt); cudaFree(d_embs_alt); cudaFree(d_streams_alt);
+    }
     if (reid) reid_free(reid);
     cudaFree(d_warp); cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
     cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_docs); cudaFree(d_ss); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
@@ -376,6 +404,7 @@ Engine::~Engine() {
 }
 
 void Engine::reset() {
+    if (reid_stream) CUDA_OK(cudaStreamSynchronize(reid_stream));
     if (is_docs || is_ss) {
         CUDA_OK(cudaStreamSynchronize(stream));
         for (int i = 0; i < S; ++i) CUDA_OK(cudaMemsetAsync(d_mem + stream_bytes * i, 0, persistent_bytes, stream));
@@ -402,6 +431,7 @@ void Engine::ensure_images(int rows, int cols, bool host_too) {
 void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total) {
     launches = 0;
     CUDA_OK(cudaEventRecord(ev[0], stream));
+    ev_recorded = true;
     if (is_ss) {
         const size_t CD = cfg.cap_dets, F = cfg.feat_dim;
         if (!embs_dev) {
@@ -472,29 +502,10 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
             src = d_embs;
         }
         CUDA_OK(cudaEventRecord(ev[1], stream));
-        dim3 g1((cfg.cap_dets + 7) / 8, S);
-        k_feat_prepare<<<g1, 256, 0, stream>>>(cfg, d_streams, src);
-        dim3 g2((cfg.cap_dets + EMB_TD - 1) / EMB_TD, (cfg.cap_tracks + EMB_TR - 1) / EMB_TR, S);
-        k_embedding_cost<<<g2, 256, 0, stream>>>(cfg, d_streams);
-        launches += 2;
+        enqueue_association(d_streams, src);
     } else {
         CUDA_OK(cudaEventRecord(ev[1], stream));
-    }
-    {
-        const size_t lb = lap_smem_bytes(cfg.cap_tracks, cfg.cap_dets);
-        const bool in_smem = lb <= 160 * 1024;
-        if (in_smem && lb > 48 * 1024)
-            CUDA_OK(cudaFuncSetAttribute(k_tracker_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb));
-        k_tracker_frame<<<S, 256, in_smem ? lb : 0, stream>>>(cfg, d_streams, in_smem ? 1 : 0);
-        ++launches;
-        if (cfg.with_reid) {
-            k_feat_ema<<<dim3((cfg.cap_dets + 7) / 8, S), 256, 0, stream>>>(cfg, d_streams);
-            ++launches;
-        }
-        if (warp_dirty) {  // a supplied camera-motion warp applies to exactly one frame
-            CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
-            warp_dirty = false;
-        }
+        enqueue_association(d_streams, nullptr);
     }
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(ev[2], stream));
@@ -504,6 +515,31 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         cudaEventElapsedTime(&b, ev[1], ev[2]);
         assoc_ms_accum += b;
         assoc_frames += 1;
+    }
+}
+
+// appearance prep + cosine cost (wide grids), the per-stream frame kernel, the deferred appearance EMA: on `stream`
+void Engine::enqueue_association(TrkStream* streams_dev, const float* embs_src) {
+    if (cfg.with_reid) {
+        dim3 g1((cfg.cap_dets + 7) / 8, S);
+        k_feat_prepare<<<g1, 256, 0, stream>>>(cfg, streams_dev, embs_src);
+        dim3 g2((cfg.cap_dets + EMB_TD - 1) / EMB_TD, (cfg.cap_tracks + EMB_TR - 1) / EMB_TR, S);
+        k_embedding_cost<<<g2, 256, 0, stream>>>(cfg, streams_dev);
+        launches += 2;
+    }
+    const size_t lb = lap_smem_bytes(cfg.cap_tracks, cfg.cap_dets);
+    const bool in_smem = lb <= 160 * 1024;
+    if (in_smem && lb > 48 * 1024)
+        CUDA_OK(cudaFuncSetAttribute(k_tracker_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb));
+    k_tracker_frame<<<S, BMB_FRAME_THREADS, in_smem ? lb : 0, stream>>>(cfg, streams_dev, in_smem ? 1 : 0);
+    ++launches;
+    if (cfg.with_reid) {
+        k_feat_ema<<<dim3((cfg.cap_dets + 7) / 8, S), 256, 0, stream>>>(cfg, streams_dev);
+        ++launches;
+    }
+    if (warp_dirty) {  // a supplied camera-motion warp applies to exactly one frame
+        CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
+        warp_dirty = false;
     }
 }
 
@@ -546,6 +582,7 @@ void Engine::profile_read(double* ms, int* launch_counts) {
 void Engine::mark_event(int which) {
     if (which < 0 || which > 1) throw std::runtime_error("mark index must be 0 or 1");
     CUDA_OK(cudaEventRecord(mark[which], stream));
+    if (reid_stream && which == 0) CUDA_OK(cudaStreamWaitEvent(reid_stream, mark[0], 0));   // timed region starts here
 }
 
 double Engine::marks_elapsed_ms() {
@@ -585,11 +622,13 @@ void Engine::finish_fetch(float* const* out, const int* out_cap, int* out_rows) 
             o[8] = 0.f;
         }
     }
-    float a = 0.f, b = 0.f;
-    cudaEventElapsedTime(&a, ev[0], ev[1]);
-    cudaEventElapsedTime(&b, ev[1], ev[2]);
-    last_reid_ms = a;
-    last_assoc_ms = b;
+    if (ev_recorded) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        last_reid_ms = a;
+        last_assoc_ms = b;
+    }
 }
 
 void Engine::update_batch(const float* const* dets, const int* det_rows, const float* const* embs,
@@ -598,6 +637,7 @@ void Engine::update_batch(const float* const* dets, const int* det_rows, const f
     const size_t CD = cfg.cap_dets, F = cfg.feat_dim > 0 ? cfg.feat_dim : 1;
     int total = 0;
     bool have_embs = cfg.with_reid && embs != nullptr;
+    if (reid_stream) CUDA_OK(cudaStreamSynchronize(reid_stream));   // no pipelined frame may still own an input set
     for (int i = 0; i < S; ++i) {
         const int n = det_rows[i];
         if (n < 0 || n > (int)CD) throw std::runtime_error("det_rows exceeds cap_dets");
@@ -650,6 +690,33 @@ void Engine::update_device(const float* dets_dev, const int* det_rows, const flo
         slot[i] = det_rows[i];
         total += det_rows[i];
     }
+    if (can_pipeline() && !embs_dev && images_dev && !sync) {
+        // frame pipeline: crops + ReID of this frame on reid_stream (input set p), association on `stream` once the
+        // embeddings are there; the ReID of the next frame overlaps this frame's association
+        const int pp = pipe_parity;
+        pipe_parity ^= 1;
+        float* dd = pp ? d_dets_alt : d_dets;
+        int* dn = pp ? d_ndets_alt : d_ndets;
+        float* de = pp ? d_embs_alt : d_embs;
+        TrkStream* ds = pp ? d_streams_alt : d_streams;
+        CUDA_OK(cudaStreamWaitEvent(reid_stream, ev_assoc_done[pp], 0));   // set p is free again
+        CUDA_OK(cudaMemcpyAsync(dn, slot, sizeof(int) * S, cudaMemcpyHostToDevice, reid_stream));
+        if (dets_dev != dd)
+            CUDA_OK(cudaMemcpyAsync(dd, dets_dev, sizeof(float) * 6 * CD * S, cudaMemcpyDeviceToDevice, reid_stream));
+        launches = 0;
+        ev_recorded = false;   // the per-frame ReID / association split is not timed in pipelined mode
+        k_build_crops<<<1, 32, 0, reid_stream>>>(cfg, ds, S, d_crops, d_ncrops);
+        ++launches;
+        launches += reid_forward(reid, images_dev, (size_t)rows * cols * 3, rows, cols, d_crops, d_ncrops, total, de,
+                                 cfg.feat_dim, reid_stream);
+        CUDA_OK(cudaEventRecord(ev_reid_done[pp], reid_stream));
+        CUDA_OK(cudaStreamWaitEvent(stream, ev_reid_done[pp], 0));
+        enqueue_association(ds, de);
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaEventRecord(ev_assoc_done[pp], stream));
+        return;
+    }
+    if (reid_stream) CUDA_OK(cudaStreamSynchronize(reid_stream));   // leave the pipelined mode in order
     CUDA_OK(cudaMemcpyAsync(d_ndets, slot, sizeof(int) * S, cudaMemcpyHostToDevice, stream));
     if (dets_dev != d_dets)
         CUDA_OK(cudaMemcpyAsync(d_dets, dets_dev, sizeof(float) * 6 * CD * S, cudaMemcpyDeviceToDevice, stream));
