@@ -64,6 +64,7 @@ struct DocsStream {
     double* tbox;      // [CT][4] predicted boxes by list position
     double* kobs;      // [CT][5]
     double* iou;       // [CD][LD]
+    double* embq;      // [CD][CT] appearance similarity by (raw detection, slot): filled by the wide k_docs_embcost
     double* embc;      // [CD][LD]
     double* cost;      // [max(CD,CT)][LD2] assignment cost (possibly transposed)
     double* top;       // [2*(CD+CT)] row / column top-2 values
@@ -78,6 +79,15 @@ struct DocsStream {
     int* lap_tl; int* lap_sc; int* csr_ptr; int* csr_col;
     float* out;        // [CD][8]
 };
+
+// one entry of the appearance similarity matrix (float32 detection row x float64 track EMA, float64 accumulate)
+BMB_FN double docs_emb_dot(const DocsCfg& c, const DocsStream& s, int d_raw, int slot) {
+    const float* de = s.embs + (size_t)d_raw * c.feat_dim;
+    const double* te = s.emb + (size_t)slot * c.feat_dim;
+    double acc = 0.0;
+    for (int q = 0; q < c.feat_dim; ++q) acc += (double)de[q] * te[q];
+    return acc;
+}
 
 BMB_FN double iou_ff(const double* a, const double* b) {
     double xx1 = a[0] > b[0] ? a[0] : b[0];
@@ -365,7 +375,8 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
     const int frame = s.scalars[SC_FRAME] + 1;
     const int n_trk0 = s.scalars[SC_N_ACTIVE];
     const bool use_emb = !c.embedding_off && s.embs != nullptr;
-    BMB_SYNC();
+    long long _t_prev = BMB_CLOCK();   // phase clocks: 0 dets+predict, 1 iou/appearance, 2 first assignment (cost + solver:
+    BMB_SYNC();                        // 8..10 inside), 3 updates, 4 second round, 5 misses+births, 6 emit+cull
 
     // ---- kept detections (scores > det_thresh in float32), trust -> alpha (deepocsort.py:330-354) ----
     if (BMB_WARP == 0) {
@@ -411,6 +422,7 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
     }
     BMB_SYNC();
 
+    BMB_PHASE(0);
     // ---- first association (association.py:61-152) ----
     int n_und = 0, n_unt = 0;
     if (T == 0) {
@@ -424,19 +436,14 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
             s.iou[(size_t)d * LD + k] = iou_ff(s.dbox + d * 5, s.tbox + k * 4);
         }
         if (use_emb) {
-            for (int e = BMB_WARP; e < nk * T; e += BMB_NW) {
+            // dets_embs @ trk_embs.T (deepocsort.py:391) was computed for every (detection, slot) by the wide grid
+            for (int e = BMB_TID; e < nk * T; e += BMB_NT) {
                 const int d = e / T, k = e - d * T;
-                const float* de = s.embs + (size_t)s.kdet[d] * F;
-                const double* te = s.emb + (size_t)s.tracks[k] * F;
-                double acc = 0.0;
-                for (int q = BMB_LANE; q < F; q += BMB_NL) acc += (double)de[q] * te[q];
-#if BMB_DEVICE
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-#endif
-                if (BMB_LANE == 0) s.embc[(size_t)d * LD + k] = acc;
+                s.embc[(size_t)d * LD + k] = s.embq[(size_t)s.kdet[d] * CT + s.tracks[k]];
             }
         }
         BMB_SYNC();
+        BMB_PHASE(1);
         // 1-1 shortcut test: every row and column has at most one entry above the threshold, and some row has one
         if (BMB_TID == 0) { mb[2] = 0; mb[3] = 0; }
         BMB_SYNC();
@@ -547,6 +554,7 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
         BMB_SYNC();
         n_und = mb[4]; n_unt = mb[5];
     }
+    BMB_PHASE(2);
     // apply the first-round matches
     for (int d = BMB_TID; d < nk; d += BMB_NT)
         if (s.mrow[d] >= 0) docs_track_update(c, s, s.tracks[s.mrow[d]], d);
@@ -555,6 +563,7 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
             if (s.mrow[d] >= 0) docs_emb_update(c, s, s.tracks[s.mrow[d]], d);
     BMB_SYNC();
 
+    BMB_PHASE(3);
     // ---- second round: observation-centric recovery on the last observations (deepocsort.py:414-450) ----
     if (n_und > 0 && n_unt > 0) {
         // last_boxes were gathered before any update: unmatched tracks have not been touched this frame
@@ -611,6 +620,7 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
             n_und = mb[4]; n_unt = mb[5];
         }
     }
+    BMB_PHASE(4);
     // ---- misses, births (deepocsort.py:452-466) ----
     for (int k = BMB_TID; k < n_unt; k += BMB_NT) docs_kf_miss(s, s.tracks[s.unt[k]]);
     for (int k = BMB_TID; k < CT; k += BMB_NT) s.mark[k] = 0;
@@ -670,6 +680,7 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
     }
     BMB_SYNC();
     const int n_all = T + n_birth;
+    BMB_PHASE(5);
     // ---- emit (reversed list order) and cull (deepocsort.py:467-489) ----
     for (int k = BMB_TID; k < n_all; k += BMB_NT) {
         const int t = s.tracks[k];
@@ -705,6 +716,7 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
         s.scalars[SC_NEXT_ID] += n_birth;
     }
     BMB_SYNC();
+    BMB_PHASE(6);
 }
 
 }  // namespace bmb

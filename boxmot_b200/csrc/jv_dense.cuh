@@ -39,6 +39,10 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
     BMB_SYNC();
     if (BMB_WARP == 0) {
         const int lane = BMB_LANE;
+        long long _jt = BMB_CLOCK();   // solver phase clocks (timers 8..11) and work counters (12..13), diagnostics
+        auto tick = [&](int slot) {
+            if (lane == 0) { const long long now = BMB_CLOCK(); s.timers[slot] += now - _jt; _jt = now; }
+        };
         if (lane == 0) {
             for (int j = n - 1; j >= 0; --j) {
                 const int i = y[j];
@@ -63,6 +67,7 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
             if (lane == 0) v[xi] -= m;
             BMB_SYNCWARP();
         }
+        tick(8);
         // ---- augmenting row reduction, two passes ----
         for (int pass = 0; pass < 2 && n_free > 0; ++pass) {
             int cur = 0, kept = 0;
@@ -120,6 +125,8 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
             }
             n_free = kept;
         }
+        tick(9);
+        if (lane == 0) s.timers[12] += n_free;
         // ---- augmentation ----
         for (int f = 0; f < n_free; ++f) {
             const int start = free_rows[f];
@@ -131,24 +138,53 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
             BMB_SYNCWARP();
             while (final_j == -1) {
                 if (lo == hi) {
-                    // _find_dense: sequential (its swaps define the scan order of ties)
-                    if (lane == 0) {
+                    // _find_dense.  lapjv scans cols[lo+1..n) once, keeping the running minimum: a column at or below
+                    // it is a "hit" (strictly below: the tie list restarts at lo) and is swapped to the front; the
+                    // swaps define the scan order of later ties, so they are replayed exactly -- but only the hits are
+                    // sequential.  The lanes find them with a warp prefix-minimum per 32 columns (a hit at position k
+                    // only rewrites positions <= k, so the columns of a chunk can be read before its hits are applied).
+                    {
                         int h2 = lo + 1;
                         double mind = d[cols[lo]];
-                        for (int k = lo + 1; k < n; ++k) {
-                            const int j = cols[k];
-                            const double dj = d[j];
+                        for (int k0 = lo + 1; k0 < n; k0 += BMB_NL) {
+                            const int k = k0 + lane;
+                            const int j = k < n ? cols[k] : -1;
+                            const double dj = k < n ? d[j] : BIG;
+#if BMB_DEVICE
+                            double pm = dj;   // inclusive prefix minimum over the lanes of this chunk
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const double t = __shfl_up_sync(0xffffffffu, pm, o);
+                                if (lane >= o && t < pm) pm = t;
+                            }
+                            const double excl = __shfl_up_sync(0xffffffffu, pm, 1);
+                            const double before = lane == 0 ? mind : (excl < mind ? excl : mind);   // running minimum
+                            unsigned hits = __ballot_sync(0xffffffffu, k < n && dj <= before);
+                            while (hits) {
+                                const int src = __ffs(hits) - 1;
+                                hits &= hits - 1;
+                                const double dh = __shfl_sync(0xffffffffu, dj, src);
+                                const int jh = __shfl_sync(0xffffffffu, j, src);
+                                if (dh < mind) { h2 = lo; mind = dh; }
+                                if (lane == 0) { cols[k0 + src] = cols[h2]; cols[h2] = jh; }
+                                ++h2;
+                                __syncwarp();
+                            }
+#else
                             if (dj <= mind) {
                                 if (dj < mind) { h2 = lo; mind = dj; }
                                 cols[k] = cols[h2];
                                 cols[h2++] = j;
                             }
+#endif
                         }
-                        int fj = -1;
-                        for (int k = lo; k < h2; ++k)
-                            if (y[cols[k]] < 0) fj = cols[k];
-                        s.free_l[MB_COUNT - 1] = h2;
-                        s.free_l[MB_COUNT - 2] = fj;
+                        BMB_SYNCWARP();
+                        if (lane == 0) {
+                            int fj = -1;
+                            for (int k = lo; k < h2; ++k)
+                                if (y[cols[k]] < 0) fj = cols[k];
+                            s.free_l[MB_COUNT - 1] = h2;
+                            s.free_l[MB_COUNT - 2] = fj;
+                        }
                     }
                     BMB_SYNCWARP();
                     n_ready = lo;
@@ -160,6 +196,7 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
                 if (final_j == -1) {
                     // _scan_dense over the ready band
                     while (lo != hi && final_j == -1) {
+                        if (lane == 0) s.timers[13] += 1;
                         const int j = cols[lo++];
                         const int i = y[j];
                         const double mind = d[j];
@@ -222,6 +259,7 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
             }
             BMB_SYNCWARP();
         }
+        tick(10);
     }
     BMB_SYNC();
 }

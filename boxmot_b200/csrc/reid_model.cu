@@ -620,6 +620,194 @@ __global__ void __launch_bounds__(256, MINB) k_lightconv2(const LightArgs a, con
     }
 }
 
+// K6 v3: a whole OSBlock branch (1-4 LightConv3x3 layers) per CTA.  The per-level kernel spends a third of its time
+// waiting for its input tile and writes every intermediate level back to HBM; here a CTA stages the conv1 output once
+// (tile rows + `depth` halo rows each side), runs  1x1 -> depthwise 3x3 + bias + ReLU  `depth` times between two
+// shared-memory buffers (X -> T -> X ...), and only the last level goes to global memory (plus the per-tile channel
+// sums for the ChannelGate).  Rows outside the image stay zero in both buffers, which is exactly the zero padding
+// every layer of the reference applies; level l only computes the rows level `depth` still needs.
+// grid = (row tiles, 4 branches (deepest first), crops); ~12 % redundant halo rows at R = 16, none for full-height tiles.
+struct ChainArgs {
+    const float* in;        // conv1 output [crops][H][W][C]
+    float* out[4];          // final activation of each branch
+    const float* wpw[10];   // per LightConv (index = branch*(branch+1)/2 + level-1)
+    const float* wdw[10];
+    const float* bias[10];
+    float* sums[4];         // [crops][tiles][C]
+    int H;
+};
+
+template <int C, int W, int R, int NT>
+__host__ __device__ static constexpr int chain_n_pxp() {
+    return (((R + 8) * (W + 2) + 64 + 7) / 8) * 8 + 2;   // room for a trailing 64-pixel group; planes 8 banks apart
+}
+template <int C, int W, int R, int NT>
+static constexpr size_t chain_smem_bytes() {
+    return sizeof(float) * ((size_t)2 * chain_n_pxp<C, W, R, NT>() * C + 4 * ((size_t)C * C + 9 * C + C));
+}
+
+template <int C, int W, int R, int NT>
+__global__ void __launch_bounds__(NT) k_lightchain(const ChainArgs a, const int* __restrict__ d_n, int off, int cap) {
+    const int n = blockIdx.z;
+    if (n >= chunk_count(d_n, off, cap)) return;
+    const int br = 3 - (int)blockIdx.y, depth = br + 1, tile = blockIdx.x;
+    const int l0 = br * (br + 1) / 2;
+    const int H = a.H;
+    constexpr int TW = W + 2, C4 = C / 4, PPL = 2, G = 32 * PPL;   // buffers hold R + 8 padded rows
+    constexpr int n_pxp = chain_n_pxp<C, W, R, NT>();
+    extern __shared__ __align__(16) float smem[];
+    float4* sX = reinterpret_cast<float4*>(smem);     // [C4][n_pxp]  level input (planar: K-chunk major)
+    float4* sT = sX + (size_t)C4 * n_pxp;             // [C4][n_pxp]  1x1 result
+    float* sW = reinterpret_cast<float*>(sT + (size_t)C4 * n_pxp);   // [4][C][C]
+    float* sD = sW + 4 * C * C;                       // [4][9][C]
+    float* sB = sD + 4 * 9 * C;                       // [4][C]
+    float* sP = reinterpret_cast<float*>(sT);         // [NT / C4][C]  (aliases T: only used after the last level)
+    const int y0 = tile * R;
+    const int g0 = y0 - 4;                            // global row of local row 0
+    const float* in = a.in + (size_t)n * H * W * C;
+    // ---- stage: zero both buffers, weights of this branch, the input rows level 1 needs ----
+    for (int e = threadIdx.x; e < 2 * C4 * n_pxp; e += NT) sX[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < depth; ++l) {
+        for (int e = threadIdx.x; e < C * C / 4; e += NT)
+            reinterpret_cast<float4*>(sW + l * C * C)[e] = reinterpret_cast<const float4*>(a.wpw[l0 + l])[e];
+        for (int e = threadIdx.x; e < 9 * C; e += NT) sD[l * 9 * C + e] = a.wdw[l0 + l][e];
+        for (int e = threadIdx.x; e < C; e += NT) sB[l * C + e] = a.bias[l0 + l][e];
+    }
+    __syncthreads();   // the zero fill must land before cp.async writes into the same buffer
+    {
+        const int ga = max(y0 - depth, 0), gb = min(y0 + R + depth, H);
+        const int n_in = (gb - ga) * W * C4;
+        for (int e = threadIdx.x; e < n_in; e += NT) {
+            const int ch = e % C4, px = e / C4;
+            const int gy = ga + px / W, gx = px % W;
+            cp_async16(sX + ch * n_pxp + (gy - g0) * TW + gx + 1, in + ((size_t)gy * W + gx) * C + ch * 4);
+        }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int n_cc = C >> 3;
+    constexpr int walkers = W * C4;
+    constexpr int n_grp = NT / C4;
+    constexpr int act = n_grp * C4;
+    constexpr int n_split = (act / walkers) < 1 ? 1 : (act / walkers);
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int lv = 1; lv <= depth; ++lv) {
+        const int ext = depth - lv;                                   // extra rows each side this level still feeds
+        const float* w = sW + (lv - 1) * C * C;
+        // ---- phase A: T = X * Wpw on image rows [ya-1, yb+1) of this level (whole padded rows) ----
+        const int ya = max(y0 - ext, 0), yb = min(y0 + R + ext, H);   // rows phase B produces
+        {
+            const int ta = max(ya - 1, 0), tb = min(yb + 1, H);
+            const int pa = (ta - g0) * TW, pb = (tb - g0) * TW;
+            const int n_pg = (pb - pa + G - 1) / G;
+            for (int item = warp; item < n_pg * n_cc; item += NT / 32) {
+                const int pg = item % n_pg, cc = (item / n_pg) * 8;
+                const int p0 = pa + pg * G + lane;
+                float acc[PPL][8];
+#pragma unroll
+                for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+#pragma unroll 2
+                for (int kc = 0; kc < C4; ++kc) {
+                    float xv[PPL][4];
+#pragma unroll
+                    for (int q = 0; q < PPL; ++q) {
+                        const float4 x = sX[kc * n_pxp + p0 + 32 * q];
+                        xv[q][0] = x.x; xv[q][1] = x.y; xv[q][2] = x.z; xv[q][3] = x.w;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(w + (kc * 4 + kk) * C + cc);
+                        const float4 w1 = *reinterpret_cast<const float4*>(w + (kc * 4 + kk) * C + cc + 4);
+                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                        for (int q = 0; q < PPL; ++q)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(xv[q][kk], wv[j], acc[q][j]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < PPL; ++q) {
+                    const int p = p0 + 32 * q;
+                    if (p < pb) {
+                        sT[(cc / 4) * n_pxp + p] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+                        sT[(cc / 4 + 1) * n_pxp + p] = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase B: depthwise 3x3 + bias + ReLU on rows [ya, yb): next level's X, or the branch output ----
+        const bool last = lv == depth;
+        const int rows_lv = yb - ya;
+        const int rows_per = (rows_lv + n_split - 1) / n_split;
+        float* outp = a.out[br] + (size_t)n * H * W * C;
+        if (threadIdx.x < act) {
+            for (int wk = threadIdx.x; wk < walkers * n_split; wk += act) {
+                const int c4 = wk % C4, x = (wk / C4) % W, sp = wk / walkers;
+                const int ra = ya + sp * rows_per, rb = min(ra + rows_per, yb);
+                if (ra >= rb) continue;
+                const float* dwp = sD + (lv - 1) * 9 * C + c4 * 4;
+                float4 wv[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const float4*>(dwp + t * C);
+                const float4 bv = *reinterpret_cast<const float4*>(sB + (lv - 1) * C + c4 * 4);
+                const float4* tbase = sT + c4 * n_pxp + x;              // column x-1 of the padded row
+                float4* xdst = sX + c4 * n_pxp + x + 1;
+                float4 win[3][3];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    win[0][kx] = tbase[(ra - 1 - g0) * TW + kx];
+                    win[1][kx] = tbase[(ra - g0) * TW + kx];
+                }
+                for (int y = ra; y < rb; y += 3) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        if (y + u < rb) {
+                            const int i0 = u % 3, i1 = (u + 1) % 3, i2 = (u + 2) % 3;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) win[i2][kx] = tbase[(y + u + 1 - g0) * TW + kx];
+                            float4 acc = bv;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 w0 = wv[kx], w1 = wv[3 + kx], w2 = wv[6 + kx];
+                                const float4 t0 = win[i0][kx], t1 = win[i1][kx], t2 = win[i2][kx];
+                                acc.x = fmaf(t0.x, w0.x, acc.x); acc.y = fmaf(t0.y, w0.y, acc.y);
+                                acc.z = fmaf(t0.z, w0.z, acc.z); acc.w = fmaf(t0.w, w0.w, acc.w);
+                                acc.x = fmaf(t1.x, w1.x, acc.x); acc.y = fmaf(t1.y, w1.y, acc.y);
+                                acc.z = fmaf(t1.z, w1.z, acc.z); acc.w = fmaf(t1.w, w1.w, acc.w);
+                                acc.x = fmaf(t2.x, w2.x, acc.x); acc.y = fmaf(t2.y, w2.y, acc.y);
+                                acc.z = fmaf(t2.z, w2.z, acc.z); acc.w = fmaf(t2.w, w2.w, acc.w);
+                            }
+                            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+                            acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                            if (last) {
+                                *reinterpret_cast<float4*>(outp + ((size_t)(y + u) * W + x) * C + c4 * 4) = acc;
+                                psum.x += acc.x; psum.y += acc.y; psum.z += acc.z; psum.w += acc.w;
+                            } else {
+                                xdst[(y + u - g0) * TW] = acc;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // per-tile channel sums of the branch output (fixed slot per thread, fixed combination order)
+    if (threadIdx.x < act)
+        *reinterpret_cast<float4*>(sP + (threadIdx.x / C4) * C + (threadIdx.x % C4) * 4) = psum;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += NT) {
+        float s = 0.f;
+        for (int g = 0; g < n_grp; ++g) s += sP[g * C + c];
+        a.sums[br][((size_t)n * gridDim.x + tile) * C + c] = s;
+    }
+}
+
 // K5 v2.  Same contract as k_pointwise.  ncu on v1: long-scoreboard bound (global loads serialised with the math:
 // load chunk -> sync -> compute -> sync) and 16 scalar shared stores per thread per chunk for the k-major transpose.
 // v2 streams A with cp.async straight into a K-chunk-planar layout As[4][BM] of float4 (rows interleaved over the
@@ -937,6 +1125,8 @@ struct ReidModel {
     float* d_wtc = nullptr;    // all packed tensor-core weights
     bool use_tc = false;
     bool pw_v2 = true;      // BOXMOT_B200_PW_V1=1 selects the first-generation pointwise GEMM (A/B runs)
+    bool light_chain = true;   // BOXMOT_B200_LIGHT_CHAIN=0: per-level LightConv launches instead of whole-branch CTAs
+    int chain_var = 0;         // BOXMOT_B200_CHAIN_VAR=1: stage-2 tiles of 16 rows with 512 threads (1 CTA / SM)
     bool light_v2 = true;   // BOXMOT_B200_LIGHT_V1=1 selects the first-generation LightConv kernel (A/B runs)
     // workspace for one chunk of crops
     int chunk = 256;
@@ -1086,6 +1276,8 @@ ReidModel* reid_load(const char* path) {
             m->use_tc = env && env[0] == '1';
             const char* lv = getenv("BOXMOT_B200_LIGHT_V1");
             m->light_v2 = !(lv && lv[0] == '1');
+            if (const char* cv = getenv("BOXMOT_B200_LIGHT_CHAIN")) m->light_chain = !(cv[0] == '0');
+            if (const char* cv = getenv("BOXMOT_B200_CHAIN_VAR")) m->chain_var = atoi(cv);
             const char* pv = getenv("BOXMOT_B200_PW_V1");
             m->pw_v2 = !(pv && pv[0] == '1');
             std::vector<float> packed;
@@ -1264,6 +1456,26 @@ struct Launcher {
         end();
         ++launches;
     }
+    template <int C, int W, int R, int NT>
+    void launch_chain(const ChainArgs& a) {
+        const int tiles = a.H / R;
+        constexpr size_t smem = chain_smem_bytes<C, W, R, NT>();
+        RCUDA_OK(cudaFuncSetAttribute(k_lightchain<C, W, R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        begin(CLS_LIGHTCONV);
+        k_lightchain<C, W, R, NT><<<dim3(tiles, 4, upper), NT, smem, st>>>(a, d_n, off, cap);
+        end();
+        ++launches;
+    }
+    // whole-branch LightConv chains for the osnet_x0_25 stage shapes; returns the tile rows used (0 = not covered)
+    int light_chain(const ChainArgs& a, int C, int W) {
+        if (C == 16 && W == 32) {
+            if (m->chain_var == 1) { launch_chain<16, 32, 16, 512>(a); return 16; }
+            launch_chain<16, 32, 8, 256>(a); return 8;
+        }
+        if (C == 24 && W == 16) { launch_chain<24, 16, 16, 256>(a); return 16; }
+        if (C == 32 && W == 8) { launch_chain<32, 8, 16, 256>(a); return 16; }
+        return 0;
+    }
     // shape-specialised LightConv (the three OSBlock stages of osnet_x0_25 and osnet_x1_0); false = not covered
     bool light2(const LightArgs& a, int n_branches) {
 #define BMB_LIGHT2(CC, WW, RR) \
@@ -1408,10 +1620,21 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                 p.K = b.cin; p.N = b.mid; p.HW = HW; p.relu = 1;
                 p.w_tc = b.tc_c1.w; p.Kpad = b.tc_c1.Kpad; p.Npad = b.tc_c1.Npad;
                 L.pointwise(p);
-                const int R = m->light_v2 ? pick_tile_rows2(H, Wd, b.mid) : pick_tile_rows(H, Wd, b.mid);
+                int R = 0;
+                if (m->light_chain && m->light_v2) {
+                    ChainArgs ca{};
+                    ca.in = m->x1; ca.H = H;
+                    for (int br = 0; br < 4; ++br) { ca.out[br] = m->Y[br][kDepth[br] & 1]; ca.sums[br] = m->sums[br]; }
+                    for (int l = 0; l < 10; ++l) {
+                        ca.wpw[l] = W + b.light[l].pw; ca.wdw[l] = W + b.light[l].dw; ca.bias[l] = W + b.light[l].b;
+                    }
+                    R = L.light_chain(ca, b.mid, Wd);
+                }
+                const bool chained = R > 0;
+                if (!chained) R = m->light_v2 ? pick_tile_rows2(H, Wd, b.mid) : pick_tile_rows(H, Wd, b.mid);
                 const int tiles = H / R;
                 const int threads = (256 / (b.mid / 4)) * (b.mid / 4);  // a multiple of the channel groups
-                for (int level = 1; level <= 4; ++level) {
+                for (int level = 1; level <= 4 && !chained; ++level) {
                     LightArgs la{};
                     la.H = H; la.W = Wd; la.C = b.mid; la.R = R;
                     int nb = 0;

@@ -132,6 +132,42 @@ __global__ void __launch_bounds__(256) k_embedding_cost(const TrkCfg cfg, TrkStr
     }
 }
 
+// DeepOCSORT appearance similarity dets_embs @ trk_embs.T (deepocsort.py:391) for every (detection, live slot):
+// float32 detection rows x float64 track EMAs, float64 accumulate.  Inside the one-CTA frame kernel this product was
+// 7 of the 8 ms of a 256-detection frame; on a wide grid it is microseconds.  Tile = 8 tracks x 32 detections.
+__global__ void __launch_bounds__(256) k_docs_embcost(const DocsCfg cfg, DocsStream* streams) {
+    const DocsStream& s = streams[blockIdx.z];
+    const int D = min(*s.n_dets, cfg.cap_dets);
+    const int T = s.scalars[SC_N_ACTIVE];
+    const int r0 = blockIdx.y * EMB_TR, d0 = blockIdx.x * EMB_TD;
+    if (r0 >= T || d0 >= D) return;
+    __shared__ double sa[EMB_TR][EMB_TK + 1];
+    __shared__ float sb[EMB_TD][EMB_TK + 1];
+    __shared__ int slot_of[EMB_TR];
+    const int F = cfg.feat_dim;
+    const int tr = threadIdx.x / EMB_TD, td = threadIdx.x % EMB_TD;
+    if (threadIdx.x < EMB_TR) slot_of[threadIdx.x] = r0 + threadIdx.x < T ? s.tracks[r0 + threadIdx.x] : -1;
+    __syncthreads();
+    double dot = 0.0;
+    for (int k0 = 0; k0 < F; k0 += EMB_TK) {
+        for (int e = threadIdx.x; e < EMB_TR * EMB_TK; e += blockDim.x) {
+            const int r = e / EMB_TK, k = e % EMB_TK;
+            const int slot = slot_of[r];
+            sa[r][k] = (slot >= 0 && k0 + k < F) ? s.emb[(size_t)slot * F + k0 + k] : 0.0;
+        }
+        for (int e = threadIdx.x; e < EMB_TD * EMB_TK; e += blockDim.x) {
+            const int d = e / EMB_TK, k = e % EMB_TK;
+            sb[d][k] = (d0 + d < D && k0 + k < F) ? s.embs[(size_t)(d0 + d) * F + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < EMB_TK; ++k) dot += (double)sb[td][k] * sa[tr][k];
+        __syncthreads();
+    }
+    const int slot = slot_of[tr];
+    if (slot >= 0 && d0 + td < D) s.embq[(size_t)(d0 + td) * cfg.cap_tracks + slot] = dot;
+}
+
 // shared-memory residency of the dense JV solver's per-column / per-row state (prices, distances, column list, ...)
 __host__ __device__ inline size_t jv_smem_bytes(int MX) {
     return (size_t)MX * (2 * sizeof(double) + 6 * sizeof(int)) + 16;
@@ -470,6 +506,11 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
                                      max_dets_total, d_embs, cfg.feat_dim, stream);
         }
         CUDA_OK(cudaEventRecord(ev[1], stream));
+        if (cfg.with_reid) {
+            dim3 g((dcfg.cap_dets + EMB_TD - 1) / EMB_TD, (dcfg.cap_tracks + EMB_TR - 1) / EMB_TR, S);
+            k_docs_embcost<<<g, 256, 0, stream>>>(dcfg, d_docs);
+            ++launches;
+        }
         {
             const int MX = dcfg.cap_tracks > dcfg.cap_dets ? dcfg.cap_tracks : dcfg.cap_dets;
             const size_t jb = jv_smem_bytes(MX);
@@ -574,7 +615,7 @@ void Engine::profile_read(double* ms, int* launch_counts) {
     for (int c = 0; c < REID_N_CLASSES + 1; ++c) { ms[c] = 0.0; launch_counts[c] = 0; }
     if (reid) reid_profile_collect(reid, ms, launch_counts);
     ms[REID_N_CLASSES] = assoc_ms_accum;
-    launch_counts[REID_N_CLASSES] = assoc_frames * (is_docs ? 1 : (cfg.with_reid ? 4 : 1));
+    launch_counts[REID_N_CLASSES] = assoc_frames * (is_docs ? (cfg.with_reid ? 2 : 1) : (cfg.with_reid ? 4 : 1));
     assoc_ms_accum = 0.0;
     assoc_frames = 0;
 }
@@ -670,9 +711,17 @@ void Engine::update_batch(const float* const* dets, const int* det_rows, const f
         const size_t ib = (size_t)rows * cols * 3;
         for (int i = 0; i < S; ++i) {
             if (!images[i]) throw std::runtime_error("image pointer is NULL");
-            memcpy(h_images + ib * i, images[i], ib);
+            // a frame that already lives in page-locked memory goes to the device straight from the caller's
+            // buffer (the call returns only after the stream has drained); pageable frames are staged first
+            cudaPointerAttributes attr{};
+            const bool pinned = cudaPointerGetAttributes(&attr, images[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+            if (!pinned) {
+                cudaGetLastError();   // unregistered host pointers report an error on some drivers: clear it
+                memcpy(h_images + ib * i, images[i], ib);
+            }
+            CUDA_OK(cudaMemcpyAsync(d_images + ib * i, pinned ? images[i] : h_images + ib * i, ib,
+                                    cudaMemcpyHostToDevice, stream));
         }
-        CUDA_OK(cudaMemcpyAsync(d_images, h_images, ib * S, cudaMemcpyHostToDevice, stream));
         img_dev = d_images;
     }
     enqueue_frame(have_embs ? d_embs : nullptr, img_dev, rows, cols, total);

@@ -120,6 +120,7 @@ inline size_t carve_docs(const DocsCfg& c, uint8_t* base, DocsStream* s, size_t*
     t.kobs = k.take<double>(CT * 5);
     t.iou = k.take<double>(CD * CT);
     t.embc = k.take<double>(CD * CT);
+    t.embq = k.take<double>(CD * CT);
     t.cost = k.take<double>(MX * MX);   // lapjv's zero-padded square problem
     t.top = k.take<double>(2 * (CD + CT));
     t.mrow = k.take<int>(CD);

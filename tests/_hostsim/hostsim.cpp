@@ -132,6 +132,10 @@ int docs_update(DocsSim* h, const float* dets, int n, const float* embs, float* 
     } else {
         h->s.embs = embs ? h->embs.data() : nullptr;
     }
+    if (h->s.embs && !c.embedding_off)   // the wide appearance kernel: every live slot against every detection
+        for (int k = 0; k < h->s.scalars[SC_N_ACTIVE]; ++k)
+            for (int d = 0; d < n; ++d)
+                h->s.embq[(size_t)d * c.cap_tracks + h->s.tracks[k]] = docs_emb_dot(c, h->s, d, h->s.tracks[k]);
     docs_frame(c, h->s);
     if (h->s.scalars[SC_ERROR]) return -h->s.scalars[SC_ERROR];
     const int m = h->s.scalars[SC_N_OUT];
