@@ -1469,6 +1469,7 @@ struct Launcher {
     // whole-branch LightConv chains for the osnet_x0_25 stage shapes; returns the tile rows used (0 = not covered)
     int light_chain(const ChainArgs& a, int C, int W) {
         if (C == 16 && W == 32) {
+            if (m->chain_var == 2) return 0;   // stage 2 per level (8-row chain tiles recompute 25 % halo rows)
             if (m->chain_var == 1) { launch_chain<16, 32, 16, 512>(a); return 16; }
             launch_chain<16, 32, 8, 256>(a); return 8;
         }
