@@ -351,6 +351,13 @@ def run_b200(args):
     fps = sum(frames_per_rank) / (value_ms * 1e-3)
     e2e_fps = sum(frames_per_rank) / (e2e_ms * 1e-3)
     total_flop = 2 * sum(mac.values()) * crops
+    traffic = None   # DRAM bytes of the dominant class per step, from the committed ncu capture (same shapes)
+    try:
+        tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        if dom in tj and tj[dom].get("crops_per_step") == crops:
+            traffic = tj[dom]["dram_bytes_per_step"]
+    except Exception:
+        traffic = None
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": WORLD, "steps": K, "warmup": Wm,
         "ms_per_step": value_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -370,7 +377,7 @@ def run_b200(args):
         "launches_per_step": launches_per_step,
         "clocks": clock_info,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": dom_bytes / dom_s / 1e9, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                     "unit": "GB/s", "frac": dom_bytes / dom_s / 1e9 / peaks["hbm_gbs"], "traffic": traffic,
                      "peak_source": peaks["source"], "algorithmic_bytes_per_step": dom_bytes,
                      "ms_per_step": prof[dom]["ms_per_step"], "share_of_reid": prof[dom]["ms_per_step"] / max(reid_ms, 1e-9)},
         "reid_conv_roofline": {"achieved_tflops": total_flop / (reid_ms * 1e-3) / 1e12, "peak_tflops": peaks["tensor_tflops"],

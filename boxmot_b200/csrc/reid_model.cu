@@ -1126,7 +1126,9 @@ struct ReidModel {
     bool use_tc = false;
     bool pw_v2 = true;      // BOXMOT_B200_PW_V1=1 selects the first-generation pointwise GEMM (A/B runs)
     bool light_chain = true;   // BOXMOT_B200_LIGHT_CHAIN=0: per-level LightConv launches instead of whole-branch CTAs
-    int chain_var = 0;         // BOXMOT_B200_CHAIN_VAR=1: stage-2 tiles of 16 rows with 512 threads (1 CTA / SM)
+    int chain_var = 2;         // BOXMOT_B200_CHAIN_VAR: 2 (default) stage 2 per level + stages 3-4 chained (measured best:
+                               // 8-row stage-2 chain tiles recompute 25 % halo rows); 0 all chained; 1 stage-2 chain
+                               // tiles of 16 rows with 512 threads (1 CTA / SM)
     bool light_v2 = true;   // BOXMOT_B200_LIGHT_V1=1 selects the first-generation LightConv kernel (A/B runs)
     // workspace for one chunk of crops
     int chunk = 256;
