@@ -120,9 +120,13 @@ def test_reid_abi_errors(tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"BOXMOT_B200_REID_TC": "1"}, {"BOXMOT_B200_REID_CHUNK": "32"},
-                                 {"BOXMOT_B200_REID_CHUNK": "256", "BOXMOT_B200_REID_TC": "1"}])
+                                 {"BOXMOT_B200_REID_CHUNK": "256", "BOXMOT_B200_REID_TC": "1"},
+                                 {"BOXMOT_B200_LIGHT_CHAIN": "0"}, {"BOXMOT_B200_CHAIN_VAR": "0"},
+                                 {"BOXMOT_B200_CHAIN_VAR": "1", "BOXMOT_B200_REID_CHUNK": "24"},
+                                 {"BOXMOT_B200_LIGHT_V1": "1"}, {"BOXMOT_B200_PW_V1": "1"}])
 def test_alternative_kernel_paths_keep_parity(tmp_path, monkeypatch, env):
-    """tcgen05 (tf32 x3) pointwise path and other chunk sizes: same embeddings within the bound."""
+    """Every selectable kernel generation / configuration keeps the embeddings within the bound: tcgen05 (tf32 x3)
+    pointwise path, other chunk sizes, per-level vs whole-branch LightConv, first-generation kernels."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     sd, reid = _model(tmp_path, seed=9)
