@@ -351,6 +351,7 @@ struct LightArgs {
     const float* bias[4];
     float* sums[4];   // [crops][tiles][C] or null
     int H, W, C, R;   // R = tile rows
+    const float* wtc[4];   // 1x1 weights as canonical K-major hi / lo blocks (tc::pack_weights) for the tcgen05 stage
 };
 
 __global__ void k_lightconv(const LightArgs a, const int* __restrict__ d_n, int off, int cap) {
@@ -462,9 +463,10 @@ __global__ void k_lightconv(const LightArgs a, const int* __restrict__ d_n, int 
 //   * phase B loaded 9 float4 per output from shared memory.  v2 walks columns: a thread owns (x, 4 channels),
 //     slides down its rows keeping a 3x3 window in registers and loads 3 float4 per output.
 // Shared memory: sX + sT (2 x tile) + weights; pick_tile_rows2 keeps two CTAs per SM for the narrow models.
-static inline size_t light2_smem_bytes(int n_px, int C, int threads, int ppl = 4) {
+static inline size_t light2_smem_bytes(int n_px, int C, int threads, int ppl = 4, bool tc_stage = false) {
     const int n_pxp = ((n_px + 32 * ppl - 1) / (32 * ppl)) * (32 * ppl) + 2;
-    return sizeof(float) * (2 * (size_t)n_pxp * C + (size_t)C * C + 9 * C + (size_t)(threads / (C / 4)) * C);
+    return sizeof(float) * (2 * (size_t)n_pxp * C + (size_t)C * C * (tc_stage ? 2 : 1) + 9 * C +
+                            (size_t)(threads / (C / 4)) * C);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -472,7 +474,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
 }
 
-template <int C, int W, int R, int PPL = 4, int MINB = 2>
+template <int C, int W, int R, int PPL = 4, int MINB = 2, bool TC = false>
 __global__ void __launch_bounds__(256, MINB) k_lightconv2(const LightArgs a, const int* __restrict__ d_n, int off, int cap) {
     const int n = blockIdx.z;
     if (n >= chunk_count(d_n, off, cap)) return;
@@ -508,6 +510,95 @@ __global__ void __launch_bounds__(256, MINB) k_lightconv2(const LightArgs a, con
     for (int e = threadIdx.x; e < 9 * C; e += NT) sD[e] = a.wdw[br][e];
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_group 0;");
+    if constexpr (TC) {
+        // ---- phase A on the tensor cores: T = X * Wpw as tcgen05.mma kind::tf32 with the 3-term hi/lo split
+        // (float32-class accuracy).  The staged tile IS the canonical no-swizzle K-major operand: a core matrix is 8
+        // consecutive pixels x 16 bytes of one K-chunk plane (contiguous 128 B), the next K chunk is one plane further
+        // (LBO = n_pxp * 16 B), the next 8 pixels 128 B further (SBO).  X is split in place (hi) and into the T buffer
+        // (lo); the accumulators of all 128-pixel tiles live in TMEM at once, one commit, then T overwrites lo.
+        static_assert(!TC || (C % 16 == 0 && C <= 64), "tcgen05 stage: N must be a multiple of 16");
+        __shared__ __align__(8) uint64_t bar_mma;
+        __shared__ uint32_t tmem_base_s;
+        constexpr int n_mt = (n_px + 127) / 128;
+        constexpr uint32_t tmem_cols = n_mt * C <= 32 ? 32u : (n_mt * C <= 64 ? 64u : (n_mt * C <= 128 ? 128u : (n_mt * C <= 256 ? 256u : 512u)));
+        static_assert(!TC || n_mt * 128 <= n_pxp, "tile rows must stay inside the padded planes");
+        static_assert(!TC || n_mt * C <= 512, "accumulators must fit TMEM");
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base_s)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        if (threadIdx.x == 0) {
+            tc::mbar_init(&bar_mma, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // packed weights (hi block then lo block, canonical [n][k]) over the plain copy in sW: 2 * C * C floats fit
+        // because sW + sD + sP follow each other (C*C + 9C + 64C >= 2*C*C for C <= 64)
+        __syncthreads();   // cp.async data + the plain sW copy are complete: sW may be overwritten
+        float* sWtc = sW;
+        for (int e = threadIdx.x; e < 2 * C * C / 4; e += NT)
+            reinterpret_cast<float4*>(sWtc)[e] = reinterpret_cast<const float4*>(a.wtc[br])[e];
+        // sD was staged before and sits behind sW: re-stage it after the packed weights
+        float* sD2 = sWtc + 2 * C * C;
+        for (int e = threadIdx.x; e < 9 * C; e += NT) sD2[e] = a.wdw[br][e];
+        // split X -> hi (in place) / lo (T buffer), pads included
+        for (int e = threadIdx.x; e < C4 * n_pxp; e += NT) {
+            const float4 v = sX[e];
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+            hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+            hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+            hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+            sX[e] = hi;
+            sT[e] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_base = tmem_base_s;
+        if (threadIdx.x == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t a_hi = tc::smem_u32(sX), a_lo = tc::smem_u32(sT);
+            const uint32_t b_hi = tc::smem_u32(sWtc), b_lo = tc::smem_u32(sWtc + C * C);
+            const uint32_t lbo_a = (uint32_t)n_pxp * 16u, sbo_a = 128u, lbo_b = 128u, sbo_b = (uint32_t)C * 32u;
+#pragma unroll 1
+            for (int t = 0; t < n_mt; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < C; ks += 8) {
+                    const uint32_t ao = (uint32_t)t * 2048u + (uint32_t)(ks >> 2) * lbo_a, bo = (uint32_t)(ks >> 2) * 128u;
+                    const uint64_t dah = tc::make_desc(a_hi + ao, lbo_a, sbo_a), dal = tc::make_desc(a_lo + ao, lbo_a, sbo_a);
+                    const uint64_t dbh = tc::make_desc(b_hi + bo, lbo_b, sbo_b), dbl = tc::make_desc(b_lo + bo, lbo_b, sbo_b);
+                    const uint32_t d = tmem_base + (uint32_t)(t * C);
+                    tc::mma_tf32(d, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+                    tc::mma_tf32(d, dah, dbl, idesc, 1u);
+                    tc::mma_tf32(d, dal, dbh, idesc, 1u);
+                }
+            }
+            tc::mma_commit(&bar_mma);
+        }
+        tc::mbar_wait(&bar_mma, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // TMEM -> T (planar): warp w reads lanes 32*(w%4).. of the tiles t = w/4, w/4 + 2, ...
+        for (int t = warp >> 2; t < n_mt; t += 2) {
+            const int p = t * 128 + (warp & 3) * 32 + lane;
+#pragma unroll
+            for (int c0 = 0; c0 < C; c0 += 8) {
+                float v[8];
+                tc::tmem_ld8(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(t * C + c0), v);
+                if (p < n_px) {
+                    sT[(c0 / 4) * n_pxp + p] = make_float4(v[0], v[1], v[2], v[3]);
+                    sT[(c0 / 4 + 1) * n_pxp + p] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        sD = sD2;
+        sP = sD2 + 9 * C;
+    } else {
     __syncthreads();
     // ---- phase A: T = X * Wpw, warp item = (128-pixel group, 8 output channels), 4 pixels per lane ----
     {
@@ -552,6 +643,7 @@ __global__ void __launch_bounds__(256, MINB) k_lightconv2(const LightArgs a, con
         }
     }
     __syncthreads();
+    }
     // ---- phase B: depthwise 3x3 + bias + ReLU, column walkers with a register window ----
     const int rows_here = min(R, H - y0);
     constexpr int walkers = W * C4;
@@ -1102,6 +1194,7 @@ struct BlockW {
     size_t g1w, g1b, g2w, g2b;
     size_t cw, cb;
     TcW tc_c1, tc_c;
+    TcW light_tc[10];   // LightConv 1x1 weights packed for the tcgen05 stage (mid % 16 == 0)
 };
 
 struct MbBlock {
@@ -1125,6 +1218,7 @@ struct ReidModel {
     float* d_wtc = nullptr;    // all packed tensor-core weights
     bool use_tc = false;
     bool pw_v2 = true;      // BOXMOT_B200_PW_V1=1 selects the first-generation pointwise GEMM (A/B runs)
+    bool light_tc = false;     // BOXMOT_B200_LIGHT_TC=1: the stage-2 LightConv 1x1 stage on tcgen05 (tf32 x3)
     bool light_chain = true;   // BOXMOT_B200_LIGHT_CHAIN=0: per-level LightConv launches instead of whole-branch CTAs
     int chain_var = 2;         // BOXMOT_B200_CHAIN_VAR: 2 (default) stage 2 per level + stages 3-4 chained (measured best:
                                // 8-row stage-2 chain tiles recompute 25 % halo rows); 0 all chained; 1 stage-2 chain
@@ -1279,6 +1373,7 @@ ReidModel* reid_load(const char* path) {
             const char* lv = getenv("BOXMOT_B200_LIGHT_V1");
             m->light_v2 = !(lv && lv[0] == '1');
             if (const char* cv = getenv("BOXMOT_B200_LIGHT_CHAIN")) m->light_chain = !(cv[0] == '0');
+            if (const char* cv = getenv("BOXMOT_B200_LIGHT_TC")) m->light_tc = cv[0] == '1';
             if (const char* cv = getenv("BOXMOT_B200_CHAIN_VAR")) m->chain_var = atoi(cv);
             const char* pv = getenv("BOXMOT_B200_PW_V1");
             m->pw_v2 = !(pv && pv[0] == '1');
@@ -1296,6 +1391,8 @@ ReidModel* reid_load(const char* path) {
                 BlockW& b = m->blocks[bi];
                 add(&b.tc_c1, b.c1w, b.cin, b.mid);
                 add(&b.tc_c, b.cw, b.mid + (b.has_ds ? b.cin : 0), b.cout);
+                if (b.mid % 16 == 0)
+                    for (int l = 0; l < 10; ++l) add(&b.light_tc[l], b.light[l].pw, b.mid, b.mid);
             }
             for (int s = 0; s < 2; ++s) add(&m->tc_trans[s], m->trans_w[s], m->c[s + 1], m->c[s + 1]);
             add(&m->tc_c5, m->c5w, m->c[3], m->c[3]);
@@ -1447,14 +1544,14 @@ struct Launcher {
         end();
         ++launches;
     }
-    template <int C, int W, int R, int PPL = 4, int MINB = 2>
+    template <int C, int W, int R, int PPL = 4, int MINB = 2, bool TC = false>
     void launch_light2(const LightArgs& a, int n_branches) {
         const int tiles = (a.H + R - 1) / R;
-        const size_t smem = light2_smem_bytes((R + 2) * (W + 2), C, 256, PPL);
+        const size_t smem = light2_smem_bytes((R + 2) * (W + 2), C, 256, PPL, TC);
         if (smem > 48 * 1024)
-            RCUDA_OK(cudaFuncSetAttribute(k_lightconv2<C, W, R, PPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RCUDA_OK(cudaFuncSetAttribute(k_lightconv2<C, W, R, PPL, MINB, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         begin(CLS_LIGHTCONV);
-        k_lightconv2<C, W, R, PPL, MINB><<<dim3(tiles, n_branches, upper), 256, smem, st>>>(a, d_n, off, cap);
+        k_lightconv2<C, W, R, PPL, MINB, TC><<<dim3(tiles, n_branches, upper), 256, smem, st>>>(a, d_n, off, cap);
         end();
         ++launches;
     }
@@ -1483,6 +1580,10 @@ struct Launcher {
     bool light2(const LightArgs& a, int n_branches) {
 #define BMB_LIGHT2(CC, WW, RR) \
         if (a.C == CC && a.W == WW && a.R == RR) { launch_light2<CC, WW, RR>(a, n_branches); return true; }
+        if (m->light_tc && a.C == 16 && a.W == 32 && a.R == 16 && a.wtc[0]) {   // tcgen05 1x1 stage (opt-in)
+            launch_light2<16, 32, 16, 4, 2, true>(a, n_branches);
+            return true;
+        }
         BMB_LIGHT2(16, 32, 16) BMB_LIGHT2(24, 16, 16) BMB_LIGHT2(32, 8, 16)
         BMB_LIGHT2(64, 32, 8) BMB_LIGHT2(96, 16, 4) BMB_LIGHT2(128, 8, 8)
 #undef BMB_LIGHT2
@@ -1649,6 +1750,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
                         la.wpw[nb] = W + b.light[l].pw;
                         la.wdw[nb] = W + b.light[l].dw;
                         la.bias[nb] = W + b.light[l].b;
+                        la.wtc[nb] = b.light_tc[l].w;
                         la.sums[nb] = kDepth[br] == level ? m->sums[br] : nullptr;
                         ++nb;
                     }
