@@ -31,7 +31,7 @@ int reid_feature_dim(const ReidModel* m);
 // Row r of the result goes to d_out + crops[r].out_row * out_ld.  Returns the number of kernel launches.
 int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int rows, int cols,
                  const CropDesc* d_crops, const int* d_ncrops, int max_crops, float* d_out, int out_ld,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int first_crop = 0, int last_crop = -1);
 // staged access for the reid C ABI / tests: the normalised input blob (N,256,128,3) float32 NHWC
 const float* reid_last_input_blob(const ReidModel* m);
 // per-kernel-class device timing: crop, stem, maxpool, pointwise, lightconv, gates, avgpool, head
@@ -91,6 +91,14 @@ struct Engine {
     // frame pipeline of the device-resident path (update_device): ReID of frame f+1 runs on its own stream while
     // the single-CTA-per-stream association of frame f runs on `stream`; inputs are double-buffered (BoT-SORT family)
     cudaStream_t reid_stream = nullptr;
+    // extra ReID workspaces: slices of a frame's crop list run concurrently on helper streams (the tile kernels
+    // are latency-bound with short waves; concurrent slices fill each other's tails)
+    static constexpr int MAX_SPLIT = 4;
+    int n_split = 1;
+    ReidModel* reid_extra[MAX_SPLIT - 1]{};
+    cudaStream_t split_stream[MAX_SPLIT - 1]{};
+    cudaEvent_t ev_crops = nullptr;
+    cudaEvent_t ev_slice_done[MAX_SPLIT - 1]{};
     float* d_dets_alt = nullptr;
     int* d_ndets_alt = nullptr;
     float* d_embs_alt = nullptr;
@@ -129,6 +137,7 @@ struct Engine {
     void enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total);
     bool can_pipeline() const { return reid && cfg.with_reid && !is_docs && !is_ss && !profile; }
     void enqueue_association(TrkStream* streams_dev, const float* embs_src);
+    int run_reid(cudaStream_t main_stream, const uint8_t* images_dev, int rows, int cols, int total, float* embs_out);
     void enqueue_fetch();
     void finish_fetch(float* const* out, const int* out_cap, int* out_rows);
 };

@@ -124,7 +124,8 @@ def test_reid_abi_errors(tmp_path):
                                  {"BOXMOT_B200_LIGHT_CHAIN": "0"}, {"BOXMOT_B200_CHAIN_VAR": "0"},
                                  {"BOXMOT_B200_CHAIN_VAR": "1", "BOXMOT_B200_REID_CHUNK": "24"},
                                  {"BOXMOT_B200_LIGHT_V1": "1"}, {"BOXMOT_B200_PW_V1": "1"},
-                                 {"BOXMOT_B200_LIGHT_TC": "1"}])
+                                 {"BOXMOT_B200_LIGHT_TC": "1"}, {"BOXMOT_B200_LIGHT_SMALL": "1"},
+                                 {"BOXMOT_B200_PW_SMALL": "0"}])
 def test_alternative_kernel_paths_keep_parity(tmp_path, monkeypatch, env):
     """Every selectable kernel generation / configuration keeps the embeddings within the bound: tcgen05 (tf32 x3)
     pointwise path, other chunk sizes, per-level vs whole-branch LightConv, first-generation kernels."""
