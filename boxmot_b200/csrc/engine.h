@@ -98,6 +98,8 @@ struct Engine {
     ReidModel* reid_extra[MAX_SPLIT - 1]{};
     cudaStream_t split_stream[MAX_SPLIT - 1]{};
     cudaEvent_t ev_crops = nullptr;
+    int* h_crops_hint = nullptr;           // mapped host word: crop count of a recent frame (slice balancing hint)
+    int* d_crops_hint = nullptr;
     cudaEvent_t ev_slice_done[MAX_SPLIT - 1]{};
     float* d_dets_alt = nullptr;
     int* d_ndets_alt = nullptr;
@@ -143,7 +145,8 @@ struct Engine {
 };
 
 // ---- StrongSORT kernels (ss_kernels.cu) ---------------------------------------------------------------------
-void ss_build_crops(const SsCfg& cfg, SsStream* d_streams, int S, CropDesc* crops, int* n_crops, cudaStream_t stream);
+void ss_build_crops(const SsCfg& cfg, SsStream* d_streams, int S, CropDesc* crops, int* n_crops, int* hint,
+                    cudaStream_t stream);
 // unit detection rows -> gallery distances -> per-stream frame -> appearance / gallery update; returns launches
 int ss_enqueue_frame(const SsCfg& cfg, SsStream* d_streams, int S, cudaStream_t stream);
 int standalone_lsa(const double* cost, int R, int C, int* row_ind, int* col_ind);

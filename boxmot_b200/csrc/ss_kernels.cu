@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) k_ss_features(const SsCfg cfg, SsStream* 
 }
 
 // crop list for on-device ReID: every detection with conf >= min_conf (strongsort.py:74-91), ordered
-__global__ void k_ss_build_crops(const SsCfg cfg, SsStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
+__global__ void k_ss_build_crops(const SsCfg cfg, SsStream* streams, int n_streams, CropDesc* crops, int* n_crops,
+                                 int* hint) {
     if (threadIdx.x >= 32 || blockIdx.x != 0) return;
     const int lane = threadIdx.x;
     int n = 0;
@@ -167,11 +168,12 @@ __global__ void k_ss_build_crops(const SsCfg cfg, SsStream* streams, int n_strea
             n += __popc(m);
         }
     }
-    if (lane == 0) *n_crops = n;
+    if (lane == 0) { *n_crops = n; if (hint) *hint = n; }
 }
 
-void ss_build_crops(const SsCfg& cfg, SsStream* d_streams, int S, CropDesc* crops, int* n_crops, cudaStream_t stream) {
-    k_ss_build_crops<<<1, 32, 0, stream>>>(cfg, d_streams, S, crops, n_crops);
+void ss_build_crops(const SsCfg& cfg, SsStream* d_streams, int S, CropDesc* crops, int* n_crops, int* hint,
+                    cudaStream_t stream) {
+    k_ss_build_crops<<<1, 32, 0, stream>>>(cfg, d_streams, S, crops, n_crops, hint);
 }
 
 int ss_enqueue_frame(const SsCfg& cfg, SsStream* d_streams, int S, cudaStream_t stream) {

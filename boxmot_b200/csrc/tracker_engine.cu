@@ -215,7 +215,8 @@ __device__ __forceinline__ int append_crops(const float* dets, int D, int sidx, 
     return n;
 }
 
-__global__ void k_build_crops_docs(const DocsCfg cfg, DocsStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
+__global__ void k_build_crops_docs(const DocsCfg cfg, DocsStream* streams, int n_streams, CropDesc* crops, int* n_crops,
+                                   int* hint) {
     if (threadIdx.x >= 32 || blockIdx.x != 0) return;
     int n = 0;
     for (int sidx = 0; sidx < n_streams; ++sidx) {
@@ -224,11 +225,12 @@ __global__ void k_build_crops_docs(const DocsCfg cfg, DocsStream* streams, int n
         n = append_crops(s.dets, min(*s.n_dets, cfg.cap_dets), sidx, cfg.cap_dets, crops, n,
                          [thr](const float* r) { return r[4] > thr; });
     }
-    if (threadIdx.x == 0) *n_crops = n;
+    if (threadIdx.x == 0) { *n_crops = n; if (hint) *hint = n; }   // hint: host-mapped, read without synchronisation
 }
 
 // crop list for on-device ReID: one entry per first-round detection, ordered by (stream, detection).
-__global__ void k_build_crops(const TrkCfg cfg, TrkStream* streams, int n_streams, CropDesc* crops, int* n_crops) {
+__global__ void k_build_crops(const TrkCfg cfg, TrkStream* streams, int n_streams, CropDesc* crops, int* n_crops,
+                              int* hint) {
     if (threadIdx.x >= 32 || blockIdx.x != 0) return;
     int n = 0;
     for (int sidx = 0; sidx < n_streams; ++sidx) {
@@ -237,7 +239,7 @@ __global__ void k_build_crops(const TrkCfg cfg, TrkStream* streams, int n_stream
         n = append_crops(s.dets, min(*s.n_dets, cfg.cap_dets), sidx, cfg.cap_dets, crops, n,
                          [thr](const float* r) { return (double)r[4] > thr; });
     }
-    if (threadIdx.x == 0) *n_crops = n;
+    if (threadIdx.x == 0) { *n_crops = n; if (hint) *hint = n; }   // hint: host-mapped, read without synchronisation
 }
 
 __global__ void k_reset_streams(TrkStream* streams, size_t persistent_bytes) {
@@ -413,6 +415,11 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     if (reid) {
         CUDA_OK(cudaMalloc(&d_crops, sizeof(CropDesc) * CD * S));
         CUDA_OK(cudaMalloc(&d_ncrops, sizeof(int)));
+        // crop count of the most recent frame, written by the crop-list kernel into mapped host memory and read by
+        // the host WITHOUT synchronisation: only a balancing hint for the slices (a stale value is still correct)
+        CUDA_OK(cudaHostAlloc(&h_crops_hint, sizeof(int), cudaHostAllocMapped));
+        *h_crops_hint = 0;
+        CUDA_OK(cudaHostGetDevicePointer(&d_crops_hint, h_crops_hint, 0));
         n_split = 3;   // measured at 208 crops: 1 slice 518 / 407 frames/s (value / e2e), 2: 560 / 432, 3: 570 / 443, 4: 579 / 434
         if (const char* sp = getenv("BOXMOT_B200_REID_SPLIT")) n_split = atoi(sp);
         n_split = n_split < 1 ? 1 : (n_split > MAX_SPLIT ? MAX_SPLIT : n_split);
@@ -440,6 +447,7 @@ Engine::~Engine() {
         if (reid_extra[k]) reid_free(reid_extra[k]);
     }
     if (ev_crops) cudaEventDestroy(ev_crops);
+    if (h_crops_hint) cudaFreeHost(h_crops_hint);
     if (reid_stream) {
         cudaStreamSynchronize(reid_stream);
         cudaStreamDestroy(reid_stream);
@@ -490,7 +498,7 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         if (!embs_dev) {
             if (!reid) throw std::runtime_error("StrongSORT needs embeddings or a ReID model");
             if (!images_dev) throw std::runtime_error("ReID inside update() needs an image");
-            ss_build_crops(scfg, d_ss, S, d_crops, d_ncrops, stream);
+            ss_build_crops(scfg, d_ss, S, d_crops, d_ncrops, d_crops_hint, stream);
             ++launches;
             launches += run_reid(stream, images_dev, rows, cols, max_dets_total, d_embs);
         } else if (embs_dev != d_embs) {
@@ -516,7 +524,7 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         if (cfg.with_reid && !embs_dev) {
             if (!reid) throw std::runtime_error("DeepOCSORT needs embeddings, a ReID model, or embedding_off");
             if (!images_dev) throw std::runtime_error("ReID inside update() needs an image");
-            k_build_crops_docs<<<1, 32, 0, stream>>>(dcfg, d_docs, S, d_crops, d_ncrops);
+            k_build_crops_docs<<<1, 32, 0, stream>>>(dcfg, d_docs, S, d_crops, d_ncrops, d_crops_hint);
             ++launches;
             launches += run_reid(stream, images_dev, rows, cols, max_dets_total, d_embs);
         }
@@ -551,7 +559,7 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         if (!src) {
             if (!reid) throw std::runtime_error("with_reid tracker needs embeddings or a ReID model");
             if (!images_dev) throw std::runtime_error("ReID inside update() needs an image");
-            k_build_crops<<<1, 32, 0, stream>>>(cfg, d_streams, S, d_crops, d_ncrops);
+            k_build_crops<<<1, 32, 0, stream>>>(cfg, d_streams, S, d_crops, d_ncrops, d_crops_hint);
             ++launches;
             launches += run_reid(stream, images_dev, rows, cols, max_dets_total, d_embs);
             src = d_embs;
@@ -580,10 +588,12 @@ int Engine::run_reid(cudaStream_t main_stream, const uint8_t* images_dev, int ro
     const int ns = (profile || total < 32) ? 1 : n_split;
     if (ns <= 1)
         return reid_forward(reid, images_dev, stride, rows, cols, d_crops, d_ncrops, total, embs_out, cfg.feat_dim, main_stream);
-    const int per = (((total + ns - 1) / ns) + 7) & ~7;
+    int expect = *(volatile int*)h_crops_hint;   // crops of a recent frame (0 before the first one)
+    if (expect <= 0 || expect > total) expect = total;
+    const int per = (((expect + ns - 1) / ns) + 7) & ~7;   // the last slice runs to `total` whatever the hint was
     CUDA_OK(cudaEventRecord(ev_crops, main_stream));
     for (int k = 1; k < ns; ++k) {
-        const int a = k * per, b = (k + 1) * per < total ? (k + 1) * per : total;
+        const int a = k * per, b = (k + 1 == ns || (k + 1) * per > total) ? total : (k + 1) * per;
         if (a >= b) continue;
         CUDA_OK(cudaStreamWaitEvent(split_stream[k - 1], ev_crops, 0));
         n += reid_forward(reid_extra[k - 1], images_dev, stride, rows, cols, d_crops, d_ncrops, total, embs_out, cfg.feat_dim,
@@ -792,7 +802,7 @@ void Engine::update_device(const float* dets_dev, const int* det_rows, const flo
             CUDA_OK(cudaMemcpyAsync(dd, dets_dev, sizeof(float) * 6 * CD * S, cudaMemcpyDeviceToDevice, reid_stream));
         launches = 0;
         ev_recorded = false;   // the per-frame ReID / association split is not timed in pipelined mode
-        k_build_crops<<<1, 32, 0, reid_stream>>>(cfg, ds, S, d_crops, d_ncrops);
+        k_build_crops<<<1, 32, 0, reid_stream>>>(cfg, ds, S, d_crops, d_ncrops, d_crops_hint);
         ++launches;
         launches += run_reid(reid_stream, images_dev, rows, cols, total, de);
         CUDA_OK(cudaEventRecord(ev_reid_done[pp], reid_stream));
