@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 > gpurun_out/rp_pytest.txt
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/rp_smoke.txt 2>&1
 python bench.py > gpurun_out/rp_bench_n1.json 2> gpurun_out/rp_bench_n1.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/rp_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 760 --csv --log-file gpurun_out/rp_launches.csv \
     python bench.py --steps 3 --warmup 3 --skip-cpu > gpurun_out/rp_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_lightconv2|k_lightchain" -s 12 -c 12 -f \
     -o gpurun_out/rp_light_full python bench.py --steps 2 --warmup 3 --skip-cpu > gpurun_out/rp_light_full.log 2>&1
