@@ -106,6 +106,8 @@ struct Engine {
     float* d_embs_alt = nullptr;
     TrkStream* d_streams_alt = nullptr;
     std::vector<TrkStream> h_streams_alt;
+    DocsStream* d_docs_alt = nullptr;
+    SsStream* d_ss_alt = nullptr;
     cudaEvent_t ev_reid_done[2]{};
     cudaEvent_t ev_assoc_done[2]{};
     int pipe_parity = 0;
@@ -137,8 +139,10 @@ struct Engine {
    private:
     void ensure_images(int rows, int cols, bool host_too);
     void enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total);
-    bool can_pipeline() const { return reid && cfg.with_reid && !is_docs && !is_ss && !profile; }
+    bool can_pipeline() const { return reid_stream != nullptr && !profile; }
     void enqueue_association(TrkStream* streams_dev, const float* embs_src);
+    void enqueue_crops(int parity, cudaStream_t st);            // crop list of the family, from input set `parity`
+    void enqueue_family_association(int parity);                // association launches of the family on `stream`
     int run_reid(cudaStream_t main_stream, const uint8_t* images_dev, int rows, int cols, int total, float* embs_out);
     void enqueue_fetch();
     void finish_fetch(float* const* out, const int* out_cap, int* out_rows);

@@ -391,13 +391,33 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
         }
         CUDA_OK(cudaMalloc(&d_streams, sizeof(TrkStream) * S));
         CUDA_OK(cudaMemcpy(d_streams, h_streams.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
-        if (reid && cfg.with_reid) {   // second input set for the frame pipeline of update_device
-            CUDA_OK(cudaStreamCreateWithFlags(&reid_stream, cudaStreamNonBlocking));
-            CUDA_OK(cudaMalloc(&d_dets_alt, sizeof(float) * 6 * CD * S));
-            CUDA_OK(cudaMalloc(&d_ndets_alt, sizeof(int) * S));
-            CUDA_OK(cudaMemset(d_ndets_alt, 0, sizeof(int) * S));
-            CUDA_OK(cudaMalloc(&d_embs_alt, sizeof(float) * F * CD * S));
-            CUDA_OK(cudaMemset(d_embs_alt, 0, sizeof(float) * F * CD * S));
+    }
+    if (reid && cfg.with_reid) {   // second input set for the frame pipeline of update_device (all families)
+        CUDA_OK(cudaStreamCreateWithFlags(&reid_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaMalloc(&d_dets_alt, sizeof(float) * 6 * CD * S));
+        CUDA_OK(cudaMalloc(&d_ndets_alt, sizeof(int) * S));
+        CUDA_OK(cudaMemset(d_ndets_alt, 0, sizeof(int) * S));
+        CUDA_OK(cudaMalloc(&d_embs_alt, sizeof(float) * F * CD * S));
+        CUDA_OK(cudaMemset(d_embs_alt, 0, sizeof(float) * F * CD * S));
+        if (is_ss) {
+            std::vector<SsStream> alt = h_ss;
+            for (int i = 0; i < S; ++i) {
+                alt[i].dets = d_dets_alt + (size_t)i * CD * 6;
+                alt[i].n_dets = d_ndets_alt + i;
+                alt[i].embs = d_embs_alt + (size_t)i * CD * F;
+            }
+            CUDA_OK(cudaMalloc(&d_ss_alt, sizeof(SsStream) * S));
+            CUDA_OK(cudaMemcpy(d_ss_alt, alt.data(), sizeof(SsStream) * S, cudaMemcpyHostToDevice));
+        } else if (is_docs) {
+            std::vector<DocsStream> alt = h_docs;
+            for (int i = 0; i < S; ++i) {
+                alt[i].dets = d_dets_alt + (size_t)i * CD * 6;
+                alt[i].n_dets = d_ndets_alt + i;
+                alt[i].embs = d_embs_alt + (size_t)i * CD * F;
+            }
+            CUDA_OK(cudaMalloc(&d_docs_alt, sizeof(DocsStream) * S));
+            CUDA_OK(cudaMemcpy(d_docs_alt, alt.data(), sizeof(DocsStream) * S, cudaMemcpyHostToDevice));
+        } else {
             h_streams_alt = h_streams;
             for (int i = 0; i < S; ++i) {
                 h_streams_alt[i].dets = d_dets_alt + (size_t)i * CD * 6;
@@ -405,11 +425,10 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
             }
             CUDA_OK(cudaMalloc(&d_streams_alt, sizeof(TrkStream) * S));
             CUDA_OK(cudaMemcpy(d_streams_alt, h_streams_alt.data(), sizeof(TrkStream) * S, cudaMemcpyHostToDevice));
-            for (int k = 0; k < 2; ++k) {
-                CUDA_OK(cudaEventCreateWithFlags(&ev_reid_done[k], cudaEventDisableTiming));
-                CUDA_OK(cudaEventCreateWithFlags(&ev_assoc_done[k], cudaEventDisableTiming));
-            }
-
+        }
+        for (int k = 0; k < 2; ++k) {
+            CUDA_OK(cudaEventCreateWithFlags(&ev_reid_done[k], cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&ev_assoc_done[k], cudaEventDisableTiming));
         }
     }
     if (reid) {
@@ -453,6 +472,7 @@ Engine::~Engine() {
         cudaStreamDestroy(reid_stream);
         for (int k = 0; k < 2; ++k) { cudaEventDestroy(ev_reid_done[k]); cudaEventDestroy(ev_assoc_done[k]); }
         cudaFree(d_dets_alt); cudaFree(d_ndets_alt); cudaFree(d_embs_alt); cudaFree(d_streams_alt);
+        cudaFree(d_docs_alt); cudaFree(d_ss_alt);
     }
     if (reid) reid_free(reid);
     cudaFree(d_warp); cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
@@ -579,6 +599,42 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
         assoc_ms_accum += b;
         assoc_frames += 1;
     }
+}
+
+// crop list of the tracker family from input set `parity` (0: d_dets / d_ndets, 1: the alternate set)
+void Engine::enqueue_crops(int parity, cudaStream_t st) {
+    if (is_ss) ss_build_crops(scfg, parity ? d_ss_alt : d_ss, S, d_crops, d_ncrops, d_crops_hint, st);
+    else if (is_docs) k_build_crops_docs<<<1, 32, 0, st>>>(dcfg, parity ? d_docs_alt : d_docs, S, d_crops, d_ncrops, d_crops_hint);
+    else k_build_crops<<<1, 32, 0, st>>>(cfg, parity ? d_streams_alt : d_streams, S, d_crops, d_ncrops, d_crops_hint);
+    ++launches;
+}
+
+// association launches of the family on `stream`, reading input set `parity` (embeddings included)
+void Engine::enqueue_family_association(int parity) {
+    if (is_ss) {
+        launches += ss_enqueue_frame(scfg, parity ? d_ss_alt : d_ss, S, stream);
+        if (warp_dirty) {
+            CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
+            warp_dirty = false;
+        }
+    } else if (is_docs) {
+        DocsStream* ds = parity ? d_docs_alt : d_docs;
+        if (cfg.with_reid) {
+            dim3 g((dcfg.cap_dets + EMB_TD - 1) / EMB_TD, (dcfg.cap_tracks + EMB_TR - 1) / EMB_TR, S);
+            k_docs_embcost<<<g, 256, 0, stream>>>(dcfg, ds);
+            ++launches;
+        }
+        const int MX = dcfg.cap_tracks > dcfg.cap_dets ? dcfg.cap_tracks : dcfg.cap_dets;
+        const size_t jb = jv_smem_bytes(MX);
+        const bool in_smem = jb <= 200 * 1024;
+        if (in_smem && jb > 48 * 1024)
+            CUDA_OK(cudaFuncSetAttribute(k_docs_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb));
+        k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, ds, in_smem ? 1 : 0);
+        ++launches;
+    } else {
+        enqueue_association(parity ? d_streams_alt : d_streams, cfg.with_reid ? (parity ? d_embs_alt : d_embs) : nullptr);
+    }
+    CUDA_OK(cudaGetLastError());
 }
 
 // crop list (already built on main_stream) -> embeddings; slices of the list run concurrently on the helper streams
@@ -787,7 +843,7 @@ void Engine::update_device(const float* dets_dev, const int* det_rows, const flo
         slot[i] = det_rows[i];
         total += det_rows[i];
     }
-    if (can_pipeline() && !embs_dev && images_dev && !sync) {
+    if (can_pipeline() && cfg.with_reid && !embs_dev && images_dev && !sync) {
         // frame pipeline: crops + ReID of this frame on reid_stream (input set p), association on `stream` once the
         // embeddings are there; the ReID of the next frame overlaps this frame's association
         const int pp = pipe_parity;
@@ -795,20 +851,17 @@ void Engine::update_device(const float* dets_dev, const int* det_rows, const flo
         float* dd = pp ? d_dets_alt : d_dets;
         int* dn = pp ? d_ndets_alt : d_ndets;
         float* de = pp ? d_embs_alt : d_embs;
-        TrkStream* ds = pp ? d_streams_alt : d_streams;
         CUDA_OK(cudaStreamWaitEvent(reid_stream, ev_assoc_done[pp], 0));   // set p is free again
         CUDA_OK(cudaMemcpyAsync(dn, slot, sizeof(int) * S, cudaMemcpyHostToDevice, reid_stream));
         if (dets_dev != dd)
             CUDA_OK(cudaMemcpyAsync(dd, dets_dev, sizeof(float) * 6 * CD * S, cudaMemcpyDeviceToDevice, reid_stream));
         launches = 0;
         ev_recorded = false;   // the per-frame ReID / association split is not timed in pipelined mode
-        k_build_crops<<<1, 32, 0, reid_stream>>>(cfg, ds, S, d_crops, d_ncrops, d_crops_hint);
-        ++launches;
+        enqueue_crops(pp, reid_stream);
         launches += run_reid(reid_stream, images_dev, rows, cols, total, de);
         CUDA_OK(cudaEventRecord(ev_reid_done[pp], reid_stream));
         CUDA_OK(cudaStreamWaitEvent(stream, ev_reid_done[pp], 0));
-        enqueue_association(ds, de);
-        CUDA_OK(cudaGetLastError());
+        enqueue_family_association(pp);
         CUDA_OK(cudaEventRecord(ev_assoc_done[pp], stream));
         return;
     }

@@ -162,9 +162,14 @@ def test_mobilenetv2_x1_4_embeddings_match_oracle(tmp_path):
     _emb_ok(got, want)
 
 
-def test_pipelined_device_path_equals_synchronous(tmp_path):
-    """update_device without per-frame sync overlaps ReID(f+1) with association(f) on two CUDA streams; the tracker
-    state after N frames must be identical to the frame-by-frame synchronous run."""
+@pytest.mark.parametrize("kind,kw", [
+    ("botsort", dict(track_high_thresh=0.6, new_track_thresh=0.62, appearance_thresh=0.6, proximity_thresh=0.6)),
+    ("deepocsort", dict(det_thresh=0.3)),
+    ("strongsort", dict(min_conf=0.3, max_cos_dist=0.4, n_init=2))])
+def test_pipelined_device_path_equals_synchronous(tmp_path, kind, kw):
+    """update_device without per-frame sync overlaps ReID(f+1) with association(f) on two CUDA streams (every tracker
+    family with on-device ReID); the tracker state after N frames must be identical to the frame-by-frame synchronous
+    run."""
     import ctypes
 
     import torch
@@ -181,10 +186,9 @@ def test_pipelined_device_path_equals_synchronous(tmp_path):
     d_imgs = torch.from_numpy(imgs).cuda()
     d_dets = torch.from_numpy(np.stack(dets)[:, None].astype(np.float32)).cuda().contiguous()
     rows = (ctypes.c_int * 1)(48)
-    kw = dict(track_high_thresh=0.6, new_track_thresh=0.62, appearance_thresh=0.6, proximity_thresh=0.6)
     snaps = []
     for sync in (1, 0):
-        trk = bb.MultiStreamTracker("botsort", n_streams=1, cap_tracks=256, cap_dets=48, feat_dim=512,
+        trk = bb.MultiStreamTracker(kind, n_streams=1, cap_tracks=256, cap_dets=48, feat_dim=512,
                                     reid_blob=str(blob), **kw)
         for f in range(len(dets)):
             ok = lib.boxmot_b200_tracker_update_device(trk.handle, d_dets[f].data_ptr(), rows, None,
@@ -203,3 +207,56 @@ def test_pipelined_device_path_equals_synchronous(tmp_path):
     assert sorted(st_a) == sorted(st_b)
     for k in st_a:
         assert np.array_equal(st_a[k][0], st_b[k][0]) and np.array_equal(st_a[k][1], st_b[k][1])
+
+
+@pytest.mark.parametrize("n_dets", [5, 70])
+def test_pipelined_multistream_with_empty_frames(tmp_path, n_dets):
+    """Two streams in one handle, frames where a stream has no detections, crop counts below and above the slicing
+    threshold: the pipelined device path (ReID slices on helper streams, association on the main stream) must leave
+    exactly the state of the synchronous path."""
+    import ctypes
+
+    import torch
+
+    import boxmot_b200 as bb
+    from boxmot_b200 import _lib
+    from boxmot_b200.synthetic import bench_stream, make_osnet_state
+    from boxmot_b200.weights import export_blob
+
+    lib = _lib.require_device()
+    blob = export_blob(make_osnet_state("osnet_x0_25", seed=5), tmp_path / "pipe2.b200reid")
+    S, F, CD = 2, 16, 80
+    img, d0 = bench_stream(n_dets, F, hw=(360, 640))
+    _, d1 = bench_stream(n_dets, F, hw=(360, 640), stream=1)
+    imgs = torch.from_numpy(np.stack([img, np.roll(img, 11, axis=0)])).cuda()          # one frame per stream
+    dets = np.zeros((F, S, CD, 6), np.float32)
+    counts = np.zeros((F, S), np.int32)
+    for f in range(F):
+        for si, d in enumerate((d0[f], d1[f])):
+            n = 0 if (f % 5 == 2 and si == 1) or f == 7 else len(d)       # empty stream / entirely empty frame
+            dets[f, si, :n] = d[:n]
+            counts[f, si] = n
+    d_dets = torch.from_numpy(dets).cuda().contiguous()
+    kw = dict(track_high_thresh=0.6, new_track_thresh=0.62, appearance_thresh=0.6, proximity_thresh=0.6)
+    results = []
+    for sync in (1, 0):
+        trk = bb.MultiStreamTracker("botsort", n_streams=S, cap_tracks=256, cap_dets=CD, feat_dim=512,
+                                    reid_blob=str(blob), **kw)
+        for f in range(F):
+            rows = (ctypes.c_int * S)(*counts[f].tolist())
+            ok = lib.boxmot_b200_tracker_update_device(trk.handle, d_dets[f].data_ptr(), rows, None,
+                                                       imgs.data_ptr(), 360, 640, sync)
+            assert ok, _lib.last_error(lib)
+        outs = [np.zeros((CD, 9), np.float32) for _ in range(S)]
+        o_ptr = (ctypes.c_void_p * S)(*[o.ctypes.data for o in outs])
+        o_cap = (ctypes.c_int * S)(*[CD] * S)
+        o_rows = (ctypes.c_int * S)()
+        assert lib.boxmot_b200_tracker_fetch(trk.handle, o_ptr, o_cap, o_rows), _lib.last_error(lib)
+        results.append(([outs[i][: o_rows[i]].copy() for i in range(S)], [trk.snapshot(i) for i in range(S)]))
+        trk.close()
+    (rows_a, st_a), (rows_b, st_b) = results
+    for i in range(S):
+        assert np.array_equal(rows_a[i], rows_b[i])
+        assert sorted(st_a[i]) == sorted(st_b[i]) and len(st_a[i]) > 0
+        for k in st_a[i]:
+            assert np.array_equal(st_a[i][k][0], st_b[i][k][0]) and np.array_equal(st_a[i][k][1], st_b[i][k][1])
