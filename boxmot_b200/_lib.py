@@ -96,6 +96,7 @@ SYMBOLS = {
     "boxmot_b200_tracker_profile_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "boxmot_b200_last_error": (c_char_p, []),
     "boxmot_b200_jv_dense": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "boxmot_b200_jv_dense_mode": (c_int, [c_int]),
     "boxmot_b200_lsa_solve": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(c_int)]),
     "boxmot_b200_lap_solve": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "boxmot_b200_kalman_predict": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int]),

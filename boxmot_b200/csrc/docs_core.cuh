@@ -78,6 +78,7 @@ struct DocsStream {
     int* lap_x; int* lap_y; double* lap_u; double* lap_v; double* lap_spc; int* lap_path; int* lap_insc;
     int* lap_tl; int* lap_sc; int* csr_ptr; int* csr_col;
     float* out;        // [CD][8]
+    int jv_wide;       // CTA-wide augmentation in the dense JV solver (set per launch, not part of the carved state)
 };
 
 // one entry of the appearance similarity matrix (float32 detection row x float64 track EMA, float64 accumulate)
@@ -359,7 +360,7 @@ BMB_FN void docs_assign(DocsStream& s, int R, int C, int ld2, int* result, CostA
         s.cost[(size_t)i * ld2 + j] = (i < R && j < C) ? cost_at(i, j) : 0.0;
     }
     BMB_SYNC();
-    jv_dense_solve(s, n, ld2);
+    jv_dense_solve(s, n, ld2, R, s.jv_wide);
     for (int r = BMB_TID; r < R; r += BMB_NT) result[r] = s.lap_x[r] < C ? s.lap_x[r] : -1;
     BMB_SYNC();
 }

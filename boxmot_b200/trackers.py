@@ -260,6 +260,67 @@ class MultiStreamTracker:
         self.frame_count += 1
         return [TrackResults(outs[i][: o_rows[i], :8].copy()) for i in range(S)]
 
+    # ---- device-resident frame loop ---------------------------------------------------------------
+    @staticmethod
+    def _dev_ptr(obj, what: str, dtype: str, min_elems: int):
+        """Raw device address of a CUDA tensor (`data_ptr()` / `__cuda_array_interface__`) or a plain integer."""
+        if obj is None:
+            return None
+        if isinstance(obj, int):
+            return obj
+        if hasattr(obj, "data_ptr"):  # torch.Tensor
+            if not obj.is_cuda:
+                raise B200Error(f"{what} must live in device memory for update_device (got a host tensor)")
+            if not obj.is_contiguous():
+                raise B200Error(f"{what} must be contiguous")
+            if str(obj.dtype).split(".")[-1] != dtype:
+                raise B200Error(f"{what} must be {dtype}, got {obj.dtype}")
+            if obj.numel() < min_elems:
+                raise B200Error(f"{what} holds {obj.numel()} elements, {min_elems} are addressed")
+            return int(obj.data_ptr())
+        cai = getattr(obj, "__cuda_array_interface__", None)
+        if cai is not None:
+            if int(np.prod(cai["shape"])) < min_elems:
+                raise B200Error(f"{what} is smaller than the {min_elems} elements addressed")
+            return int(cai["data"][0])
+        raise B200Error(f"{what}: expected a CUDA tensor or a device address")
+
+    def update_device(self, d_dets, det_rows: Sequence[int], d_embs=None, d_images=None,
+                      image_hw: Optional[Sequence[int]] = None, sync: bool = True) -> None:
+        """Advance every stream by one frame from inputs that already live in HBM (a detector's output boxes and the
+        decoded frames): `d_dets` `[n_streams][cap_dets][6]` float32, `d_embs` `[n_streams][cap_dets][feat_dim]`
+        float32 or None, `d_images` `[n_streams][H][W][3]` uint8 or None, `det_rows` host ints.  With `sync=False`
+        the call returns after enqueueing: ReID of the next frame overlaps this frame's association.  Rows stay on
+        the device until `fetch()`."""
+        S = self.n_streams
+        assert len(det_rows) == S, f"expected {S} detection counts"
+        if max(det_rows, default=0) > self.cap_dets:
+            raise B200Error(f"{max(det_rows)} detections exceed cap_dets={self.cap_dets}")
+        rows = (ctypes.c_int * S)(*[int(r) for r in det_rows])
+        ih, iw = (0, 0) if image_hw is None else (int(image_hw[0]), int(image_hw[1]))
+        if d_images is not None and image_hw is None:
+            shp = tuple(getattr(d_images, "shape", ()))
+            if len(shp) < 3:
+                raise B200Error("image_hw is required when d_images is a raw address")
+            ih, iw = int(shp[-3]), int(shp[-2])
+        p_d = self._dev_ptr(d_dets, "d_dets", "float32", S * self.cap_dets * 6)
+        p_e = self._dev_ptr(d_embs, "d_embs", "float32", S * self.cap_dets * self.feat_dim)
+        p_i = self._dev_ptr(d_images, "d_images", "uint8", S * ih * iw * 3)
+        if not self.lib.boxmot_b200_tracker_update_device(self.handle, p_d, rows, p_e, p_i, ih, iw, int(bool(sync))):
+            raise B200Error(_lib.last_error(self.lib))
+        self.frame_count += 1
+
+    def fetch(self):
+        """Rows of the last frame enqueued by `update_device` (waits for the device), one `TrackResults` per stream."""
+        S = self.n_streams
+        outs = [np.empty((self.cap_dets, 9), np.float32) for _ in range(S)]
+        o_ptr = (ctypes.c_void_p * S)(*[o.ctypes.data for o in outs])
+        o_cap = (ctypes.c_int * S)(*[self.cap_dets] * S)
+        o_rows = (ctypes.c_int * S)()
+        if not self.lib.boxmot_b200_tracker_fetch(self.handle, o_ptr, o_cap, o_rows):
+            raise B200Error(_lib.last_error(self.lib))
+        return [TrackResults(outs[i][: o_rows[i], :8].copy()) for i in range(S)]
+
     def snapshot(self, stream: int = 0):
         cap = self.cap_tracks
         ids = np.empty(cap, np.int32)

@@ -154,13 +154,15 @@ int docs_snapshot(DocsSim* h, int* ids, double* xs, double* Ps, int cap) {
     return n;
 }
 
+void docs_set_jv_wide(DocsSim* h, int wide) { h->s.jv_wide = wide; }
+
 int docs_jv(DocsSim* h, const double* cost, int R, int C, int* x, int* y) {
     const int n = R > C ? R : C;
     const int ld = h->cfg.cap_tracks > h->cfg.cap_dets ? h->cfg.cap_tracks : h->cfg.cap_dets;
     if (n > ld) return -1;
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) h->s.cost[(size_t)i * ld + j] = (i < R && j < C) ? cost[(size_t)i * C + j] : 0.0;
-    jv_dense_solve(h->s, n, ld);
+    jv_dense_solve(h->s, n, ld, R, h->s.jv_wide);
     for (int i = 0; i < R; ++i) x[i] = h->s.lap_x[i] < C ? h->s.lap_x[i] : -1;
     for (int j = 0; j < C; ++j) y[j] = h->s.lap_y[j] < R ? h->s.lap_y[j] : -1;
     return 0;

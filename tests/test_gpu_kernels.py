@@ -120,23 +120,29 @@ def test_iou_and_cosine_cost():
     np.testing.assert_allclose(out, embedding_cost(a, b), rtol=0, atol=1e-13)
 
 
+@pytest.mark.parametrize("wide", [1, 0])
 @pytest.mark.parametrize("seed,r,c", [(0, 1, 1), (1, 7, 30), (2, 33, 32), (3, 64, 64), (4, 65, 200), (5, 200, 65),
-                                      (6, 130, 131), (7, 300, 300), (8, 97, 512), (9, 512, 97)])
-def test_dense_jv_reproduces_lapjv_ties(seed, r, c):
-    """GPU dense Jonker-Volgenant (lane-parallel scans) vs the oracle's lapjv on tie-heavy matrices: identical x / y,
-    i.e. identical tie-breaking, which DeepOCSORT's birth order (ids) depends on."""
+                                      (6, 130, 131), (7, 300, 300), (8, 97, 512), (9, 512, 97), (10, 40, 700)])
+def test_dense_jv_reproduces_lapjv_ties(seed, r, c, wide):
+    """GPU dense Jonker-Volgenant vs the oracle's lapjv on tie-heavy matrices: identical x / y, i.e. identical
+    tie-breaking, which DeepOCSORT's birth order (ids) depends on.  Both augmentation variants: CTA-wide search
+    (`wide`, the default) and the one-warp search."""
     lib = _lib()
-    rng = np.random.default_rng(seed)
-    cost = np.zeros((r, c))
-    k = int(rng.integers(0, r * c // 2 + 1))
-    cost.flat[rng.choice(r * c, size=k, replace=False)] = -np.round(rng.random(k), 2)
-    x = np.empty(r, np.int32)
-    y = np.empty(c, np.int32)
-    assert lib.boxmot_b200_jv_dense(cost.ctypes.data, r, c, x.ctypes.data, y.ctypes.data) == 1
-    _, xo, yo = lapjv(cost, extend_cost=True)
-    assert np.array_equal(x, xo) and np.array_equal(y, yo)
-    # continuous costs as well (unique optimum)
-    cost = -rng.random((r, c))
-    assert lib.boxmot_b200_jv_dense(cost.ctypes.data, r, c, x.ctypes.data, y.ctypes.data) == 1
-    _, xo, yo = lapjv(cost, extend_cost=True)
-    assert np.array_equal(x, xo) and np.array_equal(y, yo)
+    assert lib.boxmot_b200_jv_dense_mode(wide) == 1
+    try:
+        rng = np.random.default_rng(seed)
+        x = np.empty(r, np.int32)
+        y = np.empty(c, np.int32)
+        k = int(rng.integers(0, r * c // 2 + 1))
+        tie = np.zeros((r, c))
+        tie.flat[rng.choice(r * c, size=k, replace=False)] = -np.round(rng.random(k), 2)
+        sparse = np.zeros((r, c))   # mostly zeros: long runs of equal distances (the config-3 regime)
+        k2 = max(1, r * c // 50)
+        sparse.flat[rng.choice(r * c, size=k2, replace=False)] = -np.round(rng.random(k2), 1)
+        # continuous costs as well (unique optimum), and all-zero
+        for cost in (tie, sparse, -rng.random((r, c)), np.zeros((r, c))):
+            assert lib.boxmot_b200_jv_dense(cost.ctypes.data, r, c, x.ctypes.data, y.ctypes.data) == 1
+            _, xo, yo = lapjv(cost, extend_cost=True)
+            assert np.array_equal(x, xo) and np.array_equal(y, yo)
+    finally:
+        lib.boxmot_b200_jv_dense_mode(1)
