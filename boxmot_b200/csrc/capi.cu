@@ -253,7 +253,7 @@ int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y)
     return guard([&] { standalone_jv(cost, rows, cols, x, y); });
 }
 int boxmot_b200_jv_dense_mode(int cta_wide) {
-    return guard([&] { set_jv_wide(cta_wide != 0); });
+    return guard([&] { set_jv_wide(cta_wide); });
 }
 int boxmot_b200_lsa_solve(const double* cost, int rows, int cols, int* row_ind, int* col_ind, int* out_pairs) {
     return guard([&] {

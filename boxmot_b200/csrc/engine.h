@@ -156,7 +156,7 @@ int ss_enqueue_frame(const SsCfg& cfg, SsStream* d_streams, int S, cudaStream_t 
 int standalone_lsa(const double* cost, int R, int C, int* row_ind, int* col_ind);
 
 void standalone_jv(const double* cost, int R, int C, int* x, int* y);
-void set_jv_wide(bool wide);   // dense-JV augmentation variant used by every later launch of this process
+void set_jv_wide(int mode);   // dense-JV augmentation variant used by every later launch of this process
 void standalone_lap(const double* cost, int T, int D, double thresh, int* x, int* y);
 void standalone_kf(int op, int kind, double* mean, double* cov, const int* tracked, const float* meas, int n);
 void standalone_iou(const double* t, int T, const float* d, int D, double* out);

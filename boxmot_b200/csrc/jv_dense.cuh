@@ -216,6 +216,315 @@ BMB_FN void jv_augment_wide(S& s, int n, int ld, int zrow, int n_free, int* mbx)
     if (BMB_TID == 0) { s.timers[13] += n_steps; s.timers[11] += c_find; s.timers[14] += c_replay; s.timers[15] += c_edge; }
 }
 
+// ---- column-owned CTA-wide augmentation (wide == 2) --------------------------------------------------------------
+// jv_augment_wide walks the open part of the column LIST, so every relaxed entry costs a chain of shared-memory reads
+// (cols[k] -> v[jj], d[jj]); measured 1 200 cycles per band column at n = 1 500.  Here every thread OWNS the columns
+// tid, tid + NT, ... and keeps their distance d and the negated price (0.0 - v) in registers; "open" (position >= hi)
+// is a bit per owned column refreshed from the inverse permutation pos[] whenever the band changes.  A band column
+// then costs one pass of register arithmetic and one barrier.  The band-minimum hits are recovered in POSITION order
+// (lapjv's order) by the same mask-and-replay pass as in jv_augment_wide: an open column's distance equals the band
+// minimum iff it was a hit of this step (shared-memory copies of d are refreshed at every _find_dense and on hits).
+// _find_dense is split into a parallel part (chunk minima -> running minimum at every chunk start -> hit masks, all
+// warps) and the inherently sequential replay of the hits by one thread.
+#if BMB_DEVICE
+#define JV_OWN 12        // owned columns per thread: n <= JV_OWN * blockDim
+#define JV_CHUNKS 128    // 32-position chunks _find_dense can hold: n <= 4096
+#else
+#define JV_OWN 4096
+#define JV_CHUNKS 4104
+#endif
+
+template <typename S>
+BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx) {
+    int* x = s.lap_x; int* y = s.lap_y; double* v = s.lap_v; double* d = s.lap_spc;
+    int* pred = s.lap_path; int* cols = s.lap_tl; const int* free_rows = s.lap_sc;
+    int* pos = s.lap_insc;   // inverse of cols (the `once` flags are dead after the reduction transfer)
+    const double* c = s.cost;
+    const double BIG = 1.7976931348623157e308;
+    const int lane = BMB_LANE;
+#if BMB_DEVICE
+    __shared__ double cmin[JV_CHUNKS];
+    __shared__ unsigned hmask[JV_CHUNKS];
+    __shared__ unsigned smask[JV_CHUNKS];
+#else
+    static double cmin[JV_CHUNKS];
+    static unsigned hmask[JV_CHUNKS];
+    static unsigned smask[JV_CHUNKS];
+#endif
+    double dq[JV_OWN];    // distance of the owned columns (registers on the device)
+    double nvq[JV_OWN];   // 0.0 - v[jj]: a zero-padding row relaxes with r = (0.0 - v) - h, the same two operations
+    long long n_steps = 0, c_find = 0, c_replay = 0, c_edge = 0;
+    for (int f = 0; f < n_free; ++f) {
+        const int start = free_rows[f];
+        int lo = 0, hi = 0, n_ready = 0, band = 0, final_j = -1;
+        unsigned open = 0u;   // bit q: owned column q is still outside the band (position >= hi)
+#if !BMB_DEVICE
+        unsigned char open_h[JV_OWN];
+#endif
+        long long c0 = BMB_CLOCK();
+        {
+            const bool zr = start >= zrow;
+            const double* cs = c + (size_t)start * ld;
+#pragma unroll
+            for (int q = 0; q < JV_OWN; ++q) {
+                const int jj = BMB_TID + q * BMB_NT;
+                if (jj < n) {
+                    const double vj = v[jj];
+                    const double dj = (zr ? 0.0 : cs[jj]) - vj;
+                    dq[q] = dj;
+                    nvq[q] = 0.0 - vj;
+                    d[jj] = dj;
+                    cols[jj] = jj;
+                    pos[jj] = jj;
+                    pred[jj] = start;
+#if BMB_DEVICE
+                    open |= 1u << q;
+#else
+                    open_h[q] = 1;
+#endif
+                }
+#if !BMB_DEVICE
+                else break;
+#endif
+            }
+        }
+        BMB_SYNC();
+        c_edge += BMB_CLOCK() - c0;
+        while (final_j == -1) {
+            if (lo == hi) {
+                // ---- _find_dense over positions [lo, n): distances of the open columns go back to shared memory ----
+                c0 = BMB_CLOCK();
+#pragma unroll
+                for (int q = 0; q < JV_OWN; ++q) {
+                    const int jj = BMB_TID + q * BMB_NT;
+#if BMB_DEVICE
+                    if ((open >> q) & 1u) d[jj] = dq[q];
+#else
+                    if (jj >= n) break;
+                    if (open_h[q]) d[jj] = dq[q];
+#endif
+                }
+                BMB_SYNC();
+                const int base = lo + 1;
+                const int C = (n - base + BMB_NL - 1) / BMB_NL;   // chunks of one warp width
+                // (1) chunk minima
+                for (int cc = BMB_WARP; cc < C; cc += BMB_NW) {
+                    const int k = base + cc * BMB_NL + lane;
+                    double m = k < n ? d[cols[k]] : BIG;
+#if BMB_DEVICE
+                    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (t < m) m = t; }
+#endif
+                    if (lane == 0) cmin[cc] = m;
+                }
+                BMB_SYNC();
+                // (2) running minimum at the start of every chunk (exclusive prefix minimum, seeded with position lo)
+                if (BMB_WARP == 0) {
+                    double run = d[cols[lo]];
+                    for (int c0i = 0; c0i < C; c0i += BMB_NL) {
+                        const int cc = c0i + lane;
+                        const double mc = cc < C ? cmin[cc] : BIG;
+#if BMB_DEVICE
+                        double pm = mc;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double t = __shfl_up_sync(0xffffffffu, pm, o);
+                            if (lane >= o && t < pm) pm = t;
+                        }
+                        const double excl = __shfl_up_sync(0xffffffffu, pm, 1);
+                        const double before = lane == 0 ? run : (excl < run ? excl : run);
+                        const double tot = __shfl_sync(0xffffffffu, pm, 31);
+#else
+                        const double before = run;
+                        const double tot = mc;
+#endif
+                        if (cc < C) cmin[cc] = before;
+                        if (tot < run) run = tot;
+                    }
+                }
+                BMB_SYNC();
+                // (3) hit masks: a position is a hit when its distance is at or below the running minimum before it
+                for (int cc = BMB_WARP; cc < C; cc += BMB_NW) {
+                    const int k = base + cc * BMB_NL + lane;
+                    const double dj = k < n ? d[cols[k]] : BIG;
+                    const double at_start = cmin[cc];
+#if BMB_DEVICE
+                    double pm = dj;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double t = __shfl_up_sync(0xffffffffu, pm, o);
+                        if (lane >= o && t < pm) pm = t;
+                    }
+                    const double excl = __shfl_up_sync(0xffffffffu, pm, 1);
+                    const double before = lane == 0 ? at_start : (excl < at_start ? excl : at_start);
+#else
+                    const double before = at_start;
+#endif
+                    const unsigned hm = BMB_BALLOT(k < n && dj <= before);
+                    const unsigned sm = BMB_BALLOT(k < n && dj < at_start);   // the minimum moves inside this chunk
+                    if (lane == 0) { hmask[cc] = hm; smask[cc] = sm; }
+                }
+                BMB_SYNC();
+                // (4) the swaps are sequential by nature: one thread replays the hits in position order
+                if (BMB_TID == 0) {
+                    int h2 = lo + 1;
+                    double mind = d[cols[lo]];
+                    for (int cc = 0; cc < C; ++cc) {
+                        unsigned m = hmask[cc];
+                        if (!m) continue;
+                        const int kb = base + cc * BMB_NL;
+                        if (smask[cc] == 0u && kb == h2 && (m & (m + 1u)) == 0u) {   // ties at h2, h2+1, ...: self-swaps
+                            h2 += BMB_POPC(m);
+                            continue;
+                        }
+                        while (m) {
+                            const int k = kb + BMB_FFS(m);
+                            m &= m - 1;
+                            const int j = cols[k];
+                            const double dj = d[j];
+                            if (dj < mind) { h2 = lo; mind = dj; }
+                            cols[k] = cols[h2];
+                            cols[h2] = j;
+                            ++h2;
+                        }
+                    }
+                    mbx[0] = h2;
+                    mbx[1] = -1;
+                }
+                BMB_SYNC();
+                hi = mbx[0];
+                // (5) inverse permutation, and lapjv's choice among free columns of the band: the LAST one
+                {
+                    int last = -1;
+                    for (int k = BMB_TID; k < n; k += BMB_NT) {
+                        const int j = cols[k];
+                        pos[j] = k;
+                        if (k >= lo && k < hi && y[j] < 0) last = k;
+                    }
+                    if (last >= 0) BMB_ATOMIC_MAX(&mbx[1], last);
+                }
+                BMB_SYNC();
+                n_ready = lo;
+                band = lo;
+                final_j = mbx[1] >= 0 ? cols[mbx[1]] : -1;
+#pragma unroll
+                for (int q = 0; q < JV_OWN; ++q) {
+                    const int jj = BMB_TID + q * BMB_NT;
+#if BMB_DEVICE
+                    if (jj < n && pos[jj] < hi) open &= ~(1u << q);
+#else
+                    if (jj >= n) break;
+                    if (pos[jj] < hi) open_h[q] = 0;
+#endif
+                }
+                BMB_SYNC();   // mbx is rewritten by the next replay / find only after everyone has read it
+                c_find += BMB_CLOCK() - c0;
+            }
+            // ---- _scan_dense over the ready band: register arithmetic and one barrier per band column ----
+            while (lo != hi && final_j == -1) {
+                ++n_steps;
+                const int j = cols[lo++];
+                const int i = y[j];
+                const double mind = d[j];
+                const bool zr = i >= zrow;
+                const double* ci = c + (size_t)i * ld;
+                const double h = (zr ? 0.0 : ci[j]) - v[j] - mind;
+                const double* cn = nullptr;   // row of the next band column (prefetch target)
+                if (lo != hi) {
+                    const int jn = cols[lo];
+                    const int in = y[jn];
+                    if (in < zrow) { cn = c + (size_t)in * ld; if (BMB_TID == 0) BMB_PREFETCH_L1(cn + jn); }
+                }
+                int any = 0;
+#pragma unroll
+                for (int q = 0; q < JV_OWN; ++q) {
+                    const int jj = BMB_TID + q * BMB_NT;
+#if BMB_DEVICE
+                    if ((open >> q) & 1u) {
+#else
+                    if (jj >= n) break;
+                    if (open_h[q]) {
+#endif
+                        const double r = zr ? nvq[q] - h : (ci[jj] - v[jj]) - h;
+                        if (cn) BMB_PREFETCH_L1(cn + jj);
+                        if (r < dq[q]) {
+                            dq[q] = r;
+                            pred[jj] = i;
+                            if (r == mind) { d[jj] = r; any = 1; }
+                        }
+                    }
+                }
+                any = BMB_SYNC_OR(any);
+                if (any) {
+                    c0 = BMB_CLOCK();
+                    // the hits, in position order: open positions whose distance now equals the band minimum
+                    const int hi0 = hi;
+                    int slot = BMB_WARP;
+                    for (int k0 = hi0; k0 < n; k0 += BMB_NT, slot += BMB_NW) {
+                        const int k = k0 + BMB_TID;
+                        const unsigned m = BMB_BALLOT(k < n && d[cols[k]] == mind);
+                        if (lane == 0) hmask[slot] = m;
+                    }
+                    BMB_SYNC();
+                    if (BMB_TID == 0) {
+                        int h2 = hi0, fj = -1;
+                        const int n_slots = ((n - hi0 + BMB_NT - 1) / BMB_NT) * BMB_NW;
+                        for (int qq = 0; qq < n_slots && fj < 0; ++qq) {
+                            unsigned m = hmask[qq];
+                            const int kb = hi0 + (qq / BMB_NW) * BMB_NT + (qq % BMB_NW) * BMB_NL;
+                            while (m) {
+                                const int kq = kb + BMB_FFS(m);
+                                m &= m - 1;
+                                const int jq = cols[kq];
+                                if (y[jq] < 0) { fj = jq; break; }
+                                const int other = cols[h2];
+                                cols[kq] = other;
+                                pos[other] = kq;
+                                cols[h2] = jq;
+                                pos[jq] = h2;
+                                ++h2;
+                            }
+                        }
+                        mbx[0] = h2;
+                        mbx[1] = fj;
+                    }
+                    BMB_SYNC();
+                    hi = mbx[0];
+                    final_j = mbx[1];
+#pragma unroll
+                    for (int q = 0; q < JV_OWN; ++q) {
+                        const int jj = BMB_TID + q * BMB_NT;
+#if BMB_DEVICE
+                        if (((open >> q) & 1u) && pos[jj] < hi) open &= ~(1u << q);
+#else
+                        if (jj >= n) break;
+                        if (open_h[q] && pos[jj] < hi) open_h[q] = 0;
+#endif
+                    }
+                    BMB_SYNC();
+                    c_replay += BMB_CLOCK() - c0;
+                }
+            }
+        }
+        c0 = BMB_CLOCK();
+        // price update for the columns scanned before the last band, then augment along the path
+        {
+            const double mind = d[cols[band]];
+            for (int k = BMB_TID; k < n_ready; k += BMB_NT) { const int j = cols[k]; v[j] += d[j] - mind; }
+        }
+        if (BMB_TID == 0) {
+            int j = final_j, i = -1;
+            while (i != start) {
+                i = pred[j];
+                y[j] = i;
+                const int prev = x[i];
+                x[i] = j;
+                j = prev;
+            }
+        }
+        BMB_SYNC();
+        c_edge += BMB_CLOCK() - c0;
+    }
+    if (BMB_TID == 0) { s.timers[13] += n_steps; s.timers[11] += c_find; s.timers[14] += c_replay; s.timers[15] += c_edge; }
+}
+
 // S provides: cost (n x n, leading dimension ld), lap_x, lap_y, lap_v, lap_spc (d), lap_path (pred),
 // lap_tl (cols), lap_sc (free rows), lap_insc (once flags).  Called by the whole CTA.
 //
@@ -225,6 +534,8 @@ template <typename S>
 BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide = 0) {
     if (n <= 0) return;
     const bool wide_eff = wide && n >= 64;
+    // column-owned variant: every thread keeps JV_OWN columns in registers, _find_dense holds JV_CHUNKS chunks
+    const bool owned_eff = wide_eff && wide == 2 && n <= JV_OWN * BMB_NT && n <= (JV_CHUNKS - 8) * BMB_NL;
 #if BMB_DEVICE
     __shared__ int jv_mbx[2];
 #else
@@ -266,9 +577,10 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide 
             if (xi < 0) { if (lane == 0) free_rows[n_free] = i; ++n_free; continue; }
             if (!once[i]) continue;
             const double* ci = c + (size_t)i * ld;
+            const bool zr = i >= zrow;   // zero padding row: nothing to load
             double m = BIG;
             for (int k = lane; k < n; k += BMB_NL)
-                if (k != xi) { const double r = ci[k] - v[k]; if (r < m) m = r; }
+                if (k != xi) { const double r = (zr ? 0.0 : ci[k]) - v[k]; if (r < m) m = r; }
 #if BMB_DEVICE
             for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); if (t < m) m = t; }
 #endif
@@ -284,10 +596,11 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide 
                 ++rounds;
                 const int fi = free_rows[cur++];
                 const double* ci = c + (size_t)fi * ld;
+                const bool zr = fi >= zrow;
                 // lexicographic (value, index) minimum and the minimum over the remaining indices
                 double a1 = BIG, a2 = BIG; int i1 = -1, i2 = -1;
                 for (int j = lane; j < n; j += BMB_NL) {
-                    const double r = ci[j] - v[j];
+                    const double r = (zr ? 0.0 : ci[j]) - v[j];
                     if (i1 < 0 || r < a1) { a2 = a1; i2 = i1; a1 = r; i1 = j; }
                     else if (i2 < 0 || r < a2) { a2 = r; i2 = j; }
                 }
@@ -472,7 +785,8 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide 
     BMB_SYNC();
     if (wide_eff) {
         const long long t0 = BMB_CLOCK();
-        jv_augment_wide(s, n, ld, zrow, jv_mbx[0], jv_mbx);
+        if (owned_eff) jv_augment_owned(s, n, ld, zrow, jv_mbx[0], jv_mbx);
+        else jv_augment_wide(s, n, ld, zrow, jv_mbx[0], jv_mbx);
         if (BMB_TID == 0) s.timers[10] += BMB_CLOCK() - t0;
     }
 }

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) k_docs_embcost(const DocsCfg cfg, DocsStr
 static int& jv_wide_flag() {
     static int v = [] {
         const char* e = getenv("BOXMOT_B200_JV_WIDE");
-        return e ? (e[0] != '0' ? 1 : 0) : 1;
+        return e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
     }();
     return v;
 }
@@ -189,7 +189,7 @@ __host__ __device__ inline size_t jv_smem_bytes(int MX) {
 __global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStream* streams, int jv_in_smem) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     DocsStream s = streams[blockIdx.x];
-    s.jv_wide = (jv_in_smem >> 1) & 1;
+    s.jv_wide = (jv_in_smem >> 1) & 3;
     if (jv_in_smem & 1) {
         const int MX = cfg.cap_tracks > cfg.cap_dets ? cfg.cap_tracks : cfg.cap_dets;
         double* pd = reinterpret_cast<double*>(dyn_smem);
@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(256) k_jv_only(DocsStream* streams, int n, int
     jv_dense_solve(s, n, ld, zrow, wide);
 }
 
-void set_jv_wide(bool wide) { jv_wide_flag() = wide ? 1 : 0; }
+void set_jv_wide(int mode) { jv_wide_flag() = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 // lapjv(cost, extend_cost=True) on an (R, C) float64 host matrix with lapjv's own tie-breaking
 void standalone_jv(const double* cost, int R, int C, int* x, int* y) {

@@ -143,12 +143,30 @@ class DeviceFrameLoop:
 
     `step()` only enqueues work (ReID of the next frame overlaps the association of this one on the engine's two
     CUDA streams); `rows()` waits and copies the last frame's rows out; `run()` is the loop of `_run_tracker`
-    returning MOT rows per stream."""
+    returning MOT rows per stream.
 
-    def __init__(self, tracker: MultiStreamTracker, timing_stats: Optional[TimingStats] = None):
+    Stream-ordering contract.  The engine runs on its own CUDA streams, which are not ordered with the producer's
+    (the detector's / decoder's torch stream).  `det_rows` is a host array, so the producer has already been waited
+    for when the counts were read; `step()` makes that explicit by synchronising torch's current stream when it is
+    handed torch tensors.  On the consumer side the loop keeps a reference to every input it has enqueued until the
+    engine has provably finished with it (a `fetch()`), and never lets more than `max_in_flight` frames queue up, so a
+    caching allocator cannot hand an input buffer to the next frame while a queued kernel still reads it."""
+
+    def __init__(self, tracker: MultiStreamTracker, timing_stats: Optional[TimingStats] = None,
+                 max_in_flight: int = 4):
         self.tracker = tracker
         self.timing_stats = timing_stats
         self.frame_idx = 0
+        self.max_in_flight = max(1, int(max_in_flight))
+        self._in_flight: list = []
+
+    def _producer_ready(self, *tensors) -> None:
+        for t in tensors:
+            if t is not None and hasattr(t, "data_ptr") and getattr(t, "is_cuda", False):
+                import torch
+
+                torch.cuda.current_stream(t.device).synchronize()
+                return
 
     def step(self, d_dets, det_rows: Sequence[int], d_frames=None, d_embs=None, sync: bool = False) -> None:
         ts = self.timing_stats
@@ -156,7 +174,15 @@ class DeviceFrameLoop:
             ts.start_frame()
             ts.reset_frame_reid()
             ts.start_tracking()
+        if len(self._in_flight) >= self.max_in_flight:
+            self.tracker.fetch()          # waits for everything queued so far
+            self._in_flight.clear()
+        self._producer_ready(d_dets, d_frames, d_embs)
         self.tracker.update_device(d_dets, det_rows, d_embs=d_embs, d_images=d_frames, sync=sync)
+        if sync:
+            self._in_flight.clear()
+        else:
+            self._in_flight.append((d_dets, d_frames, d_embs))
         if ts is not None:
             ts.end_tracking()
             if sync:
@@ -165,7 +191,9 @@ class DeviceFrameLoop:
         self.frame_idx += 1
 
     def rows(self) -> List[TrackResults]:
-        return self.tracker.fetch()
+        out = self.tracker.fetch()
+        self._in_flight.clear()
+        return out
 
     def run(self, frames, every_frame: bool = True) -> List[np.ndarray]:
         """`frames`: iterable of `(d_dets, det_rows, d_frames_or_None, d_embs_or_None)`.  With `every_frame` the rows of

@@ -227,8 +227,9 @@ BOXMOT_B200_API int boxmot_b200_lap_solve(const double* cost, int rows, int cols
 /* lapjv(cost, extend_cost=True) (no cost limit, zero-padded to square) with lapjv's own tie-breaking -- the dense
  * Jonker-Volgenant solver DeepOCSORT's association needs for bit-exact ids. cost (rows, cols) float64 host. */
 BOXMOT_B200_API int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y);
-/* Augmentation variant of the dense solver for this process: 1 = CTA-wide search (default), 0 = one-warp search;
- * both reproduce lapjv's results, the parity tests run both (env BOXMOT_B200_JV_WIDE sets the initial value). */
+/* Augmentation variant of the dense solver for this process: 2 = CTA-wide search with the columns owned by threads
+ * (distances in registers), 1 = CTA-wide search over list positions, 0 = one-warp search; all reproduce lapjv's
+ * results, the parity tests run every variant (env BOXMOT_B200_JV_WIDE sets the initial value). */
 BOXMOT_B200_API int boxmot_b200_jv_dense_mode(int cta_wide);
 /* scipy.optimize.linear_sum_assignment(cost) with scipy's own tie-breaking (StrongSORT's min_cost_matching,
  * trackers/bbox/strongsort/sort/linear_assignment.py:62): cost (rows, cols) float64 host -> min(rows, cols) pairs

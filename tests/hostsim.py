@@ -181,10 +181,11 @@ class HostSimDeepOcSort:
             raise RuntimeError(f"hostsim error {-m}")
         return out[:m].copy()
 
-    def set_jv_wide(self, wide: bool):
-        """Select the CTA-wide augmentation path of jv_dense.cuh (one "thread" here: same control flow, masks of 1 bit)."""
+    def set_jv_wide(self, mode: int):
+        """Augmentation variant of jv_dense.cuh: 0 one warp, 1 CTA-wide over list positions, 2 CTA-wide with owned
+        columns (one "thread" here: same control flow, masks of 1 bit)."""
         self.lib.docs_set_jv_wide.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        self.lib.docs_set_jv_wide(self.h, int(bool(wide)))
+        self.lib.docs_set_jv_wide(self.h, int(mode))
 
     def jv(self, cost):
         cost = np.ascontiguousarray(cost, dtype=np.float64)

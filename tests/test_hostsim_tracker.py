@@ -85,8 +85,9 @@ def test_hostsim_dense_jv_reproduces_lapjv_ties(seed):
     assert np.array_equal(x, xo) and np.array_equal(y, yo)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("seed", range(24))
-def test_hostsim_dense_jv_wide_augmentation_reproduces_lapjv_ties(seed):
+def test_hostsim_dense_jv_wide_augmentation_reproduces_lapjv_ties(seed, mode):
     """The CTA-wide augmentation (jv_augment_wide: relax every open position, then replay the band-minimum hits in
     position order; zero-padding rows never loaded) against the oracle's lapjv, at sizes where it is active (n >= 64)."""
     rng = np.random.default_rng(1000 + seed)
@@ -94,21 +95,25 @@ def test_hostsim_dense_jv_wide_augmentation_reproduces_lapjv_ties(seed):
     if max(r, c) < 64:
         c = 64 + seed
     sim = HostSimDeepOcSort(deepocsort_cfg(cap_tracks=256, cap_dets=256, feat_dim=0))
-    sim.set_jv_wide(True)
-    for cost in (_tie_heavy(rng, r, c), -rng.random((r, c)), -np.round(rng.random((r, c)), 1)):
+    sim.set_jv_wide(mode)
+    sparse = np.zeros((r, c))
+    k2 = max(1, r * c // 50)
+    sparse.flat[rng.choice(r * c, size=k2, replace=False)] = -np.round(rng.random(k2), 1)
+    for cost in (_tie_heavy(rng, r, c), -rng.random((r, c)), -np.round(rng.random((r, c)), 1), sparse, np.zeros((r, c))):
         x, y = sim.jv(cost)
         _, xo, yo = lapjv(cost, extend_cost=True)
         assert np.array_equal(x, xo) and np.array_equal(y, yo)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n][0] == "deepocsort"))
-def test_hostsim_deepocsort_golden_with_wide_augmentation(name):
+def test_hostsim_deepocsort_golden_with_wide_augmentation(name, mode):
     kind, kwargs, make_frames, make_embs = CASES[name]
     frames = make_frames()
     embs = make_embs(frames) if make_embs else None
     want, _ = load_golden(name)
     trk = _make(kind, kwargs)
-    trk.set_jv_wide(True)
+    trk.set_jv_wide(mode)
     for f, dets in enumerate(frames):
         assert_rows_match(trk.update(dets, None, None if embs is None else embs[f]), want[f], f, box_rtol=1e-4)
 
