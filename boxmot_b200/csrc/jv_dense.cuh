@@ -283,7 +283,9 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                     open_h[q] = 1;
 #endif
                 }
-#if !BMB_DEVICE
+#if BMB_DEVICE
+                else { dq[q] = -BIG; nvq[q] = 0.0; }   // a closed column carries -BIG: `r < dq` never holds
+#else
                 else break;
 #endif
             }
@@ -408,7 +410,7 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                 for (int q = 0; q < JV_OWN; ++q) {
                     const int jj = BMB_TID + q * BMB_NT;
 #if BMB_DEVICE
-                    if (jj < n && pos[jj] < hi) open &= ~(1u << q);
+                    if (jj < n && pos[jj] < hi) { open &= ~(1u << q); dq[q] = -BIG; }
 #else
                     if (jj >= n) break;
                     if (pos[jj] < hi) open_h[q] = 0;
@@ -433,17 +435,46 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                     if (in < zrow) { cn = c + (size_t)in * ld; if (BMB_TID == 0) BMB_PREFETCH_L1(cn + jn); }
                 }
                 int any = 0;
+#if BMB_DEVICE
+                // straight-line relax: no per-column branch (closed columns hold -BIG), improvements and band-minimum
+                // hits are collected as bit masks and written back afterwards (they are rare)
+                unsigned imp = 0u, hitq = 0u;
+                if (zr) {
 #pragma unroll
+                    for (int q = 0; q < JV_OWN; ++q) {
+                        const double r = nvq[q] - h;
+                        const bool better = r < dq[q];
+                        dq[q] = better ? r : dq[q];
+                        imp |= (better ? 1u : 0u) << q;
+                        hitq |= ((better && r == mind) ? 1u : 0u) << q;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < JV_OWN; ++q) {
+                        const int jj = BMB_TID + q * BMB_NT;
+                        if ((open >> q) & 1u) {
+                            const double r = (ci[jj] - v[jj]) - h;
+                            if (cn) BMB_PREFETCH_L1(cn + jj);
+                            const bool better = r < dq[q];
+                            dq[q] = better ? r : dq[q];
+                            imp |= (better ? 1u : 0u) << q;
+                            hitq |= ((better && r == mind) ? 1u : 0u) << q;
+                        }
+                    }
+                }
+                while (imp) {
+                    const int q = __ffs(imp) - 1;
+                    imp &= imp - 1u;
+                    const int jj = BMB_TID + q * BMB_NT;
+                    pred[jj] = i;
+                    if ((hitq >> q) & 1u) { d[jj] = mind; any = 1; }
+                }
+#else
                 for (int q = 0; q < JV_OWN; ++q) {
                     const int jj = BMB_TID + q * BMB_NT;
-#if BMB_DEVICE
-                    if ((open >> q) & 1u) {
-#else
                     if (jj >= n) break;
                     if (open_h[q]) {
-#endif
                         const double r = zr ? nvq[q] - h : (ci[jj] - v[jj]) - h;
-                        if (cn) BMB_PREFETCH_L1(cn + jj);
                         if (r < dq[q]) {
                             dq[q] = r;
                             pred[jj] = i;
@@ -451,6 +482,7 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                         }
                     }
                 }
+#endif
                 any = BMB_SYNC_OR(any);
                 if (any) {
                     c0 = BMB_CLOCK();
@@ -492,7 +524,7 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                     for (int q = 0; q < JV_OWN; ++q) {
                         const int jj = BMB_TID + q * BMB_NT;
 #if BMB_DEVICE
-                        if (((open >> q) & 1u) && pos[jj] < hi) open &= ~(1u << q);
+                        if (((open >> q) & 1u) && pos[jj] < hi) { open &= ~(1u << q); dq[q] = -BIG; }
 #else
                         if (jj >= n) break;
                         if (open_h[q] && pos[jj] < hi) open_h[q] = 0;
