@@ -412,6 +412,27 @@ class _SingleStreamTracker:
     def snapshot(self):
         return self._engine.snapshot(0)
 
+    # ---- attributes the reference's callers read (basetracker.py:76, 374-390) --------------------------------------
+    class TrackView:
+        """Read-only view of one live track: `id`, Kalman `mean` / `covariance` (float64 copies of the device state)."""
+
+        __slots__ = ("id", "mean", "covariance")
+
+        def __init__(self, tid, mean, cov):
+            self.id, self.mean, self.covariance = tid, mean, cov
+
+    @property
+    def active_tracks(self):
+        """The live tracks as views of the device-resident state (one synchronising snapshot per access)."""
+        return [self.TrackView(k, m, c) for k, (m, c) in sorted(self._engine.snapshot(0).items())]
+
+    # the lost / removed lists live on the device and are not exposed through the ABI; display helpers get empty lists
+    lost_stracks = ()
+    removed_stracks = ()
+
+    def get_active_tracks_for_display(self) -> list:
+        return list(self.active_tracks)
+
 
 class ByteTrack(_SingleStreamTracker):
     """ByteTrack on the GPU; arguments as boxmot/trackers/bbox/bytetrack/bytetrack.py:226-257."""
