@@ -21,6 +21,39 @@ BOTSORT_YAML = dict(
 STRONGSORT_YAML = dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
                        mc_lambda=0.98, nn_budget=100)
 
+
+
+def mot17_stream(seq: str):
+    """Per-frame `(n, 6)` detections of the committed MOT17-mini fixture (tests/golden/make_mot17_golden.py): public FRCNN
+    detections of the reference's own assets, real confidences (3 decimals) and real crowding; frames without
+    detections are empty arrays."""
+    z = np.load(GOLDEN / "mot17_mini_dets.npz")
+    dets, n = z[f"dets_{seq}"], int(z[f"frames_{seq}"])
+    fid = dets[:, 0].astype(int)
+    return [np.ascontiguousarray(dets[fid == f, 1:7]) for f in range(1, n + 1)]
+
+
+def mot17_embeddings(seq: str, frames, dim: int = 512, seed: int = 7, noise: float = 0.45, unit: bool = False):
+    """Appearance vectors for `mot17_stream(seq)`: a prototype per ground-truth identity plus per-detection noise
+    (detections that match no ground-truth person get a vector of their own), non-negative like ReLU features."""
+    z = np.load(GOLDEN / "mot17_mini_dets.npz")
+    dets, gid = z[f"dets_{seq}"], z[f"gid_{seq}"]
+    fid = dets[:, 0].astype(int)
+    rng = np.random.default_rng(seed)
+    protos = np.abs(rng.normal(size=(int(gid.max()) + 2, dim))).astype(np.float32)
+    out = []
+    for f, d in enumerate(frames, start=1):
+        g = gid[fid == f]
+        assert len(g) == len(d)
+        e = np.abs(rng.normal(size=(len(d), dim))).astype(np.float32)
+        known = g >= 0
+        e[known] = np.maximum(protos[g[known]] + noise * rng.normal(size=(int(known.sum()), dim)).astype(np.float32), 0)
+        if unit:
+            e = e / np.maximum(np.linalg.norm(e, axis=1, keepdims=True), 1e-12)
+        out.append(e.astype(np.float32))
+    return out
+
+
 # name -> (tracker kind, kwargs, frames factory, embeddings factory or None)
 CASES = {
     "bytetrack_bench64": ("bytetrack", BYTETRACK_YAML, lambda: bench_stream(64, 300)[1], None),
@@ -52,6 +85,15 @@ CASES = {
                                  lambda fr: stress_embeddings(fr, 64, seed=31)),
     "strongsort_bench128": ("strongsort", {}, lambda: bench_stream(128, 30, hw=(360, 640))[1],
                             lambda fr: stress_embeddings(fr, 128, seed=3)),
+    # realistic stream: public FRCNN detections of the reference's MOT17-mini assets, YAML defaults
+    "bytetrack_mot17_04": ("bytetrack", BYTETRACK_YAML, lambda: mot17_stream("04"), None),
+    "bytetrack_mot17_02": ("bytetrack", BYTETRACK_YAML, lambda: mot17_stream("02"), None),
+    "botsort_mot17_04": ("botsort", BOTSORT_YAML, lambda: mot17_stream("04"), lambda fr: mot17_embeddings("04", fr)),
+    "botsort_mot17_02": ("botsort", BOTSORT_YAML, lambda: mot17_stream("02"), lambda fr: mot17_embeddings("02", fr, seed=9)),
+    "deepocsort_mot17_04": ("deepocsort", {}, lambda: mot17_stream("04"),
+                            lambda fr: mot17_embeddings("04", fr, seed=11, unit=True)),
+    "strongsort_mot17_04": ("strongsort", STRONGSORT_YAML, lambda: mot17_stream("04"),
+                            lambda fr: mot17_embeddings("04", fr, seed=13)),
 }
 # per-frame camera warps of the cases that exercise SURVEY row a15 through the golden table
 WARPS = {"strongsort_warp_stress64": lambda: warp_sequence(100)}
