@@ -27,8 +27,10 @@ TRACKER_DEFAULTS = {
         proximity_thresh=0.6084297894561342, appearance_thresh=0.6188818853936099,
         unconfirmed_emb_scale=2.5445206391993294, second_match_thresh=0.28795081514328974,
         unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329),
-    "deepocsort": dict(det_thresh=0.3, max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2,
-                       w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False,
+    # configs/trackers/deepocsort.yaml: det_thresh 0.5 and w_association_emb 0.75 differ from the constructor defaults
+    # (0.3 / 0.5); its `iou_thresh: 0.3` is swallowed by **kwargs in the reference, so iou_threshold keeps its 0.3
+    "deepocsort": dict(det_thresh=0.5, max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2,
+                       w_association_emb=0.75, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False,
                        cmc_off=True, aw_off=False, Q_xy_scaling=0.01, Q_s_scaling=0.0001),
     "strongsort": dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
                        mc_lambda=0.98, nn_budget=100),

@@ -18,6 +18,8 @@ BOTSORT_YAML = dict(
     unconfirmed_match_thresh=0.41148010638233784, removed_stracks_buffer=329, fuse_first_associate=True,
     frame_rate=30, with_reid=True)
 
+DEEPOCSORT_YAML = dict(det_thresh=0.5, w_association_emb=0.75)
+
 STRONGSORT_YAML = dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
                        mc_lambda=0.98, nn_budget=100)
 
@@ -94,6 +96,10 @@ CASES = {
                             lambda fr: mot17_embeddings("04", fr, seed=11, unit=True)),
     "strongsort_mot17_04": ("strongsort", STRONGSORT_YAML, lambda: mot17_stream("04"),
                             lambda fr: mot17_embeddings("04", fr, seed=13)),
+    # DeepOCSORT with the values create_tracker reads from configs/trackers/deepocsort.yaml (they differ from the
+    # constructor defaults the other DeepOCSORT cases use)
+    "deepocsort_yaml_mot17_02": ("deepocsort", DEEPOCSORT_YAML, lambda: mot17_stream("02"),
+                                 lambda fr: mot17_embeddings("02", fr, seed=15, unit=True)),
 }
 # per-frame camera warps of the cases that exercise SURVEY row a15 through the golden table
 WARPS = {"strongsort_warp_stress64": lambda: warp_sequence(100)}

@@ -1,0 +1,68 @@
+"""Host-side contract of the Python class seam that needs no GPU: the input assertions of
+basetracker.py:356-372 as the reference's own tests exercise them (tests/unit/test_trackers.py:561-598, 639-650),
+`TrackResults` (track_results.py:12-31), `create_tracker` name / scope errors."""
+import numpy as np
+import pytest
+
+from boxmot_b200.trackers import TRACKER_DEFAULTS, TrackResults, _check_inputs, create_tracker
+
+
+def test_input_assertions_match_the_reference_messages():
+    img = np.zeros((640, 640, 3), np.uint8)
+    ok = np.array([[10, 10, 20, 20, 0.7, 0]], np.float32)
+    _check_inputs(ok, img, None)
+    _check_inputs(ok, None, np.zeros((1, 512), np.float32))
+    with pytest.raises(AssertionError, match="Missmatch between detections and embeddings sizes"):
+        _check_inputs(ok, img, np.random.rand(2, 512))                       # test_emb_trackers_requires_embeddings
+    with pytest.raises(AssertionError, match="2nd dimension length"):
+        _check_inputs(np.random.rand(2, 5), img, None)                       # test_invalid_det_array_shape
+    with pytest.raises(AssertionError, match="valid format is np.ndarray"):
+        _check_inputs([[1, 2, 3, 4, 0.5, 0]], img, None)
+    with pytest.raises(AssertionError, match="valid number of dimensions is two"):
+        _check_inputs(np.zeros((6,), np.float32), img, None)
+    with pytest.raises(AssertionError, match="img_numpy"):
+        _check_inputs(ok, "frame.jpg", None)
+
+
+def test_track_results_views():
+    rows = np.array([[1, 2, 3, 4, 7, 0.5, 2, 9], [5, 6, 7, 8, 8, 0.25, 0, 3]], np.float64)
+    tr = TrackResults(rows)
+    assert tr.dtype == np.float32 and tr.shape == (2, 8)
+    assert tr.id.tolist() == [7, 8] and tr.cls.tolist() == [2, 0] and tr.det_ind.tolist() == [9, 3]
+    assert np.array_equal(tr.xyxy, rows[:, :4].astype(np.float32)) and tr.conf.tolist() == [0.5, 0.25]
+    assert TrackResults(rows[0]).shape == (1, 8)                 # a single 1-d row becomes (1, 8)
+    assert TrackResults(np.array([])).shape == (0, 0)            # DeepOCSORT's empty return
+    assert TrackResults(np.empty((0, 8))).shape == (0, 8)
+
+
+def test_create_tracker_rejects_unknown_and_out_of_scope_names():
+    with pytest.raises(ValueError, match="not part of the B200 hot path"):
+        create_tracker("nonexistent_tracker")
+    with pytest.raises(ValueError):
+        create_tracker("ocsort")
+    assert set(TRACKER_DEFAULTS) == {"bytetrack", "botsort", "deepocsort", "strongsort"}
+    # the YAML defaults the reference's create_tracker would read
+    assert TRACKER_DEFAULTS["botsort"]["track_high_thresh"] == 0.6296854875023994
+    assert TRACKER_DEFAULTS["botsort"]["removed_stracks_buffer"] == 329
+    assert TRACKER_DEFAULTS["bytetrack"]["track_thresh"] == 0.6 and TRACKER_DEFAULTS["strongsort"]["min_conf"] == 0.6
+
+
+def test_tracker_defaults_are_the_reference_yaml_defaults():
+    """`create_tracker` must start from what the reference's `create_tracker` reads out of configs/trackers/*.yaml
+    (dumped by tests/golden/make_yaml_defaults.py), not from the constructor defaults."""
+    import json
+    from pathlib import Path
+
+    ref = json.loads((Path(__file__).parent / "golden" / "tracker_yaml_defaults.json").read_text())
+    # documented deviations: camera-motion estimation is outside the path (CMC off), and two YAML keys the reference's
+    # constructors swallow in **kwargs without effect
+    deviations = {("botsort", "use_cmc"), ("botsort", "cmc_method"), ("deepocsort", "cmc_off"),
+                  ("deepocsort", "iou_thresh"), ("deepocsort", "asso_func")}
+    for kind, params in ref.items():
+        mine = TRACKER_DEFAULTS[kind]
+        for name, value in params.items():
+            if (kind, name) in deviations:
+                continue
+            assert name in mine, f"{kind}.{name} missing"
+            assert mine[name] == value, f"{kind}.{name}: {mine[name]} != YAML {value}"
+    assert TRACKER_DEFAULTS["deepocsort"]["cmc_off"] is True and TRACKER_DEFAULTS["deepocsort"]["iou_threshold"] == 0.3
