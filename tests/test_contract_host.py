@@ -66,3 +66,44 @@ def test_tracker_defaults_are_the_reference_yaml_defaults():
             assert name in mine, f"{kind}.{name} missing"
             assert mine[name] == value, f"{kind}.{name}: {mine[name]} != YAML {value}"
     assert TRACKER_DEFAULTS["deepocsort"]["cmc_off"] is True and TRACKER_DEFAULTS["deepocsort"]["iou_threshold"] == 0.3
+
+
+def test_reid_box_normalisation_follows_base_backend():
+    """`B200ReID._boxes` == `BaseModelBackend._boxes_to_xyxy` (base_backend.py:125-146) on the AABB inputs of the
+    reference's tests/unit/test_base_backend.py:36-43; OBB layouts (5 / 7 / 9 columns) are refused, not mis-read."""
+    from boxmot_b200.reid import B200ReID
+
+    xyxy = B200ReID._boxes(np.array([[10, 20, 30, 40, 0.9, 0]], dtype=np.float32))
+    assert xyxy.shape == (1, 4) and xyxy.dtype == np.float32 and xyxy.flags["C_CONTIGUOUS"]
+    np.testing.assert_array_equal(xyxy[0], np.array([10, 20, 30, 40], dtype=np.float32))
+    assert B200ReID._boxes(np.array([1.0, 2.0, 3.0, 4.0])).shape == (1, 4)            # 1-d row
+    assert B200ReID._boxes(np.empty((0, 6))).shape == (0, 4) and B200ReID._boxes([]).shape == (0, 4)
+    assert B200ReID._boxes(np.zeros((3, 8))).shape == (3, 4)                           # tracker output rows
+    with pytest.raises(ValueError, match="at least 4 coordinates"):
+        B200ReID._boxes(np.zeros((2, 3)))
+    for cols in (5, 7, 9):
+        with pytest.raises(NotImplementedError, match="OBB"):
+            B200ReID._boxes(np.zeros((1, cols)))
+
+
+def test_constructor_signatures_match_the_reference():
+    """Same parameter names and default values as the reference constructors (tests/golden/make_ctor_defaults.py),
+    apart from the documented camera-motion switches (estimation is outside this path, so the safe value is the default)."""
+    import inspect
+    import json
+    from pathlib import Path
+
+    import boxmot_b200 as bb
+    from boxmot_b200.trackers import _SingleStreamTracker
+
+    ref = json.loads((Path(__file__).parent / "golden" / "tracker_ctor_defaults.json").read_text())
+    deviations = {("BotSort", "use_cmc"): False, ("DeepOcSort", "cmc_off"): True}
+    base = {n: p.default for n, p in inspect.signature(_SingleStreamTracker.__init__).parameters.items()}
+    for name, value in ref["BaseTracker"].items():
+        assert name in base and base[name] == value, f"BaseTracker.{name}"
+    for cls_name in ("ByteTrack", "BotSort", "DeepOcSort", "StrongSort"):
+        mine = {n: p.default for n, p in inspect.signature(getattr(bb, cls_name).__init__).parameters.items()}
+        for name, value in ref[cls_name].items():
+            assert name in mine, f"{cls_name}.{name} missing"
+            want = deviations.get((cls_name, name), value)
+            assert mine[name] == want, f"{cls_name}.{name}: {mine[name]} != {want}"
