@@ -95,7 +95,7 @@ class TrackerRuntime:
                evolve_param_dict: Optional[dict] = None, timing_stats: Optional[TimingStats] = None,
                **kwargs: Any) -> "TrackerRuntime":
         tracker = create_tracker(str(tracker_name).lower(), reid_weights=reid_weights, device=device, half=half,
-                                 per_class=per_class, **(evolve_param_dict or {}), **kwargs)
+                                 per_class=per_class, evolve_param_dict=evolve_param_dict, **kwargs)
         return cls(tracker, timing_stats=timing_stats)
 
     @staticmethod

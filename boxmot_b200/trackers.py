@@ -511,27 +511,77 @@ class StrongSort(_SingleStreamTracker):
                          ema_alpha=ema_alpha, **kwargs)
 
 
-def create_tracker(tracker_type: str, reid_weights=None, device=None, half: bool = False, per_class: bool = False,
-                   reid_model: Any = None, **overrides: Any):
-    """YAML-default construction like boxmot/trackers/tracker_zoo.py:33-147 for the four trackers of the path.
+def _flatten_yaml_defaults(node, acc=None):
+    """`<param>: {default: ...}` entries of a reference tracker YAML, nested conditional parameters included
+    (what `flatten_yaml_config` + `details["default"]` produce in tracker_zoo.py:112-119)."""
+    acc = {} if acc is None else acc
+    if isinstance(node, dict):
+        for k, v in node.items():
+            if isinstance(v, dict) and "default" in v:
+                acc[str(k)] = v["default"]
+            _flatten_yaml_defaults(v, acc)
+    elif isinstance(node, list):
+        for v in node:
+            _flatten_yaml_defaults(v, acc)
+    return acc
+
+
+def resolve_tracker_args(tracker_type, tracker_config=None, evolve_param_dict=None, overrides=None):
+    """(kind, class, constructor kwargs) exactly as the reference's `create_tracker` would assemble them
+    (tracker_zoo.py:103-147): `evolve_param_dict` replaces the YAML defaults wholesale, `tracker_config` is a YAML file
+    in the reference's format (default: the built-in copy of configs/trackers/<kind>.yaml), keys the reference's
+    constructors swallow in **kwargs are dropped.  Camera-motion estimation is outside this path: `use_cmc` is forced
+    off / `cmc_off` on whatever the configuration says.  No GPU is touched here."""
+    import inspect
+
+    kind = str(tracker_type).lower()
+    classes = {"bytetrack": ByteTrack, "botsort": BotSort, "deepocsort": DeepOcSort, "strongsort": StrongSort}
+    if kind not in classes:
+        raise ValueError(f"Unknown tracker type: '{tracker_type}'. Available trackers are: {', '.join(classes)} "
+                         "(the trackers that are part of the B200 hot path)")
+    if evolve_param_dict is not None:
+        args = dict(evolve_param_dict)
+    elif tracker_config is not None:
+        import yaml
+
+        with open(tracker_config, "r", encoding="utf-8") as f:
+            args = _flatten_yaml_defaults(yaml.safe_load(f) or {})
+    else:
+        args = dict(TRACKER_DEFAULTS[kind])
+    args.update(overrides or {})
+    cls = classes[kind]
+    accepted = set(inspect.signature(cls.__init__).parameters) | set(
+        inspect.signature(_SingleStreamTracker.__init__).parameters) | {"cap_tracks", "cap_dets", "feat_dim"}
+    accepted -= {"self", "params", "kwargs"}
+    args = {k: v for k, v in args.items() if k in accepted}   # the reference's **kwargs swallows the rest
+    args.pop("cmc_method", None)
+    if kind == "botsort":
+        args["use_cmc"] = False
+    if kind == "deepocsort":
+        args["cmc_off"] = True
+    args.pop("per_class", None)
+    return kind, cls, args
+
+
+def create_tracker(tracker_type, tracker_config=None, reid_weights=None, device=None, half=None, per_class=None,
+                   evolve_param_dict=None, reid_preprocess=None, reid_model: Any = None, tracker_backend: str = "python",
+                   **overrides: Any):
+    """Same signature and argument meaning as boxmot/trackers/tracker_zoo.py:33-147 (positional callers included) for
+    the four trackers of the path; `tracker_backend` "python" and "cpp" both resolve to this library.
 
     `reid_weights` may be a `.pt` state dict or a `.b200reid` blob; it is converted once and loaded on the GPU.
-    CMC defaults to off (see BotSort)."""
-    kind = tracker_type.lower()
-    if kind not in TRACKER_DEFAULTS:
-        raise ValueError(f"tracker '{tracker_type}' is not part of the B200 hot path")
-    args = dict(TRACKER_DEFAULTS[kind])
-    args.pop("cmc_method", None)
-    args["use_cmc"] = False if kind == "botsort" else None
-    if args["use_cmc"] is None:
-        args.pop("use_cmc")
-    args.update(overrides)
+    `**overrides` (an extension) are applied on top of the configuration.  CMC is always off (see BotSort)."""
+    kind, cls, args = resolve_tracker_args(tracker_type, tracker_config, evolve_param_dict, overrides)
+    per_class = bool(per_class)
     if kind == "bytetrack":
-        return ByteTrack(per_class=per_class, **args)
+        return cls(per_class=per_class, **args)
     wants_reid = args.get("with_reid", True) and not args.get("embedding_off", False)
     if reid_model is None and reid_weights is not None and wants_reid:
         from .reid import B200ReID
 
-        reid_model = B200ReID(reid_weights, half=half)
-    cls = {"botsort": BotSort, "deepocsort": DeepOcSort, "strongsort": StrongSort}[kind]
-    return cls(reid_model=reid_model, per_class=per_class, **args)
+        reid_model = B200ReID(reid_weights, device=device, half=bool(half), preprocess=reid_preprocess)
+    tracker = cls(reid_model=reid_model, per_class=per_class, **args)
+    # the reference warms the backend up here (tracker_zoo.py:145-146); a B200ReID has nothing lazy to warm
+    if getattr(tracker, "model", None) is not None and not tracker.provides_reid and hasattr(tracker.model, "warmup"):
+        tracker.model.warmup()
+    return tracker

@@ -36,15 +36,68 @@ def test_track_results_views():
 
 
 def test_create_tracker_rejects_unknown_and_out_of_scope_names():
-    with pytest.raises(ValueError, match="not part of the B200 hot path"):
-        create_tracker("nonexistent_tracker")
-    with pytest.raises(ValueError):
+    # the reference's own test matches this text (tests/unit/test_trackers.py:639-650)
+    with pytest.raises(ValueError, match="Unknown tracker type: 'nonexistent_tracker'"):
+        create_tracker(tracker_type="nonexistent_tracker", tracker_config=None, reid_weights="x.pt", device="cpu",
+                       half=False, per_class=False)
+    with pytest.raises(ValueError, match="Unknown tracker type"):
         create_tracker("ocsort")
     assert set(TRACKER_DEFAULTS) == {"bytetrack", "botsort", "deepocsort", "strongsort"}
     # the YAML defaults the reference's create_tracker would read
     assert TRACKER_DEFAULTS["botsort"]["track_high_thresh"] == 0.6296854875023994
     assert TRACKER_DEFAULTS["botsort"]["removed_stracks_buffer"] == 329
     assert TRACKER_DEFAULTS["bytetrack"]["track_thresh"] == 0.6 and TRACKER_DEFAULTS["strongsort"]["min_conf"] == 0.6
+
+
+def test_create_tracker_has_the_reference_signature_and_argument_resolution(tmp_path):
+    """Positional callers of tracker_zoo.create_tracker keep working (tracker_type, tracker_config, reid_weights, device,
+    half, per_class, evolve_param_dict, reid_preprocess, reid_model, tracker_backend), and the constructor arguments
+    are assembled like tracker_zoo.py:103-147: evolve_param_dict replaces the YAML defaults wholesale, a YAML path in
+    the reference's format is flattened (nested conditional parameters included), keys the reference's constructors
+    swallow in **kwargs are dropped, CMC is forced off."""
+    import inspect
+
+    from boxmot_b200.trackers import BotSort, DeepOcSort, resolve_tracker_args
+
+    names = list(inspect.signature(create_tracker).parameters)
+    assert names[:10] == ["tracker_type", "tracker_config", "reid_weights", "device", "half", "per_class",
+                          "evolve_param_dict", "reid_preprocess", "reid_model", "tracker_backend"]
+    kind, cls, args = resolve_tracker_args("BotSort")
+    assert (kind, cls) == ("botsort", BotSort) and args["use_cmc"] is False and "cmc_method" not in args
+    assert args["proximity_thresh"] == 0.6084297894561342 and args["track_buffer"] == 40
+    # a YAML file in the reference's layout: typed entries with `default`, conditional children nested under a parent
+    y = tmp_path / "deepocsort.yaml"
+    y.write_text("""
+det_thresh:
+  type: uniform
+  default: 0.41
+  range: [0.3, 0.6]
+iou_thresh:
+  type: uniform
+  default: 0.25
+asso_func:
+  type: choice
+  default: iou
+embedding_off:
+  type: choice
+  default: false
+  conditional:
+    false:
+      w_association_emb:
+        type: uniform
+        default: 0.66
+cmc_off:
+  type: choice
+  default: false
+""")
+    kind, cls, args = resolve_tracker_args("deepocsort", str(y))
+    assert cls is DeepOcSort and args["det_thresh"] == 0.41 and args["w_association_emb"] == 0.66
+    assert args["cmc_off"] is True and "iou_thresh" not in args and args["asso_func"] == "iou"
+    # evolve_param_dict: used INSTEAD of the YAML; everything else falls back to the constructor defaults
+    _, _, args = resolve_tracker_args("botsort", None, {"track_high_thresh": 0.7, "not_a_parameter": 1, "cmc_method": "ecc"})
+    assert args == {"track_high_thresh": 0.7, "use_cmc": False}
+    _, _, args = resolve_tracker_args("bytetrack", None, None, {"track_thresh": 0.5, "cap_dets": 64})
+    assert args["track_thresh"] == 0.5 and args["cap_dets"] == 64 and args["match_thresh"] == 0.9
 
 
 def test_tracker_defaults_are_the_reference_yaml_defaults():
