@@ -38,20 +38,42 @@ TRACKER_DEFAULTS = {
 
 
 class TrackResults(np.ndarray):
-    """float32 view over the (M, 8) output rows [x1,y1,x2,y2,id,conf,cls,det_ind] (track_results.py:12-31)."""
+    """float32 view over the (M, 8) output rows [x1,y1,x2,y2,id,conf,cls,det_ind] with the named accessors and export
+    helpers of the reference class (track_results.py:12-200); AABB layout only (OBB is outside this path)."""
 
-    def __new__(cls, data):
+    def __new__(cls, data, masks=None):
         arr = np.asarray(data, dtype=np.float32)
         if arr.ndim == 1 and arr.size > 0:
             arr = arr.reshape(1, -1)
         elif arr.size == 0:
             cols = arr.shape[1] if arr.ndim == 2 else 0
             arr = arr.reshape(0, cols)
-        return arr.view(cls)
+        obj = arr.view(cls)
+        obj._masks = masks
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._masks = getattr(obj, "_masks", None)
+
+    @property
+    def masks(self):
+        return self._masks
+
+    @property
+    def is_obb(self) -> bool:
+        return self.shape[1] >= 9 if self.ndim == 2 else False
 
     @property
     def xyxy(self):
         return np.asarray(self[:, :4])
+
+    @property
+    def xywh(self):
+        boxes = np.asarray(self[:, :4])
+        if boxes.size == 0:
+            return np.empty((0, 4), dtype=np.float32)
+        x1, y1, x2, y2 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+        return np.stack([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], axis=1)
 
     @property
     def id(self):
@@ -68,6 +90,60 @@ class TrackResults(np.ndarray):
     @property
     def det_ind(self):
         return np.asarray(self[:, 7]).astype(int)
+
+    # ---- export helpers (track_results.py:96-200) ----
+    _csv_fields = ["x1", "y1", "x2", "y2", "id", "conf", "cls", "det_ind"]
+
+    def _row(self, i: int):
+        return [float(v) for v in self.xyxy[i]] + [int(self.id[i]), float(self.conf[i]), int(self.cls[i]),
+                                                   int(self.det_ind[i])]
+
+    def summary(self):
+        out = []
+        for i in range(len(self)):
+            x1, y1, x2, y2 = self.xyxy[i]
+            out.append({"id": int(self.id[i]), "conf": float(self.conf[i]), "cls": int(self.cls[i]),
+                        "box": {"x1": float(x1), "y1": float(y1), "x2": float(x2), "y2": float(y2)}})
+        return out
+
+    def to_json(self, indent=None) -> str:
+        import json
+
+        return json.dumps(self.summary(), indent=indent)
+
+    def to_csv(self, frame_id=None) -> str:
+        import csv
+        import io
+
+        buf = io.StringIO()
+        writer = csv.writer(buf)
+        for i in range(len(self)):
+            writer.writerow(([frame_id] + self._row(i)) if frame_id is not None else self._row(i))
+        return buf.getvalue()
+
+    def save_csv(self, path, frame_id=None, header: bool = True) -> None:
+        import csv
+        from pathlib import Path
+
+        path = Path(path)
+        write_header = header and not path.exists()
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with open(path, "a", newline="") as f:
+            if write_header:
+                csv.writer(f).writerow((["frame"] + self._csv_fields) if frame_id is not None else self._csv_fields)
+            f.write(self.to_csv(frame_id=frame_id))
+
+    def save_mot(self, path, frame_id: int = 0) -> None:
+        from pathlib import Path
+
+        path = Path(path)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with open(path, "a") as f:
+            for i in range(len(self)):
+                x1, y1, x2, y2 = self.xyxy[i]
+                w, h = x2 - x1, y2 - y1
+                f.write(f"{frame_id},{int(self.id[i])},{x1:.2f},{y1:.2f},{w:.2f},{h:.2f},"
+                        f"{self.conf[i]:.6f},{int(self.cls[i])},-1\n")
 
 
 def _check_inputs(dets, img, embs):

@@ -160,3 +160,26 @@ def test_constructor_signatures_match_the_reference():
             assert name in mine, f"{cls_name}.{name} missing"
             want = deviations.get((cls_name, name), value)
             assert mine[name] == want, f"{cls_name}.{name}: {mine[name]} != {want}"
+
+
+def test_track_results_exports_equal_the_reference(tmp_path):
+    """`xywh`, `summary`, `to_json`, `to_csv`, `save_csv`, `save_mot` against strings produced by the reference class
+    (tests/golden/make_trackresults_golden.py)."""
+    import json
+    from pathlib import Path
+
+    from tests.golden.make_trackresults_golden import ROWS
+
+    g = json.loads((Path(__file__).parent / "golden" / "trackresults_exports.json").read_text())
+    tr = TrackResults(np.asarray(ROWS, dtype=np.float64))
+    assert tr.summary() == g["summary"] and tr.to_json() == g["json"] and tr.to_json(indent=1) == g["json_indent"]
+    assert tr.to_csv() == g["csv"] and tr.to_csv(frame_id=17) == g["csv_frame"]
+    assert tr.xywh.tolist() == g["xywh"] and tr.is_obb is g["is_obb"] and tr.masks is None
+    p = tmp_path / "a" / "t.csv"
+    tr.save_csv(p, frame_id=3)
+    tr.save_csv(p, frame_id=4)
+    assert p.read_text() == g["save_csv"]
+    m = tmp_path / "b" / "t.txt"
+    tr.save_mot(m, frame_id=9)
+    assert m.read_text() == g["save_mot"]
+    assert TrackResults(np.empty((0, 8))).xywh.shape == (0, 4) and tr[:2].masks is None
