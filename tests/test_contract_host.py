@@ -183,3 +183,51 @@ def test_track_results_exports_equal_the_reference(tmp_path):
     tr.save_mot(m, frame_id=9)
     assert m.read_text() == g["save_mot"]
     assert TrackResults(np.empty((0, 8))).xywh.shape == (0, 4) and tr[:2].masks is None
+
+
+def test_create_tracker_call_chain_with_a_stub_engine(monkeypatch):
+    """The whole construction path (create_tracker -> tracker class -> engine arguments; TrackerRuntime.create) with the
+    CUDA engine replaced by a recorder: positional reference-style calls, on-device ReID detection, warm-up only for
+    foreign backends."""
+    import boxmot_b200.trackers as T
+    from boxmot_b200.runtime import TimingStats, TrackerRuntime
+
+    made = []
+
+    class Engine:
+        def __init__(self, kind, n_streams, cap_tracks, cap_dets, feat_dim, reid_blob=None, **params):
+            self.kind, self.params, self.feat_dim = kind, params, feat_dim
+            self.with_reid, self.has_reid_model = kind != "bytetrack", reid_blob is not None
+            made.append((kind, cap_tracks, cap_dets, feat_dim, reid_blob, params))
+
+    monkeypatch.setattr(T, "MultiStreamTracker", Engine)
+
+    class OnDevice:
+        blob_path, feature_dim = "/tmp/m.b200reid", 1792
+
+        def warmup(self):
+            raise AssertionError("an on-device backend has nothing to warm up")
+
+    warmed = []
+
+    class Foreign:
+        def get_features(self, xyxys, img):
+            return np.zeros((len(xyxys), 512), np.float32)
+
+        def warmup(self):
+            warmed.append(1)
+
+    rt = TrackerRuntime.create("botsort", reid_model=OnDevice(), timing_stats=TimingStats(), cap_tracks=128, cap_dets=64)
+    kind, ct, cd, fd, blob, params = made[-1]
+    assert (kind, ct, cd, fd, blob) == ("botsort", 128, 64, 1792, "/tmp/m.b200reid") and rt.tracker.provides_reid
+    assert params["track_high_thresh"] == 0.6296854875023994 and "use_cmc" not in params
+    for name in ("bytetrack", "deepocsort", "strongsort"):   # the reference tests call positionally like this
+        t = T.create_tracker(name, None, None, "cpu", False, False)
+        assert made[-1][0] == name and t.per_class is False
+    assert made[-2][5]["det_thresh"] == 0.5 and made[-2][5]["w_association_emb"] == 0.75      # deepocsort YAML values
+    T.create_tracker("deepocsort", evolve_param_dict={"det_thresh": 0.4, "embedding_off": True}, reid_weights="never_loaded.pt")
+    assert made[-1][5]["det_thresh"] == 0.4 and made[-1][5]["w_association_emb"] == 0.5     # constructor default now
+    T.create_tracker("strongsort", reid_model=Foreign())
+    assert warmed == [1] and made[-1][4] is None
+    with pytest.raises(NotImplementedError, match="per_class"):
+        T.create_tracker("bytetrack", per_class=True)
