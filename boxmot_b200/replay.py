@@ -13,6 +13,8 @@ Reference behaviour restated here (nothing is imported from the reference):
 * ``replay_sequences``  -- the frame loop of `boxmot/engine/eval/replay.py:311-350` (`process_sequence`): confidence
   filter on the cached rows, frames without detections are NOT passed to the tracker, embeddings/detections row
   mismatch is an error, rows formatted by `convert_to_mot_format` (`engine/tracking/mot.py:255-271`).
+* ``fill_embeddings``   -- the embeddings-only fill of `engine/eval/cache.py:252-308`: an existing detections cache gets its
+  row-aligned embeddings file from any `get_features(boxes, frame)` backend (a `B200ReID` keeps that on the GPU).
 * ``cache_paths``       -- the directory layout of `engine/eval/cache.py:371-424, 503-512` / `data/dataset.py:154-175`.
 
 B200 angle: sequences are independent units, so S cached sequences advance together as the S streams of one
@@ -343,3 +345,41 @@ def write_cache(dets_path, embs_path, frames: Sequence[Tuple[int, np.ndarray, Op
         dw.close()
         if ew is not None:
             ew.close()
+
+
+def fill_embeddings(dets_path, embs_path, reid_model, load_frame: Callable[[int], Optional[np.ndarray]],
+                    on_progress: Optional[Callable[[int, int], None]] = None) -> int:
+    """Embeddings-only fill of a cached sequence (`engine/eval/cache.py:252-308`): the detections file is immutable; its
+    rows are read back in stored order, each run of equal frame id is embedded with one
+    `reid_model.get_features(boxes (n, 4), frame)` call (a `B200ReID` keeps crops, network and normalisation on the
+    GPU) and appended to `embs_path` row-aligned with the detections.  `load_frame(frame_id)` returns the BGR frame or
+    None (such frames are skipped, as the reference does for unreadable images).  Returns the rows written."""
+    dets = np.load(dets_path).astype(np.float32, copy=False)
+    if dets.ndim != 2 or dets.shape[0] == 0:
+        return 0
+    writer = NpyAppender(embs_path, dtype=np.float32, trailing_shape=None, empty_trailing_shape=(0,))
+    written = 0
+    try:
+        n_rows, i = dets.shape[0], 0
+        while i < n_rows:
+            fid = int(dets[i, 0])
+            j = i
+            while j < n_rows and int(dets[j, 0]) == fid:
+                j += 1
+            boxes = dets[i:j, 1:5].copy()
+            img = load_frame(fid)
+            if img is not None:
+                feats = np.asarray(reid_model.get_features(boxes, img), dtype=np.float32)
+                if feats.ndim == 1:
+                    feats = feats.reshape(1, -1) if feats.size else feats
+                if feats.shape[0] != boxes.shape[0]:
+                    raise RuntimeError(f"Embedding count mismatch during fill for {Path(dets_path).stem}: "
+                                       f"dets={boxes.shape[0]} embs={feats.shape[0]}")
+                writer.append(feats)
+                written += boxes.shape[0]
+            if on_progress is not None:
+                on_progress(j, n_rows)
+            i = j
+    finally:
+        writer.close()
+    return written

@@ -177,3 +177,43 @@ def test_runner_rejects_misaligned_or_missing_embeddings(tmp_path):
         rp.SequenceCache(np.asarray(cache.dets), np.asarray(cache.embs)[:-1], name="S")
     with pytest.raises(ValueError, match="32-d"):
         rp.replay_sequences(_OracleStreams(BotSortOracle, 1, 64, True), [cache])
+
+
+def test_fill_embeddings_is_row_aligned_with_the_cached_detections(tmp_path):
+    """Embeddings-only fill (engine/eval/cache.py:252-308) with a stand-in ReID model: one get_features call per
+    frame run in stored order, rows aligned with the dets cache, unreadable frames skipped, count mismatch raised."""
+    frames = synthetic_sequence(n_frames=12, dim=4)
+    dp = tmp_path / "dets" / "S.npy"
+    rp.write_cache(dp, None, frames)
+    dets = np.load(dp)
+    calls = []
+
+    class Model:
+        def get_features(self, boxes, img):
+            calls.append((len(boxes), int(img[0, 0, 0])))
+            return np.column_stack([boxes[:, 0], boxes[:, 3], np.full(len(boxes), img[0, 0, 0]), np.ones(len(boxes))])
+
+    def load(fid):
+        return np.full((4, 4, 3), fid, np.uint8)
+
+    ep = tmp_path / "embs" / "reid" / "resize" / "S.npy"
+    n = rp.fill_embeddings(dp, ep, Model(), load)
+    embs = np.load(ep)
+    assert n == len(dets) == len(embs) and embs.dtype == np.float32
+    assert np.array_equal(embs[:, 0], dets[:, 1]) and np.array_equal(embs[:, 1], dets[:, 4])
+    assert np.array_equal(embs[:, 2], dets[:, 0])                       # each run saw its own frame
+    assert [c[1] for c in calls] == sorted({int(f) for f in dets[:, 0]})
+    rp.SequenceCache(dp, ep, name="S")                                  # loads: rows match
+    # an unreadable frame is skipped (the reference guards the same way) -> fewer rows, which SequenceCache refuses
+    ep2 = tmp_path / "e2.npy"
+    n2 = rp.fill_embeddings(dp, ep2, Model(), lambda fid: None if fid == 3 else load(fid))
+    assert n2 == len(dets) - int((dets[:, 0] == 3).sum())
+    with pytest.raises(ValueError, match="Row mismatch"):
+        rp.SequenceCache(dp, ep2, name="S")
+
+    class Bad:
+        def get_features(self, boxes, img):
+            return np.zeros((len(boxes) + 1, 4), np.float32)
+
+    with pytest.raises(RuntimeError, match="Embedding count mismatch"):
+        rp.fill_embeddings(dp, tmp_path / "e3.npy", Bad(), load)
