@@ -279,12 +279,16 @@ def _frame_inputs(cache: SequenceCache, conf_threshold: float):
 
 
 def replay_sequences(tracker, caches: Sequence[SequenceCache], conf_threshold: float = 0.0,
-                     on_step: Optional[Callable[[int], None]] = None) -> List[np.ndarray]:
+                     on_step: Optional[Callable[[int], None]] = None, timing=None) -> List[np.ndarray]:
     """Replay `len(caches)` cached sequences through `tracker`, a multi-stream tracker with one stream per cache
     (`MultiStreamTracker.update(dets_list, imgs, embs_list) -> rows_list`).  Returns one MOT array per sequence.
 
     Every stream consumes its own non-empty frames in order; the streams advance together, one tracker step for all
-    of them.  A stream that has finished receives empty detections and its outputs are discarded."""
+    of them.  A stream that has finished receives empty detections and its outputs are discarded.
+
+    `timing`: optional `runtime.TimingStats`-like object; every step adds the engine's CUDA-event ReID / association
+    durations (`tracker.last_device_ms()`), the split `process_sequence` reports as ReID time vs tracker-rest time
+    (`replay.py:333-335`)."""
     S = len(caches)
     if getattr(tracker, "n_streams", S) != S:
         raise ValueError(f"tracker has {tracker.n_streams} streams for {S} sequences")
@@ -315,6 +319,9 @@ def replay_sequences(tracker, caches: Sequence[SequenceCache], conf_threshold: f
         if all(f is None for f in fids):
             break
         out = tracker.update(dets, None, embs if wants_embs else None)
+        if timing is not None and hasattr(tracker, "last_device_ms"):
+            timing.add_device_times(*tracker.last_device_ms())
+            timing.frames += 1
         for i, fid in enumerate(fids):
             if fid is not None and len(out[i]):
                 rows[i].append(to_mot_rows(np.asarray(out[i]), fid))

@@ -118,6 +118,9 @@ class _OracleStreams:
         self.n_streams, self.feat_dim, self.with_reid = n, feat_dim, with_reid
         self.calls = [0] * n
 
+    def last_device_ms(self):
+        return 0.25, 0.75
+
     def update(self, dets, imgs, embs):
         out = []
         for i, t in enumerate(self.t):
@@ -147,8 +150,13 @@ def test_runner_equals_one_reference_style_loop_per_sequence(tmp_path):
     caches, seqs = zip(*[_cohort_cache(tmp_path, f"S{i}", 20 + i, n, gaps=g)
                          for i, (n, g) in enumerate([(30, (4, 5)), (18, ()), (25, (0, 24))])])
     thr = 0.3
+    from boxmot_b200.runtime import TimingStats
+
     multi = _OracleStreams(BotSortOracle, 3, 32, True)
-    got = rp.replay_sequences(multi, caches, conf_threshold=thr)
+    ts = TimingStats()
+    got = rp.replay_sequences(multi, caches, conf_threshold=thr, timing=ts)
+    assert ts.frames == max(multi.calls) and ts.totals["reid_device"] == 0.25 * ts.frames
+    assert ts.totals["assoc_device"] == 0.75 * ts.frames
     for i, seq in enumerate(seqs):
         ref, rows = BotSortOracle(), []
         n_calls = 0
