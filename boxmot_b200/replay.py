@@ -390,3 +390,23 @@ def fill_embeddings(dets_path, embs_path, reid_model, load_frame: Callable[[int]
     finally:
         writer.close()
     return written
+
+
+def write_mot_results(txt_path, mot_rows: np.ndarray) -> None:
+    """Append MOT rows to a result file exactly as the reference does (`engine/tracking/mot.py:318-344`): the file is
+    created even when there is nothing to write; 9-column rows use `%d,%d,%d,%d,%d,%d,%.6f,%d,%d`."""
+    if mot_rows is None:
+        return
+    txt_path = Path(txt_path)
+    txt_path.parent.mkdir(parents=True, exist_ok=True)
+    txt_path.touch(exist_ok=True)
+    mot_rows = np.asarray(mot_rows)
+    if mot_rows.size == 0:
+        return
+    if mot_rows.ndim == 1:
+        mot_rows = mot_rows.reshape(1, -1)
+    with open(str(txt_path), "a") as f:
+        if mot_rows.shape[1] == 9:
+            np.savetxt(f, mot_rows, fmt="%d,%d,%d,%d,%d,%d,%.6f,%d,%d")
+        else:
+            np.savetxt(f, mot_rows, fmt="%g", delimiter=",")

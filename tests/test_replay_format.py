@@ -225,3 +225,32 @@ def test_fill_embeddings_is_row_aligned_with_the_cached_detections(tmp_path):
 
     with pytest.raises(RuntimeError, match="Embedding count mismatch"):
         rp.fill_embeddings(dp, tmp_path / "e3.npy", Bad(), load)
+
+
+@pytest.mark.parametrize("tracker", ["bytetrack", "botsort"])
+def test_replay_end_to_end_equals_the_references_process_sequence(tracker, tmp_path):
+    """The whole cached-replay path against the result files the reference's own `process_sequence` wrote
+    (tests/golden/make_replay_e2e_golden.py: MOTDataset -> TrackerRuntime -> convert_to_mot_format ->
+    write_mot_results) for two MOT17-mini sequences of different length replayed TOGETHER here: cache written by
+    `write_cache`, read by `SequenceCache`, confidence filter 0.2, lock-step runner, `write_mot_results`."""
+    from oracle.trackers import BotSortOracle, ByteTrackOracle
+    from tests import common
+    from tests.golden.make_replay_e2e_golden import N_FRAMES, REID_KEY, SEQ, build_tree
+
+    with_embs = tracker == "botsort"
+    build_tree(tmp_path, common, with_embs)
+    caches = []
+    for key, seq in SEQ.items():
+        dp, ep = rp.cache_paths(tmp_path / "proj", "public", seq, reid_key=REID_KEY if with_embs else None)
+        caches.append(rp.SequenceCache(dp, ep, frame_ids=np.arange(1, N_FRAMES[key] + 1), name=seq))
+    make = (lambda: ByteTrackOracle(**common.BYTETRACK_YAML)) if tracker == "bytetrack" else \
+        (lambda: BotSortOracle(**common.BOTSORT_YAML))
+    multi = _OracleStreams(make, len(caches), 512, with_embs)
+    rows = rp.replay_sequences(multi, caches, conf_threshold=0.2)
+    got = ""
+    for (key, seq), r in zip(SEQ.items(), rows):
+        out = tmp_path / "exp" / f"{seq}.txt"
+        rp.write_mot_results(out, r)
+        got += f"# {seq} frames={N_FRAMES[key]}\n" + out.read_text()
+    want = (GOLD / f"replay_e2e_{tracker}.txt").read_text()
+    assert got == want
