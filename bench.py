@@ -164,7 +164,7 @@ def make_blob(tmpdir: Path) -> Path:
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------------
-def cpu_arm(sample_frames: int, warm: int, budget_s: float = 25.0):
+def cpu_arm(sample_frames: int, warm: int, budget_s: float = 25.0, stream_index: int = 0, threads: int = 0):
     """Oracle port of the reference path on the host cores, bounded by wall-clock: the host of a GPU box can be
     anything from 8 fast cores to a heavily shared 128-thread part, so the sample is 'as many frames as fit in
     `budget_s` seconds' (at least one), after a thread-count probe that is itself time-bounded."""
@@ -175,12 +175,13 @@ def cpu_arm(sample_frames: int, warm: int, budget_s: float = 25.0):
     from oracle.trackers import BotSortOracle
 
     sd = make_osnet_state("osnet_x0_25", seed=0)
-    imgs, dets = make_inputs(0, warm + sample_frames + 1)
+    imgs, dets = make_inputs(stream_index, warm + sample_frames + 1)
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     probe_x = orid.get_crops(dets[0][:16, :4], imgs[0])
     best = (min(avail, 8), 1e30)
     t_probe = time.perf_counter()
-    for th in sorted({min(avail, 8), min(avail, 16), min(avail, 32), avail}):
+    # `threads` > 0: one of several concurrent stream workers with a fixed share of the cores (no probe)
+    for th in ([threads] if threads > 0 else sorted({min(avail, 8), min(avail, 16), min(avail, 32), avail})):
         torch.set_num_threads(th)
         t0 = time.perf_counter()
         orid.osnet_forward(sd, probe_x)
@@ -214,15 +215,42 @@ def cpu_arm(sample_frames: int, warm: int, budget_s: float = 25.0):
             "ms_per_frame": 1e3 * dt / n}
 
 
+def _cpu_stream_worker(job):
+    steps, stream_index, threads = job
+    return cpu_arm(steps, 1, budget_s=40.0, stream_index=stream_index, threads=threads)
+
+
 def run_reference(args):
+    """The reference path on the host cores for the SAME workload as the B200 arm at this --gpus: one 256-detection
+    stream per GPU, i.e. N independent streams.  N == 1: one tracker with the fastest thread count of a bounded probe.
+    N > 1: N concurrent tracker processes (the reference's own replay parallelism is one process per sequence,
+    engine/eval/replay.py:27-115), each with an equal share of the usable cores; value = sum of the streams' rates."""
     if RANK != 0:
         return
     steps = max(2, min(args.steps, 12))
-    base = cpu_arm(steps, 1, budget_s=40.0)
+    n_streams = max(1, int(args.gpus))
+    if n_streams == 1:
+        base = cpu_arm(steps, 1, budget_s=40.0)
+        note = "single stream on the host cores; steps bounded to keep the run short"
+    else:
+        import multiprocessing as mp
+
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        threads = max(1, avail // n_streams)
+        with mp.get_context("spawn").Pool(n_streams) as pool:
+            parts = pool.map(_cpu_stream_worker, [(steps, i, threads) for i in range(n_streams)])
+        value = sum(p["value"] for p in parts)
+        frames = min(p["frames"] for p in parts)
+        base = {"value": value, "unit": "frames/s", "cores": threads * n_streams, "kind": "port", "frames": frames,
+                "warm": min(p["warm"] for p in parts), "ms_per_frame": 1e3 / value,
+                "sample": f"{n_streams} concurrent stream processes x {threads} threads, {[p['frames'] for p in parts]} frames "
+                          f"each after a warm-up frame (time-bounded to ~40 s), oracle port (numpy/scipy/lapjv-C + "
+                          f"torch-CPU OSNet fp32); value = sum of the per-stream rates"}
+        note = f"{n_streams} independent streams on the host cores (one process per stream), like one stream per GPU"
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": base["frames"], "warmup": base["warm"], "ms_per_step": base["ms_per_frame"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "single stream on the host cores; steps bounded to keep the run short"},
+            "config": {"workload": WORKLOAD, "note": note},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
