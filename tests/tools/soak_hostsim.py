@@ -1,0 +1,79 @@
+"""Randomised soak of the device tracker source (host simulation) against the oracle: many seeded stress streams with
+varied crowding, drop-out, class counts, empty frames and thresholds, all four trackers.  A disagreement is a parity bug
+in the device core or the oracle.   python tests/tools/soak_hostsim.py [n_cases] [first_seed]"""
+from __future__ import annotations
+
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from oracle.deepocsort import DeepOcSortOracle  # noqa: E402
+from oracle.streams import stress_embeddings, stress_stream, unit_embeddings  # noqa: E402
+from oracle.strongsort import StrongSortOracle  # noqa: E402
+from oracle.trackers import BotSortOracle, ByteTrackOracle  # noqa: E402
+from tests.common import BOTSORT_YAML, BYTETRACK_YAML, DEEPOCSORT_YAML, STRONGSORT_YAML, assert_rows_match  # noqa: E402
+from tests.hostsim import (HostSimDeepOcSort, HostSimStrongSort, HostSimTracker, botsort_cfg, bytetrack_cfg,  # noqa: E402
+                           deepocsort_cfg, strongsort_cfg)
+
+
+def case(seed):
+    rng = np.random.default_rng(seed)
+    kind = ["bytetrack", "botsort", "deepocsort", "strongsort"][seed % 4]
+    n_obj = int(rng.integers(8, 90))
+    n_frames = int(rng.integers(40, 140))
+    kw_stream = dict(seed=int(rng.integers(1, 10**6)), n_classes=int(rng.integers(1, 4)),
+                     empty_every=int(rng.choice([0, 0, 17, 29])), dropout=float(rng.choice([0.05, 0.2, 0.4])))
+    frames = stress_stream(n_obj, n_frames, **kw_stream)
+    dim = 64
+    if kind == "bytetrack":
+        kw = dict(BYTETRACK_YAML, track_thresh=float(rng.uniform(0.3, 0.7)), match_thresh=float(rng.uniform(0.6, 0.95)),
+                  track_buffer=int(rng.integers(5, 40)), frame_rate=int(rng.choice([25, 30])))
+        return kind, kw, frames, None, HostSimTracker(bytetrack_cfg(**kw)), ByteTrackOracle(**kw)
+    if kind == "botsort":
+        kw = dict(BOTSORT_YAML, track_high_thresh=float(rng.uniform(0.4, 0.7)), new_track_thresh=float(rng.uniform(0.4, 0.75)),
+                  match_thresh=float(rng.uniform(0.6, 0.9)), appearance_thresh=float(rng.uniform(0.2, 0.7)),
+                  proximity_thresh=float(rng.uniform(0.4, 0.7)), fuse_first_associate=bool(rng.integers(0, 2)),
+                  track_buffer=int(rng.integers(5, 50)), removed_stracks_buffer=int(rng.choice([3, 20, 329])))
+        embs = stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+        return kind, kw, frames, embs, HostSimTracker(botsort_cfg(feat_dim=dim, **kw)), BotSortOracle(**kw)
+    if kind == "deepocsort":
+        kw = dict(DEEPOCSORT_YAML, det_thresh=float(rng.uniform(0.2, 0.6)), w_association_emb=float(rng.uniform(0.2, 0.9)),
+                  inertia=float(rng.uniform(0.05, 0.4)), delta_t=int(rng.integers(1, 5)), max_age=int(rng.integers(5, 35)),
+                  min_hits=int(rng.integers(1, 4)), aw_off=bool(rng.integers(0, 2)), iou_threshold=float(rng.uniform(0.2, 0.4)))
+        embs = unit_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+        sim = HostSimDeepOcSort(deepocsort_cfg(feat_dim=dim, **kw))
+        sim.set_jv_wide(int(rng.integers(0, 3)))
+        return kind, kw, frames, embs, sim, DeepOcSortOracle(**kw)
+    kw = dict(STRONGSORT_YAML, min_conf=float(rng.uniform(0.2, 0.6)), max_cos_dist=float(rng.uniform(0.2, 0.5)),
+              n_init=int(rng.integers(1, 4)), nn_budget=int(rng.choice([5, 30, 100])), max_age=int(rng.integers(5, 35)),
+              ema_alpha=float(rng.choice([0.8, 0.9])), mc_lambda=float(rng.choice([0.9, 0.98])))
+    embs = stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+    return kind, kw, frames, embs, HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=dim, **kw)), StrongSortOracle(**kw)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    bad = 0
+    t0 = time.time()
+    for seed in range(first, first + n):
+        kind, kw, frames, embs, sim, orc = case(seed)
+        try:
+            for f, d in enumerate(frames):
+                e = None if embs is None else embs[f]
+                got = sim.update(d, None, e)
+                want = orc.update(d, None) if embs is None else orc.update(d, None, e.copy())
+                assert_rows_match(got, want, f, box_rtol=1e-4)
+        except AssertionError as ex:
+            bad += 1
+            print(f"seed {seed} {kind} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
+    print(f"{n} cases, {bad} diverged, {time.time() - t0:.0f} s")
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
