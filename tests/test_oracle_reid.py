@@ -87,3 +87,20 @@ def test_mobilenetv2_folded_blob_equals_oracle(tmp_path):
     want = orid.mobilenetv2_forward(sd, x)
     got = blob_forward(blob, x.permute(0, 2, 3, 1).contiguous())
     assert float((got - want).abs().max()) < 5e-6 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("arch", ["osnet_x1_0", "mobilenetv2_x1_4"])
+def test_other_architectures_match_the_reference_classes(arch):
+    """`osnet_forward` at x1_0 width and `mobilenetv2_forward` against embeddings the reference's own model classes
+    produced through `BaseModelBackend.get_features` (tests/golden/make_reid_arch_golden.py) -- these functional
+    restatements are the oracle of the OSNet_x1_0 / MobileNetV2_x1_4 GPU tests."""
+    from boxmot_b200.synthetic import make_mobilenetv2_state, make_osnet_state
+    from tests.golden.make_reid_arch_golden import IMAGE_SEED, MBV2_SEED, OSNET_SEED
+
+    z = np.load(GOLDEN / "reid_arch_reference.npz")
+    img = np.random.default_rng(IMAGE_SEED).integers(0, 255, size=(540, 960, 3), dtype=np.uint8)
+    sd = make_osnet_state("osnet_x1_0", seed=OSNET_SEED) if arch == "osnet_x1_0" else make_mobilenetv2_state(1.4, seed=MBV2_SEED)
+    feats = orid.get_features(sd, z["boxes"], img)
+    assert feats.shape == z[arch].shape and feats.shape[1] == (512 if arch == "osnet_x1_0" else 1792)
+    np.testing.assert_allclose(feats, z[arch], rtol=0, atol=2e-6)
+    assert abs(np.linalg.norm(feats, axis=1) - 1).max() < 1e-6
