@@ -79,6 +79,7 @@ struct DocsStream {
     int* lap_tl; int* lap_sc; int* csr_ptr; int* csr_col;
     float* out;        // [CD][8]
     int jv_wide;       // CTA-wide augmentation in the dense JV solver (set per launch, not part of the carved state)
+    const double* warp;  // [8]: supplied 2x3 camera-motion matrix (row major), warp[6] != 0 when one is pending; may be null
 };
 
 // one entry of the appearance similarity matrix (float32 detection row x float64 track EMA, float64 accumulate)
@@ -128,6 +129,25 @@ BMB_FN void xysr_predict(const DocsCfg& c, double* x, double* P) {
     xysr_enforce(x, P);
 }
 
+// lower Cholesky factor of the symmetric 4x4 S + ridge*I; false as soon as a pivot is not positive (LAPACK potrf's
+// criterion: ajj <= 0 or NaN)
+BMB_FN bool xysr_chol4(const double* S, double ridge, double* Lc) {
+    for (int i = 0; i < 16; ++i) Lc[i] = 0.0;
+    for (int j = 0; j < 4; ++j) {
+        double d = S[j * 4 + j] + ridge;
+        for (int k = 0; k < j; ++k) d -= Lc[j * 4 + k] * Lc[j * 4 + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        Lc[j * 4 + j] = d;
+        for (int i = j + 1; i < 4; ++i) {
+            double v = S[i * 4 + j];
+            for (int k = 0; k < j; ++k) v -= Lc[i * 4 + k] * Lc[j * 4 + k];
+            Lc[i * 4 + j] = v / d;
+        }
+    }
+    return true;
+}
+
 // base.py:414-459 with R = diag(1,1,10,10), H = [I4 | 0]
 BMB_FN void xysr_update_state(double* x, double* P, const double* z) {
     const double Rd[4] = {1.0, 1.0, 10.0, 10.0};
@@ -139,17 +159,19 @@ BMB_FN void xysr_update_state(double* x, double* P, const double* z) {
             const double v = 0.5 * (S[i * 4 + j] + S[j * 4 + i]);
             S[i * 4 + j] = v; S[j * 4 + i] = v;
         }
-    for (int i = 0; i < 16; ++i) Lc[i] = 0.0;
-    for (int j = 0; j < 4; ++j) {
-        double d = S[j * 4 + j];
-        for (int k = 0; k < j; ++k) d -= Lc[j * 4 + k] * Lc[j * 4 + k];
-        d = sqrt(d);
-        Lc[j * 4 + j] = d;
-        for (int i = j + 1; i < 4; ++i) {
-            double v = S[i * 4 + j];
-            for (int k = 0; k < j; ++k) v -= Lc[i * 4 + k] * Lc[j * 4 + k];
-            Lc[i * 4 + j] = v / d;
-        }
+    // _safe_cho_factor (base.py:462-500): plain Cholesky; when a pivot is not positive, a ridge of
+    // max|diag S| * 10^e, e = -12 .. 3, is added until the factorisation goes through.  Camera-motion correction
+    // (apply_affine_correction transforms the position and velocity blocks of P but not their cross terms) makes this
+    // the normal path of young tracks, not a rarity.  The eigenvalue-clipping last resort is only reachable with
+    // non-finite input, where the reference raises as well.
+    if (!xysr_chol4(S, 0.0, Lc)) {
+        double scale = 0.0;
+        for (int i = 0; i < 4; ++i) { const double a = fabs(S[i * 4 + i]); if (a > scale) scale = a; }
+        if (!(scale > 0.0) || scale > 1.7976931348623157e308) scale = 1.0;
+        const double p10[16] = {1e-12, 1e-11, 1e-10, 1e-09, 1e-08, 1e-07, 1e-06, 1e-05, 0.0001, 0.001, 0.01, 0.1,
+                                1.0, 10.0, 100.0, 1000.0};
+        for (int e = 0; e < 16; ++e)
+            if (xysr_chol4(S, scale * p10[e], Lc)) break;
     }
     double K[28];  // [7][4]
     for (int r = 0; r < 7; ++r) {
@@ -330,6 +352,60 @@ BMB_FN void docs_emb_update(const DocsCfg& c, DocsStream& s, int t, int kd) {
     BMB_SYNCWARP();
 }
 
+// KalmanBoxTracker.apply_affine_correction (deepocsort.py:189-206) + KalmanFilterXYSR.apply_affine_correction
+// (xysr.py:311-366) for a supplied 2x3 warp W.  In the reference `last_observation` and `observations[age]` are views of
+// the same detection row, so the newest observation is warped by the first statement AND again by the window loop when
+// it lies inside the velocity window: both copies kept here follow that.  The pre-gap measurement used by the
+// un-freeze replay comes from the live history, which the reference does not warp (zlast stays).
+BMB_FN void docs_warp_box(const double* W, double* b) {
+    const double x1 = W[0] * b[0] + W[1] * b[1] + W[2], y1 = W[3] * b[0] + W[4] * b[1] + W[5];
+    const double x2 = W[0] * b[2] + W[1] * b[3] + W[2], y2 = W[3] * b[2] + W[4] * b[3] + W[5];
+    b[0] = x1; b[1] = y1; b[2] = x2; b[3] = y2;
+}
+
+BMB_FN void docs_warp_state(const double* W, double* x, double* P) {
+    const double m00 = W[0], m01 = W[1], m10 = W[3], m11 = W[4];
+    const double px = m00 * x[0] + m01 * x[1] + W[2], py = m10 * x[0] + m11 * x[1] + W[5];
+    x[0] = px; x[1] = py;
+    const double vx = m00 * x[4] + m01 * x[5], vy = m10 * x[4] + m11 * x[5];
+    x[4] = vx; x[5] = vy;
+    for (int b = 0; b < 2; ++b) {   // P[o:o+2, o:o+2] <- (m @ P_blk) @ m^T, numpy's left-to-right order
+        const int o = b * 4;
+        const double a = P[o * 7 + o], bq = P[o * 7 + o + 1], cq = P[(o + 1) * 7 + o], dq = P[(o + 1) * 7 + o + 1];
+        const double t00 = m00 * a + m01 * cq, t01 = m00 * bq + m01 * dq;
+        const double t10 = m10 * a + m11 * cq, t11 = m10 * bq + m11 * dq;
+        P[o * 7 + o] = t00 * m00 + t01 * m01;
+        P[o * 7 + o + 1] = t00 * m10 + t01 * m11;
+        P[(o + 1) * 7 + o] = t10 * m00 + t11 * m01;
+        P[(o + 1) * 7 + o + 1] = t10 * m10 + t11 * m11;
+    }
+}
+
+BMB_FN void docs_apply_warp(const DocsCfg& c, DocsStream& s, int t, const double* W) {
+    double* lo = s.last_obs + t * 5;
+    const int n = s.obs_n[t];
+    int newest = -1;   // the ring entry that aliases last_observation in the reference
+    for (int k = 0; k < DOCS_RING && k < n; ++k)
+        if (newest < 0 || s.obs_age[t * DOCS_RING + k] > s.obs_age[t * DOCS_RING + newest]) newest = k;
+    if (lo[0] + lo[1] + lo[2] + lo[3] + lo[4] > 0) {
+        docs_warp_box(W, lo);
+        if (newest >= 0) for (int i = 0; i < 4; ++i) s.obs_box[(t * DOCS_RING + newest) * 5 + i] = lo[i];
+    }
+    for (int dt = c.delta_t; dt >= 0; --dt) {
+        const int want = s.age[t] - dt;
+        for (int k = 0; k < DOCS_RING && k < n; ++k)
+            if (s.obs_age[t * DOCS_RING + k] == want) {
+                double* ob = s.obs_box + (t * DOCS_RING + k) * 5;
+                docs_warp_box(W, ob);
+                if (k == newest) for (int i = 0; i < 4; ++i) lo[i] = ob[i];
+                break;
+            }
+    }
+    docs_warp_state(W, s.x + t * 8, s.P + t * 56);
+    if (!s.observed[t] && s.has_saved[t]) docs_warp_state(W, s.xs + t * 8, s.Ps + t * 56);
+    xysr_enforce(s.x + t * 8, s.P + t * 56);
+}
+
 // k_previous_obs (deepocsort.py:13-22)
 BMB_FN void docs_k_prev(const DocsCfg& c, const DocsStream& s, int t, double* o) {
     const int n = s.obs_n[t];
@@ -395,8 +471,10 @@ BMB_FN void docs_frame(const DocsCfg& c, DocsStream& s) {
         s.dalpha[k] = c.alpha_fixed + (1 - c.alpha_fixed) * (1 - trust);
     }
     // ---- predict every track (deepocsort.py:361-368, :208-223), drop NaN boxes ----
+    const bool warp_pending = s.warp != nullptr && s.warp[6] != 0.0;   // deepocsort.py:345-348, estimator replaced by input
     for (int k = BMB_TID; k < n_trk0; k += BMB_NT) {
         const int t = s.tracks[k];
+        if (warp_pending) docs_apply_warp(c, s, t, s.warp);
         double* x = s.x + t * 8;
         if (x[6] + x[2] <= 0) x[6] *= 0.0;
         xysr_predict(c, x, s.P + t * 56);

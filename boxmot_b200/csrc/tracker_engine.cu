@@ -388,6 +388,7 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
             h_docs[i].dets = d_dets + (size_t)i * CD * 6;
             h_docs[i].n_dets = d_ndets + i;
             h_docs[i].embs = cfg.with_reid ? d_embs + (size_t)i * CD * F : nullptr;
+            h_docs[i].warp = d_warp + (size_t)i * 8;
             out_ptr[i] = h_docs[i].out; scalars_ptr[i] = h_docs[i].scalars; timers_ptr[i] = h_docs[i].timers;
         }
         CUDA_OK(cudaMalloc(&d_docs, sizeof(DocsStream) * S));
@@ -576,6 +577,10 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
             k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, d_docs, (in_smem ? 1 : 0) | (jv_wide_default() << 1));
         }
         ++launches;
+        if (warp_dirty) {  // a supplied camera-motion warp applies to exactly one frame
+            CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
+            warp_dirty = false;
+        }
         CUDA_OK(cudaGetLastError());
         CUDA_OK(cudaEventRecord(ev[2], stream));
         if (profile) {
@@ -644,6 +649,10 @@ void Engine::enqueue_family_association(int parity) {
             CUDA_OK(cudaFuncSetAttribute(k_docs_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb));
         k_docs_frame<<<S, 256, in_smem ? jb : 0, stream>>>(dcfg, ds, (in_smem ? 1 : 0) | (jv_wide_default() << 1));
         ++launches;
+        if (warp_dirty) {
+            CUDA_OK(cudaMemsetAsync(d_warp, 0, sizeof(double) * 8 * S, stream));
+            warp_dirty = false;
+        }
     } else {
         enqueue_association(parity ? d_streams_alt : d_streams, cfg.with_reid ? (parity ? d_embs_alt : d_embs) : nullptr);
     }
@@ -703,8 +712,8 @@ void Engine::enqueue_association(TrkStream* streams_dev, const float* embs_src) 
 
 void Engine::set_warp(int sidx, const double* warp6) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
-    if (!is_ss && (is_docs || cfg.kind != KIND_XYWH))
-        throw std::runtime_error("camera-motion warps apply to BoT-SORT and StrongSORT only");
+    if (!is_ss && !is_docs && cfg.kind != KIND_XYWH)
+        throw std::runtime_error("camera-motion warps apply to BoT-SORT, DeepOCSORT and StrongSORT (ByteTrack has none)");
     double w[8] = {warp6[0], warp6[1], warp6[2], warp6[3], warp6[4], warp6[5], 1.0, 0.0};
     CUDA_OK(cudaStreamSynchronize(stream));
     CUDA_OK(cudaMemcpy(d_warp + (size_t)sidx * 8, w, sizeof(w), cudaMemcpyHostToDevice));

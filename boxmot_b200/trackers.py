@@ -282,7 +282,7 @@ class MultiStreamTracker:
 
     def set_warp(self, stream: int, warp) -> None:
         """Camera-motion warp (2x3) to apply on the next update of `stream` (BoT-SORT multi_gmc, StrongSORT
-        camera_update)."""
+        camera_update, DeepOCSORT apply_affine_correction)."""
         w = np.ascontiguousarray(warp, dtype=np.float64).reshape(6)
         if not self.lib.boxmot_b200_tracker_set_warp(self.handle, int(stream), w.ctypes.data):
             raise B200Error(_lib.last_error(self.lib))
@@ -460,8 +460,9 @@ class _SingleStreamTracker:
         self.frame_count = 0
 
     def update(self, dets, img=None, embs=None, masks=None, warp=None) -> TrackResults:
-        """`warp`: optional 2x3 camera-motion matrix for this frame (BoT-SORT); the reference estimates it with
-        OpenCV inside update() (botsort.py:142-144), here the caller supplies it."""
+        """`warp`: optional 2x3 camera-motion matrix for this frame (BoT-SORT, DeepOCSORT, StrongSORT); the reference
+        estimates it with OpenCV inside update() (botsort.py:142-144, deepocsort.py:345-348, strongsort.py:83-86), here the
+        caller supplies it."""
         if warp is not None:
             self._engine.set_warp(0, warp)
         if hasattr(dets, "data") and not isinstance(dets, np.ndarray):
@@ -553,7 +554,9 @@ class BotSort(_SingleStreamTracker):
 
 class DeepOcSort(_SingleStreamTracker):
     """DeepOCSORT on the GPU; arguments as boxmot/trackers/bbox/deepocsort/deepocsort.py:263-300.  `cmc_off` must be
-    True (camera-motion estimation is outside this hot path)."""
+    True: camera-motion ESTIMATION is outside this hot path; a warp obtained elsewhere is applied exactly
+    as the reference applies its own (`apply_affine_correction` on every track before the predict step) when passed
+    as `update(dets, img, embs, warp=warp_2x3)`."""
 
     _kind = "deepocsort"
 

@@ -203,7 +203,9 @@ BOXMOT_B200_API int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* handle
  * BoT-SORT to the predicted pool and the unconfirmed tracks exactly as STrack.multi_gmc does
  * (trackers/bbox/botsort/botsort_track.py:117-132); StrongSORT through Track.camera_update
  * (trackers/bbox/strongsort/sort/track.py:139-148; without a supplied warp it runs with the identity, as the
- * reference does whenever tracks exist).  Estimating the warp (motion/cmc/*) is out of scope. */
+ * reference does whenever tracks exist); DeepOCSORT through KalmanBoxTracker.apply_affine_correction before the
+ * predict step (trackers/bbox/deepocsort/deepocsort.py:189-206, 345-348; motion/kalman_filters/xysr.py:311-366).
+ * Estimating the warp (motion/cmc/*) is out of scope. */
 BOXMOT_B200_API int boxmot_b200_tracker_set_warp(BoxMOTB200Tracker* handle, int stream, const double* warp2x3);
 /* Device timing on the handle's own CUDA stream: record mark 0 / mark 1 around a region, then read the elapsed
  * milliseconds (synchronises on mark 1). */

@@ -51,6 +51,38 @@ def speed_direction(b1, b2):
     return speed / norm
 
 
+SAFE_CHOLESKY_EVENTS = [0]   # diagnostics for the tests: how often the jitter path was taken
+
+
+def _safe_cho_factor(matrix):
+    """BaseKalmanFilter._safe_cho_factor (base.py:462-500): plain Cholesky; on failure a ridge of
+    max|diag| * 10**e, e = -12 .. 3, is added until it succeeds; last resort: clip the eigenvalues."""
+    try:
+        return scipy.linalg.cho_factor(matrix, lower=True, check_finite=False)
+    except scipy.linalg.LinAlgError:
+        pass
+    SAFE_CHOLESKY_EVENTS[0] += 1
+    n = matrix.shape[0]
+    diag = np.diagonal(matrix)
+    scale = float(np.max(np.abs(diag))) if diag.size else 1.0
+    if not np.isfinite(scale) or scale <= 0.0:
+        scale = 1.0
+    eye = np.eye(n)
+    for exponent in range(-12, 4):
+        jitter = scale * (10.0 ** exponent)
+        try:
+            return scipy.linalg.cho_factor(matrix + jitter * eye, lower=True, check_finite=False)
+        except scipy.linalg.LinAlgError:
+            continue
+    symmetric = 0.5 * (matrix + matrix.T)
+    eigvals, eigvecs = np.linalg.eigh(symmetric)
+    floor = max(scale * 1e-6, 1e-12)
+    eigvals = np.clip(eigvals, floor, None)
+    repaired = (eigvecs * eigvals) @ eigvecs.T
+    repaired = 0.5 * (repaired + repaired.T)
+    return scipy.linalg.cho_factor(repaired, lower=True, check_finite=False)
+
+
 class XYSRFilter:
     """KalmanFilterXYSR(dim_x=7, dim_z=4) as configured by KalmanBoxTracker (deepocsort.py:82-114)."""
 
@@ -84,13 +116,28 @@ class XYSRFilter:
         pm = np.dot(_H, self.x)
         pc = np.dot(np.dot(_H, self.P), _H.T) + self.R
         pc = 0.5 * (pc + pc.T)
-        chol = scipy.linalg.cho_factor(pc, lower=True, check_finite=False)
+        chol = _safe_cho_factor(pc)
         K = scipy.linalg.cho_solve(chol, np.dot(self.P, _H.T).T, check_finite=False).T
         y = z - pm
         self.x = self.x + np.dot(K, y)
         i_kh = _I7 - np.dot(K, _H)
         self.P = np.linalg.multi_dot((i_kh, self.P, i_kh.T)) + np.linalg.multi_dot((K, self.R, K.T))
         self.P = 0.5 * (self.P + self.P.T)
+
+    def apply_affine(self, m, t):
+        """KalmanFilterXYSR.apply_affine_correction (xysr.py:311-366), AABB: position and velocity through the 2x2 part,
+        their covariance blocks likewise; the frozen copy too while the track is unobserved.  The pre-gap measurement
+        the un-freeze replay starts from is the LIVE history entry, which the reference does not warp."""
+        def one(x, P):
+            x[:2] = m @ x[:2] + t
+            x[4:6] = m @ x[4:6]
+            P[:2, :2] = m @ P[:2, :2] @ m.T
+            P[4:6, 4:6] = m @ P[4:6, 4:6] @ m.T
+
+        one(self.x, self.P)
+        if not self.observed and self.saved is not None:
+            one(self.saved[0], self.saved[1])
+        self._enforce()
 
     @staticmethod
     def _prepare(z):
@@ -178,6 +225,24 @@ class _Track:
             self.kf.update(xyxy2xysr(bbox))
         else:
             self.kf.update(None)
+
+    def apply_affine_correction(self, affine):
+        """KalmanBoxTracker.apply_affine_correction (deepocsort.py:189-206), statement for statement: the last
+        observation and the observations inside the velocity window are views of the same detection rows, so the
+        newest one is warped by both loops -- as in the reference."""
+        affine = np.asarray(affine, dtype=float)
+        m = affine[:, :2]
+        t = affine[:, 2].reshape(2, 1)
+        if self.last_observation.sum() > 0:
+            ps = self.last_observation[:4].reshape(2, 2).T
+            ps = m @ ps + t
+            self.last_observation[:4] = ps.T.reshape(-1)
+        for dt in range(self.delta_t, -1, -1):
+            if self.age - dt in self.observations:
+                ps = self.observations[self.age - dt][:4].reshape(2, 2).T
+                ps = m @ ps + t
+                self.observations[self.age - dt][:4] = ps.T.reshape(-1)
+        self.kf.apply_affine(m, t)
 
     def update_emb(self, emb, alpha=0.9):
         self.emb = alpha * self.emb + (1 - alpha) * emb
@@ -300,7 +365,9 @@ class DeepOcSortOracle:
         self.frame_count = 0
         self._next = 1
 
-    def update(self, dets, img=None, embs=None):
+    def update(self, dets, img=None, embs=None, warp=None):
+        """`warp`: the 2x3 matrix the reference's CMC estimator would return for this frame (deepocsort.py:345-348);
+        estimation itself is outside the path."""
         dets = np.asarray(dets)
         if dets.size == 0:
             dets = np.empty((0, 6), dtype=np.float32)
@@ -318,6 +385,9 @@ class DeepOcSortOracle:
             dets_embs = np.asarray(embs)[keep]
         else:
             dets_embs = self.model.get_features(dets[:, 0:4], img)
+        if warp is not None:
+            for trk in self.tracks:
+                trk.apply_affine_correction(warp)
         trust = (dets[:, 4] - self.det_thresh) / (1 - self.det_thresh)
         dets_alpha = self.af + (1 - self.af) * (1 - trust)
         trks = np.zeros((len(self.tracks), 5))

@@ -100,6 +100,7 @@ int hostsim_snapshot(HostSim* h, int* ids, double* means, double* covs, int cap)
 struct DocsSim {
     DocsCfg cfg;
     DocsStream s;
+    double warp[8];
     std::vector<uint8_t> mem;
     std::vector<float> dets, embs;
     int n_dets;
@@ -116,9 +117,15 @@ DocsSim* docs_create(const DocsCfg* cfg) {
     h->s.dets = h->dets.data();
     h->s.n_dets = &h->n_dets;
     h->s.embs = nullptr;
+    for (double& w : h->warp) w = 0.0;
+    h->s.warp = h->warp;
     return h;
 }
 void docs_destroy(DocsSim* h) { delete h; }
+void docs_set_warp(DocsSim* h, const double* w6) {
+    for (int i = 0; i < 6; ++i) h->warp[i] = w6[i];
+    h->warp[6] = 1.0;
+}
 int docs_cfg_size() { return (int)sizeof(DocsCfg); }
 
 int docs_update(DocsSim* h, const float* dets, int n, const float* embs, float* out) {
@@ -137,6 +144,7 @@ int docs_update(DocsSim* h, const float* dets, int n, const float* embs, float* 
             for (int d = 0; d < n; ++d)
                 h->s.embq[(size_t)d * c.cap_tracks + h->s.tracks[k]] = docs_emb_dot(c, h->s, d, h->s.tracks[k]);
     docs_frame(c, h->s);
+    h->warp[6] = 0.0;  // a warp applies to one frame
     if (h->s.scalars[SC_ERROR]) return -h->s.scalars[SC_ERROR];
     const int m = h->s.scalars[SC_N_OUT];
     memcpy(out, h->s.out, sizeof(float) * 8 * m);

@@ -96,13 +96,17 @@ CASES = {
                             lambda fr: mot17_embeddings("04", fr, seed=11, unit=True)),
     "strongsort_mot17_04": ("strongsort", STRONGSORT_YAML, lambda: mot17_stream("04"),
                             lambda fr: mot17_embeddings("04", fr, seed=13)),
+    # DeepOCSORT with a supplied camera-motion warp every frame (apply_affine_correction), gaps included
+    "deepocsort_warp_stress64": ("deepocsort", {}, lambda: stress_stream(64, 160, seed=31, empty_every=41),
+                                 lambda fr: unit_embeddings(fr, 64, seed=33)),
     # DeepOCSORT with the values create_tracker reads from configs/trackers/deepocsort.yaml (they differ from the
     # constructor defaults the other DeepOCSORT cases use)
     "deepocsort_yaml_mot17_02": ("deepocsort", DEEPOCSORT_YAML, lambda: mot17_stream("02"),
                                  lambda fr: mot17_embeddings("02", fr, seed=15, unit=True)),
 }
 # per-frame camera warps of the cases that exercise SURVEY row a15 through the golden table
-WARPS = {"strongsort_warp_stress64": lambda: warp_sequence(100)}
+WARPS = {"strongsort_warp_stress64": lambda: warp_sequence(100),
+         "deepocsort_warp_stress64": lambda: warp_sequence(160, seed=23)}
 
 
 def load_golden(name):

@@ -169,7 +169,11 @@ class HostSimDeepOcSort:
             self.lib.docs_destroy(self.h)
             self.h = None
 
-    def update(self, dets, img=None, embs=None):
+    def update(self, dets, img=None, embs=None, warp=None):
+        if warp is not None:
+            w = np.ascontiguousarray(warp, dtype=np.float64).reshape(6)
+            self.lib.docs_set_warp.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+            self.lib.docs_set_warp(self.h, w.ctypes.data)
         dets = np.ascontiguousarray(dets, dtype=np.float32).reshape(-1, 6)
         n = len(dets)
         out = np.empty((max(n, 1), 8), np.float32)

@@ -114,8 +114,10 @@ def test_hostsim_deepocsort_golden_with_wide_augmentation(name, mode):
     want, _ = load_golden(name)
     trk = _make(kind, kwargs)
     trk.set_jv_wide(mode)
+    warps = WARPS[name]() if name in WARPS else None
     for f, dets in enumerate(frames):
-        assert_rows_match(trk.update(dets, None, None if embs is None else embs[f]), want[f], f, box_rtol=1e-4)
+        extra = {} if warps is None else {"warp": warps[f]}
+        assert_rows_match(trk.update(dets, None, None if embs is None else embs[f], **extra), want[f], f, box_rtol=1e-4)
 
 
 @pytest.mark.parametrize("seed", range(40))

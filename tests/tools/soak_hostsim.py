@@ -12,12 +12,21 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle.deepocsort import DeepOcSortOracle  # noqa: E402
-from oracle.streams import stress_embeddings, stress_stream, unit_embeddings  # noqa: E402
+from oracle.streams import stress_embeddings, stress_stream, unit_embeddings, warp_sequence  # noqa: E402
 from oracle.strongsort import StrongSortOracle  # noqa: E402
 from oracle.trackers import BotSortOracle, ByteTrackOracle  # noqa: E402
 from tests.common import BOTSORT_YAML, BYTETRACK_YAML, DEEPOCSORT_YAML, STRONGSORT_YAML, assert_rows_match  # noqa: E402
 from tests.hostsim import (HostSimDeepOcSort, HostSimStrongSort, HostSimTracker, botsort_cfg, bytetrack_cfg,  # noqa: E402
                            deepocsort_cfg, strongsort_cfg)
+
+
+def case_with_warps(seed):
+    """case(seed) plus, for every second seed of the trackers that take one, a supplied camera-motion warp per frame."""
+    kind, kw, frames, embs, sim, orc = case(seed)
+    warps = None
+    if kind != "bytetrack" and (seed // 4) % 2 == 1:
+        warps = warp_sequence(len(frames), seed=seed + 77)
+    return kind, kw, frames, embs, sim, orc, warps
 
 
 def case(seed):
@@ -61,16 +70,17 @@ def main():
     bad = 0
     t0 = time.time()
     for seed in range(first, first + n):
-        kind, kw, frames, embs, sim, orc = case(seed)
+        kind, kw, frames, embs, sim, orc, warps = case_with_warps(seed)
         try:
             for f, d in enumerate(frames):
                 e = None if embs is None else embs[f]
-                got = sim.update(d, None, e)
-                want = orc.update(d, None) if embs is None else orc.update(d, None, e.copy())
+                x = {} if warps is None else {"warp": warps[f]}
+                got = sim.update(d, None, e, **x)
+                want = orc.update(d, None) if embs is None else orc.update(d, None, e.copy(), **x)
                 assert_rows_match(got, want, f, box_rtol=1e-4)
         except AssertionError as ex:
             bad += 1
-            print(f"seed {seed} {kind} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
+            print(f"seed {seed} {kind} warps={warps is not None} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
     print(f"{n} cases, {bad} diverged, {time.time() - t0:.0f} s")
     return bad
 

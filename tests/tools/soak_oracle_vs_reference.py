@@ -32,16 +32,23 @@ from boxmot.trackers.bbox.deepocsort.deepocsort import DeepOcSort  # noqa: E402
 from boxmot.trackers.bbox.strongsort.strongsort import StrongSort  # noqa: E402
 
 
-def reference_tracker(kind, kw, n_frames):
+def reference_tracker(kind, kw, n_frames, warps):
+    """The reference tracker with its camera-motion estimator replaced by the supplied matrices (or switched off)."""
     if kind == "bytetrack":
         bt_base.BaseTrack._count = 0
         return ByteTrack(**kw)
     if kind == "botsort":
-        return BotSort(reid_model=None, use_cmc=False, **kw)
+        trk = BotSort(reid_model=None, use_cmc=warps is not None, **kw)
+        if warps is not None:
+            trk.cmc = mg._GivenWarps(warps)
+        return trk
     if kind == "deepocsort":
-        return DeepOcSort(reid_model=None, cmc_off=True, **kw)
+        trk = DeepOcSort(reid_model=None, cmc_off=warps is None, **kw)
+        if warps is not None:
+            trk.cmc = mg._GivenWarps(warps)
+        return trk
     trk = StrongSort(reid_model=None, **kw)
-    trk.cmc = mg._FrameWarps([np.eye(2, 3)] * n_frames)
+    trk.cmc = mg._FrameWarps(warps if warps is not None else [np.eye(2, 3)] * n_frames)
     return trk
 
 
@@ -52,19 +59,22 @@ def main():
     bad = 0
     t0 = time.time()
     for seed in range(first, first + n):
-        kind, kw, frames, embs, _sim, orc = soak.case(seed)
-        ref = reference_tracker(kind, kw, len(frames))
+        kind, kw, frames, embs, _sim, orc, warps = soak.case_with_warps(seed)
+        ref = reference_tracker(kind, kw, len(frames), warps)
         try:
             for f, d in enumerate(frames):
                 e = None if embs is None else embs[f]
+                if isinstance(getattr(ref, "cmc", None), mg._FrameWarps):
+                    ref.cmc.f = f
+                x = {} if warps is None else {"warp": warps[f]}
                 want = ref.update(d.copy(), img) if e is None else ref.update(d.copy(), img, e.copy())
-                got = orc.update(d, None) if e is None else orc.update(d, None, e.copy())
+                got = orc.update(d, None) if e is None else orc.update(d, None, e.copy(), **x)
                 want = np.asarray(want, np.float32)
                 want = want.reshape(-1, 8) if want.size else np.empty((0, 8), np.float32)
                 soak.assert_rows_match(got, want, f, exact_boxes=True)
         except AssertionError as ex:
             bad += 1
-            print(f"seed {seed} {kind} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
+            print(f"seed {seed} {kind} warps={warps is not None} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
     print(f"{n} cases, {bad} diverged, {time.time() - t0:.0f} s")
     return bad
 
