@@ -104,6 +104,10 @@ CASES = {
     "deepocsort_yaml_mot17_02": ("deepocsort", DEEPOCSORT_YAML, lambda: mot17_stream("02"),
                                  lambda fr: mot17_embeddings("02", fr, seed=15, unit=True)),
 }
+# cases added after the round-1 GPU budget was spent: verified on the CPU (oracle vs reference, host simulation of the
+# device source) but not yet on hardware -- their GPU test lives in tests/test_zgpu_late_goldens.py so that it runs last
+LATE_CASES = tuple(n for n in CASES if "_mot17_" in n or n == "deepocsort_warp_stress64")
+
 # per-frame camera warps of the cases that exercise SURVEY row a15 through the golden table
 WARPS = {"strongsort_warp_stress64": lambda: warp_sequence(100),
          "deepocsort_warp_stress64": lambda: warp_sequence(160, seed=23)}
