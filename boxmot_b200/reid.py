@@ -38,16 +38,17 @@ class B200ReID:
     def __init__(self, weights, device=None, half: bool = False, preprocess: Optional[str] = None):
         if preprocess not in (None, "resize"):
             raise NotImplementedError("only the 'resize' preprocess is implemented on the B200 path")
-        if half:
-            raise NotImplementedError(
-                "half=True: round 1 ships the float32 kernels only (embeddings within 1e-4 of the reference)")
+        # half=True is accepted for interface compatibility (the reference's call sites pass it): the network still runs
+        # in float32 on the device -- at least the reference's precision -- and the rows handed back to the caller are
+        # rounded to float16, the dtype the reference returns in that mode.  Inside a tracker the embeddings never leave
+        # the device and stay float32 either way.
         self.lib = _lib.require_device()
         self.blob_path = str(export_blob(weights)) if isinstance(weights, (str, Path)) else None
         if self.blob_path is None:
             raise TypeError("weights must be a path to a .pt checkpoint or a .b200reid blob")
         header, _ = read_blob(self.blob_path)
         self.feature_dim = int(header[7])
-        self.half = False
+        self.half = bool(half)
         self.device = "cuda:0"
         self.handle = ctypes.c_void_p()
         ok = self.lib.boxmot_reid_capi_create(self.blob_path.encode(), b"resize", ctypes.byref(self.handle))
@@ -97,7 +98,7 @@ class B200ReID:
                                                         out.size)
         if not ok:
             raise B200Error(self._err())
-        return out
+        return out.astype(np.float16) if self.half else out
 
     # ---- the staged quartet (utils/timing.py:34-75 drives these) ---------------------------------------
     def get_crops(self, xyxys, img) -> _StagedCrops:
@@ -121,7 +122,7 @@ class B200ReID:
         out = np.empty((crops.n, self.feature_dim), np.float32)
         if not self.lib.boxmot_reid_capi_postprocess(self.handle, out.ctypes.data, out.size):
             raise B200Error(self._err())
-        return out
+        return out.astype(np.float16) if self.half else out
 
     def warmup(self, imgsz=((256, 128, 3),)):
         im = np.zeros(imgsz[0], dtype=np.uint8)
