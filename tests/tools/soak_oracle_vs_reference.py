@@ -4,8 +4,12 @@ keyword arguments (CMC off / identity warp, ids from 1 per stream).  A disagreem
     python tests/tools/soak_oracle_vs_reference.py [n_cases] [first_seed]"""
 from __future__ import annotations
 
+import os
 import sys
 import time
+
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # tiny matrices: BLAS threads only contend
+    os.environ.setdefault(_v, "1")
 from pathlib import Path
 
 import numpy as np
@@ -75,6 +79,8 @@ def main():
         except AssertionError as ex:
             bad += 1
             print(f"seed {seed} {kind} warps={warps is not None} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
+        if (seed - first + 1) % 50 == 0:
+            print(f"  ... {seed - first + 1} cases, {bad} diverged, {time.time() - t0:.0f} s", flush=True)
     print(f"{n} cases, {bad} diverged, {time.time() - t0:.0f} s")
     return bad
 
