@@ -22,6 +22,8 @@ REF_CASES = {
     "xywh": (np.array([100.0, 80.0, 40.0, 20.0]), np.array([101.0, 79.5, 40.5, 20.5])),
     "xyah": (np.array([100.0, 80.0, 1.6, 60.0]), np.array([100.5, 80.2, 1.58, 60.1])),
 }
+UNFREEZE_OBS = [np.array([[300.0], [200.0], [50000.0], [1.5]]), np.array([[320.0], [210.0], [51000.0], [1.4]]),
+                np.array([[350.0], [230.0], [52000.0], [1.3]])]
 XYSR_CASE = (np.array([[300.0], [200.0], [50000.0], [1.5]]), np.array([[305.0], [202.0], [50500.0], [1.45]]))
 
 
@@ -79,6 +81,26 @@ def main():
     out["xysr_ref_pred_x"], out["xysr_ref_pred_P"] = kf.x.copy(), kf.P.copy()
     kf.update(z1)
     out["xysr_ref_upd_x"], out["xysr_ref_upd_P"] = kf.x.copy(), kf.P.copy()
+    # the reference's un-freeze regression scenario (test_kalman_filters_modes.py:164-193, issue #2207): two observations,
+    # five missed frames, a third observation -> freeze, virtual-trajectory replay, update
+    kf = KalmanFilterXYSR(dim_x=7, dim_z=4, max_obs=50)
+    kf.F = np.eye(7)
+    kf.F[:4, 4:] = np.pad(np.eye(3), ((0, 1), (0, 0)))
+    kf.H = np.zeros((4, 7))
+    kf.H[:4, :4] = np.eye(4)
+    kf.R *= 10.0
+    out["unfreeze_x0"], out["unfreeze_P0"] = kf.x.copy(), kf.P.copy()
+    out["unfreeze_Q"], out["unfreeze_R"] = kf.Q.copy(), kf.R.copy()
+    for k, obs in enumerate(UNFREEZE_OBS[:2]):
+        kf.predict()
+        kf.update(obs)
+    for _ in range(5):
+        kf.predict()
+        kf.update(None)
+    out["unfreeze_gap_x"], out["unfreeze_gap_P"] = kf.x.copy(), kf.P.copy()
+    kf.predict()
+    kf.update(UNFREEZE_OBS[2])
+    out["unfreeze_x"], out["unfreeze_P"] = kf.x.copy(), kf.P.copy()
     np.savez_compressed(HERE / "kalman_reference.npz", **out)
     print("wrote kalman_reference.npz", len(out), "arrays")
 

@@ -62,3 +62,27 @@ def test_xysr_reference_unit_test_inputs():
     f.update(z1)
     np.testing.assert_allclose(f.x, G["xysr_ref_upd_x"], rtol=1e-10, atol=1e-9)
     np.testing.assert_allclose(f.P, G["xysr_ref_upd_P"], rtol=1e-9, atol=1e-9)
+
+
+def test_xysr_unfreeze_regression_scenario_of_the_reference():
+    """tests/unit/test_kalman_filters_modes.py:164-193 (issue #2207): two observations, five missed frames, a third one ->
+    freeze, virtual-trajectory replay from the pre-gap measurement, update.  State and covariance after the gap and after
+    the re-observation against the reference filter."""
+    from oracle.deepocsort import XYSRFilter
+    from tests.golden.make_kalman_golden import UNFREEZE_OBS
+
+    f = XYSRFilter(np.zeros((4, 1)))
+    f.x, f.P = G["unfreeze_x0"].copy(), G["unfreeze_P0"].copy()
+    f.Q, f.R = G["unfreeze_Q"].copy(), G["unfreeze_R"].copy()
+    for obs in UNFREEZE_OBS[:2]:
+        f.predict()
+        f.update(obs)
+    for _ in range(5):
+        f.predict()
+        f.update(None)
+    np.testing.assert_allclose(f.x, G["unfreeze_gap_x"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(f.P, G["unfreeze_gap_P"], rtol=1e-11, atol=1e-8)
+    f.predict()
+    f.update(UNFREEZE_OBS[2])
+    np.testing.assert_allclose(f.x, G["unfreeze_x"], rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(f.P, G["unfreeze_P"], rtol=1e-9, atol=1e-7)
