@@ -446,6 +446,10 @@ class _SingleStreamTracker:
         blob = getattr(reid_model, "blob_path", None)
         if reid_model is not None and blob is not None:
             feat_dim = int(getattr(reid_model, "feature_dim", feat_dim))
+        if self._kind == "deepocsort" and max_obs < max_age + 4:
+            # the reference's un-freeze replay looks its pre-gap anchor up in a history deque of max_obs entries
+            # (xysr.py:384-399) and silently skips the replay once a gap has pushed it out; the device keeps the anchor
+            raise NotImplementedError("DeepOCSORT needs max_obs >= max_age + 4 (history window of the un-freeze replay)")
         if self._kind == "deepocsort":  # BaseTracker settings that DeepOCSORT's update actually reads
             params = dict(params, det_thresh=det_thresh, max_age=max_age, min_hits=min_hits, iou_threshold=iou_threshold)
         if self._kind == "strongsort":  # Tracker(max_age=self.max_age) (strongsort.py:56-64)
