@@ -44,26 +44,34 @@ def case(seed):
     dim = 64
     if kind == "bytetrack":
         kw = dict(BYTETRACK_YAML, track_thresh=float(rng.uniform(0.3, 0.7)), match_thresh=float(rng.uniform(0.6, 0.95)),
-                  track_buffer=int(rng.integers(5, 40)), frame_rate=int(rng.choice([25, 30])))
+                  track_buffer=int(rng.integers(5, 40)), frame_rate=int(rng.choice([25, 30])),
+                  min_conf=float(rng.uniform(0.05, 0.3)))
         return kind, kw, frames, None, HostSimTracker(bytetrack_cfg(**kw)), ByteTrackOracle(**kw)
     if kind == "botsort":
         kw = dict(BOTSORT_YAML, track_high_thresh=float(rng.uniform(0.4, 0.7)), new_track_thresh=float(rng.uniform(0.4, 0.75)),
                   match_thresh=float(rng.uniform(0.6, 0.9)), appearance_thresh=float(rng.uniform(0.2, 0.7)),
                   proximity_thresh=float(rng.uniform(0.4, 0.7)), fuse_first_associate=bool(rng.integers(0, 2)),
-                  track_buffer=int(rng.integers(5, 50)), removed_stracks_buffer=int(rng.choice([3, 20, 329])))
+                  track_buffer=int(rng.integers(5, 50)), removed_stracks_buffer=int(rng.choice([3, 20, 329])),
+                  track_low_thresh=float(rng.uniform(0.05, 0.3)), second_match_thresh=float(rng.uniform(0.2, 0.6)),
+                  unconfirmed_match_thresh=float(rng.uniform(0.3, 0.8)), unconfirmed_emb_scale=float(rng.uniform(1.0, 3.0)),
+                  with_reid=bool(rng.integers(0, 4) > 0), frame_rate=int(rng.choice([25, 30])))
         embs = stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
         return kind, kw, frames, embs, HostSimTracker(botsort_cfg(feat_dim=dim, **kw)), BotSortOracle(**kw)
     if kind == "deepocsort":
         kw = dict(DEEPOCSORT_YAML, det_thresh=float(rng.uniform(0.2, 0.6)), w_association_emb=float(rng.uniform(0.2, 0.9)),
                   inertia=float(rng.uniform(0.05, 0.4)), delta_t=int(rng.integers(1, 5)), max_age=int(rng.integers(5, 35)),
-                  min_hits=int(rng.integers(1, 4)), aw_off=bool(rng.integers(0, 2)), iou_threshold=float(rng.uniform(0.2, 0.4)))
+                  min_hits=int(rng.integers(1, 4)), aw_off=bool(rng.integers(0, 2)), iou_threshold=float(rng.uniform(0.2, 0.4)),
+                  embedding_off=bool(rng.integers(0, 5) == 0), alpha_fixed_emb=float(rng.uniform(0.8, 0.98)),
+                  aw_param=float(rng.uniform(0.3, 0.7)), Q_xy_scaling=float(rng.choice([0.01, 0.05])),
+                  Q_s_scaling=float(rng.choice([0.0001, 0.001])))
         embs = unit_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
         sim = HostSimDeepOcSort(deepocsort_cfg(feat_dim=dim, **kw))
         sim.set_jv_wide(int(rng.integers(0, 3)))
         return kind, kw, frames, embs, sim, DeepOcSortOracle(**kw)
     kw = dict(STRONGSORT_YAML, min_conf=float(rng.uniform(0.2, 0.6)), max_cos_dist=float(rng.uniform(0.2, 0.5)),
               n_init=int(rng.integers(1, 4)), nn_budget=int(rng.choice([5, 30, 100])), max_age=int(rng.integers(5, 35)),
-              ema_alpha=float(rng.choice([0.8, 0.9])), mc_lambda=float(rng.choice([0.9, 0.98])))
+              ema_alpha=float(rng.choice([0.8, 0.9])), mc_lambda=float(rng.choice([0.9, 0.98])),
+              max_iou_dist=float(rng.uniform(0.5, 0.9)))
     embs = stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
     return kind, kw, frames, embs, HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=dim, **kw)), StrongSortOracle(**kw)
 
