@@ -42,6 +42,15 @@ def case(seed):
                      empty_every=int(rng.choice([0, 0, 17, 29])), dropout=float(rng.choice([0.05, 0.2, 0.4])))
     frames = stress_stream(n_obj, n_frames, **kw_stream)
     dim = 64
+    real = (seed // 8) % 3 == 0   # every third block of seeds: a window of the MOT17-mini public detections instead
+    if real:
+        from tests.common import mot17_embeddings, mot17_stream
+
+        seq = "04" if seed % 2 else "02"
+        full = mot17_stream(seq)
+        start = int(rng.integers(0, len(full) - n_frames))
+        all_embs = mot17_embeddings(seq, full, dim=dim, seed=seed + 9, unit=(kind == "deepocsort"))
+        frames, real_embs = full[start:start + n_frames], all_embs[start:start + n_frames]
     if kind == "bytetrack":
         kw = dict(BYTETRACK_YAML, track_thresh=float(rng.uniform(0.3, 0.7)), match_thresh=float(rng.uniform(0.6, 0.95)),
                   track_buffer=int(rng.integers(5, 40)), frame_rate=int(rng.choice([25, 30])),
@@ -55,7 +64,7 @@ def case(seed):
                   track_low_thresh=float(rng.uniform(0.05, 0.3)), second_match_thresh=float(rng.uniform(0.2, 0.6)),
                   unconfirmed_match_thresh=float(rng.uniform(0.3, 0.8)), unconfirmed_emb_scale=float(rng.uniform(1.0, 3.0)),
                   with_reid=bool(rng.integers(0, 4) > 0), frame_rate=int(rng.choice([25, 30])))
-        embs = stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+        embs = real_embs if real else stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
         return kind, kw, frames, embs, HostSimTracker(botsort_cfg(feat_dim=dim, **kw)), BotSortOracle(**kw)
     if kind == "deepocsort":
         kw = dict(DEEPOCSORT_YAML, det_thresh=float(rng.uniform(0.2, 0.6)), w_association_emb=float(rng.uniform(0.2, 0.9)),
@@ -64,7 +73,7 @@ def case(seed):
                   embedding_off=bool(rng.integers(0, 5) == 0), alpha_fixed_emb=float(rng.uniform(0.8, 0.98)),
                   aw_param=float(rng.uniform(0.3, 0.7)), Q_xy_scaling=float(rng.choice([0.01, 0.05])),
                   Q_s_scaling=float(rng.choice([0.0001, 0.001])))
-        embs = unit_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+        embs = real_embs if real else unit_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
         sim = HostSimDeepOcSort(deepocsort_cfg(feat_dim=dim, **kw))
         sim.set_jv_wide(int(rng.integers(0, 3)))
         return kind, kw, frames, embs, sim, DeepOcSortOracle(**kw)
@@ -72,7 +81,7 @@ def case(seed):
               n_init=int(rng.integers(1, 4)), nn_budget=int(rng.choice([5, 30, 100])), max_age=int(rng.integers(5, 35)),
               ema_alpha=float(rng.choice([0.8, 0.9])), mc_lambda=float(rng.choice([0.9, 0.98])),
               max_iou_dist=float(rng.uniform(0.5, 0.9)))
-    embs = stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+    embs = real_embs if real else stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
     return kind, kw, frames, embs, HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=dim, **kw)), StrongSortOracle(**kw)
 
 
