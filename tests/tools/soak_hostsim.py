@@ -36,8 +36,9 @@ def case_with_warps(seed):
 def case(seed):
     rng = np.random.default_rng(seed)
     kind = ["bytetrack", "botsort", "deepocsort", "strongsort"][seed % 4]
-    n_obj = int(rng.integers(8, 90))
-    n_frames = int(rng.integers(40, 140))
+    heavy = os.environ.get("SOAK_HEAVY") == "1"   # crowded, long streams (slow): rare lifecycle paths
+    n_obj = int(rng.integers(100, 200)) if heavy else int(rng.integers(8, 90))
+    n_frames = int(rng.integers(150, 260)) if heavy else int(rng.integers(40, 140))
     kw_stream = dict(seed=int(rng.integers(1, 10**6)), n_classes=int(rng.integers(1, 4)),
                      empty_every=int(rng.choice([0, 0, 17, 29])), dropout=float(rng.choice([0.05, 0.2, 0.4])))
     frames = stress_stream(n_obj, n_frames, **kw_stream)
@@ -48,6 +49,7 @@ def case(seed):
 
         seq = "04" if seed % 2 else "02"
         full = mot17_stream(seq)
+        n_frames = min(n_frames, len(full) - 1)
         start = int(rng.integers(0, len(full) - n_frames))
         all_embs = mot17_embeddings(seq, full, dim=dim, seed=seed + 9, unit=(kind == "deepocsort"))
         frames, real_embs = full[start:start + n_frames], all_embs[start:start + n_frames]
