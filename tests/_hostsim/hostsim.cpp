@@ -252,6 +252,12 @@ int ss_snapshot(SsSim* h, int* ids, double* means, double* covs, int cap) {
 }
 
 // scipy.optimize.linear_sum_assignment(cost (R, C)) -> row_ind, col_ind (min(R, C) pairs, rows ascending)
+// diagnostics for the soak tools: the cost matrix of the last matching stage, in solver orientation
+int ss_debug_cost(SsSim* h, double* out, int n) {
+    memcpy(out, h->s.cost, sizeof(double) * (size_t)n);
+    return 0;
+}
+
 int ss_lsa(SsSim* h, const double* cost, int R, int C, int* row_ind, int* col_ind) {
     const SsCfg& c = h->cfg;
     if ((size_t)R * C > (size_t)c.cap_tracks * c.cap_dets) return -1;
