@@ -6,7 +6,7 @@ read them, accumulation kept in float32 like the tensor core's accumulator; dept
 the normalisations stay float32 (they are CUDA-core work in every design).  Output: max |e - e_fp32| / max |e_fp32| per
 crop set, the quantity tests/test_gpu_reid.py bounds by 1e-4 (BASELINE.json north_star).
 
-    python tests/tools/precision_study.py [osnet_x0_25|osnet_x1_0] [n_crops]
+    python tests/tools/precision_study.py [osnet_x0_25|osnet_x1_0|mobilenetv2_x1_4] [n_crops]
 """
 from __future__ import annotations
 
@@ -61,7 +61,12 @@ MODES = {
 
 
 def run(arch="osnet_x0_25", n=24, seed=5):
-    sd = make_osnet_state(arch, seed=seed)
+    if arch.startswith("mobilenetv2"):
+        from boxmot_b200.synthetic import make_mobilenetv2_state
+
+        sd = make_mobilenetv2_state(1.4, seed=seed)
+    else:
+        sd = make_osnet_state(arch, seed=seed)
     rng = np.random.default_rng(3)
     img = rng.integers(0, 255, size=(480, 640, 3), dtype=np.uint8)
     cx, cy = rng.uniform(0, 640, n), rng.uniform(0, 480, n)
