@@ -87,6 +87,29 @@ def case(seed):
     return kind, kw, frames, embs, HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=dim, **kw)), StrongSortOracle(**kw)
 
 
+def same_up_to_an_id_permutation(seed) -> bool:
+    """True when the two outputs of a diverged case agree in every row except for a consistent renaming of track ids
+    (the StrongSORT birth-order limit of DESIGN 3.1c), False for any other difference."""
+    kind, kw, frames, embs, sim, orc, warps = case_with_warps(seed)
+    fwd, bwd = {}, {}
+    for f, d in enumerate(frames):
+        e = None if embs is None else embs[f]
+        x = {} if warps is None else {"warp": warps[f]}
+        got = np.asarray(sim.update(d, None, e, **x), np.float32).reshape(-1, 8)
+        want = orc.update(d, None) if embs is None else orc.update(d, None, e.copy(), **x)
+        want = np.asarray(want, np.float32).reshape(-1, 8)
+        if got.shape != want.shape:
+            return False
+        a = got[np.argsort(got[:, 7], kind="stable")]
+        b = want[np.argsort(want[:, 7], kind="stable")]
+        if not np.array_equal(a[:, 5:], b[:, 5:]) or not np.allclose(a[:, :4], b[:, :4], rtol=1e-4, atol=1e-3):
+            return False
+        for i, j in zip(a[:, 4].tolist(), b[:, 4].tolist()):
+            if fwd.setdefault(i, j) != j or bwd.setdefault(j, i) != i:
+                return False
+    return True
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -103,7 +126,8 @@ def main():
                 assert_rows_match(got, want, f, box_rtol=1e-4)
         except AssertionError as ex:
             bad += 1
-            print(f"seed {seed} {kind} warps={warps is not None} DIVERGED: {str(ex).splitlines()[0]}  kw={kw}")
+            tag = "ids permuted, everything else equal" if same_up_to_an_id_permutation(seed) else "REAL DIFFERENCE"
+            print(f"seed {seed} {kind} warps={warps is not None} DIVERGED ({tag}): {str(ex).splitlines()[0]}  kw={kw}")
         if (seed - first + 1) % 50 == 0:
             print(f"  ... {seed - first + 1} cases, {bad} diverged, {time.time() - t0:.0f} s", flush=True)
     print(f"{n} cases, {bad} diverged, {time.time() - t0:.0f} s")
