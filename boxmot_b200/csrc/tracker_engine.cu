@@ -170,12 +170,14 @@ __global__ void __launch_bounds__(256) k_docs_embcost(const DocsCfg cfg, DocsStr
 }
 
 // CTA-wide augmentation of the dense JV solver (jv_dense.cuh::jv_augment_wide): measured 4.2 s -> 0.65 s per frame
-// on the BASELINE config-3 shape (512 detections, 1 500 live tracks), identical results.  BOXMOT_B200_JV_WIDE=0/1
-// sets the initial value, boxmot_b200_jv_dense_mode() changes it (parity tests run both variants).
+// on the BASELINE config-3 shape (512 detections, 1 500 live tracks), identical results; the column-owned variant
+// (jv_augment_owned, mode 2) 0.53 s and is the default since its tracker-level GPU run (goldens + config-3 ids) went
+// green in round 2.  BOXMOT_B200_JV_WIDE=0/1/2 sets the initial value, boxmot_b200_jv_dense_mode() changes it
+// (parity tests run every variant).
 static int& jv_wide_flag() {
     static int v = [] {
         const char* e = getenv("BOXMOT_B200_JV_WIDE");
-        return e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
+        return e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
     }();
     return v;
 }

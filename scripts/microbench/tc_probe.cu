@@ -1,0 +1,320 @@
+// tc_probe.cu -- hardware probe for the round-2 ReID tensor-core design (run under gpurun, prints JSON lines):
+//   1. correctness of kind::f16 / BF16 no-swizzle descriptors in the channel-blocked plane layout, including a
+//      pixel-shifted A operand (convolution tap = start-address shift) and the 3-term hi/lo split;
+//   2. 5-D TMA box load with negative start coordinates (zero fill = convolution padding) into that layout;
+//   3. issue rate of back-to-back tcgen05.mma M=128, N in {16..256}, K=16 with one and two CTAs per SM;
+//   4. tcgen05.ld epilogue rate.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I boxmot_b200/csrc -o scripts/microbench/tc_probe scripts/microbench/tc_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cstring>
+
+#include "umma.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("{\"error\": \"%s at %s:%d\"}\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+namespace bmb {
+PFN_encodeTiled tensor_map_encoder() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+void make_act_map(CUtensorMap* out, const void* base, int crops, int C, int H, int W, int box_w, int box_h, int box_c8) {
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)crops};
+    cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(C / 8) * H * W * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c8, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = tensor_map_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("{\"error\": \"cuTensorMapEncodeTiled %d\"}\n", (int)r); exit(1); }
+}
+}  // namespace bmb
+using namespace bmb;
+
+static inline uint16_t f2bf(float x) { __nv_bfloat16 b = __float2bfloat16_rn(x); uint16_t u; memcpy(&u, &b, 2); return u; }
+static inline float bf2f(uint16_t u) { uint32_t w = (uint32_t)u << 16; float f; memcpy(&f, &w, 4); return f; }
+
+// ---------------- 1. MMA correctness: D[128][N] = sum_taps A[p + shift_t][K] * B_t[N][K], 3-term split ----------------
+// A planes: [K/8][NPX][8] bf16 (hi and lo), B: [taps][K/8][N][8] (hi and lo)
+template <int N, int K, int TAPS>
+__global__ void k_mma_check(const uint16_t* __restrict__ a_hi, const uint16_t* __restrict__ a_lo,
+                            const uint16_t* __restrict__ b_hi, const uint16_t* __restrict__ b_lo, int npx, int p0,
+                            const int* __restrict__ shifts, float* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int a_bytes = (K / 8) * npx * 16, b_bytes = TAPS * (K / 8) * N * 16;
+    unsigned char* sAh = smem;
+    unsigned char* sAl = sAh + a_bytes;
+    unsigned char* sBh = sAl + a_bytes;
+    unsigned char* sBl = sBh + b_bytes;
+    for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) {
+        reinterpret_cast<uint4*>(sAh)[i] = reinterpret_cast<const uint4*>(a_hi)[i];
+        reinterpret_cast<uint4*>(sAl)[i] = reinterpret_cast<const uint4*>(a_lo)[i];
+    }
+    for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x) {
+        reinterpret_cast<uint4*>(sBh)[i] = reinterpret_cast<const uint4*>(b_hi)[i];
+        reinterpret_cast<uint4*>(sBl)[i] = reinterpret_cast<const uint4*>(b_lo)[i];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) um::tmem_alloc(&tmem_slot, um::tmem_cols_pow2(N));
+    if (threadIdx.x == 0) { um::mbar_init(&bar, 1); um::fence_mbar_init(); }
+    um::fence_async_smem();
+    um::tc_fence_before();
+    __syncthreads();
+    um::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = um::idesc_bf16(128, N);
+        const uint32_t lbo_a = (uint32_t)npx * 16u, lbo_b = (uint32_t)N * 16u;
+        uint32_t acc = 0;
+        for (int t = 0; t < TAPS; ++t) {
+            const uint32_t ao = (uint32_t)(p0 + shifts[t]) * 16u;
+            for (int ks = 0; ks < K; ks += 16) {
+                const uint32_t ak = ao + (uint32_t)(ks / 8) * lbo_a, bk = (uint32_t)(t * (K / 8) + ks / 8) * lbo_b;
+                const uint64_t dah = um::make_desc(um::smem_u32(sAh) + ak, lbo_a, 128), dal = um::make_desc(um::smem_u32(sAl) + ak, lbo_a, 128);
+                const uint64_t dbh = um::make_desc(um::smem_u32(sBh) + bk, lbo_b, 128), dbl = um::make_desc(um::smem_u32(sBl) + bk, lbo_b, 128);
+                um::mma_bf16(tmem, dah, dbh, idesc, acc); acc = 1;
+                um::mma_bf16(tmem, dah, dbl, idesc, 1);
+                um::mma_bf16(tmem, dal, dbh, idesc, 1);
+            }
+        }
+        um::mma_commit(&bar);
+    }
+    um::mbar_wait(&bar, 0);
+    um::tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t r[16];
+        um::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        um::tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) out[(size_t)(warp * 32 + lane) * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    um::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) um::tmem_dealloc(tmem, um::tmem_cols_pow2(N));
+}
+
+template <int N, int K, int TAPS>
+static double run_mma_check() {
+    const int npx = 128 + 80, p0 = 40;
+    int shifts[9] = {-35, -34, -33, -1, 0, 1, 33, 34, 35};
+    if (TAPS == 1) shifts[0] = 3;
+    std::vector<float> A((size_t)npx * K), B((size_t)TAPS * N * K);
+    srand(7);
+    for (auto& v : A) v = (float)rand() / RAND_MAX * 2.f - 1.f;
+    for (auto& v : B) v = ((float)rand() / RAND_MAX * 2.f - 1.f) * 0.3f;
+    std::vector<uint16_t> ah((size_t)(K / 8) * npx * 8), al(ah.size()), bh((size_t)TAPS * (K / 8) * N * 8), bl(bh.size());
+    for (int p = 0; p < npx; ++p)
+        for (int k = 0; k < K; ++k) {
+            const float x = A[(size_t)p * K + k];
+            const uint16_t h = f2bf(x);
+            const size_t o = ((size_t)(k / 8) * npx + p) * 8 + k % 8;
+            ah[o] = h; al[o] = f2bf(x - bf2f(h));
+        }
+    for (int t = 0; t < TAPS; ++t)
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) {
+                const float x = B[((size_t)t * N + n) * K + k];
+                const uint16_t h = f2bf(x);
+                const size_t o = (((size_t)t * (K / 8) + k / 8) * N + n) * 8 + k % 8;
+                bh[o] = h; bl[o] = f2bf(x - bf2f(h));
+            }
+    uint16_t *dah, *dal, *dbh, *dbl; int* dsh; float* dout;
+    CK(cudaMalloc(&dah, ah.size() * 2)); CK(cudaMalloc(&dal, al.size() * 2));
+    CK(cudaMalloc(&dbh, bh.size() * 2)); CK(cudaMalloc(&dbl, bl.size() * 2));
+    CK(cudaMalloc(&dsh, sizeof(shifts))); CK(cudaMalloc(&dout, sizeof(float) * 128 * N));
+    CK(cudaMemcpy(dah, ah.data(), ah.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dal, al.data(), al.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbh, bh.data(), bh.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dbl, bl.data(), bl.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsh, shifts, sizeof(shifts), cudaMemcpyHostToDevice));
+    const size_t smem = 2 * (ah.size() * 2 + bh.size() * 2) + 128;
+    CK(cudaFuncSetAttribute(k_mma_check<N, K, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mma_check<N, K, TAPS><<<1, 128, smem>>>(dah, dal, dbh, dbl, npx, p0, dsh, dout);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> out((size_t)128 * N);
+    CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+    double worst = 0, scale = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            double ref = 0;
+            for (int t = 0; t < TAPS; ++t)
+                for (int k = 0; k < K; ++k) ref += (double)A[(size_t)(p0 + shifts[t] + m) * K + k] * B[((size_t)t * N + n) * K + k];
+            worst = fmax(worst, fabs(ref - out[(size_t)m * N + n]));
+            scale = fmax(scale, fabs(ref));
+        }
+    cudaFree(dah); cudaFree(dal); cudaFree(dbh); cudaFree(dbl); cudaFree(dsh); cudaFree(dout);
+    return worst / scale;
+}
+
+// ---------------- 2. TMA 5-D box with negative coordinates ----------------
+__global__ void k_tma_check(const __grid_constant__ CUtensorMap map, int x0, int y0, int n, int box_elems, uint16_t* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) { um::mbar_init(&bar, 1); um::fence_mbar_init(); }
+    for (int i = threadIdx.x; i < box_elems; i += blockDim.x) reinterpret_cast<uint16_t*>(smem)[i] = 0x7777;
+    um::fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        um::mbar_expect_tx(&bar, (uint32_t)box_elems * 2u);
+        um::tma_load_5d(smem, &map, 0, x0, y0, 0, n, &bar);
+    }
+    um::mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < box_elems; i += blockDim.x) out[i] = reinterpret_cast<uint16_t*>(smem)[i];
+}
+
+static int run_tma_check() {
+    const int crops = 3, C = 16, H = 8, W = 8, bw = W + 2, bh = 6, bc8 = C / 8;
+    std::vector<uint16_t> t((size_t)crops * C * H * W);
+    for (size_t i = 0; i < t.size(); ++i) t[i] = (uint16_t)(i + 1);
+    uint16_t* dt; CK(cudaMalloc(&dt, t.size() * 2));
+    CK(cudaMemcpy(dt, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
+    CUtensorMap map;
+    make_act_map(&map, dt, crops, C, H, W, bw, bh, bc8);
+    const int box = 8 * bw * bh * bc8;
+    uint16_t* dout; CK(cudaMalloc(&dout, box * 2));
+    int bad = 0;
+    for (int y0 : {-2, 1, 5}) {
+        k_tma_check<<<1, 128, box * 2 + 128>>>(map, -1, y0, 2, box, dout);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint16_t> o(box);
+        CK(cudaMemcpy(o.data(), dout, box * 2, cudaMemcpyDeviceToHost));
+        for (int c8 = 0; c8 < bc8; ++c8)
+            for (int y = 0; y < bh; ++y)
+                for (int x = 0; x < bw; ++x)
+                    for (int j = 0; j < 8; ++j) {
+                        const int gy = y0 + y, gx = x - 1;
+                        uint16_t want = 0;
+                        if (gy >= 0 && gy < H && gx >= 0 && gx < W) want = t[((((size_t)2 * bc8 + c8) * H + gy) * W + gx) * 8 + j];
+                        if (o[(((size_t)c8 * bh + y) * bw + x) * 8 + j] != want) ++bad;
+                    }
+    }
+    cudaFree(dt); cudaFree(dout);
+    return bad;
+}
+
+// ---------------- 3. MMA issue rate ----------------
+template <int N>
+__global__ void __launch_bounds__(128) k_mma_rate(int reps, int taps_shift, long long* __restrict__ cycles) {
+    extern __shared__ __align__(128) unsigned char smem[];   // A: 2 planes x 512 px, B: 2 planes x N  (contents irrelevant)
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (2 * 512 * 16 + 2 * 256 * 16) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (warp == 0) um::tmem_alloc(&tmem_slot, um::tmem_cols_pow2(N));
+    if (threadIdx.x == 0) { um::mbar_init(&bar, 1); um::fence_mbar_init(); }
+    um::fence_async_smem();
+    um::tc_fence_before();
+    __syncthreads();
+    um::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = um::idesc_bf16(128, N);
+        const uint32_t a0 = um::smem_u32(smem), b0 = a0 + 2 * 512 * 16;
+        t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            const uint32_t sh = taps_shift ? (uint32_t)((r % 9) * 37) * 16u : 0u;
+            um::mma_bf16(tmem, um::make_desc(a0 + sh, 512 * 16, 128), um::make_desc(b0, N * 16, 128), idesc, r > 0);
+        }
+        um::mma_commit(&bar);
+        t1 = clock64();
+    }
+    um::mbar_wait(&bar, 0);
+    if (threadIdx.x == 0) {
+        t2 = clock64();
+        cycles[blockIdx.x * 2] = t1 - t0;
+        cycles[blockIdx.x * 2 + 1] = t2 - t0;
+    }
+    um::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) um::tmem_dealloc(tmem, um::tmem_cols_pow2(N));
+}
+
+template <int N>
+static void run_rate(int grid, int shift) {
+    const int reps = 1024;
+    long long* d; CK(cudaMalloc(&d, sizeof(long long) * 2 * grid));
+    const size_t smem = 2 * 512 * 16 + 2 * 256 * 16 + 128;
+    for (int it = 0; it < 2; ++it) k_mma_rate<N><<<grid, 128, smem>>>(reps, shift, d);
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> h(2 * grid);
+    CK(cudaMemcpy(h.data(), d, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
+    double issue = 0, total = 0;
+    for (int i = 0; i < grid; ++i) { issue += h[2 * i]; total += h[2 * i + 1]; }
+    printf("{\"probe\": \"mma_rate\", \"N\": %d, \"grid\": %d, \"tap_shift\": %d, \"issue_cyc_per_mma\": %.2f, \"total_cyc_per_mma\": %.2f}\n",
+           N, grid, shift, issue / grid / reps, total / grid / reps);
+    cudaFree(d);
+}
+
+// ---------------- 4. epilogue: tcgen05.ld + split + st.shared ----------------
+__global__ void __launch_bounds__(128) k_ld_rate(int reps, long long* __restrict__ cycles, float* sink) {
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) uint4 buf[2][2][128 + 8];
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) um::tmem_alloc(&tmem_slot, 64);
+    um::tc_fence_before();
+    __syncthreads();
+    um::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    long long t0 = clock64();
+    float acc = 0.f;
+    for (int r = 0; r < reps; ++r) {
+        uint32_t v[16];
+        um::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)((r & 3) * 16), v);
+        um::tmem_ld_wait();
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = fmaxf(__uint_as_float(v[2 * j]) + 0.5f, 0.f), b = fmaxf(__uint_as_float(v[2 * j + 1]) + 0.25f, 0.f);
+            um::split2(a, b, hi[j], lo[j]);
+        }
+        buf[0][0][threadIdx.x] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        buf[0][1][threadIdx.x] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        buf[1][0][threadIdx.x] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        buf[1][1][threadIdx.x] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        acc += __uint_as_float(v[r & 15]);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (acc == 123.456f) sink[0] = acc + (float)buf[1][1][5].x;
+    um::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) um::tmem_dealloc(tmem, 64);
+}
+
+int main() {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("{\"probe\": \"device\", \"name\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\"}\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
+    printf("{\"probe\": \"mma_check\", \"N\": 16, \"K\": 16, \"taps\": 1, \"rel_err\": %.3e}\n", run_mma_check<16, 16, 1>());
+    printf("{\"probe\": \"mma_check\", \"N\": 16, \"K\": 16, \"taps\": 9, \"rel_err\": %.3e}\n", run_mma_check<16, 16, 9>());
+    printf("{\"probe\": \"mma_check\", \"N\": 32, \"K\": 32, \"taps\": 9, \"rel_err\": %.3e}\n", run_mma_check<32, 32, 9>());
+    printf("{\"probe\": \"mma_check\", \"N\": 64, \"K\": 80, \"taps\": 1, \"rel_err\": %.3e}\n", run_mma_check<64, 80, 1>());
+    printf("{\"probe\": \"mma_check\", \"N\": 128, \"K\": 128, \"taps\": 1, \"rel_err\": %.3e}\n", run_mma_check<128, 128, 1>());
+    printf("{\"probe\": \"tma_check\", \"bad_elements\": %d}\n", run_tma_check());
+    fflush(stdout);
+    for (int grid : {1, 148, 296, 592}) {
+        run_rate<16>(grid, 0); run_rate<16>(grid, 1);
+        run_rate<32>(grid, 0); run_rate<64>(grid, 0); run_rate<128>(grid, 0); run_rate<256>(grid, 0);
+        fflush(stdout);
+    }
+    {
+        const int grid = 148 * 4, reps = 2048;
+        long long* d; float* sink;
+        CK(cudaMalloc(&d, sizeof(long long) * grid)); CK(cudaMalloc(&sink, 4));
+        for (int it = 0; it < 2; ++it) k_ld_rate<<<grid, 128>>>(reps, d, sink);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> h(grid);
+        CK(cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+        double s = 0; for (auto v : h) s += v;
+        printf("{\"probe\": \"epilogue_ld16_split_store\", \"ctas_per_sm\": 4, \"cyc_per_iter_per_cta\": %.1f}\n", s / grid / reps);
+    }
+    return 0;
+}
