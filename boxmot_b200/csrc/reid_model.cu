@@ -1197,6 +1197,8 @@ struct BlockW {
     TcW light_tc[10];   // LightConv 1x1 weights packed for the tcgen05 stage (mid % 16 == 0)
 };
 
+namespace tcx { struct Plan; }
+
 struct MbBlock {
     int cin, cout, t, stride, cinp, midp, coutp;
     size_t we, be, wd, bd, wp, bp;
@@ -1241,6 +1243,7 @@ struct ReidModel {
     std::vector<int> prof_cls;
     double prof_ms[REID_N_CLASSES] = {0};
     int prof_launches[REID_N_CLASSES] = {0};
+    tcx::Plan* tc = nullptr;   // tensor-core path (tcgen05 + TMA, reid_tc.cuh): the default for the widths it covers
     int debug_stop = -1;       // stop after this stage index and leave the tensor in debug_ptr
     const float* debug_ptr = nullptr;
     size_t debug_floats_per_crop = 0;
@@ -1249,6 +1252,14 @@ struct ReidModel {
 static const int kBranchOfLight[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
 static const int kLevelOfLight[10] = {1, 1, 2, 1, 2, 3, 1, 2, 3, 4};
 static const int kDepth[4] = {1, 2, 3, 4};
+
+}  // namespace bmb
+#include "reid_tc_host.cuh"
+namespace bmb {
+namespace tcx {
+Plan* plan_build(ReidModel* m, const float* host_w);
+bool plan_supported(const ReidModel* m);
+}
 
 ReidModel* reid_load(const char* path) {
     std::ifstream f(path, std::ios::binary);
@@ -1424,6 +1435,11 @@ ReidModel* reid_load(const char* path) {
             RCUDA_OK(cudaMalloc(&m->sums[b], sizeof(float) * CH * 64 * (m->c[3] / 4)));
         }
         RCUDA_OK(cudaMalloc(&m->gates, sizeof(float) * CH * 4 * (m->c[3] / 4)));
+        {   // tensor-core path: the default wherever its kernel instances cover the widths (BOXMOT_B200_REID_FP32=1
+            // keeps the float32 CUDA-core kernels of round 1, e.g. for A/B runs)
+            const char* fe = getenv("BOXMOT_B200_REID_FP32");
+            if (!(fe && fe[0] == '1') && tcx::plan_supported(m)) m->tc = tcx::plan_build(m, host.data());
+        }
     } catch (...) {
         reid_free(m);
         throw;
@@ -1436,6 +1452,7 @@ void reid_free(ReidModel* m) {
     cudaFree(m->d_w); cudaFree(m->d_wtc); cudaFree(m->blob); cudaFree(m->bufA); cudaFree(m->bufB); cudaFree(m->x1);
     for (int b = 0; b < 4; ++b) { cudaFree(m->Y[b][0]); cudaFree(m->Y[b][1]); cudaFree(m->sums[b]); }
     cudaFree(m->gates);
+    tcx::plan_free(m->tc);
     delete m;
 }
 
@@ -1644,6 +1661,10 @@ int pick_tile_rows(int H, int W, int C) {
 }
 }  // namespace
 
+}  // namespace bmb
+#include "reid_tc_plan.cuh"
+namespace bmb {
+
 int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int rows, int cols,
                  const CropDesc* d_crops, const int* d_ncrops, int max_crops, float* d_out, int out_ld,
                  cudaStream_t st, int first_crop, int last_crop) {
@@ -1727,6 +1748,20 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             ++L.launches;
         }
         if (stop_here(m->bufA, (size_t)8192 * m->c[0])) { launches += L.launches; continue; }
+        if (m->tc) {
+            bool tc_stopped = false;
+            L.launches += tcx::plan_run(m, d_ncrops, off, upper, st, &tc_stopped, L);
+            if (!tc_stopped) {
+                const int C = m->c[3];
+                L.begin(CLS_HEAD);
+                k_head<<<upper, 256, sizeof(float) * (C + 32 + (256 / C > 0 ? 256 / C : 1) * C), st>>>(
+                    m->tc->c5, 128, C, W + m->fcw, W + m->fcb, m->feat, d_crops, d_ncrops, off, upper, d_out, out_ld);
+                L.end();
+                ++L.launches;
+            }
+            launches += L.launches;
+            continue;
+        }
         L.begin(CLS_MAXPOOL);
         k_maxpool3s2<<<148 * 8, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_ncrops, off, upper, m->bufB);
         L.end();

@@ -1,0 +1,691 @@
+// reid_tc.cuh -- the Blackwell-native OSNet path: every 1x1 convolution of the network runs on the 5th-generation tensor
+// cores (tcgen05.mma kind::f16 on split-BF16 operands, FP32 accumulators in TMEM), activations travel between kernels as
+// channel-blocked BF16 "hi + lo" planes that TMA boxes (cp.async.bulk.tensor, zero fill = convolution padding) drop
+// straight into the UMMA canonical layout, the depthwise 3x3 / bias / ReLU / gate / pooling epilogues run on the CUDA
+// cores between the MMAs.
+//
+// Replaces (relative to /root/reference/boxmot):  reid/backbones/osnet.py:63-155 (Conv1x1, Conv1x1Linear,
+// LightConv3x3), :161-210 (ChannelGate), :212-260 (OSBlock), :380-405 (featuremaps after the stem) in eval mode.
+//
+// Numerics: a float32 value x is carried as hi = bf16(x), lo = bf16(x - hi) (|x - hi - lo| <= 2^-17 |x|); a product
+// A*W is evaluated as  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  with FP32 accumulation (the dropped lo*lo term is 2^-16
+// relative).  Measured on B200 (profiles/r2_tc_probe.jsonl): 4-6e-6 of the output scale per GEMM, and a
+// tcgen05.mma with M = 128 costs ~75 cycles whatever N <= 128 is -- so the three products are issued as TWO
+// instructions per K step: A_hi x [W_hi | W_lo] (N' = 2N columns) and A_lo x W_hi (first N columns), and the
+// epilogue adds the two column groups.
+//
+// Kernels:
+//   k_chain_tc   one OSBlock branch (1-4 LightConv3x3 = 1x1 -> depthwise 3x3 -> BN -> ReLU) per CTA on a haloed row
+//                tile: TMA box of conv1's output -> [MMA 1x1 -> TMEM -> T (smem, fp32) -> depthwise on CUDA cores ->
+//                split planes in place] x depth -> branch output planes + channel sums for the gate.
+//   k_gemm_tc    warp-specialised pointwise GEMM (TMA producer warp / MMA issuer warp / 8 epilogue warps) over 128-pixel
+//                tiles: A = up to two plane tensors streamed through an mbarrier ring, B resident in shared memory
+//                (optionally  gate (x) conv3  folded per crop), epilogue bias + ReLU -> planes, optional 2x2 average
+//                pool, optional float32 NHWC copy, optional second GEMM on the fresh tile (next block's conv1).
+#pragma once
+#include "umma.cuh"
+
+namespace bmb {
+namespace tcx {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ int tc_chunk_count(const int* d_n, int off, int cap) {
+    int n = *d_n - off;
+    n = n < 0 ? 0 : n;
+    return n > cap ? cap : n;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(um::smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// maxpool 3x3 stride 2 pad 1 on the stem output (float32 NHWC) -> split planes  [crops][C/8][H/2][W/2][8]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void k_maxpool_planes(const float* __restrict__ in, int H, int W, int C, const int* __restrict__ d_n, int off,
+                                 int cap, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+    const int n_crops = tc_chunk_count(d_n, off, cap);
+    const int OH = H / 2, OW = W / 2, C8 = C / 8;
+    const size_t total = (size_t)n_crops * C8 * OH * OW;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(e % OW);
+        size_t r = e / OW;
+        const int oy = (int)(r % OH); r /= OH;
+        const int c8 = (int)(r % C8);
+        const int n = (int)(r / C8);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float4* p = reinterpret_cast<const float4*>(in + (((size_t)n * H + iy) * W + ix) * C + c8 * 8);
+                const float4 a = p[0], b = p[1];
+                m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+                m[4] = fmaxf(m[4], b.x); m[5] = fmaxf(m[5], b.y); m[6] = fmaxf(m[6], b.z); m[7] = fmaxf(m[7], b.w);
+            }
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) um::split2(m[2 * j], m[2 * j + 1], h[j], l[j]);
+        reinterpret_cast<uint4*>(out_hi)[e] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(out_lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// planes -> float32 NHWC (diagnostics: the per-stage parity test reads block outputs through this)
+__global__ void k_planes_to_nhwc(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int C8, int HW, int C_real,
+                                 const int* __restrict__ d_n, int off, int cap, float* __restrict__ out) {
+    const int n_crops = tc_chunk_count(d_n, off, cap);
+    const size_t total = (size_t)n_crops * C8 * HW;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(e % HW);
+        size_t r = e / HW;
+        const int c8 = (int)(r % C8);
+        const int n = (int)(r / C8);
+        const uint4 h = reinterpret_cast<const uint4*>(hi)[e], l = reinterpret_cast<const uint4*>(lo)[e];
+        const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+        float* o = out + ((size_t)n * HW + p) * C_real + c8 * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 v = um::join2(hh[j], ll[j]);
+            if (c8 * 8 + 2 * j < C_real) o[2 * j] = v.x;
+            if (c8 * 8 + 2 * j + 1 < C_real) o[2 * j + 1] = v.y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_chain_tc: one branch of an OSBlock per CTA.  grid = (row tiles, 4 branches (deepest first), crops), 256 threads.
+// Shared memory: X hi / lo planes [CP/8][NPX][8] (NPX = (R + 8) padded rows of W + 2 pixels; the TMA box of conv1's
+// output lands here with zero fill outside the image = every layer's zero padding), T [CP/4][NPXT] float4 (1x1 result),
+// two weight slots.  Per level: one thread issues 2 MMAs per 128-pixel tile and K step, all warps move the TMEM
+// accumulators into T, then column walkers (3x3 register window, as in the float32 kernels of round 1) apply the
+// depthwise taps + bias + ReLU and write the next level's X as hi / lo planes in place; the last level goes to the
+// branch-output planes in HBM and leaves per-tile channel sums for the ChannelGate.
+// ------------------------------------------------------------------------------------------------------------------
+struct ChainTcArgs {
+    CUtensorMap map_hi, map_lo;      // conv1 output planes, box (8, W + 2, R + 8, CP / 8, 1)
+    const bf16* wpw[10];             // per LightConv: [CP/8][2*CP][8]  ([W_hi | W_lo] along the output channel)
+    const float* wdw[10];            // [9][CP]   (BN folded)
+    const float* bias[10];           // [CP]
+    bf16* y_hi;                      // branch outputs [crops][4*CP/8][H][W][8]
+    bf16* y_lo;
+    float* sums[4];                  // [crops][tiles][CP]
+    int H;
+};
+
+template <int CP, int W, int R>
+struct ChainGeom {
+    static constexpr int TW = W + 2, ROWS = R + 8, NPX = ROWS * TW;
+    static constexpr int NT_MAX = (NPX + 127) / 128;
+    static constexpr int NPXT = ((NPX + 7) / 8) * 8 + 2;
+    static constexpr int X_BYTES = (CP / 8) * NPX * 16;               // one of hi / lo
+    static constexpr int T_BYTES = (CP / 4) * NPXT * 16;
+    static constexpr int WSLOT_BYTES = (CP / 8) * 2 * CP * 16 + 9 * CP * 4 + CP * 4;
+    static constexpr int TMEM_COLS = NT_MAX * 2 * CP;
+    // the last M tile may read past the planes: keep one tile of slack after X so those reads stay inside the allocation
+    static constexpr size_t SMEM = 2 * (size_t)X_BYTES + T_BYTES + 2 * WSLOT_BYTES + 128;
+};
+
+template <int CP, int CR, int W, int R>
+__global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainTcArgs a, const int* __restrict__ d_n, int off, int cap) {
+    using G = ChainGeom<CP, W, R>;
+    const int n = blockIdx.z;
+    if (n >= tc_chunk_count(d_n, off, cap)) return;
+    const int br = 3 - (int)blockIdx.y, depth = br + 1, tile = blockIdx.x;
+    const int l0 = br * (br + 1) / 2;
+    const int H = a.H;
+    constexpr int TW = G::TW, NPX = G::NPX, NPXT = G::NPXT, C8 = CP / 8, C4 = CR / 4, KS = CP / 16;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    unsigned char* sXh = smem;
+    unsigned char* sXl = sXh + G::X_BYTES;
+    float4* sT = reinterpret_cast<float4*>(sXl + G::X_BYTES);
+    unsigned char* sWs = reinterpret_cast<unsigned char*>(sT) + G::T_BYTES;
+    float* sP = reinterpret_cast<float*>(sT);                     // [256 / C4][CR] channel-sum slots (after the last level)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y0 = tile * R, g0 = y0 - 4;
+
+    auto load_weights = [&](int lv) {   // level lv (1-based) -> slot (lv & 1)
+        unsigned char* dst = sWs + (size_t)(lv & 1) * G::WSLOT_BYTES;
+        const uint4* spw = reinterpret_cast<const uint4*>(a.wpw[l0 + lv - 1]);
+        for (int e = threadIdx.x; e < C8 * 2 * CP; e += 256) reinterpret_cast<uint4*>(dst)[e] = spw[e];
+        float* dd = reinterpret_cast<float*>(dst + C8 * 2 * CP * 16);
+        const float* sdw = a.wdw[l0 + lv - 1];
+        const float* sb = a.bias[l0 + lv - 1];
+        for (int e = threadIdx.x; e < 9 * CP; e += 256) dd[e] = sdw[e];
+        for (int e = threadIdx.x; e < CP; e += 256) dd[9 * CP + e] = sb[e];
+    };
+
+    if (warp == 0) um::tmem_alloc(&tmem_slot, um::tmem_cols_pow2(G::TMEM_COLS));
+    if (threadIdx.x == 0) {
+        um::mbar_init(&bar_tma, 1);
+        um::mbar_init(&bar_mma, 1);
+        um::fence_mbar_init();
+    }
+    load_weights(1);
+    um::fence_async_smem();
+    um::tc_fence_before();
+    __syncthreads();
+    um::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        um::mbar_expect_tx(&bar_tma, 2u * G::X_BYTES);
+        um::tma_load_5d(sXh, &a.map_hi, 0, -1, g0, 0, n, &bar_tma);
+        um::tma_load_5d(sXl, &a.map_lo, 0, -1, g0, 0, n, &bar_tma);
+    }
+    um::mbar_wait(&bar_tma, 0);
+
+    constexpr int walkers = W * C4;
+    constexpr int n_grp = 256 / C4;
+    constexpr int act = n_grp * C4;
+    constexpr int n_split = (act / walkers) < 1 ? 1 : (act / walkers);
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t mma_phase = 0;
+
+    for (int lv = 1; lv <= depth; ++lv) {
+        const int ext = depth - lv;
+        const unsigned char* wslot = sWs + (size_t)(lv & 1) * G::WSLOT_BYTES;
+        const int la = 4 - ext, lb = 4 + R + ext;              // local rows the depthwise stage produces
+        const int pa = (la - 1) * TW, pb = (lb + 1) * TW;      // pixels whose 1x1 result it reads
+        const int t0 = pa >> 7, t1 = (pb + 127) >> 7;
+        if (threadIdx.x == 0) {
+            const uint32_t id2 = um::idesc_bf16(128, 2 * CP), id1 = um::idesc_bf16(128, CP);
+            const uint32_t lbo_a = (uint32_t)NPX * 16u, lbo_b = 2u * CP * 16u;
+            const uint32_t xh = um::smem_u32(sXh), xl = um::smem_u32(sXl), wb = um::smem_u32(wslot);
+            for (int t = t0; t < t1; ++t)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    um::mma_bf16(tmem + (uint32_t)((t - t0) * 2 * CP), um::make_desc(xh + (uint32_t)t * 2048u + ks * 2 * lbo_a, lbo_a, 128),
+                                 um::make_desc(wb + ks * 2 * lbo_b, lbo_b, 128), id2, ks > 0);
+            for (int t = t0; t < t1; ++t)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                    um::mma_bf16(tmem + (uint32_t)((t - t0) * 2 * CP), um::make_desc(xl + (uint32_t)t * 2048u + ks * 2 * lbo_a, lbo_a, 128),
+                                 um::make_desc(wb + ks * 2 * lbo_b, lbo_b, 128), id1, 1);
+            um::mma_commit(&bar_mma);
+        }
+        if (lv < depth) load_weights(lv + 1);                  // overlaps the MMAs; published by the fence at the end of the level
+        um::mbar_wait(&bar_mma, mma_phase);
+        mma_phase ^= 1u;
+        um::tc_fence_after();
+        // ---- TMEM -> T: warp = (lane quadrant, tile parity); T = (A_hi W_hi + A_lo W_hi) + A_hi W_lo ----
+        {
+            const int q = warp & 3;
+            for (int slot = warp >> 2; slot < t1 - t0; slot += 2) {
+                const int p = (t0 + slot) * 128 + q * 32 + lane;
+#pragma unroll
+                for (int c0 = 0; c0 < CP; c0 += 16) {
+                    uint32_t v1[16], v2[16];
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 2 * CP + c0);
+                    um::tmem_ld16(ta, v1);
+                    um::tmem_ld16(ta + CP, v2);
+                    um::tmem_ld_wait();
+                    if (p < NPX) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            sT[(c0 / 4 + j) * NPXT + p] =
+                                make_float4(__uint_as_float(v1[4 * j]) + __uint_as_float(v2[4 * j]),
+                                            __uint_as_float(v1[4 * j + 1]) + __uint_as_float(v2[4 * j + 1]),
+                                            __uint_as_float(v1[4 * j + 2]) + __uint_as_float(v2[4 * j + 2]),
+                                            __uint_as_float(v1[4 * j + 3]) + __uint_as_float(v2[4 * j + 3]));
+                    }
+                }
+            }
+        }
+        um::tc_fence_before();
+        __syncthreads();
+        // ---- depthwise 3x3 + bias + ReLU on image rows [ya, yb): next level's X (planes, in place) or the branch output ----
+        const bool last = lv == depth;
+        const int ya = max(y0 - ext, 0), yb = min(y0 + R + ext, H);
+        const int rows_lv = yb - ya;
+        const int rows_per = (rows_lv + n_split - 1) / n_split;
+        const float* sD = reinterpret_cast<const float*>(wslot + C8 * 2 * CP * 16);
+        const float* sB = sD + 9 * CP;
+        if (threadIdx.x < act) {
+            for (int wk = threadIdx.x; wk < walkers * n_split; wk += act) {
+                const int c4 = wk % C4, x = (wk / C4) % W, sp = wk / walkers;
+                const int ra = ya + sp * rows_per, rb = min(ra + rows_per, yb);
+                if (ra >= rb) continue;
+                float4 wv[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const float4*>(sD + t * CP + c4 * 4);
+                const float4 bv = *reinterpret_cast<const float4*>(sB + c4 * 4);
+                const float4* tbase = sT + c4 * NPXT + x;              // column x-1 of the padded row
+                float4 win[3][3];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    win[0][kx] = tbase[(ra - 1 - g0) * TW + kx];
+                    win[1][kx] = tbase[(ra - g0) * TW + kx];
+                }
+                for (int y = ra; y < rb; y += 3) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        if (y + u < rb) {
+                            const int i0 = u % 3, i1 = (u + 1) % 3, i2 = (u + 2) % 3;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) win[i2][kx] = tbase[(y + u + 1 - g0) * TW + kx];
+                            float4 acc = bv;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 w0 = wv[kx], w1 = wv[3 + kx], w2 = wv[6 + kx];
+                                const float4 q0 = win[i0][kx], q1 = win[i1][kx], q2 = win[i2][kx];
+                                acc.x = fmaf(q0.x, w0.x, acc.x); acc.y = fmaf(q0.y, w0.y, acc.y);
+                                acc.z = fmaf(q0.z, w0.z, acc.z); acc.w = fmaf(q0.w, w0.w, acc.w);
+                                acc.x = fmaf(q1.x, w1.x, acc.x); acc.y = fmaf(q1.y, w1.y, acc.y);
+                                acc.z = fmaf(q1.z, w1.z, acc.z); acc.w = fmaf(q1.w, w1.w, acc.w);
+                                acc.x = fmaf(q2.x, w2.x, acc.x); acc.y = fmaf(q2.y, w2.y, acc.y);
+                                acc.z = fmaf(q2.z, w2.z, acc.z); acc.w = fmaf(q2.w, w2.w, acc.w);
+                            }
+                            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+                            acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                            uint32_t h0, h1, e0, e1;
+                            um::split2(acc.x, acc.y, h0, e0);
+                            um::split2(acc.z, acc.w, h1, e1);
+                            if (last) {
+                                const size_t o = ((((size_t)n * (4 * C8) + br * C8 + (c4 >> 1)) * H + (y + u)) * W + x) * 8 + (c4 & 1) * 4;
+                                *reinterpret_cast<uint2*>(a.y_hi + o) = make_uint2(h0, h1);
+                                *reinterpret_cast<uint2*>(a.y_lo + o) = make_uint2(e0, e1);
+                                psum.x += acc.x; psum.y += acc.y; psum.z += acc.z; psum.w += acc.w;
+                            } else {
+                                const int po = ((c4 >> 1) * NPX + (y + u - g0) * TW + x + 1) * 16 + (c4 & 1) * 8;
+                                *reinterpret_cast<uint2*>(sXh + po) = make_uint2(h0, h1);
+                                *reinterpret_cast<uint2*>(sXl + po) = make_uint2(e0, e1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (last && CP > CR) {
+            // padded channels of the branch output are defined zeros (the gate-folded conv3 rows they meet are zero,
+            // but stale bits could be NaN patterns)
+            constexpr int PP = (CP - CR) / 8;
+            static_assert((CP - CR) % 8 == 0, "channel padding must be whole planes");
+            for (int e = threadIdx.x; e < PP * rows_lv * W; e += 256) {
+                const int pl = e / (rows_lv * W), r = e - pl * (rows_lv * W);
+                const size_t o = (((size_t)n * (4 * C8) + br * C8 + CR / 8 + pl) * H + ya) * W + r;
+                reinterpret_cast<uint4*>(a.y_hi)[o] = make_uint4(0u, 0u, 0u, 0u);
+                reinterpret_cast<uint4*>(a.y_lo)[o] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        um::fence_async_smem();
+        um::tc_fence_before();
+        __syncthreads();
+        um::tc_fence_after();
+    }
+    // per-tile channel sums of the branch output (fixed slot per thread, fixed combination order)
+    if (threadIdx.x < act)
+        *reinterpret_cast<float4*>(sP + (threadIdx.x / C4) * CR + (threadIdx.x % C4) * 4) = psum;
+    __syncthreads();
+    for (int c = threadIdx.x; c < CP; c += 256) {
+        float s = 0.f;
+        if (c < CR)
+            for (int g = 0; g < n_grp; ++g) s += sP[g * CR + c];
+        a.sums[br][((size_t)n * gridDim.x + tile) * CP + c] = s;
+    }
+    um::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) um::tmem_dealloc(tmem, um::tmem_cols_pow2(G::TMEM_COLS));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_gemm_tc: out[p][n] = act( sum_src sum_k A_src[p][k] * B[k][n] + bias[n] ) over 128-pixel tiles of a crop.
+// grid = (tile groups, crops), 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
+// warps 2..9 = epilogue (lane quadrant = warp % 4, column half = (warp - 2) / 4).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GEMM_THREADS = 320;
+constexpr int RING_SLOT_BYTES = 2 * 8 * 128 * 16;     // 8 planes x 128 pixels x 16 B, hi then lo
+
+struct GemmTcArgs {
+    CUtensorMap map_hi[2], map_lo[2];   // A sources: box (8, W, 128 / W, kc, 1)
+    int src_planes[2];                  // planes (K / 8) per source
+    int src_kc[2];                      // planes per ring chunk (2, 4 or 8) = the box's plane extent
+    int n_src;
+    int rows_per_tile;                  // 128 / W
+    int tiles_per_crop, tiles_per_cta;
+    int n_stage;                        // ring depth
+    // B: rows [0, gate_rows) are built in the kernel as  gate[b][c] * w3[c][n]  (row = b * midp + c), the rest is copied
+    const bf16* b_packed;               // [K8][2*NP][8] packed [hi | lo]; rows below gate_rows are ignored
+    int K8;                             // total planes of K
+    int N, NP;                          // real / padded (multiple of 16) output channels
+    const float* bias;                  // [NP]
+    int relu;
+    // gate (osnet.py:161-210) folded into conv3:  mean -> fc1 -> ReLU -> fc2 -> sigmoid per branch
+    const float* w3;                    // [mid][N] float32 (null: no gate)
+    const float* sums[4];               // [crops][gate_tiles][midp]
+    const float* g1w; const float* g1b; const float* g2w; const float* g2b;
+    int mid, midp, hid, gate_tiles, HW;
+    // outputs
+    bf16* out_hi; bf16* out_lo;         // planes [crops][NP/8][H][W][8] (or pooled [..][H/2][W/2][8]); may be null
+    float* out_f32;                     // [crops][HW][N] float32 NHWC copy (may be null)
+    int pool;                           // 1: 2x2 average pool in the epilogue (W = tile width)
+    int W;
+    // second GEMM on the fresh output tile: out2 = relu(out * B2 + bias2)
+    const bf16* b2_packed;              // [NP/8][2*NP2][8] (null: none)
+    const float* bias2;
+    int N2, NP2;
+    bf16* out2_hi; bf16* out2_lo;
+};
+
+struct GemmSmem {
+    size_t b, b2, ring, a2, f, gate, total;
+};
+inline GemmSmem gemm_smem_layout(int K8, int NP, int NP2, int n_stage, bool tail, bool pool) {
+    GemmSmem s{};
+    size_t o = 0;
+    s.b = o; o += (size_t)K8 * 2 * NP * 16;
+    s.b2 = o; if (tail) o += (size_t)(NP / 8) * 2 * NP2 * 16;
+    o = (o + 127) & ~(size_t)127;
+    s.ring = o; o += (size_t)n_stage * RING_SLOT_BYTES;
+    s.a2 = o; if (tail) o += (size_t)2 * (NP / 8) * 128 * 16;
+    s.f = o; if (pool) o += (size_t)128 * (NP + 4) * 4;
+    s.gate = o; o += 4 * 32 * 4 * 2 + 64;
+    s.total = o + 128;
+    return s;
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_constant__ GemmTcArgs a, const int* __restrict__ d_n, int off, int cap,
+                                                            const GemmSmem L) {
+    const int n = blockIdx.y;
+    if (n >= tc_chunk_count(d_n, off, cap)) return;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full, bar_acc_empty, bar_a2_full, bar_acc2_full, bar_b_ready;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NP = a.NP, NP2 = a.NP2;
+    const bool tail = a.b2_packed != nullptr;
+    const int tile0 = blockIdx.x * a.tiles_per_cta;
+    const int tile1 = min(tile0 + a.tiles_per_cta, a.tiles_per_crop);
+    unsigned char* sB = smem + L.b;
+    unsigned char* sB2 = smem + L.b2;
+    unsigned char* sRing = smem + L.ring;
+    unsigned char* sA2 = smem + L.a2;
+    float* sF = reinterpret_cast<float*>(smem + L.f);
+    float* sGate = reinterpret_cast<float*>(smem + L.gate);      // [4][32] gates, then [4][32] means
+    const uint32_t acc_cols = 2u * NP, acc2_cols = tail ? 2u * NP2 : 0u;
+    const uint32_t tmem_cols = um::tmem_cols_pow2(acc_cols + acc2_cols);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.n_stage; ++i) { um::mbar_init(&bar_full[i], 1); um::mbar_init(&bar_empty[i], 1); }
+        um::mbar_init(&bar_acc_full, 1);
+        um::mbar_init(&bar_acc_empty, 256);
+        um::mbar_init(&bar_a2_full, 256);
+        um::mbar_init(&bar_acc2_full, 1);
+        um::mbar_init(&bar_b_ready, 256);
+        um::fence_mbar_init();
+    }
+    if (warp == 1) um::tmem_alloc(&tmem_slot, tmem_cols);
+    um::tc_fence_before();
+    __syncthreads();
+    um::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    // chunk table of one tile: (source, first plane, planes)
+    int n_chunks = 0;
+    for (int s = 0; s < a.n_src; ++s) n_chunks += a.src_planes[s] / a.src_kc[s];
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = tile0; tile < tile1; ++tile) {
+                for (int s = 0; s < a.n_src; ++s) {
+                    const int kc = a.src_kc[s];
+                    for (int p0 = 0; p0 < a.src_planes[s]; p0 += kc, ++it) {
+                        const uint32_t slot = it % (uint32_t)a.n_stage, ph = (it / (uint32_t)a.n_stage) & 1u;
+                        um::mbar_wait(&bar_empty[slot], ph ^ 1u);
+                        unsigned char* dst = sRing + (size_t)slot * RING_SLOT_BYTES;
+                        um::mbar_expect_tx(&bar_full[slot], (uint32_t)kc * 128u * 16u * 2u);
+                        um::tma_load_5d(dst, &a.map_hi[s], 0, 0, tile * a.rows_per_tile, p0, n, &bar_full[slot]);
+                        um::tma_load_5d(dst + RING_SLOT_BYTES / 2, &a.map_lo[s], 0, 0, tile * a.rows_per_tile, p0, n, &bar_full[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t id2 = um::idesc_bf16(128, 2 * NP), id1 = um::idesc_bf16(128, NP);
+            const uint32_t lbo_b = 2u * NP * 16u;
+            um::mbar_wait(&bar_b_ready, 0);
+            um::tc_fence_after();
+            uint32_t it = 0, ti = 0;
+            for (int tile = tile0; tile < tile1; ++tile, ++ti) {
+                um::mbar_wait(&bar_acc_empty, (ti & 1u) ^ 1u);
+                um::tc_fence_after();
+                uint32_t kplane = 0, first = 1;
+                for (int s = 0; s < a.n_src; ++s) {
+                    const int kc = a.src_kc[s];
+                    for (int p0 = 0; p0 < a.src_planes[s]; p0 += kc, ++it) {
+                        const uint32_t slot = it % (uint32_t)a.n_stage, ph = (it / (uint32_t)a.n_stage) & 1u;
+                        um::mbar_wait(&bar_full[slot], ph);
+                        um::tc_fence_after();
+                        const uint32_t ah = um::smem_u32(sRing + (size_t)slot * RING_SLOT_BYTES), al = ah + RING_SLOT_BYTES / 2;
+                        for (int ks = 0; ks < kc / 2; ++ks) {
+                            const uint64_t db = um::make_desc(um::smem_u32(sB) + (kplane + 2 * ks) * lbo_b, lbo_b, 128);
+                            um::mma_bf16(tmem, um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), db, id2, first ? 0u : 1u);
+                            um::mma_bf16(tmem, um::make_desc(al + ks * 2 * 2048u, 2048u, 128), db, id1, 1u);
+                            first = 0;
+                        }
+                        kplane += kc;
+                        um::mma_commit(&bar_empty[slot]);
+                    }
+                }
+                um::mma_commit(&bar_acc_full);
+                if (tail) {
+                    const uint32_t jd2 = um::idesc_bf16(128, 2 * NP2), jd1 = um::idesc_bf16(128, NP2);
+                    const uint32_t lbo_b2 = 2u * NP2 * 16u;
+                    um::mbar_wait(&bar_a2_full, ti & 1u);
+                    um::tc_fence_after();
+                    const uint32_t ah = um::smem_u32(sA2), al = ah + (uint32_t)(NP / 8) * 2048u;
+                    for (int ks = 0; ks < NP / 16; ++ks) {
+                        const uint64_t db = um::make_desc(um::smem_u32(sB2) + ks * 2 * lbo_b2, lbo_b2, 128);
+                        um::mma_bf16(tmem + acc_cols, um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), db, jd2, ks > 0);
+                        um::mma_bf16(tmem + acc_cols, um::make_desc(al + ks * 2 * 2048u, 2048u, 128), db, jd1, 1u);
+                    }
+                    um::mma_commit(&bar_acc2_full);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int et = threadIdx.x - 64;                       // 0..255
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int m = q * 32 + lane;                           // pixel of the tile = TMEM lane
+        // ---- B: gate-folded conv3 rows, then the packed rows; tail weights ----
+        int gate_rows = 0;
+        if (a.w3) {
+            const int mid = a.mid, midp = a.midp;
+            gate_rows = 4 * midp;
+            float* gate = sGate;
+            float* mean = sGate + 128;
+            float* hid = sGate + 256;
+            for (int e = et; e < 4 * midp; e += 256) {
+                const int b = e / midp, c = e - b * midp;
+                float s = 0.f;
+                if (c < mid)
+                    for (int t = 0; t < a.gate_tiles; ++t) s += a.sums[b][((size_t)n * a.gate_tiles + t) * midp + c];
+                mean[e] = s / (float)a.HW;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int e = et; e < 4 * a.hid; e += 256) {
+                const int b = e / a.hid, h = e - b * a.hid;
+                float s = a.g1b[h];
+                for (int c = 0; c < mid; ++c) s = fmaf(mean[b * midp + c], a.g1w[(size_t)c * a.hid + h], s);
+                hid[e] = fmaxf(s, 0.f);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int e = et; e < 4 * midp; e += 256) {
+                const int b = e / midp, c = e - b * midp;
+                float g = 0.f;
+                if (c < mid) {
+                    float s = a.g2b[c];
+                    for (int h = 0; h < a.hid; ++h) s = fmaf(hid[b * a.hid + h], a.g2w[(size_t)h * mid + c], s);
+                    g = 1.0f / (1.0f + expf(-s));
+                }
+                gate[e] = g;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // rows k = b * midp + c: an item is (k pair-of-8 plane, n pair): 8 k values x 2 n per thread step
+            const int items = (gate_rows / 8) * (NP / 2);
+            for (int e = et; e < items; e += 256) {
+                const int k8 = e / (NP / 2), n2 = (e - k8 * (NP / 2)) * 2;
+                uint32_t h0[4], l0[4], h1[4], l1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;   // (k, n), (k+1, n), (k, n+1), (k+1, n+1)
+                    const int k = k8 * 8 + 2 * j;
+                    const int b = k / midp, c = k - b * midp;            // midp is even: k and k+1 share the branch
+                    if (c < mid && n2 < a.N) {
+                        v00 = gate[k] * a.w3[(size_t)c * a.N + n2];
+                        if (n2 + 1 < a.N) v10 = gate[k] * a.w3[(size_t)c * a.N + n2 + 1];
+                    }
+                    if (c + 1 < mid && n2 < a.N) {
+                        v01 = gate[k + 1] * a.w3[(size_t)(c + 1) * a.N + n2];
+                        if (n2 + 1 < a.N) v11 = gate[k + 1] * a.w3[(size_t)(c + 1) * a.N + n2 + 1];
+                    }
+                    um::split2(v00, v01, h0[j], l0[j]);
+                    um::split2(v10, v11, h1[j], l1[j]);
+                }
+                unsigned char* row = sB + ((size_t)k8 * 2 * NP) * 16;
+                *reinterpret_cast<uint4*>(row + (size_t)n2 * 16) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+                *reinterpret_cast<uint4*>(row + (size_t)(n2 + 1) * 16) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                *reinterpret_cast<uint4*>(row + (size_t)(NP + n2) * 16) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+                *reinterpret_cast<uint4*>(row + (size_t)(NP + n2 + 1) * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+            }
+        }
+        {
+            const int first16 = (gate_rows / 8) * 2 * NP, total16 = a.K8 * 2 * NP;
+            const uint4* src = reinterpret_cast<const uint4*>(a.b_packed);
+            for (int e = first16 + et; e < total16; e += 256) reinterpret_cast<uint4*>(sB)[e] = src[e];
+            if (tail) {
+                const uint4* s2 = reinterpret_cast<const uint4*>(a.b2_packed);
+                for (int e = et; e < (NP / 8) * 2 * NP2; e += 256) reinterpret_cast<uint4*>(sB2)[e] = s2[e];
+            }
+        }
+        um::fence_async_smem();
+        mbar_arrive(&bar_b_ready);
+
+        const int cw = NP / 2;                                  // columns this warp owns: [half * cw, half * cw + cw)
+        uint32_t ti = 0;
+        for (int tile = tile0; tile < tile1; ++tile, ++ti) {
+            um::mbar_wait(&bar_acc_full, ti & 1u);
+            um::tc_fence_after();
+            const int px = tile * 128 + m;                      // pixel of the crop
+            for (int c0 = half * cw; c0 < half * cw + cw; c0 += 8) {
+                uint32_t v1[8], v2[8];
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                um::tmem_ld8(ta, v1);
+                um::tmem_ld8(ta + NP, v2);
+                um::tmem_ld_wait();
+                const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c0), b1 = *reinterpret_cast<const float4*>(a.bias + c0 + 4);
+                float o[8];
+                o[0] = __uint_as_float(v1[0]) + __uint_as_float(v2[0]) + b0.x; o[1] = __uint_as_float(v1[1]) + __uint_as_float(v2[1]) + b0.y;
+                o[2] = __uint_as_float(v1[2]) + __uint_as_float(v2[2]) + b0.z; o[3] = __uint_as_float(v1[3]) + __uint_as_float(v2[3]) + b0.w;
+                o[4] = __uint_as_float(v1[4]) + __uint_as_float(v2[4]) + b1.x; o[5] = __uint_as_float(v1[5]) + __uint_as_float(v2[5]) + b1.y;
+                o[6] = __uint_as_float(v1[6]) + __uint_as_float(v2[6]) + b1.z; o[7] = __uint_as_float(v1[7]) + __uint_as_float(v2[7]) + b1.w;
+                if (a.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+                }
+                if (a.out_f32) {
+                    float* dst = a.out_f32 + ((size_t)n * a.HW + px) * a.N + c0;
+                    if (c0 + 8 <= a.N) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    } else {
+                        for (int j = 0; j < 8; ++j)
+                            if (c0 + j < a.N) dst[j] = o[j];
+                    }
+                }
+                if (a.pool) {
+                    float* f = sF + (size_t)m * (NP + 4) + c0;
+                    *reinterpret_cast<float4*>(f) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(f + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                } else if (a.out_hi || tail) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) um::split2(o[2 * j], o[2 * j + 1], h[j], l[j]);
+                    const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+                    if (a.out_hi) {
+                        const size_t e = ((size_t)n * (NP / 8) + c0 / 8) * a.HW + px;
+                        reinterpret_cast<uint4*>(a.out_hi)[e] = hv;
+                        reinterpret_cast<uint4*>(a.out_lo)[e] = lv;
+                    }
+                    if (tail) {
+                        *reinterpret_cast<uint4*>(sA2 + ((size_t)(c0 / 8) * 128 + m) * 16) = hv;
+                        *reinterpret_cast<uint4*>(sA2 + ((size_t)(NP / 8 + c0 / 8) * 128 + m) * 16) = lv;
+                    }
+                }
+            }
+            um::tc_fence_before();
+            mbar_arrive(&bar_acc_empty);
+            if (a.pool) {
+                // 2x2 average pool of the tile (rows_per_tile x W) -> (rows/2 x W/2), same operation order as the
+                // float32 kernel of round 1: (a + b + c + d) * 0.25 with a=(y,x) b=(y,x+1) c=(y+1,x) d=(y+1,x+1)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int Wt = a.W, OW = Wt / 2, OHt = a.rows_per_tile / 2;
+                const int items = OHt * OW * (NP / 8);
+                const int OHW = a.HW / 4;
+                for (int e = et; e < items; e += 256) {
+                    const int pp = e % (OHt * OW), c8 = e / (OHt * OW);
+                    const int oy = pp / OW, ox = pp - oy * OW;
+                    const float* f0 = sF + (size_t)((2 * oy) * Wt + 2 * ox) * (NP + 4) + c8 * 8;
+                    const float* f1 = f0 + (NP + 4);
+                    const float* f2 = f0 + (size_t)Wt * (NP + 4);
+                    const float* f3 = f2 + (NP + 4);
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x0 = (f0[2 * j] + f1[2 * j] + f2[2 * j] + f3[2 * j]) * 0.25f;
+                        const float x1 = (f0[2 * j + 1] + f1[2 * j + 1] + f2[2 * j + 1] + f3[2 * j + 1]) * 0.25f;
+                        um::split2(x0, x1, h[j], l[j]);
+                    }
+                    const int opx = (tile * OHt + oy) * OW + ox;
+                    const size_t o = ((size_t)n * (NP / 8) + c8) * OHW + opx;
+                    reinterpret_cast<uint4*>(a.out_hi)[o] = make_uint4(h[0], h[1], h[2], h[3]);
+                    reinterpret_cast<uint4*>(a.out_lo)[o] = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // sF is rewritten by the next tile
+            }
+            if (tail) {
+                um::fence_async_smem();
+                mbar_arrive(&bar_a2_full);
+                um::mbar_wait(&bar_acc2_full, ti & 1u);
+                um::tc_fence_after();
+                const int cw2 = NP2 / 2;
+                for (int c0 = half * cw2; c0 < half * cw2 + cw2; c0 += 8) {
+                    uint32_t v1[8], v2[8];
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)c0;
+                    um::tmem_ld8(ta, v1);
+                    um::tmem_ld8(ta + NP2, v2);
+                    um::tmem_ld_wait();
+                    const float4 b0 = *reinterpret_cast<const float4*>(a.bias2 + c0), b1 = *reinterpret_cast<const float4*>(a.bias2 + c0 + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bb[j], 0.f);
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) um::split2(o[2 * j], o[2 * j + 1], h[j], l[j]);
+                    const size_t e = ((size_t)n * (NP2 / 8) + c0 / 8) * a.HW + px;
+                    reinterpret_cast<uint4*>(a.out2_hi)[e] = make_uint4(h[0], h[1], h[2], h[3]);
+                    reinterpret_cast<uint4*>(a.out2_lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+                um::tc_fence_before();
+            }
+        }
+    }
+    um::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) um::tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace tcx
+}  // namespace bmb

@@ -1,0 +1,285 @@
+// reid_tc_plan.cuh -- builds and replays the launch plan of the tensor-core OSNet path (included at the end of
+// reid_model.cu; needs ReidModel / BlockW).  Network graph: reid/backbones/osnet.py:380-405, blocks :212-260.
+#pragma once
+
+namespace bmb {
+namespace tcx {
+
+// stage geometry of the chain kernel instances (osnet_x0_25: mid 16 / 24 / 32 at 64x32 / 32x16 / 16x8)
+struct ChainShape { int CP, CR, W, H, R, kind; };
+static const ChainShape kChainShapes[3] = {{16, 16, 32, 64, 16, LK_CHAIN_S2}, {32, 24, 16, 32, 8, LK_CHAIN_S3}, {32, 32, 8, 16, 16, LK_CHAIN_S4}};
+
+inline bool plan_supported(const ReidModel* m) {
+    return m->arch == 1 && m->c[0] == 16 && m->c[1] == 64 && m->c[2] == 96 && m->c[3] == 128;
+}
+
+Plan* plan_build(ReidModel* m, const float* hw) {
+    Plan* P = new Plan();
+    try {
+        P->chunk = m->chunk;
+        const size_t CH = (size_t)m->chunk;
+        int dev = 0;
+        RCUDA_OK(cudaGetDevice(&dev));
+        RCUDA_OK(cudaDeviceGetAttribute(&P->smem_limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        P->smem_limit -= 1024;   // static shared memory (barriers) comes out of the same budget
+        // ---- workspace: split planes (hi, lo), sized for the widest use of each buffer ----
+        alloc_planes(P->P, CH * 2048 * 16);
+        alloc_planes(P->X1, CH * 2048 * 16);
+        alloc_planes(P->Y, CH * 2048 * 64);
+        alloc_planes(P->XA, CH * 2048 * 64);
+        alloc_planes(P->XB, CH * 2048 * 64);
+        RCUDA_OK(cudaMalloc(&P->c5, sizeof(float) * CH * 128 * m->c[3]));
+        for (int b = 0; b < 4; ++b) RCUDA_OK(cudaMalloc(&P->sums[b], sizeof(float) * CH * 8 * 32));
+        RCUDA_OK(cudaMalloc(&P->dbg, sizeof(float) * CH * 2048 * 64));
+
+        // ---- weights ----
+        std::vector<uint16_t> wb;
+        std::vector<float> wf;
+        struct BlkOff { size_t pw[10], dw[10], lb[10], c1, c1b, cx, cxb; } bo[6];
+        for (int bi = 0; bi < 6; ++bi) {
+            const BlockW& b = m->blocks[bi];
+            const int midp = pad16(b.mid);
+            for (int l = 0; l < 10; ++l) {
+                bo[bi].pw[l] = pack_b(wb, hw + b.light[l].pw, b.mid, b.mid, b.mid, midp / 8, midp);
+                // depthwise taps [9][mid] -> [9][midp]
+                size_t at = (wf.size() + 3) / 4 * 4;
+                wf.resize(at + 9 * midp, 0.f);
+                for (int t = 0; t < 9; ++t)
+                    for (int c = 0; c < b.mid; ++c) wf[at + t * midp + c] = hw[b.light[l].dw + (size_t)t * b.mid + c];
+                bo[bi].dw[l] = at;
+                bo[bi].lb[l] = pack_f(wf, hw + b.light[l].b, b.mid, midp);
+            }
+            bo[bi].c1 = pack_b(wb, hw + b.c1w, b.cin, b.mid, b.mid, b.cin / 8, midp);
+            bo[bi].c1b = pack_f(wf, hw + b.c1b, b.mid, midp);
+            // combine: K rows = [4 * midp gate-folded conv3 rows (built in the kernel)] ++ [cin rows: downsample or identity]
+            const int K8 = 4 * midp / 8 + b.cin / 8;
+            if (b.has_ds)
+                bo[bi].cx = pack_b(wb, hw + b.cw + (size_t)b.mid * b.cout, b.cin, b.cout, b.cout, K8, b.cout, 4 * midp);
+            else
+                bo[bi].cx = pack_b(wb, nullptr, b.cin, b.cout, b.cout, K8, b.cout, 4 * midp, true);
+            bo[bi].cxb = pack_f(wf, hw + b.cb, b.cout, b.cout);
+        }
+        size_t tr[2], trb[2];
+        for (int s = 0; s < 2; ++s) {
+            const int C = m->c[s + 1];
+            tr[s] = pack_b(wb, hw + m->trans_w[s], C, C, C, C / 8, C);
+            trb[s] = pack_f(wf, hw + m->trans_b[s], C, C);
+        }
+        const size_t c5 = pack_b(wb, hw + m->c5w, m->c[3], m->c[3], m->c[3], m->c[3] / 8, m->c[3]);
+        const size_t c5b = pack_f(wf, hw + m->c5b, m->c[3], m->c[3]);
+        RCUDA_OK(cudaMalloc(&P->d_wb, wb.size() * 2 + 256));
+        RCUDA_OK(cudaMemcpy(P->d_wb, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+        RCUDA_OK(cudaMalloc(&P->d_wf, wf.size() * 4 + 256));
+        RCUDA_OK(cudaMemcpy(P->d_wf, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice));
+        const bf16* WB = P->d_wb;
+        const float* WF = P->d_wf;
+        const float* W32 = m->d_w;
+
+        // ---- kernel attributes ----
+        RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<16, 16, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<16, 32, 16>::SMEM));
+        RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<32, 24, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<32, 16, 8>::SMEM));
+        RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<32, 32, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<32, 8, 16>::SMEM));
+        RCUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, P->smem_limit));
+
+        // ---- launches ----
+        struct Src { Planes* buf; int C8; };
+        auto gemm = [&](int H, int Wd, std::vector<Src> srcs, size_t b_off, int N, size_t bias_off, bool relu) -> Launch {
+            Launch L{};
+            L.kind = LK_GEMM;
+            L.cls = CLS_POINTWISE;
+            GemmTcArgs& g = L.gemm;
+            g.n_src = (int)srcs.size();
+            g.rows_per_tile = 128 / Wd;
+            g.tiles_per_crop = H * Wd / 128;
+            g.tiles_per_cta = g.tiles_per_crop >= 16 ? 4 : (g.tiles_per_crop >= 4 ? 2 : 1);
+            g.K8 = 0;
+            for (int s = 0; s < g.n_src; ++s) {
+                const int C8 = srcs[s].C8;
+                const int kc = C8 % 8 == 0 ? 8 : (C8 % 4 == 0 ? 4 : 2);
+                g.src_planes[s] = C8;
+                g.src_kc[s] = kc;
+                g.K8 += C8;
+                make_act_map(&g.map_hi[s], srcs[s].buf->hi, P->chunk, C8, H, Wd, Wd, 128 / Wd, kc);
+                make_act_map(&g.map_lo[s], srcs[s].buf->lo, P->chunk, C8, H, Wd, Wd, 128 / Wd, kc);
+            }
+            g.b_packed = WB + b_off;
+            g.N = N;
+            g.NP = pad16(N);
+            g.bias = WF + bias_off;
+            g.relu = relu ? 1 : 0;
+            g.HW = H * Wd;
+            g.W = Wd;
+            return L;
+        };
+        auto finish = [&](Launch& L) {
+            GemmTcArgs& g = L.gemm;
+            const bool tail = g.b2_packed != nullptr;
+            int ns = 4;
+            for (; ns >= 2; --ns) {
+                L.gl = gemm_smem_layout(g.K8, g.NP, g.NP2, ns, tail, g.pool != 0);
+                if ((int)L.gl.total <= P->smem_limit) break;
+            }
+            if (ns < 2) throw std::runtime_error("tensor-core GEMM does not fit shared memory");
+            if (2 * g.NP + (tail ? 2 * g.NP2 : 0) > 512) throw std::runtime_error("tensor-core GEMM does not fit TMEM");
+            g.n_stage = ns;
+            L.gemm_groups = (g.tiles_per_crop + g.tiles_per_cta - 1) / g.tiles_per_cta;
+            P->launches.push_back(L);
+        };
+        auto dbg = [&](Launch& L, int stage, const Planes& buf, int C8, int HW, int C) {
+            L.stage_after = stage;
+            L.dbg_hi = buf.hi; L.dbg_lo = buf.lo; L.dbg_C8 = C8; L.dbg_HW = HW; L.dbg_C = C;
+        };
+
+        {   // stem output (float32 NHWC in bufA) -> 3x3/2 max pool -> planes P
+            Launch L{};
+            L.kind = LK_MAXPOOL_PLANES;
+            L.cls = CLS_MAXPOOL;
+            dbg(L, 2, P->P, 2, 2048, 16);
+            P->launches.push_back(L);
+        }
+        Planes* X = &P->P;          // block input
+        Planes* Xo = &P->XA;
+        Planes* Xspare = &P->XB;
+        int xC8 = 2;
+        int H = 64, Wd = 32;
+        int stage = 3;
+        {   // conv1 of the first block
+            const BlockW& b = m->blocks[0];
+            Launch L = gemm(H, Wd, {{X, xC8}}, bo[0].c1, b.mid, bo[0].c1b, true);
+            L.gemm.out_hi = P->X1.hi; L.gemm.out_lo = P->X1.lo;
+            dbg(L, 100, P->X1, pad16(b.mid) / 8, H * Wd, pad16(b.mid));
+            finish(L);
+        }
+        for (int s = 0; s < 3; ++s) {
+            const ChainShape& cs = kChainShapes[s];
+            for (int j = 0; j < 2; ++j) {
+                const int bi = s * 2 + j;
+                const BlockW& b = m->blocks[bi];
+                const int midp = pad16(b.mid);
+                {   // the four LightConv branches
+                    Launch L{};
+                    L.kind = cs.kind;
+                    L.cls = CLS_LIGHTCONV;
+                    ChainTcArgs& c = L.chain;
+                    make_act_map(&c.map_hi, P->X1.hi, P->chunk, midp / 8, H, Wd, Wd + 2, cs.R + 8, midp / 8);
+                    make_act_map(&c.map_lo, P->X1.lo, P->chunk, midp / 8, H, Wd, Wd + 2, cs.R + 8, midp / 8);
+                    for (int l = 0; l < 10; ++l) {
+                        c.wpw[l] = WB + bo[bi].pw[l];
+                        c.wdw[l] = WF + bo[bi].dw[l];
+                        c.bias[l] = WF + bo[bi].lb[l];
+                    }
+                    c.y_hi = P->Y.hi; c.y_lo = P->Y.lo;
+                    for (int br = 0; br < 4; ++br) c.sums[br] = P->sums[br];
+                    c.H = H;
+                    L.chain_tiles = H / cs.R;
+                    dbg(L, 200 + bi, P->Y, 4 * midp / 8, H * Wd, 4 * midp);
+                    P->launches.push_back(L);
+                }
+                {   // gate + conv3 (+ downsample / identity) + ReLU, and the next block's conv1 on the fresh tile
+                    Launch L = gemm(H, Wd, {{&P->Y, 4 * midp / 8}, {X, xC8}}, bo[bi].cx, b.cout, bo[bi].cxb, true);
+                    GemmTcArgs& g = L.gemm;
+                    g.w3 = W32 + b.cw;
+                    for (int br = 0; br < 4; ++br) g.sums[br] = P->sums[br];
+                    g.g1w = W32 + b.g1w; g.g1b = W32 + b.g1b; g.g2w = W32 + b.g2w; g.g2b = W32 + b.g2b;
+                    g.mid = b.mid; g.midp = midp; g.hid = b.hid; g.gate_tiles = H / cs.R;
+                    g.out_hi = Xo->hi; g.out_lo = Xo->lo;
+                    if (j == 0) {
+                        const BlockW& nb = m->blocks[bi + 1];
+                        const int nmidp = pad16(nb.mid);
+                        const GemmSmem probe = gemm_smem_layout(g.K8, g.NP, nmidp, 2, true, false);
+                        if ((int)probe.total <= P->smem_limit) {
+                            g.b2_packed = WB + bo[bi + 1].c1;
+                            g.bias2 = WF + bo[bi + 1].c1b;
+                            g.N2 = nb.mid; g.NP2 = nmidp;
+                            g.out2_hi = P->X1.hi; g.out2_lo = P->X1.lo;
+                        }
+                    }
+                    dbg(L, stage++, *Xo, b.cout / 8, H * Wd, b.cout);
+                    const bool fused_next = g.b2_packed != nullptr;
+                    finish(L);
+                    Planes* t = X == &P->P ? Xspare : X;
+                    X = Xo; Xo = t; xC8 = b.cout / 8;
+                    if (j == 0 && !fused_next) {
+                        const BlockW& nb = m->blocks[bi + 1];
+                        Launch L2 = gemm(H, Wd, {{X, xC8}}, bo[bi + 1].c1, nb.mid, bo[bi + 1].c1b, true);
+                        L2.gemm.out_hi = P->X1.hi; L2.gemm.out_lo = P->X1.lo;
+                        dbg(L2, 100 + bi + 1, P->X1, pad16(nb.mid) / 8, H * Wd, pad16(nb.mid));
+                        finish(L2);
+                    }
+                }
+            }
+            if (s < 2) {
+                const int C = m->c[s + 1];
+                {   // transition: 1x1 + ReLU, 2x2 average pool in the epilogue
+                    Launch L = gemm(H, Wd, {{X, xC8}}, tr[s], C, trb[s], true);
+                    L.gemm.pool = 1;
+                    L.gemm.out_hi = Xo->hi; L.gemm.out_lo = Xo->lo;
+                    dbg(L, stage++, *Xo, C / 8, H * Wd / 4, C);
+                    finish(L);
+                    Planes* t = X; X = Xo; Xo = t;
+                }
+                H /= 2; Wd /= 2;
+                const BlockW& nb = m->blocks[(s + 1) * 2];
+                Launch L = gemm(H, Wd, {{X, xC8}}, bo[(s + 1) * 2].c1, nb.mid, bo[(s + 1) * 2].c1b, true);
+                L.gemm.out_hi = P->X1.hi; L.gemm.out_lo = P->X1.lo;
+                dbg(L, 100 + (s + 1) * 2, P->X1, pad16(nb.mid) / 8, H * Wd, pad16(nb.mid));
+                finish(L);
+            }
+        }
+        {   // conv5 -> float32 NHWC for the head kernel
+            Launch L = gemm(H, Wd, {{X, xC8}}, c5, m->c[3], c5b, true);
+            L.gemm.out_f32 = P->c5;
+            L.stage_after = 11;
+            finish(L);
+        }
+    } catch (...) {
+        plan_free(P);
+        throw;
+    }
+    return P;
+}
+
+// Replays the plan for one chunk of crops (the stem output of that chunk is in m->bufA).  Returns launches made.
+template <class Prof>
+int plan_run(ReidModel* m, const int* d_n, int off, int upper, cudaStream_t st, bool* stopped, Prof& prof) {
+    Plan* P = m->tc;
+    int launches = 0;
+    for (const Launch& L : P->launches) {
+        prof.begin(L.cls);
+        switch (L.kind) {
+            case LK_MAXPOOL_PLANES:
+                k_maxpool_planes<<<148 * 4, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_n, off, upper, P->P.hi, P->P.lo);
+                break;
+            case LK_CHAIN_S2:
+                k_chain_tc<16, 16, 32, 16><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<16, 32, 16>::SMEM, st>>>(L.chain, d_n, off, upper);
+                break;
+            case LK_CHAIN_S3:
+                k_chain_tc<32, 24, 16, 8><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<32, 16, 8>::SMEM, st>>>(L.chain, d_n, off, upper);
+                break;
+            case LK_CHAIN_S4:
+                k_chain_tc<32, 32, 8, 16><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<32, 8, 16>::SMEM, st>>>(L.chain, d_n, off, upper);
+                break;
+            case LK_GEMM:
+                k_gemm_tc<<<dim3(L.gemm_groups, upper), GEMM_THREADS, L.gl.total, st>>>(L.gemm, d_n, off, upper, L.gl);
+                break;
+        }
+        prof.end();
+        ++launches;
+        if (m->debug_stop >= 0 && L.stage_after == m->debug_stop) {
+            if (L.stage_after == 11) {
+                m->debug_ptr = P->c5;
+                m->debug_floats_per_crop = (size_t)128 * m->c[3];
+            } else {
+                k_planes_to_nhwc<<<148 * 4, 256, 0, st>>>(L.dbg_hi, L.dbg_lo, L.dbg_C8, L.dbg_HW, L.dbg_C, d_n, off, upper, P->dbg);
+                m->debug_ptr = P->dbg;
+                m->debug_floats_per_crop = (size_t)L.dbg_HW * L.dbg_C;
+            }
+            *stopped = true;
+            return launches;
+        }
+    }
+    return launches;
+}
+
+}  // namespace tcx
+}  // namespace bmb

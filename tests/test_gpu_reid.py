@@ -61,7 +61,9 @@ def test_every_stage_matches_oracle(tmp_path):
         w = want[name].permute(0, 2, 3, 1).contiguous().numpy().reshape(len(boxes), -1)
         g = reid.debug_stage(boxes, img, idx)
         assert g.shape == w.shape, (name, g.shape, w.shape)
-        tol = 2e-5 * max(1.0, float(np.abs(w).max()))
+        # stem / pool are float32 kernels; the blocks run on the tensor cores with split-BF16 operands (4-6e-6 of the
+        # output scale per GEMM, measured): 5e-5 of the stage's scale, the embedding bound itself stays 1e-4
+        tol = (2e-5 if idx < 3 else 5e-5) * max(1.0, float(np.abs(w).max()))
         assert np.abs(g - w).max() < tol, f"stage {name}: max err {np.abs(g - w).max():.3e}"
 
 
@@ -119,7 +121,9 @@ def test_reid_abi_errors(tmp_path):
     assert lib.boxmot_reid_capi_postprocess(reid.handle, out.ctypes.data, 512) == 0  # nothing staged
 
 
-@pytest.mark.parametrize("env", [{"BOXMOT_B200_REID_TC": "1"}, {"BOXMOT_B200_REID_CHUNK": "32"},
+@pytest.mark.parametrize("env", [{"BOXMOT_B200_REID_FP32": "0", "BOXMOT_B200_REID_CHUNK": "32"},
+                                 {"BOXMOT_B200_REID_FP32": "0", "BOXMOT_B200_REID_CHUNK": "24"}, {},
+                                 {"BOXMOT_B200_REID_TC": "1"}, {"BOXMOT_B200_REID_CHUNK": "32"},
                                  {"BOXMOT_B200_REID_CHUNK": "256", "BOXMOT_B200_REID_TC": "1"},
                                  {"BOXMOT_B200_LIGHT_CHAIN": "0"}, {"BOXMOT_B200_CHAIN_VAR": "0"},
                                  {"BOXMOT_B200_CHAIN_VAR": "1", "BOXMOT_B200_REID_CHUNK": "24"},
@@ -129,6 +133,8 @@ def test_reid_abi_errors(tmp_path):
 def test_alternative_kernel_paths_keep_parity(tmp_path, monkeypatch, env):
     """Every selectable kernel generation / configuration keeps the embeddings within the bound: tcgen05 (tf32 x3)
     pointwise path, other chunk sizes, per-level vs whole-branch LightConv, first-generation kernels."""
+    # the tensor-core path (tcgen05 + TMA) is the default; every other switch selects among the float32 kernels
+    monkeypatch.setenv("BOXMOT_B200_REID_FP32", "1")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     sd, reid = _model(tmp_path, seed=9)
