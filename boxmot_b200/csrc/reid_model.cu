@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ blob, co
             sw[e] = w[(size_t)k * C0 + co0 + c];
         }
         __syncthreads();
-        float acc0[16], acc1[16];
+        // packed FP32x2 FMAs (FFMA2, sm_100): two output channels per instruction, IEEE per lane (= fmaf bit for bit)
+        float2 acc0[8], acc1[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+        for (int c = 0; c < 8; ++c) { acc0[c] = make_float2(0.f, 0.f); acc1[c] = make_float2(0.f, 0.f); }
         for (int kh = 0; kh < 7; ++kh) {
             const float* row = sin + (size_t)(ty * 2 + kh) * ST_IC * 3;
             for (int kw = 0; kw < 7; ++kw) {
@@ -153,18 +154,16 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ blob, co
                 for (int ci = 0; ci < 3; ++ci) {
                     const float a0 = row[(tx * 2 + kw) * 3 + ci];
                     const float a1 = row[((tx + 32) * 2 + kw) * 3 + ci];
+                    const float2 a0p = make_float2(a0, a0), a1p = make_float2(a1, a1);
                     const float4* wp = reinterpret_cast<const float4*>(sw + ((kh * 7 + kw) * 3 + ci) * 16);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float4 wv = wp[q];
-                        acc0[q * 4 + 0] = fmaf(a0, wv.x, acc0[q * 4 + 0]);
-                        acc0[q * 4 + 1] = fmaf(a0, wv.y, acc0[q * 4 + 1]);
-                        acc0[q * 4 + 2] = fmaf(a0, wv.z, acc0[q * 4 + 2]);
-                        acc0[q * 4 + 3] = fmaf(a0, wv.w, acc0[q * 4 + 3]);
-                        acc1[q * 4 + 0] = fmaf(a1, wv.x, acc1[q * 4 + 0]);
-                        acc1[q * 4 + 1] = fmaf(a1, wv.y, acc1[q * 4 + 1]);
-                        acc1[q * 4 + 2] = fmaf(a1, wv.z, acc1[q * 4 + 2]);
-                        acc1[q * 4 + 3] = fmaf(a1, wv.w, acc1[q * 4 + 3]);
+                        const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
+                        acc0[q * 2 + 0] = __ffma2_rn(a0p, w01, acc0[q * 2 + 0]);
+                        acc0[q * 2 + 1] = __ffma2_rn(a0p, w23, acc0[q * 2 + 1]);
+                        acc1[q * 2 + 0] = __ffma2_rn(a1p, w01, acc1[q * 2 + 0]);
+                        acc1[q * 2 + 1] = __ffma2_rn(a1p, w23, acc1[q * 2 + 1]);
                     }
                 }
             }
@@ -174,10 +173,10 @@ __global__ void __launch_bounds__(256) k_stem(const float* __restrict__ blob, co
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(bias + co0 + q * 4);
-            float4 r0 = make_float4(fmaxf(acc0[q * 4] + b.x, 0.f), fmaxf(acc0[q * 4 + 1] + b.y, 0.f),
-                                    fmaxf(acc0[q * 4 + 2] + b.z, 0.f), fmaxf(acc0[q * 4 + 3] + b.w, 0.f));
-            float4 r1 = make_float4(fmaxf(acc1[q * 4] + b.x, 0.f), fmaxf(acc1[q * 4 + 1] + b.y, 0.f),
-                                    fmaxf(acc1[q * 4 + 2] + b.z, 0.f), fmaxf(acc1[q * 4 + 3] + b.w, 0.f));
+            float4 r0 = make_float4(fmaxf(acc0[q * 2].x + b.x, 0.f), fmaxf(acc0[q * 2].y + b.y, 0.f),
+                                    fmaxf(acc0[q * 2 + 1].x + b.z, 0.f), fmaxf(acc0[q * 2 + 1].y + b.w, 0.f));
+            float4 r1 = make_float4(fmaxf(acc1[q * 2].x + b.x, 0.f), fmaxf(acc1[q * 2].y + b.y, 0.f),
+                                    fmaxf(acc1[q * 2 + 1].x + b.z, 0.f), fmaxf(acc1[q * 2 + 1].y + b.w, 0.f));
             reinterpret_cast<float4*>(o0)[q] = r0;
             reinterpret_cast<float4*>(o1)[q] = r1;
         }

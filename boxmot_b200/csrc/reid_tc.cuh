@@ -108,7 +108,7 @@ __global__ void k_planes_to_nhwc(const bf16* __restrict__ hi, const bf16* __rest
 // branch-output planes in HBM and leaves per-tile channel sums for the ChannelGate.
 // ------------------------------------------------------------------------------------------------------------------
 struct ChainTcArgs {
-    CUtensorMap map_hi, map_lo;      // conv1 output planes, box (8, W + 2, R + 8, CP / 8, 1)
+    CUtensorMap map_hi, map_lo;      // conv1 output planes, box (W + 2 pixels, R + 8 rows, CP / 8 planes, 1 crop)
     const bf16* wpw[10];             // per LightConv: [CP/8][2*CP][8]  ([W_hi | W_lo] along the output channel)
     const float* wdw[10];            // [9][CP]   (BN folded)
     const float* bias[10];           // [CP]
@@ -150,6 +150,14 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
     float* sP = reinterpret_cast<float*>(sT);                     // [256 / C4][CR] channel-sum slots (after the last level)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y0 = tile * R, g0 = y0 - 4;
+#ifdef BMB_TC_CLOCKS
+    long long ck[24];
+    int nck = 0;
+#define TCK() do { if (threadIdx.x == 0 && nck < 24) ck[nck++] = clock64(); } while (0)
+#else
+#define TCK() do { } while (0)
+#endif
+    TCK();
 
     auto load_weights = [&](int lv) {   // level lv (1-based) -> slot (lv & 1)
         unsigned char* dst = sWs + (size_t)(lv & 1) * G::WSLOT_BYTES;
@@ -162,24 +170,26 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
         for (int e = threadIdx.x; e < CP; e += 256) dd[9 * CP + e] = sb[e];
     };
 
-    if (warp == 0) um::tmem_alloc(&tmem_slot, um::tmem_cols_pow2(G::TMEM_COLS));
+    // the input box first (its latency overlaps the TMEM allocation and the weight staging): thread 0 initialises the
+    // barriers, publishes them to the async proxy and issues the two TMA loads by itself
     if (threadIdx.x == 0) {
         um::mbar_init(&bar_tma, 1);
         um::mbar_init(&bar_mma, 1);
         um::fence_mbar_init();
+        um::mbar_expect_tx(&bar_tma, 2u * G::X_BYTES);
+        um::tma_load_4d(sXh, &a.map_hi, -4, g0, 0, n, &bar_tma);
+        um::tma_load_4d(sXl, &a.map_lo, -4, g0, 0, n, &bar_tma);
     }
+    if (warp == 1) um::tmem_alloc(&tmem_slot, um::tmem_cols_pow2(G::TMEM_COLS));
     load_weights(1);
     um::fence_async_smem();
     um::tc_fence_before();
     __syncthreads();
     um::tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    if (threadIdx.x == 0) {
-        um::mbar_expect_tx(&bar_tma, 2u * G::X_BYTES);
-        um::tma_load_5d(sXh, &a.map_hi, 0, -1, g0, 0, n, &bar_tma);
-        um::tma_load_5d(sXl, &a.map_lo, 0, -1, g0, 0, n, &bar_tma);
-    }
+    TCK();
     um::mbar_wait(&bar_tma, 0);
+    TCK();
 
     constexpr int walkers = W * C4;
     constexpr int n_grp = 256 / C4;
@@ -210,10 +220,12 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                                  um::make_desc(wb + ks * 2 * lbo_b, lbo_b, 128), id1, 1);
             um::mma_commit(&bar_mma);
         }
+        TCK();
         if (lv < depth) load_weights(lv + 1);                  // overlaps the MMAs; published by the fence at the end of the level
         um::mbar_wait(&bar_mma, mma_phase);
         mma_phase ^= 1u;
         um::tc_fence_after();
+        TCK();
         // ---- TMEM -> T: warp = (lane quadrant, tile parity); T = (A_hi W_hi + A_lo W_hi) + A_hi W_lo ----
         {
             const int q = warp & 3;
@@ -228,18 +240,20 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                     um::tmem_ld_wait();
                     if (p < NPX) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            sT[(c0 / 4 + j) * NPXT + p] =
-                                make_float4(__uint_as_float(v1[4 * j]) + __uint_as_float(v2[4 * j]),
-                                            __uint_as_float(v1[4 * j + 1]) + __uint_as_float(v2[4 * j + 1]),
-                                            __uint_as_float(v1[4 * j + 2]) + __uint_as_float(v2[4 * j + 2]),
-                                            __uint_as_float(v1[4 * j + 3]) + __uint_as_float(v2[4 * j + 3]));
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 lo2 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1])),
+                                                          make_float2(__uint_as_float(v2[4 * j]), __uint_as_float(v2[4 * j + 1])));
+                            const float2 hi2 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3])),
+                                                          make_float2(__uint_as_float(v2[4 * j + 2]), __uint_as_float(v2[4 * j + 3])));
+                            sT[(c0 / 4 + j) * NPXT + p] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                        }
                     }
                 }
             }
         }
         um::tc_fence_before();
         __syncthreads();
+        TCK();
         // ---- depthwise 3x3 + bias + ReLU on image rows [ya, yb): next level's X (planes, in place) or the branch output ----
         const bool last = lv == depth;
         const int ya = max(y0 - ext, 0), yb = min(y0 + R + ext, H);
@@ -252,54 +266,75 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                 const int c4 = wk % C4, x = (wk / C4) % W, sp = wk / walkers;
                 const int ra = ya + sp * rows_per, rb = min(ra + rows_per, yb);
                 if (ra >= rb) continue;
-                float4 wv[9];
+                // packed FP32x2 arithmetic (FFMA2, sm_100): two channels per instruction, IEEE per lane
+                float2 wv[9][2];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const float4*>(sD + t * CP + c4 * 4);
-                const float4 bv = *reinterpret_cast<const float4*>(sB + c4 * 4);
-                const float4* tbase = sT + c4 * NPXT + x;              // column x-1 of the padded row
-                float4 win[3][3];
+                for (int t = 0; t < 9; ++t) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(sD + t * CP + c4 * 4);
+                    wv[t][0] = make_float2(w4.x, w4.y);
+                    wv[t][1] = make_float2(w4.z, w4.w);
+                }
+                const float4 bv4 = *reinterpret_cast<const float4*>(sB + c4 * 4);
+                const float2 bv0 = make_float2(bv4.x, bv4.y), bv1 = make_float2(bv4.z, bv4.w);
+                const float4* tp = sT + c4 * NPXT + (ra - 1 - g0) * TW + x;      // row ra - 1, column x - 1 of the padded row
+                float2 win[3][3][2];
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    win[0][kx] = tbase[(ra - 1 - g0) * TW + kx];
-                    win[1][kx] = tbase[(ra - g0) * TW + kx];
+                    const float4 q0 = tp[kx], q1 = tp[TW + kx];
+                    win[0][kx][0] = make_float2(q0.x, q0.y); win[0][kx][1] = make_float2(q0.z, q0.w);
+                    win[1][kx][0] = make_float2(q1.x, q1.y); win[1][kx][1] = make_float2(q1.z, q1.w);
                 }
-                for (int y = ra; y < rb; y += 3) {
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        if (y + u < rb) {
-                            const int i0 = u % 3, i1 = (u + 1) % 3, i2 = (u + 2) % 3;
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) win[i2][kx] = tbase[(y + u + 1 - g0) * TW + kx];
-                            float4 acc = bv;
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float4 w0 = wv[kx], w1 = wv[3 + kx], w2 = wv[6 + kx];
-                                const float4 q0 = win[i0][kx], q1 = win[i1][kx], q2 = win[i2][kx];
-                                acc.x = fmaf(q0.x, w0.x, acc.x); acc.y = fmaf(q0.y, w0.y, acc.y);
-                                acc.z = fmaf(q0.z, w0.z, acc.z); acc.w = fmaf(q0.w, w0.w, acc.w);
-                                acc.x = fmaf(q1.x, w1.x, acc.x); acc.y = fmaf(q1.y, w1.y, acc.y);
-                                acc.z = fmaf(q1.z, w1.z, acc.z); acc.w = fmaf(q1.w, w1.w, acc.w);
-                                acc.x = fmaf(q2.x, w2.x, acc.x); acc.y = fmaf(q2.y, w2.y, acc.y);
-                                acc.z = fmaf(q2.z, w2.z, acc.z); acc.w = fmaf(q2.w, w2.w, acc.w);
-                            }
-                            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
-                            acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-                            uint32_t h0, h1, e0, e1;
-                            um::split2(acc.x, acc.y, h0, e0);
-                            um::split2(acc.z, acc.w, h1, e1);
-                            if (last) {
-                                const size_t o = ((((size_t)n * (4 * C8) + br * C8 + (c4 >> 1)) * H + (y + u)) * W + x) * 8 + (c4 & 1) * 4;
-                                *reinterpret_cast<uint2*>(a.y_hi + o) = make_uint2(h0, h1);
-                                *reinterpret_cast<uint2*>(a.y_lo + o) = make_uint2(e0, e1);
-                                psum.x += acc.x; psum.y += acc.y; psum.z += acc.z; psum.w += acc.w;
-                            } else {
-                                const int po = ((c4 >> 1) * NPX + (y + u - g0) * TW + x + 1) * 16 + (c4 & 1) * 8;
-                                *reinterpret_cast<uint2*>(sXh + po) = make_uint2(h0, h1);
-                                *reinterpret_cast<uint2*>(sXl + po) = make_uint2(e0, e1);
-                            }
-                        }
-                    }
+                tp += 2 * TW;                                                      // next row to load: ra + 1
+                unsigned char* xh = sXh + ((c4 >> 1) * NPX + (ra - g0) * TW + x + 1) * 16 + (c4 & 1) * 8;
+                unsigned char* xl = sXl + ((c4 >> 1) * NPX + (ra - g0) * TW + x + 1) * 16 + (c4 & 1) * 8;
+                size_t go = ((((size_t)n * (4 * C8) + br * C8 + (c4 >> 1)) * H + ra) * W + x) * 8 + (c4 & 1) * 4;
+                float2 ps0 = make_float2(0.f, 0.f), ps1 = make_float2(0.f, 0.f);
+#define BMB_DW_ROW(U)                                                                                                  \
+                {                                                                                                      \
+                    constexpr int i0 = (U) % 3, i1 = ((U) + 1) % 3, i2 = ((U) + 2) % 3;                                \
+                    _Pragma("unroll") for (int kx = 0; kx < 3; ++kx) {                                                 \
+                        const float4 qq = tp[kx];                                                                      \
+                        win[i2][kx][0] = make_float2(qq.x, qq.y);                                                      \
+                        win[i2][kx][1] = make_float2(qq.z, qq.w);                                                      \
+                    }                                                                                                  \
+                    tp += TW;                                                                                          \
+                    float2 a0 = bv0, a1 = bv1;                                                                         \
+                    _Pragma("unroll") for (int kx = 0; kx < 3; ++kx) {                                                 \
+                        a0 = __ffma2_rn(win[i0][kx][0], wv[kx][0], a0);                                                \
+                        a1 = __ffma2_rn(win[i0][kx][1], wv[kx][1], a1);                                                \
+                        a0 = __ffma2_rn(win[i1][kx][0], wv[3 + kx][0], a0);                                            \
+                        a1 = __ffma2_rn(win[i1][kx][1], wv[3 + kx][1], a1);                                            \
+                        a0 = __ffma2_rn(win[i2][kx][0], wv[6 + kx][0], a0);                                            \
+                        a1 = __ffma2_rn(win[i2][kx][1], wv[6 + kx][1], a1);                                            \
+                    }                                                                                                  \
+                    a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f);                                                  \
+                    a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);                                                  \
+                    uint32_t h0, h1, e0, e1;                                                                           \
+                    um::split2(a0.x, a0.y, h0, e0);                                                                    \
+                    um::split2(a1.x, a1.y, h1, e1);                                                                    \
+                    if (last) {                                                                                        \
+                        *reinterpret_cast<uint2*>(a.y_hi + go) = make_uint2(h0, h1);                                   \
+                        *reinterpret_cast<uint2*>(a.y_lo + go) = make_uint2(e0, e1);                                   \
+                        go += (size_t)W * 8;                                                                           \
+                        ps0 = __fadd2_rn(ps0, a0);                                                                     \
+                        ps1 = __fadd2_rn(ps1, a1);                                                                     \
+                    } else {                                                                                           \
+                        *reinterpret_cast<uint2*>(xh) = make_uint2(h0, h1);                                            \
+                        *reinterpret_cast<uint2*>(xl) = make_uint2(e0, e1);                                            \
+                        xh += TW * 16;                                                                                 \
+                        xl += TW * 16;                                                                                 \
+                    }                                                                                                  \
                 }
+                int y = ra;
+                for (; y + 3 <= rb; y += 3) {
+                    BMB_DW_ROW(0)
+                    BMB_DW_ROW(1)
+                    BMB_DW_ROW(2)
+                }
+                if (y < rb) BMB_DW_ROW(0)
+                if (y + 1 < rb) BMB_DW_ROW(1)
+#undef BMB_DW_ROW
+                psum.x += ps0.x; psum.y += ps0.y; psum.z += ps1.x; psum.w += ps1.y;
             }
         }
         if (last && CP > CR) {
@@ -318,7 +353,16 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
         um::tc_fence_before();
         __syncthreads();
         um::tc_fence_after();
+        TCK();
     }
+#ifdef BMB_TC_CLOCKS
+    if (threadIdx.x == 0 && blockIdx.x == 1 && n == 5) {
+        printf("chain CP%d W%d br%d: setup %lld tma %lld |", CP, W, br, ck[1] - ck[0], ck[2] - ck[1]);
+        for (int i = 2; i + 4 < nck + 1 && i + 4 <= 23; i += 4)
+            printf(" issue %lld mma %lld epi %lld dw %lld |", ck[i + 1] - ck[i], ck[i + 2] - ck[i + 1], ck[i + 3] - ck[i + 2], ck[i + 4] - ck[i + 3]);
+        printf(" total %lld\n", ck[nck - 1] - ck[0]);
+    }
+#endif
     // per-tile channel sums of the branch output (fixed slot per thread, fixed combination order)
     if (threadIdx.x < act)
         *reinterpret_cast<float4*>(sP + (threadIdx.x / C4) * CR + (threadIdx.x % C4) * 4) = psum;
@@ -331,7 +375,7 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
     }
     um::tc_fence_before();
     __syncthreads();
-    if (warp == 0) um::tmem_dealloc(tmem, um::tmem_cols_pow2(G::TMEM_COLS));
+    if (warp == 1) um::tmem_dealloc(tmem, um::tmem_cols_pow2(G::TMEM_COLS));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -340,10 +384,49 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
 // warps 2..9 = epilogue (lane quadrant = warp % 4, column half = (warp - 2) / 4).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GEMM_THREADS = 320;
-constexpr int RING_SLOT_BYTES = 2 * 8 * 128 * 16;     // 8 planes x 128 pixels x 16 B, hi then lo
+
+// ChannelGate (osnet.py:161-210) of the four branches of a block: mean -> fc1 -> ReLU -> fc2 -> sigmoid.
+// One CTA per crop; gates [crops][4][midp] (padded channels 0).  Same operation order as the float32 k_gates.
+struct GatesTcArgs {
+    const float* sums[4];               // [crops][tiles][midp]
+    const float* g1w; const float* g1b; const float* g2w; const float* g2b;   // [mid][hid], [hid], [hid][mid], [mid]
+    float* gates;
+    int mid, midp, hid, tiles, HW;
+};
+__global__ void __launch_bounds__(128) k_gates_tc(const GatesTcArgs a, const int* __restrict__ d_n, int off, int cap) {
+    const int n = blockIdx.x;
+    if (n >= tc_chunk_count(d_n, off, cap)) return;
+    __shared__ float mean[128], hid[16];
+    const int mid = a.mid, midp = a.midp;
+    for (int e = threadIdx.x; e < 4 * midp; e += 128) {
+        const int b = e / midp, c = e - b * midp;
+        float s = 0.f;
+        if (c < mid)
+            for (int t = 0; t < a.tiles; ++t) s += a.sums[b][((size_t)n * a.tiles + t) * midp + c];
+        mean[e] = s / (float)a.HW;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * a.hid; e += 128) {
+        const int b = e / a.hid, h = e - b * a.hid;
+        float s = a.g1b[h];
+        for (int c = 0; c < mid; ++c) s = fmaf(mean[b * midp + c], a.g1w[(size_t)c * a.hid + h], s);
+        hid[e] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * midp; e += 128) {
+        const int b = e / midp, c = e - b * midp;
+        float g = 0.f;
+        if (c < mid) {
+            float s = a.g2b[c];
+            for (int h = 0; h < a.hid; ++h) s = fmaf(hid[b * a.hid + h], a.g2w[(size_t)h * mid + c], s);
+            g = 1.0f / (1.0f + expf(-s));
+        }
+        a.gates[(size_t)n * 4 * midp + e] = g;
+    }
+}
 
 struct GemmTcArgs {
-    CUtensorMap map_hi[2], map_lo[2];   // A sources: box (8, W, 128 / W, kc, 1)
+    CUtensorMap map_hi[2], map_lo[2];   // A sources: box (64 pixels, 2, kc planes, 1 crop)
     int src_planes[2];                  // planes (K / 8) per source
     int src_kc[2];                      // planes per ring chunk (2, 4 or 8) = the box's plane extent
     int n_src;
@@ -356,11 +439,11 @@ struct GemmTcArgs {
     int N, NP;                          // real / padded (multiple of 16) output channels
     const float* bias;                  // [NP]
     int relu;
-    // gate (osnet.py:161-210) folded into conv3:  mean -> fc1 -> ReLU -> fc2 -> sigmoid per branch
+    // ChannelGate folded into conv3: B row (b * midp + c) = gates[crop][b][c] * w3[c][:]
     const float* w3;                    // [mid][N] float32 (null: no gate)
-    const float* sums[4];               // [crops][gate_tiles][midp]
-    const float* g1w; const float* g1b; const float* g2w; const float* g2b;
-    int mid, midp, hid, gate_tiles, HW;
+    const float* gates;                 // [crops][4][midp] (k_gates_tc)
+    int mid, midp, HW;
+    int slot_bytes;                     // ring slot: hi planes then lo planes (slot_bytes / 2 each)
     // outputs
     bf16* out_hi; bf16* out_lo;         // planes [crops][NP/8][H][W][8] (or pooled [..][H/2][W/2][8]); may be null
     float* out_f32;                     // [crops][HW][N] float32 NHWC copy (may be null)
@@ -376,26 +459,26 @@ struct GemmTcArgs {
 struct GemmSmem {
     size_t b, b2, ring, a2, f, gate, total;
 };
-inline GemmSmem gemm_smem_layout(int K8, int NP, int NP2, int n_stage, bool tail, bool pool) {
+inline GemmSmem gemm_smem_layout(int K8, int NP, int NP2, int n_stage, bool tail, bool pool, int slot_bytes) {
     GemmSmem s{};
     size_t o = 0;
     s.b = o; o += (size_t)K8 * 2 * NP * 16;
     s.b2 = o; if (tail) o += (size_t)(NP / 8) * 2 * NP2 * 16;
     o = (o + 127) & ~(size_t)127;
-    s.ring = o; o += (size_t)n_stage * RING_SLOT_BYTES;
+    s.ring = o; o += (size_t)n_stage * slot_bytes;
     s.a2 = o; if (tail) o += (size_t)2 * (NP / 8) * 128 * 16;
     s.f = o; if (pool) o += (size_t)128 * (NP + 4) * 4;
-    s.gate = o; o += 4 * 32 * 4 * 2 + 64;
+    s.gate = o; o += 4 * 32 * 4 + 64;
     s.total = o + 128;
     return s;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_constant__ GemmTcArgs a, const int* __restrict__ d_n, int off, int cap,
+__global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_constant__ GemmTcArgs a, const int* __restrict__ d_n, int off, int cap,
                                                             const GemmSmem L) {
     const int n = blockIdx.y;
     if (n >= tc_chunk_count(d_n, off, cap)) return;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full, bar_acc_empty, bar_a2_full, bar_acc2_full, bar_b_ready;
+    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full, bar_acc_empty, bar_a2_full, bar_acc2_full, bar_b_ready, bar_w;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = a.NP, NP2 = a.NP2;
@@ -418,6 +501,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
         um::mbar_init(&bar_a2_full, 256);
         um::mbar_init(&bar_acc2_full, 1);
         um::mbar_init(&bar_b_ready, 256);
+        um::mbar_init(&bar_w, 1);
         um::fence_mbar_init();
     }
     if (warp == 1) um::tmem_alloc(&tmem_slot, tmem_cols);
@@ -425,6 +509,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
     __syncthreads();
     um::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+#ifdef BMB_TC_CLOCKS
+    const long long gk0 = clock64();
+    long long gk[40];
+    int ngk = 0;
+    const bool gprint = blockIdx.x == 0 && n == 5;
+#define GCK() do { if (ngk < 40) gk[ngk++] = clock64() - gk0; } while (0)
+#else
+#define GCK() do { } while (0)
+#endif
 
     // chunk table of one tile: (source, first plane, planes)
     int n_chunks = 0;
@@ -433,6 +526,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            {   // packed weights (everything below the gate-folded rows, and the tail's B) by bulk async copies
+                const uint32_t first = (uint32_t)((a.w3 ? 4 * a.midp : 0) / 8) * 2u * NP * 16u, total = (uint32_t)a.K8 * 2u * NP * 16u;
+                const uint32_t b2 = tail ? (uint32_t)(NP / 8) * 2u * NP2 * 16u : 0u;
+                um::mbar_expect_tx(&bar_w, (total - first) + b2);
+                if (total > first) um::bulk_g2s(sB + first, reinterpret_cast<const unsigned char*>(a.b_packed) + first, total - first, &bar_w);
+                if (b2) um::bulk_g2s(sB2, a.b2_packed, b2, &bar_w);
+            }
             uint32_t it = 0;
             for (int tile = tile0; tile < tile1; ++tile) {
                 for (int s = 0; s < a.n_src; ++s) {
@@ -440,10 +540,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                     for (int p0 = 0; p0 < a.src_planes[s]; p0 += kc, ++it) {
                         const uint32_t slot = it % (uint32_t)a.n_stage, ph = (it / (uint32_t)a.n_stage) & 1u;
                         um::mbar_wait(&bar_empty[slot], ph ^ 1u);
-                        unsigned char* dst = sRing + (size_t)slot * RING_SLOT_BYTES;
+                        unsigned char* dst = sRing + (size_t)slot * a.slot_bytes;
                         um::mbar_expect_tx(&bar_full[slot], (uint32_t)kc * 128u * 16u * 2u);
-                        um::tma_load_5d(dst, &a.map_hi[s], 0, 0, tile * a.rows_per_tile, p0, n, &bar_full[slot]);
-                        um::tma_load_5d(dst + RING_SLOT_BYTES / 2, &a.map_lo[s], 0, 0, tile * a.rows_per_tile, p0, n, &bar_full[slot]);
+                        um::tma_load_4d(dst, &a.map_hi[s], 0, tile * 2, p0, n, &bar_full[slot]);
+                        um::tma_load_4d(dst + a.slot_bytes / 2, &a.map_lo[s], 0, tile * 2, p0, n, &bar_full[slot]);
                     }
                 }
             }
@@ -454,11 +554,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
             const uint32_t id2 = um::idesc_bf16(128, 2 * NP), id1 = um::idesc_bf16(128, NP);
             const uint32_t lbo_b = 2u * NP * 16u;
             um::mbar_wait(&bar_b_ready, 0);
+            um::mbar_wait(&bar_w, 0);
             um::tc_fence_after();
+            GCK();
             uint32_t it = 0, ti = 0;
             for (int tile = tile0; tile < tile1; ++tile, ++ti) {
                 um::mbar_wait(&bar_acc_empty, (ti & 1u) ^ 1u);
                 um::tc_fence_after();
+                GCK();
                 uint32_t kplane = 0, first = 1;
                 for (int s = 0; s < a.n_src; ++s) {
                     const int kc = a.src_kc[s];
@@ -466,7 +569,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                         const uint32_t slot = it % (uint32_t)a.n_stage, ph = (it / (uint32_t)a.n_stage) & 1u;
                         um::mbar_wait(&bar_full[slot], ph);
                         um::tc_fence_after();
-                        const uint32_t ah = um::smem_u32(sRing + (size_t)slot * RING_SLOT_BYTES), al = ah + RING_SLOT_BYTES / 2;
+                        const uint32_t ah = um::smem_u32(sRing + (size_t)slot * a.slot_bytes), al = ah + a.slot_bytes / 2;
                         for (int ks = 0; ks < kc / 2; ++ks) {
                             const uint64_t db = um::make_desc(um::smem_u32(sB) + (kplane + 2 * ks) * lbo_b, lbo_b, 128);
                             um::mma_bf16(tmem, um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), db, id2, first ? 0u : 1u);
@@ -478,6 +581,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                     }
                 }
                 um::mma_commit(&bar_acc_full);
+                GCK();
                 if (tail) {
                     const uint32_t jd2 = um::idesc_bf16(128, 2 * NP2), jd1 = um::idesc_bf16(128, NP2);
                     const uint32_t lbo_b2 = 2u * NP2 * 16u;
@@ -490,8 +594,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                         um::mma_bf16(tmem + acc_cols, um::make_desc(al + ks * 2 * 2048u, 2048u, 128), db, jd1, 1u);
                     }
                     um::mma_commit(&bar_acc2_full);
+                    GCK();
                 }
             }
+#ifdef BMB_TC_CLOCKS
+            if (gprint) {
+                printf("gemm K8 %d NP %d tail %d MMA thread: b_ready %lld |", a.K8, NP, (int)tail, gk[0]);
+                for (int i = 1; i < ngk; ++i) printf(" %lld", gk[i]);
+                printf("\n");
+            }
+#endif
         }
     } else {
         // ================= epilogue warps =================
@@ -504,33 +616,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
             const int mid = a.mid, midp = a.midp;
             gate_rows = 4 * midp;
             float* gate = sGate;
-            float* mean = sGate + 128;
-            float* hid = sGate + 256;
-            for (int e = et; e < 4 * midp; e += 256) {
-                const int b = e / midp, c = e - b * midp;
-                float s = 0.f;
-                if (c < mid)
-                    for (int t = 0; t < a.gate_tiles; ++t) s += a.sums[b][((size_t)n * a.gate_tiles + t) * midp + c];
-                mean[e] = s / (float)a.HW;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int e = et; e < 4 * a.hid; e += 256) {
-                const int b = e / a.hid, h = e - b * a.hid;
-                float s = a.g1b[h];
-                for (int c = 0; c < mid; ++c) s = fmaf(mean[b * midp + c], a.g1w[(size_t)c * a.hid + h], s);
-                hid[e] = fmaxf(s, 0.f);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int e = et; e < 4 * midp; e += 256) {
-                const int b = e / midp, c = e - b * midp;
-                float g = 0.f;
-                if (c < mid) {
-                    float s = a.g2b[c];
-                    for (int h = 0; h < a.hid; ++h) s = fmaf(hid[b * a.hid + h], a.g2w[(size_t)h * mid + c], s);
-                    g = 1.0f / (1.0f + expf(-s));
-                }
-                gate[e] = g;
-            }
+            for (int e = et; e < 4 * midp; e += 256) gate[e] = a.gates[(size_t)n * 4 * midp + e];
             asm volatile("bar.sync 1, 256;" ::: "memory");
             // rows k = b * midp + c: an item is (k pair-of-8 plane, n pair): 8 k values x 2 n per thread step
             const int items = (gate_rows / 8) * (NP / 2);
@@ -560,30 +646,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                 *reinterpret_cast<uint4*>(row + (size_t)(NP + n2 + 1) * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
             }
         }
-        {
-            const int first16 = (gate_rows / 8) * 2 * NP, total16 = a.K8 * 2 * NP;
-            const uint4* src = reinterpret_cast<const uint4*>(a.b_packed);
-            for (int e = first16 + et; e < total16; e += 256) reinterpret_cast<uint4*>(sB)[e] = src[e];
-            if (tail) {
-                const uint4* s2 = reinterpret_cast<const uint4*>(a.b2_packed);
-                for (int e = et; e < (NP / 8) * 2 * NP2; e += 256) reinterpret_cast<uint4*>(sB2)[e] = s2[e];
-            }
-        }
         um::fence_async_smem();
         mbar_arrive(&bar_b_ready);
+        GCK();
 
         const int cw = NP / 2;                                  // columns this warp owns: [half * cw, half * cw + cw)
         uint32_t ti = 0;
         for (int tile = tile0; tile < tile1; ++tile, ++ti) {
             um::mbar_wait(&bar_acc_full, ti & 1u);
             um::tc_fence_after();
+            GCK();
             const int px = tile * 128 + m;                      // pixel of the crop
-            for (int c0 = half * cw; c0 < half * cw + cw; c0 += 8) {
-                uint32_t v1[8], v2[8];
-                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                um::tmem_ld8(ta, v1);
-                um::tmem_ld8(ta + NP, v2);
-                um::tmem_ld_wait();
+            auto emit = [&](const uint32_t* v1, const uint32_t* v2, const int c0) {
                 const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c0), b1 = *reinterpret_cast<const float4*>(a.bias + c0 + 4);
                 float o[8];
                 o[0] = __uint_as_float(v1[0]) + __uint_as_float(v2[0]) + b0.x; o[1] = __uint_as_float(v1[1]) + __uint_as_float(v2[1]) + b0.y;
@@ -623,9 +697,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                         *reinterpret_cast<uint4*>(sA2 + ((size_t)(NP / 8 + c0 / 8) * 128 + m) * 16) = lv;
                     }
                 }
+            };
+            {   // TMEM -> registers two 8-column groups deep: the loads of the next group fly while this one is processed
+                const int cb = half * cw, ce = cb + cw;
+                const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+                uint32_t pa[8], pb[8], qa[8], qb[8];
+                um::tmem_ld8(tq + cb, pa);
+                um::tmem_ld8(tq + cb + NP, pb);
+                for (int c0 = cb; c0 < ce; c0 += 16) {
+                    um::tmem_ld_wait();
+                    if (c0 + 8 < ce) { um::tmem_ld8(tq + c0 + 8, qa); um::tmem_ld8(tq + c0 + 8 + NP, qb); }
+                    emit(pa, pb, c0);
+                    if (c0 + 8 < ce) {
+                        um::tmem_ld_wait();
+                        if (c0 + 16 < ce) { um::tmem_ld8(tq + c0 + 16, pa); um::tmem_ld8(tq + c0 + 16 + NP, pb); }
+                        emit(qa, qb, c0 + 8);
+                    }
+                }
             }
             um::tc_fence_before();
             mbar_arrive(&bar_acc_empty);
+            GCK();
             if (a.pool) {
                 // 2x2 average pool of the tile (rows_per_tile x W) -> (rows/2 x W/2), same operation order as the
                 // float32 kernel of round 1: (a + b + c + d) * 0.25 with a=(y,x) b=(y,x+1) c=(y+1,x) d=(y+1,x+1)
@@ -659,6 +751,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                 mbar_arrive(&bar_a2_full);
                 um::mbar_wait(&bar_acc2_full, ti & 1u);
                 um::tc_fence_after();
+                GCK();
                 const int cw2 = NP2 / 2;
                 for (int c0 = half * cw2; c0 < half * cw2 + cw2; c0 += 8) {
                     uint32_t v1[8], v2[8];
@@ -679,8 +772,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_tc(const __grid_consta
                     reinterpret_cast<uint4*>(a.out2_lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
                 }
                 um::tc_fence_before();
+                GCK();
             }
         }
+#ifdef BMB_TC_CLOCKS
+        if (gprint && et == 0) {
+            printf("gemm K8 %d NP %d tail %d epilogue thread: b_built %lld |", a.K8, NP, (int)tail, gk[0]);
+            for (int i = 1; i < ngk; ++i) printf(" %lld", gk[i]);
+            printf("\n");
+        }
+#endif
     }
     um::tc_fence_before();
     __syncthreads();

@@ -18,16 +18,31 @@ PFN_encodeTiled tensor_map_encoder() {
     return fn;
 }
 
-// tensor [crops][C8][H][W][8] of BF16, box (8, box_w, box_h, box_c8, 1), out-of-bounds elements read as zero
-void make_act_map(CUtensorMap* out, const void* base, int crops, int C8, int H, int W, int box_w, int box_h, int box_c8) {
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C8, (cuuint64_t)crops};
-    cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C8 * H * W * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c8, 1};
+// Tensor maps over a plane tensor [crops][C8][H][W][8] of BF16.  The same bytes are described as 32-bit elements with
+// long inner rows: a 16-byte inner box (one pixel of one plane) makes the TMA unit issue one request per pixel
+// (3 264 per chain tile, measured latency-bound in profiles/r2a); a whole padded image row / 64 pixels per request
+// brings that to ~100.  Out-of-bounds elements read as zero (= the convolution's zero padding).
+static void encode_u32_map(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                           const cuuint32_t* box) {
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = tensor_map_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = tensor_map_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                                      es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+// haloed row tile for the chain kernel: box = (W + 2 pixels, rows, all planes, 1 crop), start pixel -1
+void make_rows_map(CUtensorMap* out, const void* base, int crops, int C8, int H, int W, int box_rows) {
+    cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)C8, (cuuint64_t)crops};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C8 * H * W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(W + 2) * 4, (cuuint32_t)box_rows, (cuuint32_t)C8, 1};
+    encode_u32_map(out, base, 4, dims, strides, box);
+}
+// 128 consecutive pixels of kc planes for the GEMM kernel: box = (64 pixels, 2, kc planes, 1 crop)
+void make_tile_map(CUtensorMap* out, const void* base, int crops, int C8, int HW, int kc) {
+    cuuint64_t dims[4] = {256, (cuuint64_t)HW / 64, (cuuint64_t)C8, (cuuint64_t)crops};
+    cuuint64_t strides[3] = {1024, (cuuint64_t)HW * 16, (cuuint64_t)C8 * HW * 16};
+    cuuint32_t box[4] = {256, 2, (cuuint32_t)kc, 1};
+    encode_u32_map(out, base, 4, dims, strides, box);
 }
 
 namespace tcx {
@@ -76,13 +91,14 @@ struct Planes {
     bf16* lo = nullptr;
 };
 
-enum LaunchKind { LK_CHAIN_S2, LK_CHAIN_S3, LK_CHAIN_S4, LK_GEMM, LK_MAXPOOL_PLANES };
+enum LaunchKind { LK_CHAIN_S2, LK_CHAIN_S3, LK_CHAIN_S4, LK_GEMM, LK_MAXPOOL_PLANES, LK_GATES };
 struct Launch {
     int kind = LK_GEMM;
     int cls = 0;                // profiling class
     ChainTcArgs chain{};
     int chain_tiles = 0;
     GemmTcArgs gemm{};
+    GatesTcArgs gates{};
     GemmSmem gl{};
     int gemm_groups = 0;
     int stage_after = -1;       // debug stage index whose tensor exists after this launch
@@ -99,6 +115,7 @@ struct Plan {
     Planes P, X1, Y, XA, XB;
     float* c5 = nullptr;        // conv5 output [crops][128][C3] float32
     float* sums[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* gates = nullptr;     // [crops][4][midp]
     float* dbg = nullptr;       // float32 NHWC copy of a stage (diagnostics)
     std::vector<Launch> launches;
     int smem_limit = 0;
@@ -116,7 +133,7 @@ inline void free_planes(Planes& p) {
 
 inline void plan_free(Plan* p) {
     if (!p) return;
-    cudaFree(p->d_wb); cudaFree(p->d_wf); cudaFree(p->c5); cudaFree(p->dbg);
+    cudaFree(p->d_wb); cudaFree(p->d_wf); cudaFree(p->c5); cudaFree(p->dbg); cudaFree(p->gates);
     for (int b = 0; b < 4; ++b) cudaFree(p->sums[b]);
     free_planes(p->P); free_planes(p->X1); free_planes(p->Y); free_planes(p->XA); free_planes(p->XB);
     delete p;

@@ -30,6 +30,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         alloc_planes(P->XB, CH * 2048 * 64);
         RCUDA_OK(cudaMalloc(&P->c5, sizeof(float) * CH * 128 * m->c[3]));
         for (int b = 0; b < 4; ++b) RCUDA_OK(cudaMalloc(&P->sums[b], sizeof(float) * CH * 8 * 32));
+        RCUDA_OK(cudaMalloc(&P->gates, sizeof(float) * CH * 4 * 32));
         RCUDA_OK(cudaMalloc(&P->dbg, sizeof(float) * CH * 2048 * 64));
 
         // ---- weights ----
@@ -95,12 +96,12 @@ Plan* plan_build(ReidModel* m, const float* hw) {
             g.K8 = 0;
             for (int s = 0; s < g.n_src; ++s) {
                 const int C8 = srcs[s].C8;
-                const int kc = C8 % 8 == 0 ? 8 : (C8 % 4 == 0 ? 4 : 2);
+                const int kc = C8 % 4 == 0 ? 4 : 2;
                 g.src_planes[s] = C8;
                 g.src_kc[s] = kc;
                 g.K8 += C8;
-                make_act_map(&g.map_hi[s], srcs[s].buf->hi, P->chunk, C8, H, Wd, Wd, 128 / Wd, kc);
-                make_act_map(&g.map_lo[s], srcs[s].buf->lo, P->chunk, C8, H, Wd, Wd, 128 / Wd, kc);
+                make_tile_map(&g.map_hi[s], srcs[s].buf->hi, P->chunk, C8, H * Wd, kc);
+                make_tile_map(&g.map_lo[s], srcs[s].buf->lo, P->chunk, C8, H * Wd, kc);
             }
             g.b_packed = WB + b_off;
             g.N = N;
@@ -114,13 +115,20 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         auto finish = [&](Launch& L) {
             GemmTcArgs& g = L.gemm;
             const bool tail = g.b2_packed != nullptr;
-            int ns = 4;
-            for (; ns >= 2; --ns) {
-                L.gl = gemm_smem_layout(g.K8, g.NP, g.NP2, ns, tail, g.pool != 0);
-                if ((int)L.gl.total <= P->smem_limit) break;
-            }
-            if (ns < 2) throw std::runtime_error("tensor-core GEMM does not fit shared memory");
+            int kc_max = 2;
+            for (int s = 0; s < g.n_src; ++s) kc_max = std::max(kc_max, g.src_kc[s]);
+            g.slot_bytes = kc_max * 128 * 16 * 2;
+            // two CTAs per SM (they overlap each other's MMA / epilogue / load latencies) when a >= 2-deep ring fits half
+            // the shared memory; otherwise one CTA with the deepest ring that fits
+            const int half_limit = (P->smem_limit + 1024) / 2 - 1024 - 512;
+            int ns = 0;
+            for (int cand = 4; cand >= 2 && !ns; --cand)
+                if ((int)gemm_smem_layout(g.K8, g.NP, g.NP2, cand, tail, g.pool != 0, g.slot_bytes).total <= half_limit) ns = cand;
+            for (int cand = 4; cand >= 2 && !ns; --cand)
+                if ((int)gemm_smem_layout(g.K8, g.NP, g.NP2, cand, tail, g.pool != 0, g.slot_bytes).total <= P->smem_limit) ns = cand;
+            if (!ns) throw std::runtime_error("tensor-core GEMM does not fit shared memory");
             if (2 * g.NP + (tail ? 2 * g.NP2 : 0) > 512) throw std::runtime_error("tensor-core GEMM does not fit TMEM");
+            L.gl = gemm_smem_layout(g.K8, g.NP, g.NP2, ns, tail, g.pool != 0, g.slot_bytes);
             g.n_stage = ns;
             L.gemm_groups = (g.tiles_per_crop + g.tiles_per_cta - 1) / g.tiles_per_cta;
             P->launches.push_back(L);
@@ -161,8 +169,8 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     L.kind = cs.kind;
                     L.cls = CLS_LIGHTCONV;
                     ChainTcArgs& c = L.chain;
-                    make_act_map(&c.map_hi, P->X1.hi, P->chunk, midp / 8, H, Wd, Wd + 2, cs.R + 8, midp / 8);
-                    make_act_map(&c.map_lo, P->X1.lo, P->chunk, midp / 8, H, Wd, Wd + 2, cs.R + 8, midp / 8);
+                    make_rows_map(&c.map_hi, P->X1.hi, P->chunk, midp / 8, H, Wd, cs.R + 8);
+                    make_rows_map(&c.map_lo, P->X1.lo, P->chunk, midp / 8, H, Wd, cs.R + 8);
                     for (int l = 0; l < 10; ++l) {
                         c.wpw[l] = WB + bo[bi].pw[l];
                         c.wdw[l] = WF + bo[bi].dw[l];
@@ -175,18 +183,28 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     dbg(L, 200 + bi, P->Y, 4 * midp / 8, H * Wd, 4 * midp);
                     P->launches.push_back(L);
                 }
-                {   // gate + conv3 (+ downsample / identity) + ReLU, and the next block's conv1 on the fresh tile
+                {   // ChannelGate of the four branches (one CTA per crop)
+                    Launch L{};
+                    L.kind = LK_GATES;
+                    L.cls = CLS_GATES;
+                    GatesTcArgs& ga = L.gates;
+                    for (int br = 0; br < 4; ++br) ga.sums[br] = P->sums[br];
+                    ga.g1w = W32 + b.g1w; ga.g1b = W32 + b.g1b; ga.g2w = W32 + b.g2w; ga.g2b = W32 + b.g2b;
+                    ga.gates = P->gates;
+                    ga.mid = b.mid; ga.midp = midp; ga.hid = b.hid; ga.tiles = H / cs.R; ga.HW = H * Wd;
+                    P->launches.push_back(L);
+                }
+                {   // gate (x) conv3 (+ downsample / identity) + ReLU, and the next block's conv1 on the fresh tile
                     Launch L = gemm(H, Wd, {{&P->Y, 4 * midp / 8}, {X, xC8}}, bo[bi].cx, b.cout, bo[bi].cxb, true);
                     GemmTcArgs& g = L.gemm;
                     g.w3 = W32 + b.cw;
-                    for (int br = 0; br < 4; ++br) g.sums[br] = P->sums[br];
-                    g.g1w = W32 + b.g1w; g.g1b = W32 + b.g1b; g.g2w = W32 + b.g2w; g.g2b = W32 + b.g2b;
-                    g.mid = b.mid; g.midp = midp; g.hid = b.hid; g.gate_tiles = H / cs.R;
+                    g.gates = P->gates;
+                    g.mid = b.mid; g.midp = midp;
                     g.out_hi = Xo->hi; g.out_lo = Xo->lo;
                     if (j == 0) {
                         const BlockW& nb = m->blocks[bi + 1];
                         const int nmidp = pad16(nb.mid);
-                        const GemmSmem probe = gemm_smem_layout(g.K8, g.NP, nmidp, 2, true, false);
+                        const GemmSmem probe = gemm_smem_layout(g.K8, g.NP, nmidp, 2, true, false, 4 * 128 * 16 * 2);
                         if ((int)probe.total <= P->smem_limit) {
                             g.b2_packed = WB + bo[bi + 1].c1;
                             g.bias2 = WF + bo[bi + 1].c1b;
@@ -258,6 +276,9 @@ int plan_run(ReidModel* m, const int* d_n, int off, int upper, cudaStream_t st, 
                 break;
             case LK_CHAIN_S4:
                 k_chain_tc<32, 32, 8, 16><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<32, 8, 16>::SMEM, st>>>(L.chain, d_n, off, upper);
+                break;
+            case LK_GATES:
+                k_gates_tc<<<upper, 128, 0, st>>>(L.gates, d_n, off, upper);
                 break;
             case LK_GEMM:
                 k_gemm_tc<<<dim3(L.gemm_groups, upper), GEMM_THREADS, L.gl.total, st>>>(L.gemm, d_n, off, upper, L.gl);
