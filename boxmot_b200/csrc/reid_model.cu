@@ -1731,6 +1731,23 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             ++stage_idx;
             return false;
         };
+        if (m->tc && m->debug_stop != 0 && m->debug_stop != 1) {
+            // tensor-core path: crop staging, stem and max pool are one fused kernel (k_front_tc); diagnostic stops at the
+            // blob / stem tensors (0, 1) run the float32 kernels below instead
+            bool tc_stopped = false;
+            const tcx::FrontInput fi{d_images, image_stride, rows, cols, d_crops};
+            L.launches += tcx::plan_run(m, fi, d_ncrops, off, upper, st, &tc_stopped, L);
+            if (!tc_stopped) {
+                const int C = m->c[3];
+                L.begin(CLS_HEAD);
+                k_head<<<upper, 256, sizeof(float) * (C + 32 + (256 / C > 0 ? 256 / C : 1) * C), st>>>(
+                    m->tc->c5, 128, C, W + m->fcw, W + m->fcb, m->feat, d_crops, d_ncrops, off, upper, d_out, out_ld);
+                L.end();
+                ++L.launches;
+            }
+            launches += L.launches;
+            continue;
+        }
         L.begin(CLS_CROP);
         k_crop_resize_norm<<<upper, 256, 0, st>>>(d_images, image_stride, rows, cols, d_crops, d_ncrops, off, upper,
                                                   m->blob);
@@ -1747,20 +1764,6 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             ++L.launches;
         }
         if (stop_here(m->bufA, (size_t)8192 * m->c[0])) { launches += L.launches; continue; }
-        if (m->tc) {
-            bool tc_stopped = false;
-            L.launches += tcx::plan_run(m, d_ncrops, off, upper, st, &tc_stopped, L);
-            if (!tc_stopped) {
-                const int C = m->c[3];
-                L.begin(CLS_HEAD);
-                k_head<<<upper, 256, sizeof(float) * (C + 32 + (256 / C > 0 ? 256 / C : 1) * C), st>>>(
-                    m->tc->c5, 128, C, W + m->fcw, W + m->fcb, m->feat, d_crops, d_ncrops, off, upper, d_out, out_ld);
-                L.end();
-                ++L.launches;
-            }
-            launches += L.launches;
-            continue;
-        }
         L.begin(CLS_MAXPOOL);
         k_maxpool3s2<<<148 * 8, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_ncrops, off, upper, m->bufB);
         L.end();

@@ -788,5 +788,239 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
     if (warp == 1) um::tmem_dealloc(tmem, tmem_cols);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_front_tc: detection crop -> OpenCV-exact bilinear resize (uint8) -> 7x7 stride-2 stem (+BN, ReLU) on the tensor
+// cores -> 3x3 stride-2 max pool -> split planes P [crops][2][64][32][8].  Replaces get_crops + ConvLayer + maxpool
+// (reid/backends/base_backend.py:148-195, reid/backbones/osnet.py:27-60,380-384) and the float32 blob / stem tensors
+// of round 1 (82 MB + 109 MB per frame written and re-read).
+//
+// * The resized crop is integer valued (cv2.resize on uint8): it is EXACT in BF16, so the A operand has no low part.
+//   The input normalisation is folded into the weights, W' = w / (255 std), and into a bias table,
+//   b' = b - sum_{taps inside the image} w mean / std, one entry per (row class, column class) of the output pixel
+//   (zero padding applies to the NORMALISED input: at the border some taps do not contribute their mean term).
+// * A CTA = (crop, strip of 8 pooled columns): the 39 input columns it needs are staged column-major with 4 channels
+//   per pixel, [col][padded row][R G B 0] BF16 (8 B per pixel, 2112 B per column).  The 7 vertical taps x 4 channels of
+//   output row oy of one input column are then the 64 contiguous bytes at 16 * oy: a "Toeplitz" A operand with
+//   LBO = 16 B, SBO = 128 B (overlapping rows; validated on hardware, profiles/r2_tc_probe.jsonl).  One M tile = the
+//   128 output rows of one stem column; K = 7 kx x (8 taps x 4 channels) = 14 K steps of 16; B = [W'_hi | W'_lo].
+// * TMEM lanes = output rows: the pool's horizontal maximum runs over consecutive accumulators in the same thread, the
+//   vertical one over neighbouring lanes (shuffles; the three warp boundaries go through 3 KB of shared memory).
+// grid = (4 strips, crops), 256 threads, 2 CTAs / SM (108 KB shared memory, 256 TMEM columns each).
+// ------------------------------------------------------------------------------------------------------------------
+struct FrontTcArgs {
+    const uint8_t* images;
+    size_t image_stride;
+    int rows, cols;
+    const void* crops;                  // CropDesc[] (engine.h): x1, y1, x2, y2, image, out_row
+    const bf16* w;                      // [7 kx][4 k8][32 n'][8]: n' < 16 hi, n' >= 16 lo
+    const float* bias_tab;              // [4 row classes][4 column classes][16]
+    bf16* p_hi;
+    bf16* p_lo;
+    float* dbg_crop;                    // diagnostics: resized crop [crops][256][128][3] (RGB) as float, or null
+};
+struct FrontCrop { float x1, y1, x2, y2; int image, out_row; };
+
+constexpr int FR_COLS = 39, FR_ROWS = 264, FR_CS = FR_ROWS * 8;          // staged columns, padded rows, bytes per column
+constexpr int FR_A_BYTES = FR_COLS * FR_CS;
+constexpr int FR_W_BYTES = 7 * 4 * 32 * 16;
+constexpr size_t FR_SMEM = FR_A_BYTES + FR_W_BYTES + 128;
+
+__device__ __forceinline__ void fr_coeff(int d, int src_n, double scale, bool clamp, int& idx, int& a0, int& a1) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f = f - (float)s;
+    if (clamp) {
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src_n - 1) { s = src_n - 1; f = 0.f; }
+    }
+    idx = s;
+    a0 = (int)rintf((1.0f - f) * 2048.0f);
+    a1 = (int)rintf(f * 2048.0f);
+}
+
+__global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const int* __restrict__ d_n, int off, int cap) {
+    const int n = blockIdx.y;
+    if (n >= tc_chunk_count(d_n, off, cap)) return;
+    const int strip = blockIdx.x;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int xi[128], xa0[128], xa1[128], yi[256], ya0[256], ya1[256];
+    __shared__ __align__(16) float sBias[4 * 4 * 16];
+    __shared__ __align__(16) float sEx[3][4][16];                 // boundary rows oy = 31, 63, 95 of the 4 pooled columns of a batch
+    unsigned char* sA = smem;
+    unsigned char* sW = smem + FR_A_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const FrontCrop cd = reinterpret_cast<const FrontCrop*>(a.crops)[off + n];
+
+    if (warp == 1) um::tmem_alloc(&tmem_slot, 256);
+    if (threadIdx.x == 0) { um::mbar_init(&bar_mma, 1); um::fence_mbar_init(); }
+    // box.round().astype(int): round half to even; clip to the frame (base_backend.py:160-175)
+    const int x1 = (int)rintf(cd.x1), y1 = (int)rintf(cd.y1), x2 = (int)rintf(cd.x2), y2 = (int)rintf(cd.y2);
+    const int cx1 = max(0, x1), cy1 = max(0, y1), cx2 = min(a.cols, x2), cy2 = min(a.rows, y2);
+    const bool valid = cx2 > cx1 && cy2 > cy1;
+    const int sw = cx2 - cx1, sh = cy2 - cy1;
+    if (valid) {
+        const double sx = 1.0 / (128.0 / (double)sw), sy = 1.0 / (256.0 / (double)sh);
+        for (int d = threadIdx.x; d < 128; d += 256) fr_coeff(d, sw, sx, true, xi[d], xa0[d], xa1[d]);
+        for (int d = threadIdx.x; d < 256; d += 256) fr_coeff(d, sh, sy, false, yi[d], ya0[d], ya1[d]);
+    }
+    for (int e = threadIdx.x; e < FR_A_BYTES / 16; e += 256) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int e = threadIdx.x; e < FR_W_BYTES / 16; e += 256) reinterpret_cast<uint4*>(sW)[e] = reinterpret_cast<const uint4*>(a.w)[e];
+    for (int e = threadIdx.x; e < 256; e += 256) sBias[e] = a.bias_tab[e];
+    __syncthreads();
+    const int xin0 = 32 * strip - 5;                               // input column of staged column 0
+    if (valid) {
+        // cv2.resize(INTER_LINEAR) on uint8: 11-bit coefficients, horizontal pass in int32, vertical
+        // (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2  (bit-exact; tests pin it against OpenCV)
+        const uint8_t* img = a.images + (size_t)cd.image * a.image_stride;
+        for (int p = threadIdx.x; p < FR_COLS * 256; p += 256) {
+            const int lc = p >> 8, dy = p & 255;
+            const int dx = xin0 + lc;
+            if (dx < 0 || dx >= 128) continue;
+            const int sx0 = xi[dx], sx1 = min(sx0 + 1, sw - 1);
+            const int r0 = min(max(yi[dy], 0), sh - 1), r1 = min(max(yi[dy] + 1, 0), sh - 1);
+            const uint8_t* p0 = img + ((size_t)(cy1 + r0) * a.cols + cx1) * 3;
+            const uint8_t* p1 = img + ((size_t)(cy1 + r1) * a.cols + cx1) * 3;
+            const int a0 = xa0[dx], a1 = xa1[dx], b0 = ya0[dy], b1 = ya1[dy];
+            int v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int h0 = (int)p0[sx0 * 3 + c] * a0 + (int)p0[sx1 * 3 + c] * a1;
+                const int h1 = (int)p1[sx0 * 3 + c] * a0 + (int)p1[sx1 * 3 + c] * a1;
+                const int r = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                v[c] = min(max(r, 0), 255);
+            }
+            // BGR source -> RGB network order; integers 0..255 are exact in BF16
+            const __nv_bfloat162 rg = __floats2bfloat162_rn((float)v[2], (float)v[1]);
+            const __nv_bfloat162 b_ = __floats2bfloat162_rn((float)v[0], 0.f);
+            *reinterpret_cast<uint2*>(sA + (size_t)lc * FR_CS + (size_t)(dy + 3) * 8) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&b_));
+            if (a.dbg_crop) {
+                float* o = a.dbg_crop + (((size_t)n * 256 + dy) * 128 + dx) * 3;
+                o[0] = (float)v[2]; o[1] = (float)v[1]; o[2] = (float)v[0];
+            }
+        }
+    } else if (a.dbg_crop) {
+        for (int p = threadIdx.x; p < FR_COLS * 256; p += 256) {
+            const int dx = xin0 + (p >> 8), dy = p & 255;
+            if (dx >= 0 && dx < 128) {
+                float* o = a.dbg_crop + (((size_t)n * 256 + dy) * 128 + dx) * 3;
+                o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
+            }
+        }
+    }
+    um::fence_async_smem();
+    um::tc_fence_before();
+    __syncthreads();
+    um::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    // stem columns of this strip: j = 0..16  <->  ox = 16 * strip - 1 + j  (ox = -1 does not exist: zero)
+    const int q = warp & 3, half = warp >> 2;                      // TMEM lane quadrant, channel half (8 channels)
+    const int oy = q * 32 + lane;
+    const int rc = oy == 0 ? 0 : (oy == 1 ? 1 : (oy == 127 ? 3 : 2));
+    float prev1[8], prev2[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { prev1[c] = 0.f; prev2[c] = 0.f; }
+    uint32_t mma_phase = 0;
+    for (int j0 = 0; j0 < 17; j0 += 8) {
+        const int j1 = min(j0 + 8, 17);
+        if (threadIdx.x == 0) {
+            const uint32_t id2 = um::idesc_bf16(128, 32);
+            const uint32_t sa = um::smem_u32(sA), sw_ = um::smem_u32(sW);
+            for (int j = j0; j < j1; ++j) {
+                if (16 * strip - 1 + j < 0) continue;
+                const uint32_t d = tmem + (uint32_t)((j - j0) * 32);
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        um::mma_bf16(d, um::make_desc(sa + (uint32_t)(2 * j + kx) * FR_CS + ks * 32, 16, 128),
+                                     um::make_desc(sw_ + (uint32_t)(kx * 4 + 2 * ks) * 512u, 512u, 128), id2, (kx | ks) != 0);
+            }
+            um::mma_commit(&bar_mma);
+        }
+        um::mbar_wait(&bar_mma, mma_phase);
+        mma_phase ^= 1u;
+        um::tc_fence_after();
+        // ---- epilogue: bias + ReLU, horizontal 3-max over consecutive stem columns (registers) ----
+        float hreg[4][8];
+        int n_h = 0;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = j0 + jj;
+            if (j < j1) {
+                const int ox = 16 * strip - 1 + j;
+                float v[8];
+                if (ox >= 0) {
+                    uint32_t r1[8], r2[8];
+                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(jj * 32 + half * 8);
+                    um::tmem_ld8(ta, r1);
+                    um::tmem_ld8(ta + 16, r2);
+                    um::tmem_ld_wait();
+                    const int cc = ox == 0 ? 0 : (ox == 1 ? 1 : (ox == 63 ? 3 : 2));
+                    const float* bb = sBias + (rc * 4 + cc) * 16 + half * 8;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = fmaxf(__uint_as_float(r1[c]) + __uint_as_float(r2[c]) + bb[c], 0.f);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+                }
+                if ((j & 1) == 0 && j >= 2) {                      // ox = 2 px + 1: third column of pooled px = 8 strip + j / 2 - 1
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) hreg[(jj >> 1) & 3][c] = fmaxf(fmaxf(prev2[c], prev1[c]), v[c]);
+                    ++n_h;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { prev2[c] = prev1[c]; prev1[c] = v[c]; }
+            }
+        }
+        // pooled columns finished in this batch: j = 2, 4, 6 (batch 0: also ... ) -> slots by (jj >> 1)
+        // batch 0 (j0 = 0): j = 2, 4, 6 -> slots 1, 2, 3;  batch 1 (j0 = 8): j = 8, 10, 12, 14 -> slots 0..3;  batch 2: j = 16 -> slot 0
+        const int s_first = j0 == 0 ? 1 : 0, s_last = j0 == 0 ? 3 : (j0 == 8 ? 3 : 0);
+        // ---- vertical 3-max over lanes (oy - 1, oy, oy + 1); warp boundaries through shared memory ----
+        if (lane == 31 && q < 3) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s >= s_first && s <= s_last) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) sEx[q][s][half * 8 + c] = hreg[s][c];
+                }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s < s_first || s > s_last) continue;
+            float m[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float h = hreg[s][c];
+                float up = __shfl_up_sync(0xffffffffu, h, 1);
+                const float dn = __shfl_down_sync(0xffffffffu, h, 1);
+                if (lane == 0) up = q > 0 ? sEx[q - 1][s][half * 8 + c] : 0.f;
+                m[c] = fmaxf(fmaxf(up, h), dn);
+            }
+            if ((lane & 1) == 0) {
+                // pooled pixel (py, px): j of the slot = j0 + 2 s (+ 0), px = 8 strip + (j0 + 2 s) / 2 - 1
+                const int px = 8 * strip + (j0 + 2 * s) / 2 - 1;
+                const int py = oy >> 1;
+                uint32_t h4[4], l4[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) um::split2(m[2 * c], m[2 * c + 1], h4[c], l4[c]);
+                const size_t e = (((size_t)n * 2 + half) * 64 + py) * 32 + px;
+                reinterpret_cast<uint4*>(a.p_hi)[e] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                reinterpret_cast<uint4*>(a.p_lo)[e] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+            }
+        }
+        um::tc_fence_before();
+        __syncthreads();                                            // TMEM and sEx are reused by the next batch
+        um::tc_fence_after();
+        (void)n_h;
+    }
+    if (warp == 1) um::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace tcx
 }  // namespace bmb

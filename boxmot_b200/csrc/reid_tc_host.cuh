@@ -91,7 +91,7 @@ struct Planes {
     bf16* lo = nullptr;
 };
 
-enum LaunchKind { LK_CHAIN_S2, LK_CHAIN_S3, LK_CHAIN_S4, LK_GEMM, LK_MAXPOOL_PLANES, LK_GATES };
+enum LaunchKind { LK_CHAIN_S2, LK_CHAIN_S3, LK_CHAIN_S4, LK_GEMM, LK_MAXPOOL_PLANES, LK_GATES, LK_FRONT };
 struct Launch {
     int kind = LK_GEMM;
     int cls = 0;                // profiling class
@@ -99,6 +99,7 @@ struct Launch {
     int chain_tiles = 0;
     GemmTcArgs gemm{};
     GatesTcArgs gates{};
+    FrontTcArgs front{};
     GemmSmem gl{};
     int gemm_groups = 0;
     int stage_after = -1;       // debug stage index whose tensor exists after this launch
@@ -116,6 +117,7 @@ struct Plan {
     float* c5 = nullptr;        // conv5 output [crops][128][C3] float32
     float* sums[4] = {nullptr, nullptr, nullptr, nullptr};
     float* gates = nullptr;     // [crops][4][midp]
+    float* dbg_crop = nullptr;  // resized crops of the fused front kernel (diagnostics, allocated on first use)
     float* dbg = nullptr;       // float32 NHWC copy of a stage (diagnostics)
     std::vector<Launch> launches;
     int smem_limit = 0;
@@ -133,7 +135,7 @@ inline void free_planes(Planes& p) {
 
 inline void plan_free(Plan* p) {
     if (!p) return;
-    cudaFree(p->d_wb); cudaFree(p->d_wf); cudaFree(p->c5); cudaFree(p->dbg); cudaFree(p->gates);
+    cudaFree(p->d_wb); cudaFree(p->d_wf); cudaFree(p->c5); cudaFree(p->dbg); cudaFree(p->gates); cudaFree(p->dbg_crop);
     for (int b = 0; b < 4; ++b) cudaFree(p->sums[b]);
     free_planes(p->P); free_planes(p->X1); free_planes(p->Y); free_planes(p->XA); free_planes(p->XB);
     delete p;

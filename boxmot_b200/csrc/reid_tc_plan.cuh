@@ -68,6 +68,40 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         }
         const size_t c5 = pack_b(wb, hw + m->c5w, m->c[3], m->c[3], m->c[3], m->c[3] / 8, m->c[3]);
         const size_t c5b = pack_f(wf, hw + m->c5b, m->c[3], m->c[3]);
+        // fused front kernel: stem weights with the input normalisation folded in, W' = w / (255 std), as
+        // [7 kx][4 k8][32 n' = hi | lo][8 k] with k = ky * 4 + ci (tap 7 and channel 3 are zero), and the bias table
+        // b - sum over the taps inside the image of w mean / std per (row class, column class)
+        size_t fw, fb;
+        {
+            const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};
+            const int C0 = m->c[0];
+            fw = (wb.size() + 63) / 64 * 64;
+            wb.resize(fw + 7 * 4 * 32 * 8, 0);
+            for (int kx = 0; kx < 7; ++kx)
+                for (int ky = 0; ky < 7; ++ky)
+                    for (int ci = 0; ci < 3; ++ci)
+                        for (int co = 0; co < C0; ++co) {
+                            const float v = (float)((double)hw[m->stem_w + (size_t)((ky * 7 + kx) * 3 + ci) * C0 + co] / (255.0 * stdv[ci]));
+                            const int k = ky * 4 + ci;
+                            uint16_t* plane = wb.data() + fw + ((size_t)(kx * 4 + k / 8) * 32) * 8;
+                            const uint16_t h = f2bf(v);
+                            plane[(size_t)co * 8 + k % 8] = h;
+                            plane[(size_t)(16 + co) * 8 + k % 8] = f2bf(v - bf2f(h));
+                        }
+            fb = (wf.size() + 3) / 4 * 4;
+            wf.resize(fb + 4 * 4 * 16, 0.f);
+            const int lo_[4] = {3, 1, 0, 0}, hi_[4] = {6, 6, 6, 4};       // valid taps per class: first/second/interior/last
+            for (int rc = 0; rc < 4; ++rc)
+                for (int cc = 0; cc < 4; ++cc)
+                    for (int co = 0; co < C0; ++co) {
+                        double acc = hw[m->stem_b + co];
+                        for (int ky = lo_[rc]; ky <= hi_[rc]; ++ky)
+                            for (int kx = lo_[cc]; kx <= hi_[cc]; ++kx)
+                                for (int ci = 0; ci < 3; ++ci)
+                                    acc -= (double)hw[m->stem_w + (size_t)((ky * 7 + kx) * 3 + ci) * C0 + co] * mean[ci] / stdv[ci];
+                        wf[fb + (rc * 4 + cc) * 16 + co] = (float)acc;
+                    }
+        }
         RCUDA_OK(cudaMalloc(&P->d_wb, wb.size() * 2 + 256));
         RCUDA_OK(cudaMemcpy(P->d_wb, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
         RCUDA_OK(cudaMalloc(&P->d_wf, wf.size() * 4 + 256));
@@ -81,6 +115,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<32, 24, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<32, 16, 8>::SMEM));
         RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<32, 32, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<32, 8, 16>::SMEM));
         RCUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, P->smem_limit));
+        RCUDA_OK(cudaFuncSetAttribute(k_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
 
         // ---- launches ----
         struct Src { Planes* buf; int C8; };
@@ -138,10 +173,14 @@ Plan* plan_build(ReidModel* m, const float* hw) {
             L.dbg_hi = buf.hi; L.dbg_lo = buf.lo; L.dbg_C8 = C8; L.dbg_HW = HW; L.dbg_C = C;
         };
 
-        {   // stem output (float32 NHWC in bufA) -> 3x3/2 max pool -> planes P
+        {   // crop + resize + stem + max pool -> planes P (one fused tensor-core kernel); launches[1] is the float32-stem
+            // fallback entry used when a diagnostic stop asks for the blob / stem tensors of the round-1 kernels
             Launch L{};
-            L.kind = LK_MAXPOOL_PLANES;
-            L.cls = CLS_MAXPOOL;
+            L.kind = LK_FRONT;
+            L.cls = CLS_STEM;
+            L.front.w = WB + fw;
+            L.front.bias_tab = WF + fb;
+            L.front.p_hi = P->P.hi; L.front.p_lo = P->P.lo;
             dbg(L, 2, P->P, 2, 2048, 16);
             P->launches.push_back(L);
         }
@@ -258,13 +297,25 @@ Plan* plan_build(ReidModel* m, const float* hw) {
 }
 
 // Replays the plan for one chunk of crops (the stem output of that chunk is in m->bufA).  Returns launches made.
+struct FrontInput { const uint8_t* images; size_t image_stride; int rows, cols; const CropDesc* crops; };
+
 template <class Prof>
-int plan_run(ReidModel* m, const int* d_n, int off, int upper, cudaStream_t st, bool* stopped, Prof& prof) {
+int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int upper, cudaStream_t st, bool* stopped, Prof& prof) {
     Plan* P = m->tc;
     int launches = 0;
     for (const Launch& L : P->launches) {
         prof.begin(L.cls);
         switch (L.kind) {
+            case LK_FRONT: {
+                FrontTcArgs fa = L.front;
+                fa.images = fi.images; fa.image_stride = fi.image_stride; fa.rows = fi.rows; fa.cols = fi.cols; fa.crops = fi.crops;
+                if (m->debug_stop == 50) {
+                    if (!P->dbg_crop) RCUDA_OK(cudaMalloc(&P->dbg_crop, sizeof(float) * (size_t)P->chunk * 256 * 128 * 3));
+                    fa.dbg_crop = P->dbg_crop;
+                }
+                k_front_tc<<<dim3(4, upper), 256, FR_SMEM, st>>>(fa, d_n, off, upper);
+                break;
+            }
             case LK_MAXPOOL_PLANES:
                 k_maxpool_planes<<<148 * 4, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_n, off, upper, P->P.hi, P->P.lo);
                 break;
@@ -286,6 +337,12 @@ int plan_run(ReidModel* m, const int* d_n, int off, int upper, cudaStream_t st, 
         }
         prof.end();
         ++launches;
+        if (m->debug_stop == 50 && L.kind == LK_FRONT) {
+            m->debug_ptr = P->dbg_crop;
+            m->debug_floats_per_crop = (size_t)256 * 128 * 3;
+            *stopped = true;
+            return launches;
+        }
         if (m->debug_stop >= 0 && L.stage_after == m->debug_stop) {
             if (L.stage_after == 11) {
                 m->debug_ptr = P->c5;

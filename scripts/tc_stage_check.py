@@ -71,6 +71,9 @@ def main():
                 x = stages[f"conv{s + 2}.2"]
         c5 = F.relu(orid._bn(sd, "conv5.bn", F.conv2d(x, sd["conv5.conv.weight"])))
         want[11] = nhwc(c5)
+    g50 = reid.debug_stage(boxes, img, 50).reshape(len(boxes), 256, 128, 3)
+    w50 = orid.crop_boxes(boxes, img).astype(np.float32)
+    print("stage   50 (fused resize, uint8 RGB): mismatching values", int((g50 != w50).sum()), "of", g50.size)
     order = [1, 2, 100, 200, 3, 101, 201, 4, 5, 102, 202, 6, 103, 203, 7, 8, 104, 204, 9, 105, 205, 10, 11]
     worst = 0.0
     for st in order:
