@@ -821,7 +821,7 @@ struct FrontTcArgs {
 };
 struct FrontCrop { float x1, y1, x2, y2; int image, out_row; };
 
-constexpr int FR_COLS = 39, FR_ROWS = 264, FR_CS = FR_ROWS * 8;          // staged columns, padded rows, bytes per column
+constexpr int FR_COLS = 39, FR_ROWS = 264, FR_CS = FR_ROWS * 8 + 16;     // staged columns, padded rows, bytes per column (+16: bank spread)
 constexpr int FR_A_BYTES = FR_COLS * FR_CS;
 constexpr int FR_W_BYTES = 7 * 4 * 32 * 16;
 constexpr size_t FR_SMEM = FR_A_BYTES + FR_W_BYTES + 128;
@@ -853,6 +853,14 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
     unsigned char* sW = smem + FR_A_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const FrontCrop cd = reinterpret_cast<const FrontCrop*>(a.crops)[off + n];
+#ifdef BMB_TC_CLOCKS
+    long long fk[16];
+    int nfk = 0;
+#define FCK() do { if (threadIdx.x == 0 && nfk < 16) fk[nfk++] = clock64(); } while (0)
+#else
+#define FCK() do { } while (0)
+#endif
+    FCK();
 
     if (warp == 1) um::tmem_alloc(&tmem_slot, 256);
     if (threadIdx.x == 0) { um::mbar_init(&bar_mma, 1); um::fence_mbar_init(); }
@@ -870,42 +878,64 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
     for (int e = threadIdx.x; e < FR_W_BYTES / 16; e += 256) reinterpret_cast<uint4*>(sW)[e] = reinterpret_cast<const uint4*>(a.w)[e];
     for (int e = threadIdx.x; e < 256; e += 256) sBias[e] = a.bias_tab[e];
     __syncthreads();
+    FCK();
     const int xin0 = 32 * strip - 5;                               // input column of staged column 0
     if (valid) {
         // cv2.resize(INTER_LINEAR) on uint8: 11-bit coefficients, horizontal pass in int32, vertical
         // (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2  (bit-exact; tests pin it against OpenCV)
         const uint8_t* img = a.images + (size_t)cd.image * a.image_stride;
-        for (int p = threadIdx.x; p < FR_COLS * 256; p += 256) {
-            const int lc = p >> 8, dy = p & 255;
-            const int dx = xin0 + lc;
-            if (dx < 0 || dx >= 128) continue;
-            const int sx0 = xi[dx], sx1 = min(sx0 + 1, sw - 1);
-            const int r0 = min(max(yi[dy], 0), sh - 1), r1 = min(max(yi[dy] + 1, 0), sh - 1);
-            const uint8_t* p0 = img + ((size_t)(cy1 + r0) * a.cols + cx1) * 3;
-            const uint8_t* p1 = img + ((size_t)(cy1 + r1) * a.cols + cx1) * 3;
-            const int a0 = xa0[dx], a1 = xa1[dx], b0 = ya0[dy], b1 = ya1[dy];
-            int v[3];
+        // lanes run along the staged columns of one output row: neighbouring lanes read neighbouring source pixels of the
+        // same two source rows (coalesced); four pixels per thread are in flight at once (the loop is latency-bound:
+        // table lookups -> 12 byte loads -> integer arithmetic -> one 8-byte shared store)
+        for (int base = threadIdx.x; base < 40 * 256; base += 4 * 256) {
+            int h0[4][3], h1[4][3], bb0[4], bb1[4], so[4];
+            bool ok[4];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int h0 = (int)p0[sx0 * 3 + c] * a0 + (int)p0[sx1 * 3 + c] * a1;
-                const int h1 = (int)p1[sx0 * 3 + c] * a0 + (int)p1[sx1 * 3 + c] * a1;
-                const int r = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-                v[c] = min(max(r, 0), 255);
+            for (int u = 0; u < 4; ++u) {
+                const int p = base + u * 256;
+                const int dy = p / 40, lc = p - dy * 40;
+                const int dx = xin0 + lc;
+                ok[u] = p < 40 * 256 && lc < FR_COLS && dx >= 0 && dx < 128;
+                const int dxc = min(max(dx, 0), 127), dyc = min(dy, 255);
+                const int sx0 = xi[dxc], sx1 = min(sx0 + 1, sw - 1);
+                const int r0 = min(max(yi[dyc], 0), sh - 1), r1 = min(max(yi[dyc] + 1, 0), sh - 1);
+                const uint8_t* p0 = img + ((size_t)(cy1 + r0) * a.cols + cx1) * 3;
+                const uint8_t* p1 = img + ((size_t)(cy1 + r1) * a.cols + cx1) * 3;
+                const int a0 = xa0[dxc], a1 = xa1[dxc];
+                bb0[u] = ya0[dyc]; bb1[u] = ya1[dyc];
+                so[u] = lc * FR_CS + (dyc + 3) * 8;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    h0[u][c] = (int)__ldg(p0 + sx0 * 3 + c) * a0 + (int)__ldg(p0 + sx1 * 3 + c) * a1;
+                    h1[u][c] = (int)__ldg(p1 + sx0 * 3 + c) * a0 + (int)__ldg(p1 + sx1 * 3 + c) * a1;
+                }
             }
-            // BGR source -> RGB network order; integers 0..255 are exact in BF16
-            const __nv_bfloat162 rg = __floats2bfloat162_rn((float)v[2], (float)v[1]);
-            const __nv_bfloat162 b_ = __floats2bfloat162_rn((float)v[0], 0.f);
-            *reinterpret_cast<uint2*>(sA + (size_t)lc * FR_CS + (size_t)(dy + 3) * 8) =
-                make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&b_));
-            if (a.dbg_crop) {
-                float* o = a.dbg_crop + (((size_t)n * 256 + dy) * 128 + dx) * 3;
-                o[0] = (float)v[2]; o[1] = (float)v[1]; o[2] = (float)v[0];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                int v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int r = (((bb0[u] * (h0[u][c] >> 4)) >> 16) + ((bb1[u] * (h1[u][c] >> 4)) >> 16) + 2) >> 2;
+                    v[c] = min(max(r, 0), 255);
+                }
+                // BGR source -> RGB network order; integers 0..255 are exact in BF16
+                const __nv_bfloat162 rg = __floats2bfloat162_rn((float)v[2], (float)v[1]);
+                const __nv_bfloat162 b_ = __floats2bfloat162_rn((float)v[0], 0.f);
+                *reinterpret_cast<uint2*>(sA + so[u]) = make_uint2(*reinterpret_cast<const uint32_t*>(&rg), *reinterpret_cast<const uint32_t*>(&b_));
+                if (a.dbg_crop) {
+                    const int p = base + u * 256;
+                    const int dy = p / 40, dx = xin0 + (p - dy * 40);
+                    float* o = a.dbg_crop + (((size_t)n * 256 + dy) * 128 + dx) * 3;
+                    o[0] = (float)v[2]; o[1] = (float)v[1]; o[2] = (float)v[0];
+                }
             }
         }
     } else if (a.dbg_crop) {
-        for (int p = threadIdx.x; p < FR_COLS * 256; p += 256) {
-            const int dx = xin0 + (p >> 8), dy = p & 255;
-            if (dx >= 0 && dx < 128) {
+        for (int p = threadIdx.x; p < 40 * 256; p += 256) {
+            const int dy = p / 40, lc = p - dy * 40;
+            const int dx = xin0 + lc;
+            if (lc < FR_COLS && dx >= 0 && dx < 128) {
                 float* o = a.dbg_crop + (((size_t)n * 256 + dy) * 128 + dx) * 3;
                 o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
             }
@@ -916,6 +946,7 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
     __syncthreads();
     um::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    FCK();
 
     // stem columns of this strip: j = 0..16  <->  ox = 16 * strip - 1 + j  (ox = -1 does not exist: zero)
     const int q = warp & 3, half = warp >> 2;                      // TMEM lane quadrant, channel half (8 channels)
@@ -942,28 +973,33 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
             }
             um::mma_commit(&bar_mma);
         }
+        FCK();
         um::mbar_wait(&bar_mma, mma_phase);
         mma_phase ^= 1u;
         um::tc_fence_after();
+        FCK();
         // ---- epilogue: bias + ReLU, horizontal 3-max over consecutive stem columns (registers) ----
         float hreg[4][8];
         int n_h = 0;
+        uint32_t ra[2][8], rb[2][8];                               // double-buffered TMEM reads: the next column's loads fly
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 8);
+        {
+            const int ox0 = 16 * strip - 1 + j0;
+            if (ox0 >= 0) { um::tmem_ld8(tq, ra[0]); um::tmem_ld8(tq + 16, rb[0]); }
+        }
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
             const int j = j0 + jj;
             if (j < j1) {
                 const int ox = 16 * strip - 1 + j;
+                um::tmem_ld_wait();
+                if (jj + 1 < 8 && j + 1 < j1) { um::tmem_ld8(tq + (jj + 1) * 32, ra[(jj + 1) & 1]); um::tmem_ld8(tq + (jj + 1) * 32 + 16, rb[(jj + 1) & 1]); }
                 float v[8];
                 if (ox >= 0) {
-                    uint32_t r1[8], r2[8];
-                    const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(jj * 32 + half * 8);
-                    um::tmem_ld8(ta, r1);
-                    um::tmem_ld8(ta + 16, r2);
-                    um::tmem_ld_wait();
                     const int cc = ox == 0 ? 0 : (ox == 1 ? 1 : (ox == 63 ? 3 : 2));
                     const float* bb = sBias + (rc * 4 + cc) * 16 + half * 8;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) v[c] = fmaxf(__uint_as_float(r1[c]) + __uint_as_float(r2[c]) + bb[c], 0.f);
+                    for (int c = 0; c < 8; ++c) v[c] = fmaxf(__uint_as_float(ra[jj & 1][c]) + __uint_as_float(rb[jj & 1][c]) + bb[c], 0.f);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) v[c] = 0.f;
@@ -977,6 +1013,7 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
                 for (int c = 0; c < 8; ++c) { prev2[c] = prev1[c]; prev1[c] = v[c]; }
             }
         }
+        um::tmem_ld_wait();
         // pooled columns finished in this batch: j = 2, 4, 6 (batch 0: also ... ) -> slots by (jj >> 1)
         // batch 0 (j0 = 0): j = 2, 4, 6 -> slots 1, 2, 3;  batch 1 (j0 = 8): j = 8, 10, 12, 14 -> slots 0..3;  batch 2: j = 16 -> slot 0
         const int s_first = j0 == 0 ? 1 : 0, s_last = j0 == 0 ? 3 : (j0 == 8 ? 3 : 0);
@@ -1018,7 +1055,15 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
         __syncthreads();                                            // TMEM and sEx are reused by the next batch
         um::tc_fence_after();
         (void)n_h;
+        FCK();
     }
+#ifdef BMB_TC_CLOCKS
+    if (threadIdx.x == 0 && n == 5) {
+        printf("front strip %d: setup %lld resize %lld |", strip, fk[1] - fk[0], fk[2] - fk[1]);
+        for (int i = 2; i + 3 < nfk + 1; i += 3) printf(" issue %lld mma %lld epi %lld |", fk[i + 1] - fk[i], fk[i + 2] - fk[i + 1], fk[i + 3] - fk[i + 2]);
+        printf(" total %lld\n", fk[nfk - 1] - fk[0]);
+    }
+#endif
     if (warp == 1) um::tmem_dealloc(tmem, 256);
 }
 
