@@ -137,6 +137,8 @@ struct Engine {
     double marks_elapsed_ms();
 
    private:
+    void construct(const BoxMOTB200TrackerConfig& p);
+    void release();
     void ensure_images(int rows, int cols, bool host_too);
     void enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total);
     bool can_pipeline() const { return reid_stream != nullptr && !profile; }

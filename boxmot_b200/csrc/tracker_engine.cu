@@ -294,6 +294,15 @@ static TrkCfg make_core_cfg(const BoxMOTB200TrackerConfig& p) {
 }
 
 Engine::Engine(const BoxMOTB200TrackerConfig& p) {
+    try {
+        construct(p);
+    } catch (...) {
+        release();   // a failed create must not leak streams, events, device / pinned buffers or ReID models
+        throw;
+    }
+}
+
+void Engine::construct(const BoxMOTB200TrackerConfig& p) {
     if (p.n_streams < 1) throw std::runtime_error("n_streams must be >= 1");
     if (p.cap_tracks < 8 || p.cap_dets < 1) throw std::runtime_error("cap_tracks >= 8 and cap_dets >= 1 required");
     if (p.tracker != BOXMOT_B200_TRACKER_BOTSORT && p.tracker != BOXMOT_B200_TRACKER_BYTETRACK &&
@@ -474,8 +483,11 @@ Engine::Engine(const BoxMOTB200TrackerConfig& p) {
     CUDA_OK(cudaStreamSynchronize(stream));
 }
 
-Engine::~Engine() {
-    cudaStreamSynchronize(stream);
+Engine::~Engine() { release(); }
+
+// Everything the constructor acquires; safe on a partially constructed object (members start null).
+void Engine::release() {
+    if (stream) cudaStreamSynchronize(stream);
     for (int k = 0; k + 1 < n_split; ++k) {
         if (split_stream[k]) { cudaStreamSynchronize(split_stream[k]); cudaStreamDestroy(split_stream[k]); }
         if (ev_slice_done[k]) cudaEventDestroy(ev_slice_done[k]);
@@ -486,7 +498,10 @@ Engine::~Engine() {
     if (reid_stream) {
         cudaStreamSynchronize(reid_stream);
         cudaStreamDestroy(reid_stream);
-        for (int k = 0; k < 2; ++k) { cudaEventDestroy(ev_reid_done[k]); cudaEventDestroy(ev_assoc_done[k]); }
+        for (int k = 0; k < 2; ++k) {
+            if (ev_reid_done[k]) cudaEventDestroy(ev_reid_done[k]);
+            if (ev_assoc_done[k]) cudaEventDestroy(ev_assoc_done[k]);
+        }
         cudaFree(d_dets_alt); cudaFree(d_ndets_alt); cudaFree(d_embs_alt); cudaFree(d_streams_alt);
         cudaFree(d_docs_alt); cudaFree(d_ss_alt);
     }
@@ -495,9 +510,11 @@ Engine::~Engine() {
     cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_docs); cudaFree(d_ss); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
     cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
     cudaFreeHost(h_embs); cudaFreeHost(h_images); cudaFreeHost(h_ndets_ring);
-    cudaEventDestroy(mark[0]); cudaEventDestroy(mark[1]);
-    for (auto& e : ev) cudaEventDestroy(e);
-    cudaStreamDestroy(stream);
+    if (mark[0]) cudaEventDestroy(mark[0]);
+    if (mark[1]) cudaEventDestroy(mark[1]);
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
 }
 
 void Engine::reset() {
@@ -563,6 +580,10 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
             k_build_crops_docs<<<1, 32, 0, stream>>>(dcfg, d_docs, S, d_crops, d_ncrops, d_crops_hint);
             ++launches;
             launches += run_reid(stream, images_dev, rows, cols, max_dets_total, d_embs);
+        } else if (cfg.with_reid && embs_dev && embs_dev != d_embs) {
+            // caller-supplied device embeddings (update_device / DeviceFrameLoop): the kernels read the engine's buffer
+            CUDA_OK(cudaMemcpyAsync(d_embs, embs_dev, sizeof(float) * (size_t)cfg.feat_dim * cfg.cap_dets * S,
+                                    cudaMemcpyDeviceToDevice, stream));
         }
         CUDA_OK(cudaEventRecord(ev[1], stream));
         if (cfg.with_reid) {

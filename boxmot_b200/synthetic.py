@@ -175,3 +175,25 @@ def make_mobilenetv2_state(width_mult: float = 1.4, seed: int = 0, num_classes: 
     sd["classifier.weight"] = 0.01 * torch.randn(num_classes, feat, generator=g)
     sd["classifier.bias"] = torch.zeros(num_classes)
     return sd
+
+
+def cohort_stream(n_objects=2048, cohorts=4, frames=10, hw=(1080, 1920), seed=3, dim=512):
+    """BASELINE config 3 generator: `n_objects` fixed objects in `cohorts` cohorts, cohort f mod cohorts is
+    visible on frame f (every track is re-observed every `cohorts` frames < max_age) -> ~n_objects live tracks and
+    n_objects / cohorts detections per frame.  Returns (dets per frame, unit appearance rows per frame)."""
+    rng = np.random.default_rng(seed)
+    h, w = hw
+    cx, cy = rng.uniform(40, w - 40, n_objects), rng.uniform(60, h - 60, n_objects)
+    bw, bh = rng.uniform(20, 50, n_objects), rng.uniform(40, 100, n_objects)
+    conf = rng.uniform(0.4, 0.95, n_objects)
+    proto = np.abs(rng.normal(size=(n_objects, dim))).astype(np.float32)
+    dets, embs = [], []
+    for f in range(frames):
+        idx = np.arange(f % cohorts, n_objects, cohorts)
+        jx, jy = rng.normal(0, 2.0, idx.size), rng.normal(0, 2.0, idx.size)
+        d = np.stack([cx[idx] + jx - bw[idx] / 2, cy[idx] + jy - bh[idx] / 2, cx[idx] + jx + bw[idx] / 2,
+                      cy[idx] + jy + bh[idx] / 2, conf[idx], np.zeros(idx.size)], 1).astype(np.float32)
+        e = np.maximum(proto[idx] + 0.3 * rng.normal(size=(idx.size, dim)).astype(np.float32), 0)
+        dets.append(d)
+        embs.append((e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32))
+    return dets, embs

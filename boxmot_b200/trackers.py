@@ -246,6 +246,13 @@ class MultiStreamTracker:
         cfg.n_streams = int(n_streams)
         cfg.cap_tracks = int(cap_tracks)
         cfg.cap_dets = int(cap_dets)
+        if reid_blob:
+            # the engine takes the embedding width from the blob: keep this object's stride / width checks in step
+            import struct
+
+            with open(reid_blob, "rb") as fh:
+                hdr = struct.unpack("<16i", fh.read(64))
+            feat_dim = int(hdr[7]) if hdr[7] > 0 else feat_dim
         cfg.feat_dim = int(feat_dim)
         cfg.track_buffer = int(p["track_buffer"])
         cfg.frame_rate = int(p["frame_rate"])
@@ -483,7 +490,8 @@ class _SingleStreamTracker:
             # own device and hand the rows to the tracker, exactly where botsort.py:191-192 calls the model
             if self.model is None:
                 raise B200Error("with_reid=True needs reid_model=, embs=, or with_reid=False")
-            conf = dets[:, 4].astype(np.float64)
+            # the device re-derives the split from the float32 rows it receives: decide on the same rounded values
+            conf = np.asarray(dets, dtype=np.float32)[:, 4].astype(np.float64)
             first = conf >= eng.params["min_conf"] if eng.kind == "strongsort" else conf > eng.params["track_high_thresh"]
             embs = np.zeros((len(dets), eng.feat_dim), np.float32)
             if first.any():
@@ -609,6 +617,9 @@ def _flatten_yaml_defaults(node, acc=None):
     return acc
 
 
+_CMC_WARNED: dict = {}
+
+
 def resolve_tracker_args(tracker_type, tracker_config=None, evolve_param_dict=None, overrides=None):
     """(kind, class, constructor kwargs) exactly as the reference's `create_tracker` would assemble them
     (tracker_zoo.py:103-147): `evolve_param_dict` replaces the YAML defaults wholesale, `tracker_config` is a YAML file
@@ -637,6 +648,18 @@ def resolve_tracker_args(tracker_type, tracker_config=None, evolve_param_dict=No
         inspect.signature(_SingleStreamTracker.__init__).parameters) | {"cap_tracks", "cap_dets", "feat_dim"}
     accepted -= {"self", "params", "kwargs"}
     args = {k: v for k, v in args.items() if k in accepted}   # the reference's **kwargs swallows the rest
+    # Camera-motion estimation (motion/cmc/*, OpenCV) is outside the path: the reference's YAML defaults turn it on
+    # (botsort.yaml use_cmc: true / sof; DeepOCSORT and StrongSORT always), here the estimator is replaced by a warp
+    # the caller supplies through update(..., warp=).  Say so once instead of diverging silently.
+    wants_cmc = (kind == "botsort" and args.get("use_cmc", False)) or (kind == "deepocsort" and not args.get("cmc_off", False)) \
+        or kind == "strongsort"
+    if wants_cmc and not _CMC_WARNED.get(kind):
+        import warnings
+
+        _CMC_WARNED[kind] = True
+        warnings.warn(f"boxmot_b200.create_tracker('{kind}'): the reference configuration runs camera-motion compensation "
+                      f"({args.get('cmc_method', 'sof' if kind != 'strongsort' else 'ecc')}); this library applies only a warp "
+                      "supplied through update(..., warp=) -- without one the tracker behaves as with CMC off", stacklevel=3)
     args.pop("cmc_method", None)
     if kind == "botsort":
         args["use_cmc"] = False

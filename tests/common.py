@@ -138,3 +138,31 @@ def assert_rows_match(got, want, frame, *, exact_boxes=False, box_rtol=1e-4):
     else:
         np.testing.assert_allclose(got[:, :4], want[:, :4], rtol=box_rtol, atol=1e-3,
                                    err_msg=f"frame {frame}: boxes")
+
+
+class TorchDeviceOracleReID:
+    """TEST INFRASTRUCTURE: the oracle's functional backbone (oracle/reid.py, float32, TF32 off) evaluated by PyTorch on
+    the GPU so that end-to-end parity tests at the BASELINE configuration sizes (hundreds of crops per frame through
+    OSNet_x1_0 / MobileNetV2_x1_4, tens of frames) finish in seconds instead of tens of minutes on the host cores.  The
+    crop staging stays the oracle's CPU restatement (bit-exact cv2 arithmetic); only the convolutions move.  The product
+    never sees this class."""
+
+    def __init__(self, sd):
+        import torch
+
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        self.sd = {k: v.cuda() if hasattr(v, "cuda") else v for k, v in sd.items()}
+
+    def get_features(self, xyxys, img):
+        import torch
+
+        from oracle import reid as orid
+
+        xyxys = np.asarray(xyxys, dtype=np.float32)
+        if xyxys.size == 0:
+            return np.array([])
+        with torch.no_grad():
+            x = orid.get_crops(xyxys, img).cuda()
+            feats = torch.cat([orid.backbone_forward(self.sd, x[i:i + 128]) for i in range(0, len(x), 128)]).cpu().numpy()
+        return feats / np.linalg.norm(feats, axis=-1, keepdims=True)

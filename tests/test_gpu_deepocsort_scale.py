@@ -8,23 +8,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def cohort_stream(n_objects=2048, cohorts=4, frames=10, hw=(1080, 1920), seed=3, dim=512):
-    rng = np.random.default_rng(seed)
-    h, w = hw
-    cx, cy = rng.uniform(40, w - 40, n_objects), rng.uniform(60, h - 60, n_objects)
-    bw, bh = rng.uniform(20, 50, n_objects), rng.uniform(40, 100, n_objects)
-    conf = rng.uniform(0.4, 0.95, n_objects)
-    proto = np.abs(rng.normal(size=(n_objects, dim))).astype(np.float32)
-    dets, embs = [], []
-    for f in range(frames):
-        idx = np.arange(f % cohorts, n_objects, cohorts)
-        jx, jy = rng.normal(0, 2.0, idx.size), rng.normal(0, 2.0, idx.size)
-        d = np.stack([cx[idx] + jx - bw[idx] / 2, cy[idx] + jy - bh[idx] / 2, cx[idx] + jx + bw[idx] / 2,
-                      cy[idx] + jy + bh[idx] / 2, conf[idx], np.zeros(idx.size)], 1).astype(np.float32)
-        e = np.maximum(proto[idx] + 0.3 * rng.normal(size=(idx.size, dim)).astype(np.float32), 0)
-        dets.append(d)
-        embs.append((e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32))
-    return dets, embs
+from boxmot_b200.synthetic import cohort_stream  # noqa: E402  (the BASELINE config 3 generator, shared with bench.py)
 
 
 def test_config3_shape_ids_match_oracle_and_timing():

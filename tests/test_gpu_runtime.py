@@ -89,3 +89,30 @@ def test_tracker_runtime_reports_device_split(tmp_path):
         assert mot.shape == (len(tracks), 9) if len(tracks) else mot.shape == (0, 0)
     s = ts.summary()
     assert s["frames"] == len(frames) and s["reid_device"] > 0 and s["assoc_device"] > 0 and s["fps"] > 0
+
+
+@pytest.mark.parametrize("kind", ["deepocsort", "strongsort"])
+def test_device_resident_embeddings_reach_every_family(kind):
+    """`update_device(d_embs=...)` must associate on the caller's embeddings for DeepOCSORT and StrongSORT too (round 1
+    copied them only on the StrongSORT branch; DeepOCSORT silently used its own stale buffer)."""
+    import torch
+
+    import boxmot_b200 as bb
+
+    S, F, n, dim, CD = 2, 24, 30, 64, 64
+    frames, embs = _streams(S, F, n, dim)
+    kw = dict(n_streams=S, cap_tracks=256, cap_dets=CD, feat_dim=dim)
+    dev, host = bb.MultiStreamTracker(kind, **kw), bb.MultiStreamTracker(kind, **kw)
+    for f in range(F):
+        d = np.zeros((S, CD, 6), np.float32)
+        e = np.zeros((S, CD, dim), np.float32)
+        rows = []
+        for s in range(S):
+            k = len(frames[s][f])
+            d[s, :k], e[s, :k] = frames[s][f], embs[s][f]
+            rows.append(k)
+        dev.update_device(torch.from_numpy(d).cuda(), rows, torch.from_numpy(e).cuda())
+        got = dev.fetch()
+        want = host.update([frames[s][f] for s in range(S)], None, [embs[s][f] for s in range(S)])
+        for s in range(S):
+            assert np.array_equal(np.asarray(got[s]), np.asarray(want[s])), (kind, f, s)

@@ -24,16 +24,17 @@ from tests.hostsim import (HostSimDeepOcSort, HostSimStrongSort, HostSimTracker,
                            deepocsort_cfg, strongsort_cfg)
 
 
-def case_with_warps(seed):
-    """case(seed) plus, for every second seed of the trackers that take one, a supplied camera-motion warp per frame."""
-    kind, kw, frames, embs, sim, orc = case(seed)
+def case_with_warps(seed, build=True):
+    """case(seed) plus, for every second seed of the trackers that take one, a supplied camera-motion warp per frame.
+    build=False: inputs only (no host simulation / oracle objects), for the GPU soak."""
+    kind, kw, frames, embs, sim, orc = case(seed, build)
     warps = None
     if kind != "bytetrack" and (seed // 4) % 2 == 1:
         warps = warp_sequence(len(frames), seed=seed + 77)
     return kind, kw, frames, embs, sim, orc, warps
 
 
-def case(seed):
+def case(seed, build=True):
     rng = np.random.default_rng(seed)
     kind = ["bytetrack", "botsort", "deepocsort", "strongsort"][seed % 4]
     heavy = os.environ.get("SOAK_HEAVY") == "1"   # crowded, long streams (slow): rare lifecycle paths
@@ -57,6 +58,8 @@ def case(seed):
         kw = dict(BYTETRACK_YAML, track_thresh=float(rng.uniform(0.3, 0.7)), match_thresh=float(rng.uniform(0.6, 0.95)),
                   track_buffer=int(rng.integers(5, 40)), frame_rate=int(rng.choice([25, 30])),
                   min_conf=float(rng.uniform(0.05, 0.3)))
+        if not build:
+            return kind, kw, frames, None, None, None
         return kind, kw, frames, None, HostSimTracker(bytetrack_cfg(**kw)), ByteTrackOracle(**kw)
     if kind == "botsort":
         kw = dict(BOTSORT_YAML, track_high_thresh=float(rng.uniform(0.4, 0.7)), new_track_thresh=float(rng.uniform(0.4, 0.75)),
@@ -67,6 +70,8 @@ def case(seed):
                   unconfirmed_match_thresh=float(rng.uniform(0.3, 0.8)), unconfirmed_emb_scale=float(rng.uniform(1.0, 3.0)),
                   with_reid=bool(rng.integers(0, 4) > 0), frame_rate=int(rng.choice([25, 30])))
         embs = real_embs if real else stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+        if not build:
+            return kind, kw, frames, embs, None, None
         return kind, kw, frames, embs, HostSimTracker(botsort_cfg(feat_dim=dim, **kw)), BotSortOracle(**kw)
     if kind == "deepocsort":
         kw = dict(DEEPOCSORT_YAML, det_thresh=float(rng.uniform(0.2, 0.6)), w_association_emb=float(rng.uniform(0.2, 0.9)),
@@ -76,6 +81,9 @@ def case(seed):
                   aw_param=float(rng.uniform(0.3, 0.7)), Q_xy_scaling=float(rng.choice([0.01, 0.05])),
                   Q_s_scaling=float(rng.choice([0.0001, 0.001])))
         embs = real_embs if real else unit_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+        if not build:
+            int(rng.integers(0, 3))
+            return kind, kw, frames, embs, None, None
         sim = HostSimDeepOcSort(deepocsort_cfg(feat_dim=dim, **kw))
         sim.set_jv_wide(int(rng.integers(0, 3)))
         return kind, kw, frames, embs, sim, DeepOcSortOracle(**kw)
@@ -84,6 +92,8 @@ def case(seed):
               ema_alpha=float(rng.choice([0.8, 0.9])), mc_lambda=float(rng.choice([0.9, 0.98])),
               max_iou_dist=float(rng.uniform(0.5, 0.9)))
     embs = real_embs if real else stress_embeddings(frames, n_obj, dim=dim, seed=seed + 5)
+    if not build:
+        return kind, kw, frames, embs, None, None
     return kind, kw, frames, embs, HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=dim, **kw)), StrongSortOracle(**kw)
 
 
