@@ -153,7 +153,7 @@ def make_inputs(cfg, stream_index: int, frames: int):
     from boxmot_b200.synthetic import bench_stream, cohort_stream
 
     if cfg["gen"] == "cohort":
-        dets, _ = cohort_stream(frames=frames, hw=cfg["hw"], seed=3 + stream_index)
+        dets, _ = cohort_stream(frames=frames, hw=cfg["hw"], seed=3 + stream_index, conf_lo=0.55)
     else:
         _, dets = bench_stream(cfg["dets"], frames, hw=cfg["hw"], stream=stream_index)
     rng = np.random.default_rng(9000 + stream_index)

@@ -177,7 +177,7 @@ def make_mobilenetv2_state(width_mult: float = 1.4, seed: int = 0, num_classes: 
     return sd
 
 
-def cohort_stream(n_objects=2048, cohorts=4, frames=10, hw=(1080, 1920), seed=3, dim=512):
+def cohort_stream(n_objects=2048, cohorts=4, frames=10, hw=(1080, 1920), seed=3, dim=512, conf_lo=0.4):
     """BASELINE config 3 generator: `n_objects` fixed objects in `cohorts` cohorts, cohort f mod cohorts is
     visible on frame f (every track is re-observed every `cohorts` frames < max_age) -> ~n_objects live tracks and
     n_objects / cohorts detections per frame.  Returns (dets per frame, unit appearance rows per frame)."""
@@ -185,7 +185,7 @@ def cohort_stream(n_objects=2048, cohorts=4, frames=10, hw=(1080, 1920), seed=3,
     h, w = hw
     cx, cy = rng.uniform(40, w - 40, n_objects), rng.uniform(60, h - 60, n_objects)
     bw, bh = rng.uniform(20, 50, n_objects), rng.uniform(40, 100, n_objects)
-    conf = rng.uniform(0.4, 0.95, n_objects)
+    conf = rng.uniform(conf_lo, 0.95, n_objects)   # conf_lo above the tracker's det_thresh: every object is tracked
     proto = np.abs(rng.normal(size=(n_objects, dim))).astype(np.float32)
     dets, embs = [], []
     for f in range(frames):

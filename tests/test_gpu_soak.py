@@ -2,7 +2,7 @@
 supplied camera-motion warps in half of the BoT-SORT / DeepOCSORT / StrongSORT cases, windows of the MOT17-mini public
 detections in every third block) replayed on the DEVICE, >= 500 streams per tracker, against digests of the oracle's
 [id, conf, cls, det_ind] output (tests/golden/soak_digests.json, made on the host by tests/golden/make_soak_digests.py).
-The only tolerated divergence is the documented StrongSORT birth-order swap under a non-identity warp."""
+The only tolerated divergence is the documented StrongSORT birth-order swap (ids permuted, everything else equal)."""
 import hashlib
 import json
 from pathlib import Path
@@ -47,6 +47,16 @@ def test_device_soak_against_oracle_digests():
             bad.append((seed, kind, warped))
     print("soak:", per_kind, "diverged:", bad)
     assert min(per_kind.values()) >= 500 or len(seeds) < 2000
-    others = [b for b in bad if not (b[1] == "strongsort" and b[2])]
-    assert not others, f"device output differs from the oracle on {others}"
-    assert len(bad) <= max(3, len(seeds) // 300), f"more StrongSORT warp-order swaps than documented: {bad}"
+    # Tolerated: StrongSORT streams whose output equals the oracle's up to a consistent renaming of ids -- the order in
+    # which two simultaneously born tracks get their ids follows scipy's tie-break among fully gated entries, which runs
+    # through the last bits of LAPACK's Cholesky solve (the reference's own choice depends on its BLAS build).
+    from tests.tools.soak_hostsim import same_up_to_an_id_permutation
+
+    def make_device(kind, kw):
+        import boxmot_b200 as bb
+
+        return bb.StrongSort(cap_tracks=512, cap_dets=256, feat_dim=64, **kw)
+
+    real = [b for b in bad if b[1] != "strongsort" or not same_up_to_an_id_permutation(b[0], make_device)]
+    assert not real, f"device output differs from the oracle on {real}"
+    assert len(bad) <= max(3, len(seeds) // 300), f"more StrongSORT birth-order swaps than documented: {bad}"

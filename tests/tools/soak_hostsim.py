@@ -97,10 +97,13 @@ def case(seed, build=True):
     return kind, kw, frames, embs, HostSimStrongSort(strongsort_cfg(cap_tracks=512, cap_dets=256, feat_dim=dim, **kw)), StrongSortOracle(**kw)
 
 
-def same_up_to_an_id_permutation(seed) -> bool:
+def same_up_to_an_id_permutation(seed, make_device=None) -> bool:
     """True when the two outputs of a diverged case agree in every row except for a consistent renaming of track ids
-    (the StrongSORT birth-order limit of DESIGN 3.1c), False for any other difference."""
+    (the StrongSORT birth-order limit of DESIGN 3.1c), False for any other difference.  `make_device(kind, kw)` swaps
+    the host simulation for another implementation of the same interface (the GPU soak passes the device tracker)."""
     kind, kw, frames, embs, sim, orc, warps = case_with_warps(seed)
+    if make_device is not None:
+        sim = make_device(kind, kw)
     fwd, bwd = {}, {}
     for f, d in enumerate(frames):
         e = None if embs is None else embs[f]
