@@ -45,7 +45,8 @@ class BoxMOTB200TrackerConfig(ctypes.Structure):
                 ("w_association_emb", c_double), ("alpha_fixed_emb", c_double), ("aw_param", c_double),
                 ("q_xy_scaling", c_double), ("q_s_scaling", c_double),
                 ("n_init", c_int), ("nn_budget", c_int), ("min_conf", c_double), ("max_cos_dist", c_double),
-                ("max_iou_dist", c_double), ("mc_lambda", c_double), ("ema_alpha", c_double)]
+                ("max_iou_dist", c_double), ("mc_lambda", c_double), ("ema_alpha", c_double),
+                ("reid_preprocess", c_int)]
 
 
 # every symbol include/boxmot_b200.h declares: name -> (restype, argtypes)
@@ -86,6 +87,7 @@ SYMBOLS = {
     "boxmot_b200_tracker_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "boxmot_b200_tracker_snapshot": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                              POINTER(c_int)]),
+    "boxmot_b200_tracker_track_ids": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, POINTER(c_int)]),
     "boxmot_b200_tracker_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
     "boxmot_b200_tracker_last_device_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "boxmot_b200_tracker_set_warp": (c_int, [c_void_p, c_int, c_void_p]),

@@ -129,6 +129,12 @@ int boxmot_b200_tracker_snapshot(BoxMOTB200Tracker* h, int stream, int* ids, dou
         if (out_count) *out_count = n;
     });
 }
+int boxmot_b200_tracker_track_ids(BoxMOTB200Tracker* h, int stream, int which, int* ids, int capacity, int* out_count) {
+    return guard([&] {
+        int n = as_engine(h)->track_ids(stream, which, ids, capacity);
+        if (out_count) *out_count = n;
+    });
+}
 int boxmot_b200_tracker_last_launches(BoxMOTB200Tracker* h, int* out_launches) {
     return guard([&] { *out_launches = as_engine(h)->launches; });
 }
@@ -193,6 +199,14 @@ int boxmot_bytetrack_update(BoxMOTByteTrackHandle* h, const float* dets, int det
                          out_rows, out_is_obb);
 }
 
+// crop staging by name (reid/core/preprocessing.py:47-50).  NULL means "resize_pad" exactly as in the reference's native
+// ABI (base/src/reid_capi.cpp:83, botsort/src/c_api.cpp:35); its Python loaders always pass a name (default "resize").
+static int preprocess_mode(const char* name) {
+    if (!name || !name[0] || strcmp(name, "resize_pad") == 0) return 1;
+    if (strcmp(name, "resize") == 0) return 0;
+    throw std::runtime_error(std::string("unknown ReID preprocess '") + name + "' (resize, resize_pad)");
+}
+
 // ---- BoT-SORT (reference ABI) ------------------------------------------------------------------------------
 BoxMOTBotSortHandle* boxmot_botsort_create(const BoxMOTBotSortConfig* c) {
     Engine* e = nullptr;
@@ -200,8 +214,7 @@ BoxMOTBotSortHandle* boxmot_botsort_create(const BoxMOTBotSortConfig* c) {
         if (!c) throw std::runtime_error("NULL config");
         if (cmc_requested(c->cmc_method))
             throw std::runtime_error("camera-motion compensation is out of scope for the B200 path: pass cmc_method=NULL");
-        if (c->reid_preprocess && c->reid_preprocess[0] && strcmp(c->reid_preprocess, "resize") != 0)
-            throw std::runtime_error("only the 'resize' ReID preprocess is implemented");
+        const int prep = preprocess_mode(c->reid_preprocess);
         BoxMOTB200TrackerConfig p{};
         p.tracker = BOXMOT_B200_TRACKER_BOTSORT;
         p.n_streams = 1;
@@ -223,6 +236,7 @@ BoxMOTBotSortHandle* boxmot_botsort_create(const BoxMOTBotSortConfig* c) {
         p.proximity_thresh = c->proximity_thresh;
         p.appearance_thresh = c->appearance_thresh;
         p.reid_model_path = c->reid_model_path;
+        p.reid_preprocess = prep;
         e = new Engine(p);
     });
     return reinterpret_cast<BoxMOTBotSortHandle*>(e);
@@ -383,14 +397,14 @@ int boxmot_reid_capi_create(const char* model_path, const char* preprocess, void
         if (!out_handle) throw std::runtime_error("out_handle is NULL");
         *out_handle = nullptr;
         if (!model_path) throw std::runtime_error("model_path is NULL");
-        if (preprocess && preprocess[0] && strcmp(preprocess, "resize") != 0)
-            throw std::runtime_error("only the 'resize' preprocess is implemented on the B200 path");
+        const int prep = preprocess_mode(preprocess);
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
             throw std::runtime_error("no CUDA device: boxmot_b200 has no CPU fallback");
         ReidHandle* r = new ReidHandle();
         try {
             r->model = reid_load(model_path);
+            reid_set_preprocess(r->model, prep);
             CAPI_CUDA_OK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
         } catch (...) {
             delete r;

@@ -26,6 +26,8 @@ struct ReidModel;
 ReidModel* reid_load(const char* blob_path);  // throws std::runtime_error
 void reid_free(ReidModel* m);
 int reid_feature_dim(const ReidModel* m);
+// crop staging: 0 = resize, 1 = resize_pad (reid/core/preprocessing.py:12-45)
+void reid_set_preprocess(ReidModel* m, int mode);
 // Enqueue crop -> CNN -> L2-normalised features for up to `max_crops` crops whose descriptors and count live
 // in device memory.  Frames are `image_stride` bytes apart in `d_images` (rows x cols x 3, BGR, uint8).
 // Row r of the result goes to d_out + crops[r].out_row * out_ld.  Returns the number of kernel launches.
@@ -129,6 +131,7 @@ struct Engine {
                        const uint8_t* images_dev, int rows, int cols, bool sync);
     void fetch(float* const* out, const int* out_cap, int* out_rows);
     int snapshot(int stream_index, int* ids, double* means, double* covs, int cap);
+    int track_ids(int stream_index, int which, int* ids, int cap);
     void set_warp(int stream_index, const double* warp6);
     void read_timers(int stream_index, long long* out16, bool reset);
     void set_profile(bool on);

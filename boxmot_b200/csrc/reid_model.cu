@@ -66,7 +66,7 @@ __device__ __forceinline__ void linear_coeff(int d, int src_n, double scale, boo
 __global__ void __launch_bounds__(256) k_crop_resize_norm(const uint8_t* __restrict__ images, size_t image_stride,
                                                           int rows, int cols, const CropDesc* __restrict__ crops,
                                                           const int* __restrict__ d_n, int off, int cap,
-                                                          float* __restrict__ blob) {
+                                                          float* __restrict__ blob, int pad_mode) {
     const int n = blockIdx.x;
     if (n >= chunk_count(d_n, off, cap)) return;
     const CropDesc cd = crops[off + n];
@@ -77,10 +77,19 @@ __global__ void __launch_bounds__(256) k_crop_resize_norm(const uint8_t* __restr
     const int cx1 = max(0, x1), cy1 = max(0, y1), cx2 = min(cols, x2), cy2 = min(rows, y2);
     const bool valid = cx2 > cx1 && cy2 > cy1;
     const int sw = cx2 - cx1, sh = cy2 - cy1;
+    // resize_pad (preprocessing.py:21-45): scale = min(W / w, H / h); new = int(size * scale); centred, ImageNet-mean border
+    int nw = IN_W, nh = IN_H, pl = 0, pt = 0;
+    if (valid && pad_mode) {
+        const double sc = fmin((double)IN_W / (double)sw, (double)IN_H / (double)sh);
+        nw = max(1, (int)((double)sw * sc));
+        nh = max(1, (int)((double)sh * sc));
+        pl = (IN_W - nw) / 2;
+        pt = (IN_H - nh) / 2;
+    }
     if (valid) {
-        const double sx = 1.0 / ((double)IN_W / (double)sw), sy = 1.0 / ((double)IN_H / (double)sh);
-        for (int d = threadIdx.x; d < IN_W; d += blockDim.x) linear_coeff(d, sw, sx, true, xi[d], xa0[d], xa1[d]);
-        for (int d = threadIdx.x; d < IN_H; d += blockDim.x) linear_coeff(d, sh, sy, false, yi[d], ya0[d], ya1[d]);
+        const double sx = 1.0 / ((double)nw / (double)sw), sy = 1.0 / ((double)nh / (double)sh);
+        for (int d = threadIdx.x; d < nw; d += blockDim.x) linear_coeff(d, sw, sx, true, xi[d], xa0[d], xa1[d]);
+        for (int d = threadIdx.x; d < nh; d += blockDim.x) linear_coeff(d, sh, sy, false, yi[d], ya0[d], ya1[d]);
     }
     __syncthreads();
     const uint8_t* img = images + (size_t)cd.image * image_stride;
@@ -88,9 +97,12 @@ __global__ void __launch_bounds__(256) k_crop_resize_norm(const uint8_t* __restr
     const float mean[3] = {0.485f, 0.456f, 0.406f};
     const float stdv[3] = {0.229f, 0.224f, 0.225f};
     for (int p = threadIdx.x; p < IN_H * IN_W; p += blockDim.x) {
-        const int dy = p / IN_W, dx = p - dy * IN_W;
+        const int py = p / IN_W, px = p - py * IN_W;
+        const int dy = py - pt, dx = px - pl;
         int v[3] = {0, 0, 0};
-        if (valid) {
+        if (valid && (dx < 0 || dx >= nw || dy < 0 || dy >= nh)) {
+            v[0] = 104; v[1] = 116; v[2] = 124;      // IMAGENET_MEAN_BGR (the crop is BGR until the channel flip below)
+        } else if (valid) {
             const int sx0 = xi[dx], sx1 = min(sx0 + 1, sw - 1);
             const int r0 = min(max(yi[dy], 0), sh - 1), r1 = min(max(yi[dy] + 1, 0), sh - 1);
             const uint8_t* p0 = img + ((size_t)(cy1 + r0) * cols + cx1) * 3;
@@ -1242,6 +1254,7 @@ struct ReidModel {
     std::vector<int> prof_cls;
     double prof_ms[REID_N_CLASSES] = {0};
     int prof_launches[REID_N_CLASSES] = {0};
+    int preprocess = 0;        // 0 resize, 1 resize_pad
     tcx::Plan* tc = nullptr;   // tensor-core path (tcgen05 + TMA, reid_tc.cuh): the default for the widths it covers
     int debug_stop = -1;       // stop after this stage index and leave the tensor in debug_ptr
     const float* debug_ptr = nullptr;
@@ -1456,6 +1469,7 @@ void reid_free(ReidModel* m) {
 }
 
 int reid_feature_dim(const ReidModel* m) { return m->feat; }
+void reid_set_preprocess(ReidModel* m, int mode) { m->preprocess = mode ? 1 : 0; }
 const float* reid_last_input_blob(const ReidModel* m) { return m->blob; }
 void reid_set_profile(ReidModel* m, bool on) { m->profile = on; }
 // Fold the events recorded since the last call into per-class totals (the stream must be idle).
@@ -1679,7 +1693,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             Launcher L{m, d_ncrops, off, upper, upper, st};
             L.begin(CLS_CROP);
             k_crop_resize_norm<<<upper, 256, 0, st>>>(d_images, image_stride, rows, cols, d_crops, d_ncrops, off, upper,
-                                                      m->blob);
+                                                      m->blob, m->preprocess);
             L.end();
             ++L.launches;
             float* X = m->bufA;
@@ -1750,7 +1764,7 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
         }
         L.begin(CLS_CROP);
         k_crop_resize_norm<<<upper, 256, 0, st>>>(d_images, image_stride, rows, cols, d_crops, d_ncrops, off, upper,
-                                                  m->blob);
+                                                  m->blob, m->preprocess);
         L.end();
         ++L.launches;
         if (stop_here(m->blob, (size_t)IN_H * IN_W * 3)) { launches += L.launches; continue; }

@@ -818,6 +818,7 @@ struct FrontTcArgs {
     bf16* p_hi;
     bf16* p_lo;
     float* dbg_crop;                    // diagnostics: resized crop [crops][256][128][3] (RGB) as float, or null
+    int pad_mode;                       // 0 resize, 1 resize_pad (aspect-preserving resize, ImageNet-mean border)
 };
 struct FrontCrop { float x1, y1, x2, y2; int image, out_row; };
 
@@ -869,10 +870,19 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
     const int cx1 = max(0, x1), cy1 = max(0, y1), cx2 = min(a.cols, x2), cy2 = min(a.rows, y2);
     const bool valid = cx2 > cx1 && cy2 > cy1;
     const int sw = cx2 - cx1, sh = cy2 - cy1;
+    // resize_pad (preprocessing.py:21-45): scale = min(W / w, H / h); new = int(size * scale); centred, ImageNet-mean border
+    int nw = 128, nh = 256, pl = 0, pt = 0;
+    if (valid && a.pad_mode) {
+        const double sc = fmin(128.0 / (double)sw, 256.0 / (double)sh);
+        nw = max(1, (int)((double)sw * sc));
+        nh = max(1, (int)((double)sh * sc));
+        pl = (128 - nw) / 2;
+        pt = (256 - nh) / 2;
+    }
     if (valid) {
-        const double sx = 1.0 / (128.0 / (double)sw), sy = 1.0 / (256.0 / (double)sh);
-        for (int d = threadIdx.x; d < 128; d += 256) fr_coeff(d, sw, sx, true, xi[d], xa0[d], xa1[d]);
-        for (int d = threadIdx.x; d < 256; d += 256) fr_coeff(d, sh, sy, false, yi[d], ya0[d], ya1[d]);
+        const double sx = 1.0 / ((double)nw / (double)sw), sy = 1.0 / ((double)nh / (double)sh);
+        for (int d = threadIdx.x; d < nw; d += 256) fr_coeff(d, sw, sx, true, xi[d], xa0[d], xa1[d]);
+        for (int d = threadIdx.x; d < nh; d += 256) fr_coeff(d, sh, sy, false, yi[d], ya0[d], ya1[d]);
     }
     for (int e = threadIdx.x; e < FR_A_BYTES / 16; e += 256) reinterpret_cast<uint4*>(sA)[e] = make_uint4(0u, 0u, 0u, 0u);
     for (int e = threadIdx.x; e < FR_W_BYTES / 16; e += 256) reinterpret_cast<uint4*>(sW)[e] = reinterpret_cast<const uint4*>(a.w)[e];
@@ -889,21 +899,23 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
         // table lookups -> 12 byte loads -> integer arithmetic -> one 8-byte shared store)
         for (int base = threadIdx.x; base < 40 * 256; base += 4 * 256) {
             int h0[4][3], h1[4][3], bb0[4], bb1[4], so[4];
-            bool ok[4];
+            bool ok[4], border[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int p = base + u * 256;
                 const int dy = p / 40, lc = p - dy * 40;
                 const int dx = xin0 + lc;
                 ok[u] = p < 40 * 256 && lc < FR_COLS && dx >= 0 && dx < 128;
-                const int dxc = min(max(dx, 0), 127), dyc = min(dy, 255);
+                const int ry = dy - pt, rx = dx - pl;             // position in the resized patch (resize: the crop itself)
+                border[u] = rx < 0 || rx >= nw || ry < 0 || ry >= nh;
+                const int dxc = min(max(rx, 0), nw - 1), dyc = min(max(ry, 0), nh - 1);
                 const int sx0 = xi[dxc], sx1 = min(sx0 + 1, sw - 1);
                 const int r0 = min(max(yi[dyc], 0), sh - 1), r1 = min(max(yi[dyc] + 1, 0), sh - 1);
                 const uint8_t* p0 = img + ((size_t)(cy1 + r0) * a.cols + cx1) * 3;
                 const uint8_t* p1 = img + ((size_t)(cy1 + r1) * a.cols + cx1) * 3;
                 const int a0 = xa0[dxc], a1 = xa1[dxc];
                 bb0[u] = ya0[dyc]; bb1[u] = ya1[dyc];
-                so[u] = lc * FR_CS + (dyc + 3) * 8;
+                so[u] = lc * FR_CS + (min(dy, 255) + 3) * 8;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     h0[u][c] = (int)__ldg(p0 + sx0 * 3 + c) * a0 + (int)__ldg(p0 + sx1 * 3 + c) * a1;
@@ -919,6 +931,7 @@ __global__ void __launch_bounds__(256, 2) k_front_tc(const FrontTcArgs a, const 
                     const int r = (((bb0[u] * (h0[u][c] >> 4)) >> 16) + ((bb1[u] * (h1[u][c] >> 4)) >> 16) + 2) >> 2;
                     v[c] = min(max(r, 0), 255);
                 }
+                if (border[u]) { v[0] = 104; v[1] = 116; v[2] = 124; }      // IMAGENET_MEAN_BGR
                 // BGR source -> RGB network order; integers 0..255 are exact in BF16
                 const __nv_bfloat162 rg = __floats2bfloat162_rn((float)v[2], (float)v[1]);
                 const __nv_bfloat162 b_ = __floats2bfloat162_rn((float)v[0], 0.f);

@@ -309,6 +309,7 @@ int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int up
             case LK_FRONT: {
                 FrontTcArgs fa = L.front;
                 fa.images = fi.images; fa.image_stride = fi.image_stride; fa.rows = fi.rows; fa.cols = fi.cols; fa.crops = fi.crops;
+                fa.pad_mode = m->preprocess;
                 if (m->debug_stop == 50) {
                     if (!P->dbg_crop) RCUDA_OK(cudaMalloc(&P->dbg_crop, sizeof(float) * (size_t)P->chunk * 256 * 128 * 3));
                     fa.dbg_crop = P->dbg_crop;

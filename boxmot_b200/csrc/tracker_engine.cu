@@ -347,6 +347,7 @@ void Engine::construct(const BoxMOTB200TrackerConfig& p) {
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (p.reid_model_path && p.reid_model_path[0]) {
         reid = reid_load(p.reid_model_path);
+        reid_set_preprocess(reid, p.reid_preprocess);
         if (cfg.with_reid && reid_feature_dim(reid) != cfg.feat_dim) {
             cfg.feat_dim = reid_feature_dim(reid);
         }
@@ -470,6 +471,7 @@ void Engine::construct(const BoxMOTB200TrackerConfig& p) {
         if (n_split > 1) CUDA_OK(cudaEventCreateWithFlags(&ev_crops, cudaEventDisableTiming));
         for (int k = 0; k + 1 < n_split; ++k) {
             reid_extra[k] = reid_load(p.reid_model_path);
+            reid_set_preprocess(reid_extra[k], p.reid_preprocess);
             CUDA_OK(cudaStreamCreateWithFlags(&split_stream[k], cudaStreamNonBlocking));
             CUDA_OK(cudaEventCreateWithFlags(&ev_slice_done[k], cudaEventDisableTiming));
         }
@@ -987,6 +989,49 @@ int Engine::snapshot(int sidx, int* ids, double* means, double* covs, int cap) {
             memcpy(covs + (size_t)n * 64, cov.data() + (size_t)t * 64, sizeof(double) * 64);
         }
     }
+    return n;
+}
+
+// Ids of one of the tracker's lists, in list order: 0 = active (the rows `update` may emit), 1 = lost, 2 = removed
+// (BaseTracker attributes active_tracks / lost_stracks / removed_stracks, basetracker.py:386-390).  BoT-SORT's removed list
+// is its deque(maxlen=removed_stracks_buffer) oldest first; ByteTrack's unbounded list is kept as a per-slot flag, so it
+// comes back in slot order.  DeepOCSORT and StrongSORT keep a single list (the reference never fills the other two).
+int Engine::track_ids(int sidx, int which, int* ids, int cap) {
+    if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
+    if (which < 0 || which > 2) throw std::runtime_error("list index must be 0 (active), 1 (lost) or 2 (removed)");
+    CUDA_OK(cudaStreamSynchronize(stream));
+    const int CT = cfg.cap_tracks;
+    std::vector<int> sc(SC_COUNT), lst(CT), idv(CT);
+    int n = 0;
+    if (is_ss || is_docs) {
+        if (which != 0) return 0;
+        const int* scal = is_ss ? h_ss[sidx].scalars : h_docs[sidx].scalars;
+        const int* trk = is_ss ? h_ss[sidx].tracks : h_docs[sidx].tracks;
+        const int* idp = is_ss ? h_ss[sidx].id : h_docs[sidx].id;
+        CUDA_OK(cudaMemcpy(sc.data(), scal, sizeof(int) * SC_COUNT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(lst.data(), trk, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(idv.data(), idp, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < sc[SC_N_ACTIVE] && n < cap; ++k) ids[n++] = idv[lst[k]];
+        return n;
+    }
+    const TrkStream& s = h_streams[sidx];
+    CUDA_OK(cudaMemcpy(sc.data(), s.scalars, sizeof(int) * SC_COUNT, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(idv.data(), s.id, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+    if (which < 2) {
+        CUDA_OK(cudaMemcpy(lst.data(), which == 0 ? s.active : s.lost, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+        const int cnt = sc[which == 0 ? SC_N_ACTIVE : SC_N_LOST];
+        for (int k = 0; k < cnt && n < cap; ++k) ids[n++] = idv[lst[k]];
+        return n;
+    }
+    if (cfg.removed_cap > 0) {
+        std::vector<int> ring(cfg.removed_cap);
+        CUDA_OK(cudaMemcpy(ring.data(), s.removed_ring, sizeof(int) * cfg.removed_cap, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < sc[SC_RING_COUNT] && n < cap; ++k) ids[n++] = ring[(sc[SC_RING_HEAD] + k) % cfg.removed_cap];
+        return n;
+    }
+    CUDA_OK(cudaMemcpy(lst.data(), s.in_removed, sizeof(int) * CT, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < CT && n < cap; ++t)
+        if (lst[t]) ids[n++] = idv[t];
     return n;
 }
 

@@ -36,8 +36,9 @@ class B200ReID:
     std_array = np.array([0.229, 0.224, 0.225], dtype=np.float32)
 
     def __init__(self, weights, device=None, half: bool = False, preprocess: Optional[str] = None):
-        if preprocess not in (None, "resize"):
-            raise NotImplementedError("only the 'resize' preprocess is implemented on the B200 path")
+        if preprocess not in (None, "resize", "resize_pad"):
+            raise ValueError(f"Unknown preprocessing '{preprocess}'. Available: ['resize', 'resize_pad']")   # preprocessing.py:56-62
+        self.preprocess_name = preprocess or "resize"   # DEFAULT_PREPROCESS of the reference's Python loaders
         # half=True is accepted for interface compatibility (the reference's call sites pass it): the network still runs
         # in float32 on the device -- at least the reference's precision -- and the rows handed back to the caller are
         # rounded to float16, the dtype the reference returns in that mode.  Inside a tracker the embeddings never leave
@@ -51,7 +52,7 @@ class B200ReID:
         self.half = bool(half)
         self.device = "cuda:0"
         self.handle = ctypes.c_void_p()
-        ok = self.lib.boxmot_reid_capi_create(self.blob_path.encode(), b"resize", ctypes.byref(self.handle))
+        ok = self.lib.boxmot_reid_capi_create(self.blob_path.encode(), self.preprocess_name.encode(), ctypes.byref(self.handle))
         if not ok:
             raise B200Error(f"boxmot_reid_capi_create failed: {self._err()}")
         dim = ctypes.c_int(0)

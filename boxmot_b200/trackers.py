@@ -164,7 +164,10 @@ class MultiStreamTracker:
     Per-stream results equal `n_streams` separate reference trackers (ids start at 1 in every stream)."""
 
     def __init__(self, tracker: str, n_streams: int = 1, cap_tracks: int = 1024, cap_dets: int = 512,
-                 feat_dim: int = 512, reid_blob: Optional[str] = None, **params: Any):
+                 feat_dim: int = 512, reid_blob: Optional[str] = None, reid_preprocess: Optional[str] = None,
+                 **params: Any):
+        if reid_preprocess not in (None, "resize", "resize_pad"):
+            raise ValueError(f"Unknown preprocessing '{reid_preprocess}'. Available: ['resize', 'resize_pad']")
         self.lib = _lib.require_device()
         cfg = BoxMOTB200TrackerConfig()
         kind = tracker.lower()
@@ -258,6 +261,7 @@ class MultiStreamTracker:
         cfg.frame_rate = int(p["frame_rate"])
         self._blob = str(reid_blob).encode() if reid_blob else None
         cfg.reid_model_path = self._blob
+        cfg.reid_preprocess = 1 if reid_preprocess == "resize_pad" else 0
         self.kind = kind
         self.params = p
         self.n_streams = int(n_streams)
@@ -418,6 +422,14 @@ class MultiStreamTracker:
             raise B200Error(_lib.last_error(self.lib))
         return {int(ids[i]): (means[i].copy(), covs[i].copy()) for i in range(n.value)}
 
+    def track_ids(self, which: int, stream: int = 0):
+        """Ids of the tracker's list `which` (0 active, 1 lost, 2 removed) in list order."""
+        ids = np.empty(max(self.cap_tracks, 1024), np.int32)
+        n = ctypes.c_int(0)
+        if not self.lib.boxmot_b200_tracker_track_ids(self.handle, stream, int(which), ids.ctypes.data, len(ids), ctypes.byref(n)):
+            raise B200Error(_lib.last_error(self.lib))
+        return ids[: n.value].tolist()
+
     def last_launches(self) -> int:
         n = ctypes.c_int(0)
         self.lib.boxmot_b200_tracker_last_launches(self.handle, ctypes.byref(n))
@@ -461,7 +473,8 @@ class _SingleStreamTracker:
             params = dict(params, det_thresh=det_thresh, max_age=max_age, min_hits=min_hits, iou_threshold=iou_threshold)
         if self._kind == "strongsort":  # Tracker(max_age=self.max_age) (strongsort.py:56-64)
             params = dict(params, max_age=max_age)
-        self._engine = MultiStreamTracker(self._kind, 1, cap_tracks, cap_dets, feat_dim, reid_blob=blob, **params)
+        self._engine = MultiStreamTracker(self._kind, 1, cap_tracks, cap_dets, feat_dim, reid_blob=blob,
+                                          reid_preprocess=getattr(reid_model, "preprocess_name", None) if blob else None, **params)
         self.provides_reid = blob is not None
         self.with_reid = self._engine.with_reid
         self.frame_count = 0
@@ -512,14 +525,26 @@ class _SingleStreamTracker:
         def __init__(self, tid, mean, cov):
             self.id, self.mean, self.covariance = tid, mean, cov
 
+    def _views(self, which):
+        state = self._engine.snapshot(0)
+        return [self.TrackView(k, *state.get(k, (None, None))) for k in self._engine.track_ids(which)]
+
     @property
     def active_tracks(self):
-        """The live tracks as views of the device-resident state (one synchronising snapshot per access)."""
-        return [self.TrackView(k, m, c) for k, (m, c) in sorted(self._engine.snapshot(0).items())]
+        """The tracker's active list, in list order, as views of the device-resident state (one synchronising snapshot
+        per access).  basetracker.py:386."""
+        return self._views(0)
 
-    # the lost / removed lists live on the device and are not exposed through the ABI; display helpers get empty lists
-    lost_stracks = ()
-    removed_stracks = ()
+    @property
+    def lost_stracks(self):
+        """Lost tracks in list order (BoT-SORT / ByteTrack; the other trackers keep none).  basetracker.py:389."""
+        return self._views(1)
+
+    @property
+    def removed_stracks(self):
+        """Removed tracks: ids only (their Kalman state is gone).  BoT-SORT: the deque of `removed_stracks_buffer` ids,
+        oldest first; ByteTrack: every removed id, in slot order.  basetracker.py:390."""
+        return self._views(2)
 
     def get_active_tracks_for_display(self) -> list:
         return list(self.active_tracks)

@@ -88,7 +88,7 @@ typedef struct BoxMOTBotSortConfig {
     int with_reid;
     int max_obs;
     const char* reid_model_path; /* .b200reid blob, or NULL when embeddings are always passed in */
-    const char* reid_preprocess; /* "resize" or NULL */
+    const char* reid_preprocess; /* "resize", "resize_pad"; NULL = "resize_pad" as in botsort/src/c_api.cpp:35 */
 } BoxMOTBotSortConfig;
 
 typedef struct BoxMOTBotSortHandle BoxMOTBotSortHandle;
@@ -161,6 +161,9 @@ typedef struct BoxMOTB200TrackerConfig {
     double max_iou_dist;
     double mc_lambda;
     double ema_alpha;
+    /* crop staging of the on-device ReID (reid/core/preprocessing.py): 0 = "resize" (the Python default), 1 = "resize_pad"
+     * (aspect-preserving resize + ImageNet-mean border, the native default when the name is NULL) */
+    int reid_preprocess;
 } BoxMOTB200TrackerConfig;
 
 typedef struct BoxMOTB200Tracker BoxMOTB200Tracker;
@@ -196,6 +199,10 @@ BOXMOT_B200_API int boxmot_b200_tracker_fetch(BoxMOTB200Tracker* handle, float* 
 /* Test / diagnostics: live track ids with their Kalman mean (8) and covariance (64), float64. */
 BOXMOT_B200_API int boxmot_b200_tracker_snapshot(BoxMOTB200Tracker* handle, int stream, int* ids, double* means,
                                                  double* covs, int capacity, int* out_count);
+/* Ids of one of the tracker's lists in list order: which = 0 active, 1 lost, 2 removed -- what the reference exposes as
+ * BaseTracker.active_tracks / lost_stracks / removed_stracks (boxmot/trackers/basetracker.py:386-390, 465-466). */
+BOXMOT_B200_API int boxmot_b200_tracker_track_ids(BoxMOTB200Tracker* handle, int stream, int which, int* ids,
+                                                  int capacity, int* out_count);
 /* Kernel launches issued by the last update call, and CUDA stream / device-time accessors for benchmarks. */
 BOXMOT_B200_API int boxmot_b200_tracker_last_launches(BoxMOTB200Tracker* handle, int* out_launches);
 BOXMOT_B200_API int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* handle, double* reid_ms, double* assoc_ms);

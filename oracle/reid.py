@@ -67,7 +67,24 @@ def resize_linear_u8(src: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
-def crop_boxes(xyxys: np.ndarray, img: np.ndarray):
+IMAGENET_MEAN_BGR = (104, 116, 124)
+
+
+def resize_pad_u8(src: np.ndarray, dst_h: int, dst_w: int) -> np.ndarray:
+    """reid/core/preprocessing.py:21-45: aspect-preserving resize (scale = min(W / w, H / h), new = int(size * scale)),
+    centred, constant ImageNet-mean border (BGR order: the channel flip comes later)."""
+    h, w = src.shape[:2]
+    scale = min(dst_w / w, dst_h / h)
+    new_w, new_h = int(w * scale), int(h * scale)
+    resized = resize_linear_u8(src, new_h, new_w)
+    top, left = (dst_h - new_h) // 2, (dst_w - new_w) // 2
+    out = np.empty((dst_h, dst_w, 3), np.uint8)
+    out[:] = np.array(IMAGENET_MEAN_BGR, np.uint8)
+    out[top:top + new_h, left:left + new_w] = resized
+    return out
+
+
+def crop_boxes(xyxys: np.ndarray, img: np.ndarray, preprocess: str = "resize"):
     """uint8 RGB crops (N,256,128,3) exactly as get_crops stages them before the float conversion."""
     h, w = img.shape[:2]
     xyxys = np.asarray(xyxys, dtype=np.float32).reshape(-1, 4)
@@ -77,16 +94,17 @@ def crop_boxes(xyxys: np.ndarray, img: np.ndarray):
         cx1, cy1 = max(0, x1), max(0, y1)
         cx2, cy2 = min(w, x2), min(h, y2)
         if cx2 > cx1 and cy2 > cy1:
-            crop = resize_linear_u8(img[cy1:cy2, cx1:cx2], INPUT_HW[0], INPUT_HW[1])
+            fn = resize_pad_u8 if preprocess == "resize_pad" else resize_linear_u8
+            crop = fn(img[cy1:cy2, cx1:cx2], INPUT_HW[0], INPUT_HW[1])
         else:
             crop = np.zeros((INPUT_HW[0], INPUT_HW[1], 3), np.uint8)
         out[i] = crop[:, :, ::-1]
     return out
 
 
-def get_crops(xyxys: np.ndarray, img: np.ndarray) -> torch.Tensor:
+def get_crops(xyxys: np.ndarray, img: np.ndarray, preprocess: str = "resize") -> torch.Tensor:
     """float32 NCHW network input (N,3,256,128)."""
-    u8 = crop_boxes(xyxys, img)
+    u8 = crop_boxes(xyxys, img, preprocess)
     x = torch.from_numpy(u8).to(torch.float32).permute(0, 3, 1, 2).contiguous()
     x = x / 255.0
     mean = torch.tensor(MEAN).view(1, 3, 1, 1)
@@ -212,12 +230,12 @@ def backbone_forward(sd, x):
     return mobilenetv2_forward(sd, x) if is_mobilenetv2(sd) else osnet_forward(sd, x)
 
 
-def get_features(sd, xyxys: np.ndarray, img: np.ndarray) -> np.ndarray:
+def get_features(sd, xyxys: np.ndarray, img: np.ndarray, preprocess: str = "resize") -> np.ndarray:
     """(N, D) float32 L2-normalised embeddings, as BaseModelBackend.get_features returns them."""
     xyxys = np.asarray(xyxys, dtype=np.float32)
     if xyxys.size == 0:
         return np.array([])
-    feats = backbone_forward(sd, get_crops(xyxys, img)).numpy()
+    feats = backbone_forward(sd, get_crops(xyxys, img, preprocess)).numpy()
     return feats / np.linalg.norm(feats, axis=-1, keepdims=True)
 
 

@@ -270,3 +270,38 @@ def test_pipelined_multistream_with_empty_frames(tmp_path, n_dets):
         assert sorted(st_a[i]) == sorted(st_b[i]) and len(st_a[i]) > 0
         for k in st_a[i]:
             assert np.array_equal(st_a[i][k][0], st_b[i][k][0]) and np.array_equal(st_a[i][k][1], st_b[i][k][1])
+
+
+def test_resize_pad_preprocess_matches_oracle(tmp_path):
+    """preprocess="resize_pad" (reid/core/preprocessing.py:21-45; what a NULL preprocess name means in the reference's
+    native ABI): staged crops bit-exact on both device paths (fused tensor-core front kernel, float32 staging kernel),
+    embeddings within the bound, and NULL on the C ABI selects it."""
+    import ctypes
+
+    from boxmot_b200 import _lib
+    from boxmot_b200.reid import B200ReID
+    from boxmot_b200.weights import export_blob
+
+    sd = orid.make_osnet_state("osnet_x0_25", seed=13)
+    blob = export_blob(sd, tmp_path / "pad.b200reid")
+    reid = B200ReID(blob, preprocess="resize_pad")
+    rng = np.random.default_rng(17)
+    img = rng.integers(0, 255, size=(480, 640, 3), dtype=np.uint8)
+    boxes = np.array([[10, 20, 90, 200], [300, 100, 460, 180], [-20, -10, 60, 100], [600, 300, 700, 400], [5, 5, 300, 470],
+                      [100.5, 50.5, 101.4, 52.2], [200, 100, 230, 330]], np.float32)
+    want_u8 = orid.crop_boxes(boxes, img, "resize_pad").astype(np.float32)
+    assert np.array_equal(reid.debug_stage(boxes, img, 50).reshape(-1, 256, 128, 3), want_u8)
+    blob0 = reid.debug_stage(boxes, img, 0).reshape(-1, 256, 128, 3)
+    assert np.array_equal(blob0, orid.get_crops(boxes, img, "resize_pad").permute(0, 2, 3, 1).numpy())
+    _emb_ok(reid.get_features(boxes, img), orid.get_features(sd, boxes, img, "resize_pad"))
+    assert np.abs(reid.get_features(boxes, img) - B200ReID(blob).get_features(boxes, img)).max() > 1e-3   # it is a different staging
+    # the reference's native ABI: NULL preprocess == "resize_pad" (base/src/reid_capi.cpp:83)
+    lib = _lib.require_device()
+    h = ctypes.c_void_p()
+    assert lib.boxmot_reid_capi_create(str(blob).encode(), None, ctypes.byref(h)) == 1
+    out = np.empty((len(boxes), 512), np.float32)
+    assert lib.boxmot_reid_capi_compute_features(h, boxes.ctypes.data, len(boxes), img.ctypes.data, 480, 640, 3, out.ctypes.data, out.size) == 1
+    assert np.array_equal(out, reid.get_features(boxes, img))
+    lib.boxmot_reid_capi_destroy(h)
+    with pytest.raises(ValueError):
+        B200ReID(blob, preprocess="letterbox")

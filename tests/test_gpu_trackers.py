@@ -131,3 +131,28 @@ def test_contract_checks():
     assert b.shape == (1, 8) and b[0, 4] == trk.update(d, img)[0, 4]
     with pytest.raises(bb.B200Error):
         trk.update(np.zeros((17, 6), np.float32), img)  # cap_dets exceeded fails loudly
+
+
+def test_lost_and_removed_track_lists_match_the_oracle():
+    """BaseTracker.active_tracks / lost_stracks / removed_stracks (basetracker.py:386-390): ids in list order."""
+    import boxmot_b200 as bb
+    from oracle.streams import stress_embeddings, stress_stream
+    from oracle.trackers import BotSortOracle
+
+    frames = stress_stream(48, 120, seed=31, dropout=0.3)
+    embs = stress_embeddings(frames, 48, dim=64, seed=32)
+    kw = dict(BOTSORT_YAML, track_buffer=8, removed_stracks_buffer=20)
+    gpu = bb.BotSort(cap_tracks=256, cap_dets=64, feat_dim=64, **kw)
+    orc = BotSortOracle(**kw)
+    seen_lost = seen_removed = 0
+    for f, (d, e) in enumerate(zip(frames, embs)):
+        gpu.update(d, None, e)
+        orc.update(d, None, e.copy())
+        assert [t.id for t in gpu.active_tracks] == [t.id for t in orc.active], f
+        assert [t.id for t in gpu.lost_stracks] == [t.id for t in orc.lost], f
+        assert [t.id for t in gpu.removed_stracks] == [t.id for t in orc.removed], f
+        seen_lost += len(orc.lost)
+        seen_removed = max(seen_removed, len(orc.removed))
+    assert seen_lost > 50 and seen_removed == 20
+    for t in gpu.lost_stracks:
+        assert t.mean is not None and t.covariance.shape == (8, 8)

@@ -104,3 +104,23 @@ def test_other_architectures_match_the_reference_classes(arch):
     assert feats.shape == z[arch].shape and feats.shape[1] == (512 if arch == "osnet_x1_0" else 1792)
     np.testing.assert_allclose(feats, z[arch], rtol=0, atol=2e-6)
     assert abs(np.linalg.norm(feats, axis=1) - 1).max() < 1e-6
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resize_pad_matches_the_reference_function(seed):
+    """oracle.reid.resize_pad_u8 against reid/core/preprocessing.py:21-45 restated with the installed OpenCV
+    (cv2.resize INTER_LINEAR + cv2.copyMakeBorder with IMAGENET_MEAN_BGR): bit for bit over random crop sizes."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(40):
+        h, w = int(rng.integers(2, 400)), int(rng.integers(2, 300))
+        crop = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        th, tw = 256, 128
+        scale = min(tw / w, th / h)
+        nw, nh = int(w * scale), int(h * scale)
+        if nw < 1 or nh < 1:
+            continue
+        resized = cv2.resize(crop, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        top, left = (th - nh) // 2, (tw - nw) // 2
+        want = cv2.copyMakeBorder(resized, top, th - nh - top, left, tw - nw - left, cv2.BORDER_CONSTANT, value=(104, 116, 124))
+        assert np.array_equal(orid.resize_pad_u8(crop, th, tw), want)
