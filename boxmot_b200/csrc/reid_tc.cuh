@@ -448,6 +448,7 @@ struct GemmTcArgs {
     bf16* out_hi; bf16* out_lo;         // planes [crops][NP/8][H][W][8] (or pooled [..][H/2][W/2][8]); may be null
     float* out_f32;                     // [crops][HW][N] float32 NHWC copy (may be null)
     int pool;                           // 1: 2x2 average pool in the epilogue (W = tile width)
+    int pool2;                          // 1: 2x2 average pool on the SECOND GEMM's output (transition fused behind a block)
     int W;
     // second GEMM on the fresh output tile: out2 = relu(out * B2 + bias2)
     const bf16* b2_packed;              // [NP/8][2*NP2][8] (null: none)
@@ -459,15 +460,21 @@ struct GemmTcArgs {
 struct GemmSmem {
     size_t b, b2, ring, a2, f, gate, total;
 };
-inline GemmSmem gemm_smem_layout(int K8, int NP, int NP2, int n_stage, bool tail, bool pool, int slot_bytes) {
+inline GemmSmem gemm_smem_layout(int K8, int NP, int NP2, int n_stage, bool tail, bool pool, int slot_bytes, bool pool2 = false) {
     GemmSmem s{};
     size_t o = 0;
     s.b = o; o += (size_t)K8 * 2 * NP * 16;
     s.b2 = o; if (tail) o += (size_t)(NP / 8) * 2 * NP2 * 16;
     o = (o + 127) & ~(size_t)127;
     s.ring = o; o += (size_t)n_stage * slot_bytes;
-    s.a2 = o; if (tail) o += (size_t)2 * (NP / 8) * 128 * 16;
-    s.f = o; if (pool) o += (size_t)128 * (NP + 4) * 4;
+    s.a2 = o;
+    if (tail) {
+        size_t a2 = (size_t)2 * (NP / 8) * 128 * 16;
+        if (pool2) a2 = a2 > (size_t)128 * (NP2 + 4) * 4 ? a2 : (size_t)128 * (NP2 + 4) * 4;
+        o += a2;
+    }
+    s.f = pool2 ? s.a2 : o;
+    if (pool) o += (size_t)128 * (NP + 4) * 4;
     s.gate = o; o += 4 * 32 * 4 + 64;
     s.total = o + 128;
     return s;
@@ -718,20 +725,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
             um::tc_fence_before();
             mbar_arrive(&bar_acc_empty);
             GCK();
-            if (a.pool) {
-                // 2x2 average pool of the tile (rows_per_tile x W) -> (rows/2 x W/2), same operation order as the
-                // float32 kernel of round 1: (a + b + c + d) * 0.25 with a=(y,x) b=(y,x+1) c=(y+1,x) d=(y+1,x+1)
+            // 2x2 average pool of the tile in sF (rows_per_tile x W, row stride NPx + 4) -> (rows/2 x W/2) planes; same
+            // operation order as the float32 kernel of round 1: (a + b + c + d) * 0.25, a=(y,x) b=(y,x+1) c=(y+1,x) d=(y+1,x+1)
+            auto pool_store = [&](const int NPx, bf16* o_hi, bf16* o_lo) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int Wt = a.W, OW = Wt / 2, OHt = a.rows_per_tile / 2;
-                const int items = OHt * OW * (NP / 8);
+                const int items = OHt * OW * (NPx / 8);
                 const int OHW = a.HW / 4;
                 for (int e = et; e < items; e += 256) {
                     const int pp = e % (OHt * OW), c8 = e / (OHt * OW);
                     const int oy = pp / OW, ox = pp - oy * OW;
-                    const float* f0 = sF + (size_t)((2 * oy) * Wt + 2 * ox) * (NP + 4) + c8 * 8;
-                    const float* f1 = f0 + (NP + 4);
-                    const float* f2 = f0 + (size_t)Wt * (NP + 4);
-                    const float* f3 = f2 + (NP + 4);
+                    const float* f0 = sF + (size_t)((2 * oy) * Wt + 2 * ox) * (NPx + 4) + c8 * 8;
+                    const float* f1 = f0 + (NPx + 4);
+                    const float* f2 = f0 + (size_t)Wt * (NPx + 4);
+                    const float* f3 = f2 + (NPx + 4);
                     uint32_t h[4], l[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -740,12 +747,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
                         um::split2(x0, x1, h[j], l[j]);
                     }
                     const int opx = (tile * OHt + oy) * OW + ox;
-                    const size_t o = ((size_t)n * (NP / 8) + c8) * OHW + opx;
-                    reinterpret_cast<uint4*>(a.out_hi)[o] = make_uint4(h[0], h[1], h[2], h[3]);
-                    reinterpret_cast<uint4*>(a.out_lo)[o] = make_uint4(l[0], l[1], l[2], l[3]);
+                    const size_t o = ((size_t)n * (NPx / 8) + c8) * OHW + opx;
+                    reinterpret_cast<uint4*>(o_hi)[o] = make_uint4(h[0], h[1], h[2], h[3]);
+                    reinterpret_cast<uint4*>(o_lo)[o] = make_uint4(l[0], l[1], l[2], l[3]);
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // sF is rewritten by the next tile
-            }
+            };
+            if (a.pool) pool_store(NP, a.out_hi, a.out_lo);
             if (tail) {
                 um::fence_async_smem();
                 mbar_arrive(&bar_a2_full);
@@ -764,14 +772,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
                     float o[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bb[j], 0.f);
-                    uint32_t h[4], l[4];
+                    if (a.pool2) {
+                        float* f = sF + (size_t)m * (NP2 + 4) + c0;     // aliases the tail's A tile: its MMAs have completed
+                        *reinterpret_cast<float4*>(f) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(f + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    } else {
+                        uint32_t h[4], l[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) um::split2(o[2 * j], o[2 * j + 1], h[j], l[j]);
-                    const size_t e = ((size_t)n * (NP2 / 8) + c0 / 8) * a.HW + px;
-                    reinterpret_cast<uint4*>(a.out2_hi)[e] = make_uint4(h[0], h[1], h[2], h[3]);
-                    reinterpret_cast<uint4*>(a.out2_lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
+                        for (int j = 0; j < 4; ++j) um::split2(o[2 * j], o[2 * j + 1], h[j], l[j]);
+                        const size_t e = ((size_t)n * (NP2 / 8) + c0 / 8) * a.HW + px;
+                        reinterpret_cast<uint4*>(a.out2_hi)[e] = make_uint4(h[0], h[1], h[2], h[3]);
+                        reinterpret_cast<uint4*>(a.out2_lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
                 }
                 um::tc_fence_before();
+                if (a.pool2) pool_store(NP2, a.out2_hi, a.out2_lo);
                 GCK();
             }
         }

@@ -98,6 +98,8 @@ struct Launch {
     ChainTcArgs chain{};
     int chain_tiles = 0;
     GemmTcArgs gemm{};
+    const bf16* src_hi[2] = {nullptr, nullptr};
+    const bf16* src_lo[2] = {nullptr, nullptr};
     GatesTcArgs gates{};
     FrontTcArgs front{};
     GemmSmem gl{};
@@ -119,7 +121,8 @@ struct Plan {
     float* gates = nullptr;     // [crops][4][midp]
     float* dbg_crop = nullptr;  // resized crops of the fused front kernel (diagnostics, allocated on first use)
     float* dbg = nullptr;       // float32 NHWC copy of a stage (diagnostics)
-    std::vector<Launch> launches;
+    std::vector<Launch> launches;      // product path (transition fused behind the second block of stages 2 and 3)
+    std::vector<Launch> launches_dbg;  // same network, every block output materialised (diagnostic stops)
     int smem_limit = 0;
 };
 

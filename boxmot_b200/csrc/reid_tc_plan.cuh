@@ -135,8 +135,8 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                 g.src_planes[s] = C8;
                 g.src_kc[s] = kc;
                 g.K8 += C8;
-                make_tile_map(&g.map_hi[s], srcs[s].buf->hi, P->chunk, C8, H * Wd, kc);
-                make_tile_map(&g.map_lo[s], srcs[s].buf->lo, P->chunk, C8, H * Wd, kc);
+                L.src_hi[s] = srcs[s].buf->hi;
+                L.src_lo[s] = srcs[s].buf->lo;
             }
             g.b_packed = WB + b_off;
             g.N = N;
@@ -147,32 +147,53 @@ Plan* plan_build(ReidModel* m, const float* hw) {
             g.W = Wd;
             return L;
         };
-        auto finish = [&](Launch& L) {
+        auto finish_into = [&](Launch& L, std::vector<Launch>* out) {
             GemmTcArgs& g = L.gemm;
             const bool tail = g.b2_packed != nullptr;
-            int kc_max = 2;
-            for (int s = 0; s < g.n_src; ++s) kc_max = std::max(kc_max, g.src_kc[s]);
-            g.slot_bytes = kc_max * 128 * 16 * 2;
             // two CTAs per SM (they overlap each other's MMA / epilogue / load latencies) when a >= 2-deep ring fits half
-            // the shared memory; otherwise one CTA with the deepest ring that fits
+            // the shared memory -- with smaller ring chunks (2 planes) if that is what it takes; otherwise one CTA with
+            // the deepest ring that fits
             const int half_limit = (P->smem_limit + 1024) / 2 - 1024 - 512;
+            auto layout = [&](int ns) { return gemm_smem_layout(g.K8, g.NP, g.NP2, ns, tail, g.pool != 0, g.slot_bytes, g.pool2 != 0); };
             int ns = 0;
-            for (int cand = 4; cand >= 2 && !ns; --cand)
-                if ((int)gemm_smem_layout(g.K8, g.NP, g.NP2, cand, tail, g.pool != 0, g.slot_bytes).total <= half_limit) ns = cand;
-            for (int cand = 4; cand >= 2 && !ns; --cand)
-                if ((int)gemm_smem_layout(g.K8, g.NP, g.NP2, cand, tail, g.pool != 0, g.slot_bytes).total <= P->smem_limit) ns = cand;
+            for (int pass = 0; pass < 2 && !ns; ++pass) {
+                int kc_max = 2;
+                for (int s = 0; s < g.n_src; ++s) {
+                    if (pass == 1) g.src_kc[s] = 2;
+                    kc_max = std::max(kc_max, g.src_kc[s]);
+                }
+                g.slot_bytes = kc_max * 128 * 16 * 2;
+                for (int cand = 4; cand >= 2 && !ns; --cand)
+                    if ((int)layout(cand).total <= half_limit) ns = cand;
+            }
+            if (!ns) {
+                int kc_max = 2;
+                for (int s = 0; s < g.n_src; ++s) {
+                    g.src_kc[s] = g.src_planes[s] % 4 == 0 ? 4 : 2;
+                    kc_max = std::max(kc_max, g.src_kc[s]);
+                }
+                g.slot_bytes = kc_max * 128 * 16 * 2;
+                for (int cand = 4; cand >= 2 && !ns; --cand)
+                    if ((int)layout(cand).total <= P->smem_limit) ns = cand;
+            }
             if (!ns) throw std::runtime_error("tensor-core GEMM does not fit shared memory");
             if (2 * g.NP + (tail ? 2 * g.NP2 : 0) > 512) throw std::runtime_error("tensor-core GEMM does not fit TMEM");
-            L.gl = gemm_smem_layout(g.K8, g.NP, g.NP2, ns, tail, g.pool != 0, g.slot_bytes);
+            for (int s = 0; s < g.n_src; ++s) {   // the boxes follow the chunk size
+                make_tile_map(&g.map_hi[s], L.src_hi[s], P->chunk, g.src_planes[s], g.HW, g.src_kc[s]);
+                make_tile_map(&g.map_lo[s], L.src_lo[s], P->chunk, g.src_planes[s], g.HW, g.src_kc[s]);
+            }
+            L.gl = layout(ns);
             g.n_stage = ns;
             L.gemm_groups = (g.tiles_per_crop + g.tiles_per_cta - 1) / g.tiles_per_cta;
-            P->launches.push_back(L);
+            out->push_back(L);
         };
         auto dbg = [&](Launch& L, int stage, const Planes& buf, int C8, int HW, int C) {
             L.stage_after = stage;
             L.dbg_hi = buf.hi; L.dbg_lo = buf.lo; L.dbg_C8 = C8; L.dbg_HW = HW; L.dbg_C = C;
         };
 
+        auto build_launches = [&](bool fuse_trans, std::vector<Launch>* out) {
+            auto finish = [&](Launch& L) { finish_into(L, out); };
         {   // crop + resize + stem + max pool -> planes P (one fused tensor-core kernel); launches[1] is the float32-stem
             // fallback entry used when a diagnostic stop asks for the blob / stem tensors of the round-1 kernels
             Launch L{};
@@ -182,7 +203,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
             L.front.bias_tab = WF + fb;
             L.front.p_hi = P->P.hi; L.front.p_lo = P->P.lo;
             dbg(L, 2, P->P, 2, 2048, 16);
-            P->launches.push_back(L);
+            out->push_back(L);
         }
         Planes* X = &P->P;          // block input
         Planes* Xo = &P->XA;
@@ -199,6 +220,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         }
         for (int s = 0; s < 3; ++s) {
             const ChainShape& cs = kChainShapes[s];
+            bool trans_done = false;
             for (int j = 0; j < 2; ++j) {
                 const int bi = s * 2 + j;
                 const BlockW& b = m->blocks[bi];
@@ -220,7 +242,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     c.H = H;
                     L.chain_tiles = H / cs.R;
                     dbg(L, 200 + bi, P->Y, 4 * midp / 8, H * Wd, 4 * midp);
-                    P->launches.push_back(L);
+                    out->push_back(L);
                 }
                 {   // ChannelGate of the four branches (one CTA per crop)
                     Launch L{};
@@ -231,7 +253,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     ga.g1w = W32 + b.g1w; ga.g1b = W32 + b.g1b; ga.g2w = W32 + b.g2w; ga.g2b = W32 + b.g2b;
                     ga.gates = P->gates;
                     ga.mid = b.mid; ga.midp = midp; ga.hid = b.hid; ga.tiles = H / cs.R; ga.HW = H * Wd;
-                    P->launches.push_back(L);
+                    out->push_back(L);
                 }
                 {   // gate (x) conv3 (+ downsample / identity) + ReLU, and the next block's conv1 on the fresh tile
                     Launch L = gemm(H, Wd, {{&P->Y, 4 * midp / 8}, {X, xC8}}, bo[bi].cx, b.cout, bo[bi].cxb, true);
@@ -240,6 +262,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     g.gates = P->gates;
                     g.mid = b.mid; g.midp = midp;
                     g.out_hi = Xo->hi; g.out_lo = Xo->lo;
+                    bool fused_trans = false;
                     if (j == 0) {
                         const BlockW& nb = m->blocks[bi + 1];
                         const int nmidp = pad16(nb.mid);
@@ -250,12 +273,32 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                             g.N2 = nb.mid; g.NP2 = nmidp;
                             g.out2_hi = P->X1.hi; g.out2_lo = P->X1.lo;
                         }
+                    } else if (s < 2 && fuse_trans) {
+                        // second block of a stage: the transition (1x1 + ReLU, 2x2 average pool) runs on the fresh tile, the
+                        // block's own output never goes to HBM (nothing else reads it); diagnostic stops keep the two launches
+                        const int C = m->c[s + 1];
+                        const GemmSmem probe = gemm_smem_layout(g.K8, g.NP, C, 2, true, false, 2 * 128 * 16 * 2, true);
+                        if ((int)probe.total <= P->smem_limit && 2 * g.NP + 2 * C <= 512) {
+                            g.b2_packed = WB + tr[s];
+                            g.bias2 = WF + trb[s];
+                            g.N2 = C; g.NP2 = C;
+                            g.pool2 = 1;
+                            g.out_hi = nullptr; g.out_lo = nullptr;
+                            g.out2_hi = Xo->hi; g.out2_lo = Xo->lo;      // pooled transition output
+                            fused_trans = true;
+                        }
                     }
-                    dbg(L, stage++, *Xo, b.cout / 8, H * Wd, b.cout);
-                    const bool fused_next = g.b2_packed != nullptr;
+                    if (fused_trans) {
+                        ++stage;                                         // the block output itself is not materialised
+                        dbg(L, stage++, *Xo, m->c[s + 1] / 8, H * Wd / 4, m->c[s + 1]);
+                    } else {
+                        dbg(L, stage++, *Xo, b.cout / 8, H * Wd, b.cout);
+                    }
+                    const bool fused_next = g.b2_packed != nullptr && !fused_trans;
                     finish(L);
                     Planes* t = X == &P->P ? Xspare : X;
                     X = Xo; Xo = t; xC8 = b.cout / 8;
+                    trans_done = fused_trans;
                     if (j == 0 && !fused_next) {
                         const BlockW& nb = m->blocks[bi + 1];
                         Launch L2 = gemm(H, Wd, {{X, xC8}}, bo[bi + 1].c1, nb.mid, bo[bi + 1].c1b, true);
@@ -267,7 +310,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
             }
             if (s < 2) {
                 const int C = m->c[s + 1];
-                {   // transition: 1x1 + ReLU, 2x2 average pool in the epilogue
+                if (!trans_done) {   // transition: 1x1 + ReLU, 2x2 average pool in the epilogue
                     Launch L = gemm(H, Wd, {{X, xC8}}, tr[s], C, trb[s], true);
                     L.gemm.pool = 1;
                     L.gemm.out_hi = Xo->hi; L.gemm.out_lo = Xo->lo;
@@ -289,6 +332,9 @@ Plan* plan_build(ReidModel* m, const float* hw) {
             L.stage_after = 11;
             finish(L);
         }
+        };
+        build_launches(true, &P->launches);
+        build_launches(false, &P->launches_dbg);   // diagnostic stops at block outputs need the unfused transition
     } catch (...) {
         plan_free(P);
         throw;
@@ -303,7 +349,7 @@ template <class Prof>
 int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int upper, cudaStream_t st, bool* stopped, Prof& prof) {
     Plan* P = m->tc;
     int launches = 0;
-    for (const Launch& L : P->launches) {
+    for (const Launch& L : (m->debug_stop >= 0 ? P->launches_dbg : P->launches)) {
         prof.begin(L.cls);
         switch (L.kind) {
             case LK_FRONT: {

@@ -31,9 +31,16 @@ def cls_of(name):
     return "other"
 
 
+# one frame = the launches from k_front_tc up to the next k_front_tc: rotate the capture so that it starts there and
+# drop what exceeds one frame (the capture window may overlap the neighbouring frame by a launch)
+body = rows[2:]
+first = next((i for i, r in enumerate(body) if "k_front_tc" in r[ix["Kernel Name"]]), 0)
+per_frame = int(sys.argv[4]) if len(sys.argv) > 4 else 26
+extra = max(0, len(body) - per_frame)          # launches of the previous frame's tail that the window repeats
+body = (body[first:] + body[extra:first])[:per_frame]
 per = {}
 lines = ["| # | kernel | grid | us | tensor pipe % | issue active % | warps active % | DRAM read MB | DRAM write MB |", "|---:|---|---|---:|---:|---:|---:|---:|---:|"]
-for i, r in enumerate(rows[2:]):
+for i, r in enumerate(body):
     name = r[ix["Kernel Name"]]
     c = cls_of(name)
     us = val(r, "gpu__time_duration.sum")
