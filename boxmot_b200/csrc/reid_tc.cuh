@@ -298,15 +298,22 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                         win[i2][kx][1] = make_float2(qq.z, qq.w);                                                      \
                     }                                                                                                  \
                     tp += TW;                                                                                          \
+                    /* three independent partial sums per channel pair (one per window row): 6 chains of 3 FFMA2 */   \
                     float2 a0 = bv0, a1 = bv1;                                                                         \
-                    _Pragma("unroll") for (int kx = 0; kx < 3; ++kx) {                                                 \
+                    float2 b0 = __fmul2_rn(win[i1][0][0], wv[3][0]), b1 = __fmul2_rn(win[i1][0][1], wv[3][1]);          \
+                    float2 c0 = __fmul2_rn(win[i2][0][0], wv[6][0]), c1 = __fmul2_rn(win[i2][0][1], wv[6][1]);          \
+                    a0 = __ffma2_rn(win[i0][0][0], wv[0][0], a0);                                                      \
+                    a1 = __ffma2_rn(win[i0][0][1], wv[0][1], a1);                                                      \
+                    _Pragma("unroll") for (int kx = 1; kx < 3; ++kx) {                                                 \
                         a0 = __ffma2_rn(win[i0][kx][0], wv[kx][0], a0);                                                \
                         a1 = __ffma2_rn(win[i0][kx][1], wv[kx][1], a1);                                                \
-                        a0 = __ffma2_rn(win[i1][kx][0], wv[3 + kx][0], a0);                                            \
-                        a1 = __ffma2_rn(win[i1][kx][1], wv[3 + kx][1], a1);                                            \
-                        a0 = __ffma2_rn(win[i2][kx][0], wv[6 + kx][0], a0);                                            \
-                        a1 = __ffma2_rn(win[i2][kx][1], wv[6 + kx][1], a1);                                            \
+                        b0 = __ffma2_rn(win[i1][kx][0], wv[3 + kx][0], b0);                                            \
+                        b1 = __ffma2_rn(win[i1][kx][1], wv[3 + kx][1], b1);                                            \
+                        c0 = __ffma2_rn(win[i2][kx][0], wv[6 + kx][0], c0);                                            \
+                        c1 = __ffma2_rn(win[i2][kx][1], wv[6 + kx][1], c1);                                            \
                     }                                                                                                  \
+                    a0 = __fadd2_rn(__fadd2_rn(a0, b0), c0);                                                           \
+                    a1 = __fadd2_rn(__fadd2_rn(a1, b1), c1);                                                           \
                     a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f);                                                  \
                     a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);                                                  \
                     uint32_t h0, h1, e0, e1;                                                                           \
