@@ -32,6 +32,9 @@ TRACKER_DEFAULTS = {
     "deepocsort": dict(det_thresh=0.5, max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3, inertia=0.2,
                        w_association_emb=0.75, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False,
                        cmc_off=True, aw_off=False, Q_xy_scaling=0.01, Q_s_scaling=0.0001),
+    # configs/trackers/ocsort.yaml
+    "ocsort": dict(min_conf=0.1, det_thresh=0.6, max_age=30, min_hits=3, delta_t=3, asso_func="iou", use_byte=False,
+                   inertia=0.1, Q_xy_scaling=0.01, Q_s_scaling=0.0001),
     "strongsort": dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
                        mc_lambda=0.98, nn_budget=100),
 }
@@ -611,6 +614,28 @@ class DeepOcSort(_SingleStreamTracker):
                          iou_threshold=iou_threshold, **kwargs)
 
 
+class OcSort(_SingleStreamTracker):
+    """OC-SORT on the GPU; arguments as boxmot/trackers/bbox/ocsort/ocsort.py:331-362.  For axis-aligned boxes the
+    reference class is the DeepOCSORT update with the appearance and camera-motion terms removed (same XYSR filter, same
+    `associate()`, same observation-centric second round), so it runs on the DeepOCSORT device core with the embedding
+    term off; ids / rows are pinned on goldens from the unmodified OcSort class.  `use_byte=True` (an extra ByteTrack-style
+    round on low-confidence detections) is not implemented; `min_conf` only feeds that round."""
+
+    _kind = "deepocsort"
+
+    def __init__(self, min_conf: float = 0.1, delta_t: int = 3, inertia: float = 0.2, use_byte: bool = False,
+                 Q_xy_scaling: float = 0.01, Q_s_scaling: float = 0.0001, **kwargs: Any):
+        if use_byte:
+            raise NotImplementedError("use_byte=True (BYTE second association) is not implemented on the B200 path")
+        kwargs.pop("reid_model", None)
+        self.min_conf, self.use_byte = min_conf, False
+        super().__init__(reid_model=None, delta_t=delta_t, inertia=inertia, embedding_off=True, aw_off=True,
+                         Q_xy_scaling=Q_xy_scaling, Q_s_scaling=Q_s_scaling, **kwargs)
+
+    def update(self, dets, img=None, embs=None, masks=None, warp=None) -> TrackResults:
+        return super().update(dets, img, None, masks)
+
+
 class StrongSort(_SingleStreamTracker):
     """StrongSORT on the GPU; arguments as boxmot/trackers/bbox/strongsort/strongsort.py:38-67 (`max_age` is the
     BaseTracker setting the reference forwards to its Tracker).  The reference estimates a camera warp with ECC on
@@ -654,7 +679,7 @@ def resolve_tracker_args(tracker_type, tracker_config=None, evolve_param_dict=No
     import inspect
 
     kind = str(tracker_type).lower()
-    classes = {"bytetrack": ByteTrack, "botsort": BotSort, "deepocsort": DeepOcSort, "strongsort": StrongSort}
+    classes = {"bytetrack": ByteTrack, "botsort": BotSort, "deepocsort": DeepOcSort, "strongsort": StrongSort, "ocsort": OcSort}
     if kind not in classes:
         raise ValueError(f"Unknown tracker type: '{tracker_type}'. Available trackers are: {', '.join(classes)} "
                          "(the trackers that are part of the B200 hot path)")
@@ -704,7 +729,7 @@ def create_tracker(tracker_type, tracker_config=None, reid_weights=None, device=
     `**overrides` (an extension) are applied on top of the configuration.  CMC is always off (see BotSort)."""
     kind, cls, args = resolve_tracker_args(tracker_type, tracker_config, evolve_param_dict, overrides)
     per_class = bool(per_class)
-    if kind == "bytetrack":
+    if kind in ("bytetrack", "ocsort"):   # motion-only trackers: no ReID backend (tracker_zoo.py:124-130)
         return cls(per_class=per_class, **args)
     wants_reid = args.get("with_reid", True) and not args.get("embedding_off", False)
     if reid_model is None and reid_weights is not None and wants_reid:

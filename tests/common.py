@@ -20,6 +20,9 @@ BOTSORT_YAML = dict(
 
 DEEPOCSORT_YAML = dict(det_thresh=0.5, w_association_emb=0.75)
 
+# configs/trackers/ocsort.yaml defaults (det_thresh 0.6 and inertia 0.1 differ from the constructor's 0.3 / 0.2)
+OCSORT_YAML = dict(min_conf=0.1, det_thresh=0.6, max_age=30, min_hits=3, delta_t=3, use_byte=False, inertia=0.1,
+                   Q_xy_scaling=0.01, Q_s_scaling=0.0001)
 STRONGSORT_YAML = dict(min_conf=0.6, ema_alpha=0.9, max_cos_dist=0.4, max_iou_dist=0.7, max_age=30, n_init=3,
                        mc_lambda=0.98, nn_budget=100)
 
@@ -103,6 +106,12 @@ CASES = {
     # constructor defaults the other DeepOCSORT cases use)
     "deepocsort_yaml_mot17_02": ("deepocsort", DEEPOCSORT_YAML, lambda: mot17_stream("02"),
                                  lambda fr: mot17_embeddings("02", fr, seed=15, unit=True)),
+}
+# OC-SORT: goldens from the unmodified reference OcSort class (tests/golden/make_ocsort_golden.py)
+OCSORT_CASES = {
+    "ocsort_stress96": ("ocsort", {}, lambda: stress_stream(96, 300), None),
+    "ocsort_yaml_stress48_gaps": ("ocsort", OCSORT_YAML, lambda: stress_stream(48, 200, seed=19, n_classes=3, empty_every=37), None),
+    "ocsort_yaml_mot17_04": ("ocsort", OCSORT_YAML, lambda: mot17_stream("04"), None),
 }
 # cases added after the round-1 GPU budget was spent: verified on the CPU (oracle vs reference, host simulation of the
 # device source) but not yet on hardware -- their GPU test lives in tests/test_zgpu_late_goldens.py so that it runs last
