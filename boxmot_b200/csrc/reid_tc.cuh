@@ -98,6 +98,82 @@ __global__ void k_planes_to_nhwc(const bf16* __restrict__ hi, const bf16* __rest
     }
 }
 
+// ChannelGate (osnet.py:161-210) of the four branches of a block: mean -> fc1 -> ReLU -> fc2 -> sigmoid, and conv3 with
+// the gates folded in (the first 4 * midp rows of the combine GEMM's B operand, per crop).  Runs in the LAST k_chain_tc
+// CTA of a crop to finish (a per-crop arrival counter): no launch of its own, no redundant work.  Same operation order as
+// the float32 k_gates of round 1.
+struct GatesTcArgs {
+    const float* sums[4];               // [crops][tiles][midp]
+    const float* g1w; const float* g1b; const float* g2w; const float* g2b;   // [mid][hid], [hid], [hid][mid], [mid]
+    float* gates;                       // [crops][4][midp] (padded channels 0)
+    int mid, midp, hid, tiles, HW;
+    // bfold[crop] = [4 * midp / 8][2 * NP][8] BF16 ([hi | lo] along n), row (b * midp + c) = gates[b][c] * w3[c][:]
+    const float* w3;                    // [mid][N] float32
+    bf16* bfold;
+    int N, NP;
+    int* arrivals;                      // [crops] CTAs of the crop that have published their channel sums
+};
+template <int NT>
+__device__ void gates_fold(const GatesTcArgs& a, const int n, float* mean /*128*/, float* hid /*16*/, float* gate /*128*/) {
+    const int mid = a.mid, midp = a.midp;
+    for (int e = threadIdx.x; e < 4 * midp; e += NT) {
+        const int b = e / midp, c = e - b * midp;
+        float s = 0.f;
+        if (c < mid)
+            for (int t = 0; t < a.tiles; ++t) s += __ldcg(a.sums[b] + ((size_t)n * a.tiles + t) * midp + c);
+        mean[e] = s / (float)a.HW;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * a.hid; e += NT) {
+        const int b = e / a.hid, h = e - b * a.hid;
+        float s = a.g1b[h];
+        for (int c = 0; c < mid; ++c) s = fmaf(mean[b * midp + c], a.g1w[(size_t)c * a.hid + h], s);
+        hid[e] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * midp; e += NT) {
+        const int b = e / midp, c = e - b * midp;
+        float g = 0.f;
+        if (c < mid) {
+            float s = a.g2b[c];
+            for (int h = 0; h < a.hid; ++h) s = fmaf(hid[b * a.hid + h], a.g2w[(size_t)h * mid + c], s);
+            g = 1.0f / (1.0f + expf(-s));
+        }
+        a.gates[(size_t)n * 4 * midp + e] = g;
+        gate[e] = g;
+    }
+    __syncthreads();
+    // an item = (plane of 8 rows k, pair of output channels): 8 k values x 2 n, written as four 16-byte rows
+    const int NP = a.NP, N = a.N;
+    const int items = (4 * midp / 8) * (NP / 2);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(a.bfold) + (size_t)n * (4 * midp / 8) * 2 * NP * 16;
+    for (int e = threadIdx.x; e < items; e += NT) {
+        const int k8 = e / (NP / 2), n2 = (e - k8 * (NP / 2)) * 2;
+        uint32_t h0[4], l0[4], h1[4], l1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;   // (k, n), (k+1, n), (k, n+1), (k+1, n+1)
+            const int k = k8 * 8 + 2 * j;
+            const int b = k / midp, c = k - b * midp;            // midp is even: k and k+1 share the branch
+            if (c < mid && n2 < N) {
+                v00 = gate[k] * a.w3[(size_t)c * N + n2];
+                if (n2 + 1 < N) v10 = gate[k] * a.w3[(size_t)c * N + n2 + 1];
+            }
+            if (c + 1 < mid && n2 < N) {
+                v01 = gate[k + 1] * a.w3[(size_t)(c + 1) * N + n2];
+                if (n2 + 1 < N) v11 = gate[k + 1] * a.w3[(size_t)(c + 1) * N + n2 + 1];
+            }
+            um::split2(v00, v01, h0[j], l0[j]);
+            um::split2(v10, v11, h1[j], l1[j]);
+        }
+        unsigned char* row = dst + ((size_t)k8 * 2 * NP) * 16;
+        *reinterpret_cast<uint4*>(row + (size_t)n2 * 16) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+        *reinterpret_cast<uint4*>(row + (size_t)(n2 + 1) * 16) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+        *reinterpret_cast<uint4*>(row + (size_t)(NP + n2) * 16) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
+        *reinterpret_cast<uint4*>(row + (size_t)(NP + n2 + 1) * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_chain_tc: one branch of an OSBlock per CTA.  grid = (row tiles, 4 branches (deepest first), crops), 256 threads.
 // Shared memory: X hi / lo planes [CP/8][NPX][8] (NPX = (R + 8) padded rows of W + 2 pixels; the TMA box of conv1's
@@ -116,6 +192,7 @@ struct ChainTcArgs {
     bf16* y_lo;
     float* sums[4];                  // [crops][tiles][CP]
     int H;
+    GatesTcArgs gate;                // ChannelGate + conv3 fold, done by the crop's last CTA
 };
 
 template <int CP, int W, int R>
@@ -381,8 +458,23 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
         a.sums[br][((size_t)n * gridDim.x + tile) * CP + c] = s;
     }
     um::tc_fence_before();
+    __threadfence();                                   // publish the sums before counting this CTA in
     __syncthreads();
     if (warp == 1) um::tmem_dealloc(tmem, um::tmem_cols_pow2(G::TMEM_COLS));
+    // the last CTA of the crop (tiles x 4 branches) turns the sums into gates and folds them into conv3
+    __shared__ int s_last;
+    __shared__ float s_mean[128], s_hid[16], s_gate[128];
+    if (threadIdx.x == 0) {
+        const int total = (int)gridDim.x * 4;
+        const int prev = atomicAdd(a.gate.arrivals + n, 1);
+        s_last = prev == total - 1;
+        if (s_last) a.gate.arrivals[n] = 0;            // ready for the next block's launch
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        gates_fold<256>(a.gate, n, s_mean, s_hid, s_gate);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -391,46 +483,6 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
 // warps 2..9 = epilogue (lane quadrant = warp % 4, column half = (warp - 2) / 4).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int GEMM_THREADS = 320;
-
-// ChannelGate (osnet.py:161-210) of the four branches of a block: mean -> fc1 -> ReLU -> fc2 -> sigmoid.
-// One CTA per crop; gates [crops][4][midp] (padded channels 0).  Same operation order as the float32 k_gates.
-struct GatesTcArgs {
-    const float* sums[4];               // [crops][tiles][midp]
-    const float* g1w; const float* g1b; const float* g2w; const float* g2b;   // [mid][hid], [hid], [hid][mid], [mid]
-    float* gates;
-    int mid, midp, hid, tiles, HW;
-};
-__global__ void __launch_bounds__(128) k_gates_tc(const GatesTcArgs a, const int* __restrict__ d_n, int off, int cap) {
-    const int n = blockIdx.x;
-    if (n >= tc_chunk_count(d_n, off, cap)) return;
-    __shared__ float mean[128], hid[16];
-    const int mid = a.mid, midp = a.midp;
-    for (int e = threadIdx.x; e < 4 * midp; e += 128) {
-        const int b = e / midp, c = e - b * midp;
-        float s = 0.f;
-        if (c < mid)
-            for (int t = 0; t < a.tiles; ++t) s += a.sums[b][((size_t)n * a.tiles + t) * midp + c];
-        mean[e] = s / (float)a.HW;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 4 * a.hid; e += 128) {
-        const int b = e / a.hid, h = e - b * a.hid;
-        float s = a.g1b[h];
-        for (int c = 0; c < mid; ++c) s = fmaf(mean[b * midp + c], a.g1w[(size_t)c * a.hid + h], s);
-        hid[e] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 4 * midp; e += 128) {
-        const int b = e / midp, c = e - b * midp;
-        float g = 0.f;
-        if (c < mid) {
-            float s = a.g2b[c];
-            for (int h = 0; h < a.hid; ++h) s = fmaf(hid[b * a.hid + h], a.g2w[(size_t)h * mid + c], s);
-            g = 1.0f / (1.0f + expf(-s));
-        }
-        a.gates[(size_t)n * 4 * midp + e] = g;
-    }
-}
 
 struct GemmTcArgs {
     CUtensorMap map_hi[2], map_lo[2];   // A sources: box (64 pixels, 2, kc planes, 1 crop)
@@ -446,10 +498,9 @@ struct GemmTcArgs {
     int N, NP;                          // real / padded (multiple of 16) output channels
     const float* bias;                  // [NP]
     int relu;
-    // ChannelGate folded into conv3: B row (b * midp + c) = gates[crop][b][c] * w3[c][:]
-    const float* w3;                    // [mid][N] float32 (null: no gate)
-    const float* gates;                 // [crops][4][midp] (k_gates_tc)
-    int mid, midp, HW;
+    // ChannelGate folded into conv3: the first 4 * midp rows of B come per crop from k_gates_tc (null: no gate)
+    const bf16* bfold;                  // [crops][4 * midp / 8][2 * NP][8]
+    int midp, HW;
     int slot_bytes;                     // ring slot: hi planes then lo planes (slot_bytes / 2 each)
     // outputs
     bf16* out_hi; bf16* out_lo;         // planes [crops][NP/8][H][W][8] (or pooled [..][H/2][W/2][8]); may be null
@@ -541,9 +592,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
         // ================= TMA producer =================
         if (lane == 0) {
             {   // packed weights (everything below the gate-folded rows, and the tail's B) by bulk async copies
-                const uint32_t first = (uint32_t)((a.w3 ? 4 * a.midp : 0) / 8) * 2u * NP * 16u, total = (uint32_t)a.K8 * 2u * NP * 16u;
+                const uint32_t first = (uint32_t)((a.bfold ? 4 * a.midp : 0) / 8) * 2u * NP * 16u, total = (uint32_t)a.K8 * 2u * NP * 16u;
                 const uint32_t b2 = tail ? (uint32_t)(NP / 8) * 2u * NP2 * 16u : 0u;
-                um::mbar_expect_tx(&bar_w, (total - first) + b2);
+                um::mbar_expect_tx(&bar_w, total + b2);
+                if (first) um::bulk_g2s(sB, reinterpret_cast<const unsigned char*>(a.bfold) + (size_t)n * first, first, &bar_w);
                 if (total > first) um::bulk_g2s(sB + first, reinterpret_cast<const unsigned char*>(a.b_packed) + first, total - first, &bar_w);
                 if (b2) um::bulk_g2s(sB2, a.b2_packed, b2, &bar_w);
             }
@@ -624,42 +676,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
         const int et = threadIdx.x - 64;                       // 0..255
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int m = q * 32 + lane;                           // pixel of the tile = TMEM lane
-        // ---- B: gate-folded conv3 rows, then the packed rows; tail weights ----
-        int gate_rows = 0;
-        if (a.w3) {
-            const int mid = a.mid, midp = a.midp;
-            gate_rows = 4 * midp;
-            float* gate = sGate;
-            for (int e = et; e < 4 * midp; e += 256) gate[e] = a.gates[(size_t)n * 4 * midp + e];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // rows k = b * midp + c: an item is (k pair-of-8 plane, n pair): 8 k values x 2 n per thread step
-            const int items = (gate_rows / 8) * (NP / 2);
-            for (int e = et; e < items; e += 256) {
-                const int k8 = e / (NP / 2), n2 = (e - k8 * (NP / 2)) * 2;
-                uint32_t h0[4], l0[4], h1[4], l1[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;   // (k, n), (k+1, n), (k, n+1), (k+1, n+1)
-                    const int k = k8 * 8 + 2 * j;
-                    const int b = k / midp, c = k - b * midp;            // midp is even: k and k+1 share the branch
-                    if (c < mid && n2 < a.N) {
-                        v00 = gate[k] * a.w3[(size_t)c * a.N + n2];
-                        if (n2 + 1 < a.N) v10 = gate[k] * a.w3[(size_t)c * a.N + n2 + 1];
-                    }
-                    if (c + 1 < mid && n2 < a.N) {
-                        v01 = gate[k + 1] * a.w3[(size_t)(c + 1) * a.N + n2];
-                        if (n2 + 1 < a.N) v11 = gate[k + 1] * a.w3[(size_t)(c + 1) * a.N + n2 + 1];
-                    }
-                    um::split2(v00, v01, h0[j], l0[j]);
-                    um::split2(v10, v11, h1[j], l1[j]);
-                }
-                unsigned char* row = sB + ((size_t)k8 * 2 * NP) * 16;
-                *reinterpret_cast<uint4*>(row + (size_t)n2 * 16) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
-                *reinterpret_cast<uint4*>(row + (size_t)(n2 + 1) * 16) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
-                *reinterpret_cast<uint4*>(row + (size_t)(NP + n2) * 16) = make_uint4(l0[0], l0[1], l0[2], l0[3]);
-                *reinterpret_cast<uint4*>(row + (size_t)(NP + n2 + 1) * 16) = make_uint4(l1[0], l1[1], l1[2], l1[3]);
-            }
-        }
+        // B arrives by bulk copies (producer warp): the packed rows and, for the combine GEMM, this crop's gate-folded rows
         um::fence_async_smem();
         mbar_arrive(&bar_b_ready);
         GCK();

@@ -100,7 +100,6 @@ struct Launch {
     GemmTcArgs gemm{};
     const bf16* src_hi[2] = {nullptr, nullptr};
     const bf16* src_lo[2] = {nullptr, nullptr};
-    GatesTcArgs gates{};
     FrontTcArgs front{};
     GemmSmem gl{};
     int gemm_groups = 0;
@@ -119,6 +118,8 @@ struct Plan {
     float* c5 = nullptr;        // conv5 output [crops][128][C3] float32
     float* sums[4] = {nullptr, nullptr, nullptr, nullptr};
     float* gates = nullptr;     // [crops][4][midp]
+    int* arrivals = nullptr;    // per-crop CTA arrival counters of k_chain_tc (self-resetting)
+    bf16* bfold = nullptr;      // per-crop gate-folded conv3 rows of the combine GEMM's B operand
     float* dbg_crop = nullptr;  // resized crops of the fused front kernel (diagnostics, allocated on first use)
     float* dbg = nullptr;       // float32 NHWC copy of a stage (diagnostics)
     std::vector<Launch> launches;      // product path (transition fused behind the second block of stages 2 and 3)
@@ -138,7 +139,7 @@ inline void free_planes(Planes& p) {
 
 inline void plan_free(Plan* p) {
     if (!p) return;
-    cudaFree(p->d_wb); cudaFree(p->d_wf); cudaFree(p->c5); cudaFree(p->dbg); cudaFree(p->gates); cudaFree(p->dbg_crop);
+    cudaFree(p->d_wb); cudaFree(p->d_wf); cudaFree(p->c5); cudaFree(p->dbg); cudaFree(p->gates); cudaFree(p->bfold); cudaFree(p->arrivals); cudaFree(p->dbg_crop);
     for (int b = 0; b < 4; ++b) cudaFree(p->sums[b]);
     free_planes(p->P); free_planes(p->X1); free_planes(p->Y); free_planes(p->XA); free_planes(p->XB);
     delete p;

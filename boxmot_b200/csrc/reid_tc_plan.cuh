@@ -31,6 +31,9 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         RCUDA_OK(cudaMalloc(&P->c5, sizeof(float) * CH * 128 * m->c[3]));
         for (int b = 0; b < 4; ++b) RCUDA_OK(cudaMalloc(&P->sums[b], sizeof(float) * CH * 8 * 32));
         RCUDA_OK(cudaMalloc(&P->gates, sizeof(float) * CH * 4 * 32));
+        RCUDA_OK(cudaMalloc(&P->arrivals, sizeof(int) * CH));
+        RCUDA_OK(cudaMemset(P->arrivals, 0, sizeof(int) * CH));
+        RCUDA_OK(cudaMalloc(&P->bfold, (size_t)CH * 16 * 2 * 128 * 16));   // [crops][<= 16 planes][2 * NP <= 256][8] BF16
         RCUDA_OK(cudaMalloc(&P->dbg, sizeof(float) * CH * 2048 * 64));
 
         // ---- weights ----
@@ -240,27 +243,22 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     c.y_hi = P->Y.hi; c.y_lo = P->Y.lo;
                     for (int br = 0; br < 4; ++br) c.sums[br] = P->sums[br];
                     c.H = H;
-                    L.chain_tiles = H / cs.R;
-                    dbg(L, 200 + bi, P->Y, 4 * midp / 8, H * Wd, 4 * midp);
-                    out->push_back(L);
-                }
-                {   // ChannelGate of the four branches (one CTA per crop)
-                    Launch L{};
-                    L.kind = LK_GATES;
-                    L.cls = CLS_GATES;
-                    GatesTcArgs& ga = L.gates;
+                    GatesTcArgs& ga = c.gate;     // ChannelGate + conv3 fold: the last CTA of each crop does it
                     for (int br = 0; br < 4; ++br) ga.sums[br] = P->sums[br];
                     ga.g1w = W32 + b.g1w; ga.g1b = W32 + b.g1b; ga.g2w = W32 + b.g2w; ga.g2b = W32 + b.g2b;
                     ga.gates = P->gates;
                     ga.mid = b.mid; ga.midp = midp; ga.hid = b.hid; ga.tiles = H / cs.R; ga.HW = H * Wd;
+                    ga.w3 = W32 + b.cw; ga.bfold = P->bfold; ga.N = b.cout; ga.NP = pad16(b.cout);
+                    ga.arrivals = P->arrivals;
+                    L.chain_tiles = H / cs.R;
+                    dbg(L, 200 + bi, P->Y, 4 * midp / 8, H * Wd, 4 * midp);
                     out->push_back(L);
                 }
                 {   // gate (x) conv3 (+ downsample / identity) + ReLU, and the next block's conv1 on the fresh tile
                     Launch L = gemm(H, Wd, {{&P->Y, 4 * midp / 8}, {X, xC8}}, bo[bi].cx, b.cout, bo[bi].cxb, true);
                     GemmTcArgs& g = L.gemm;
-                    g.w3 = W32 + b.cw;
-                    g.gates = P->gates;
-                    g.mid = b.mid; g.midp = midp;
+                    g.bfold = P->bfold;
+                    g.midp = midp;
                     g.out_hi = Xo->hi; g.out_lo = Xo->lo;
                     bool fused_trans = false;
                     if (j == 0) {
@@ -374,9 +372,6 @@ int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int up
                 break;
             case LK_CHAIN_S4:
                 k_chain_tc<32, 32, 8, 16><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<32, 8, 16>::SMEM, st>>>(L.chain, d_n, off, upper);
-                break;
-            case LK_GATES:
-                k_gates_tc<<<upper, 128, 0, st>>>(L.gates, d_n, off, upper);
                 break;
             case LK_GEMM:
                 k_gemm_tc<<<dim3(L.gemm_groups, upper), GEMM_THREADS, L.gl.total, st>>>(L.gemm, d_n, off, upper, L.gl);
