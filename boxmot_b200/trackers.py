@@ -18,6 +18,8 @@ from ._lib import B200Error, BoxMOTB200TrackerConfig
 
 # YAML defaults used by the reference's create_tracker (boxmot/configs/trackers/{bytetrack,botsort}.yaml),
 # restated as data: this is the configuration contract of the path.
+UNBOUNDED_GALLERY_CAP = 1024   # samples per track kept when StrongSORT is built with nn_budget=None
+
 TRACKER_DEFAULTS = {
     "bytetrack": dict(min_conf=0.1, track_thresh=0.6, track_buffer=30, match_thresh=0.9, frame_rate=30),
     "botsort": dict(
@@ -238,7 +240,14 @@ class MultiStreamTracker:
                 raise TypeError(f"unknown StrongSort parameters: {sorted(unknown)}")
             p.update(params)
             if p["nn_budget"] is None:
-                raise NotImplementedError("nn_budget=None (unbounded gallery) is not supported; pass a sample budget")
+                # the reference keeps every sample of a track for ever (linear_assignment.py:307-331); the device gallery is a
+                # ring per track slot, so "unbounded" becomes a large ring: identical until one track has collected more than
+                # UNBOUNDED_GALLERY_CAP samples (34 s of uninterrupted matches at 30 fps), after which the oldest is dropped
+                import warnings
+
+                warnings.warn(f"StrongSORT nn_budget=None: the device gallery keeps the last {UNBOUNDED_GALLERY_CAP} samples per "
+                              "track (the reference's list is unbounded)", stacklevel=3)
+                p["nn_budget"] = UNBOUNDED_GALLERY_CAP
             cfg.tracker = _lib.TRACKER_STRONGSORT
             cfg.n_init, cfg.nn_budget, cfg.max_age = int(p["n_init"]), int(p["nn_budget"]), int(p["max_age"])
             cfg.min_conf, cfg.max_cos_dist, cfg.max_iou_dist = p["min_conf"], p["max_cos_dist"], p["max_iou_dist"]

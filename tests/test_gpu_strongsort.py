@@ -109,3 +109,23 @@ def test_gpu_strongsort_device_reid_matches_oracle(tmp_path):
     orc = StrongSortOracle(reid_model=orid.OracleReID(sd), **kw)
     for f, d in enumerate(frames):
         assert_rows_match(gpu.update(d, img), orc.update(d, img), f)
+
+
+def test_unbounded_gallery_nn_budget_none_matches_oracle():
+    """nn_budget=None (the reference's unbounded sample list, linear_assignment.py:307-331): the device keeps a ring of
+    UNBOUNDED_GALLERY_CAP samples per track, identical to the reference until a track outgrows it."""
+    import boxmot_b200 as bb
+    from oracle.streams import stress_embeddings, stress_stream
+    from oracle.strongsort import StrongSortOracle
+
+    frames = stress_stream(40, 150, seed=61, dropout=0.1)
+    embs = stress_embeddings(frames, 40, dim=64, seed=62)
+    kw = dict(min_conf=0.3, max_cos_dist=0.4, n_init=2, nn_budget=None)
+    with pytest.warns(UserWarning, match="nn_budget=None"):
+        gpu = bb.StrongSort(cap_tracks=128, cap_dets=64, feat_dim=64, **kw)
+    orc = StrongSortOracle(**kw)
+    longest = 0
+    for f, (d, e) in enumerate(zip(frames, embs)):
+        assert_rows_match(gpu.update(d, None, e), orc.update(d, None, e.copy()), f)
+        longest = max([longest] + [len(v) for v in orc.samples.values()])
+    assert longest > 100, "the stream must fill galleries beyond the default budget of 100"
