@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
     const int H = a.H;
     constexpr int TW = G::TW, NPX = G::NPX, NPXT = G::NPXT, C8 = CP / 8, C4 = CR / 4, KS = CP / 16;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_tma, bar_mma;
+    __shared__ __align__(8) uint64_t bar_tma, bar_mma, bar_w[2];
     __shared__ uint32_t tmem_slot;
     unsigned char* sXh = smem;
     unsigned char* sXl = sXh + G::X_BYTES;
@@ -236,15 +236,16 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
 #endif
     TCK();
 
-    auto load_weights = [&](int lv) {   // level lv (1-based) -> slot (lv & 1)
+    // weights of level lv (1-based) -> slot (lv & 1): two bulk copies by thread 0 (the packed [W_hi | W_lo] block, and the
+    // depthwise taps + bias, which the plan stores back to back), completing on the slot's barrier.  The copy for level
+    // lv + 1 is issued while level lv's MMAs run; nobody waits on global memory (plain loads by all threads stalled
+    // every level for 800 - 2 800 cycles).
+    constexpr uint32_t PW_BYTES = C8 * 2 * CP * 16, DW_BYTES = 10 * CP * 4;
+    auto fetch_weights = [&](int lv) {
         unsigned char* dst = sWs + (size_t)(lv & 1) * G::WSLOT_BYTES;
-        const uint4* spw = reinterpret_cast<const uint4*>(a.wpw[l0 + lv - 1]);
-        for (int e = threadIdx.x; e < C8 * 2 * CP; e += 256) reinterpret_cast<uint4*>(dst)[e] = spw[e];
-        float* dd = reinterpret_cast<float*>(dst + C8 * 2 * CP * 16);
-        const float* sdw = a.wdw[l0 + lv - 1];
-        const float* sb = a.bias[l0 + lv - 1];
-        for (int e = threadIdx.x; e < 9 * CP; e += 256) dd[e] = sdw[e];
-        for (int e = threadIdx.x; e < CP; e += 256) dd[9 * CP + e] = sb[e];
+        um::mbar_expect_tx(&bar_w[lv & 1], PW_BYTES + DW_BYTES);
+        um::bulk_g2s(dst, a.wpw[l0 + lv - 1], PW_BYTES, &bar_w[lv & 1]);
+        um::bulk_g2s(dst + PW_BYTES, a.wdw[l0 + lv - 1], DW_BYTES, &bar_w[lv & 1]);
     };
 
     // the input box first (its latency overlaps the TMEM allocation and the weight staging): thread 0 initialises the
@@ -252,14 +253,15 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
     if (threadIdx.x == 0) {
         um::mbar_init(&bar_tma, 1);
         um::mbar_init(&bar_mma, 1);
+        um::mbar_init(&bar_w[0], 1);
+        um::mbar_init(&bar_w[1], 1);
         um::fence_mbar_init();
         um::mbar_expect_tx(&bar_tma, 2u * G::X_BYTES);
         um::tma_load_4d(sXh, &a.map_hi, -4, g0, 0, n, &bar_tma);
         um::tma_load_4d(sXl, &a.map_lo, -4, g0, 0, n, &bar_tma);
+        fetch_weights(1);
     }
     if (warp == 1) um::tmem_alloc(&tmem_slot, um::tmem_cols_pow2(G::TMEM_COLS));
-    load_weights(1);
-    um::fence_async_smem();
     um::tc_fence_before();
     __syncthreads();
     um::tc_fence_after();
@@ -281,7 +283,10 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
         const int la = 4 - ext, lb = 4 + R + ext;              // local rows the depthwise stage produces
         const int pa = (la - 1) * TW, pb = (lb + 1) * TW;      // pixels whose 1x1 result it reads
         const int t0 = pa >> 7, t1 = (pb + 127) >> 7;
+        um::mbar_wait(&bar_w[lv & 1], (uint32_t)((lv - 1) >> 1) & 1u);     // this level's weights (k-th use of the slot)
         if (threadIdx.x == 0) {
+            // the other slot was last read by level lv - 1 (its MMAs were waited for, its walkers passed the barrier)
+            if (lv < depth) fetch_weights(lv + 1);
             const uint32_t id2 = um::idesc_bf16(128, 2 * CP), id1 = um::idesc_bf16(128, CP);
             const uint32_t lbo_a = (uint32_t)NPX * 16u, lbo_b = 2u * CP * 16u;
             const uint32_t xh = um::smem_u32(sXh), xl = um::smem_u32(sXl), wb = um::smem_u32(wslot);
@@ -298,7 +303,6 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
             um::mma_commit(&bar_mma);
         }
         TCK();
-        if (lv < depth) load_weights(lv + 1);                  // overlaps the MMAs; published by the fence at the end of the level
         um::mbar_wait(&bar_mma, mma_phase);
         mma_phase ^= 1u;
         um::tc_fence_after();

@@ -52,6 +52,8 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     for (int c = 0; c < b.mid; ++c) wf[at + t * midp + c] = hw[b.light[l].dw + (size_t)t * b.mid + c];
                 bo[bi].dw[l] = at;
                 bo[bi].lb[l] = pack_f(wf, hw + b.light[l].b, b.mid, midp);
+                // k_chain_tc fetches taps + bias with one bulk copy
+                if (bo[bi].lb[l] != at + (size_t)9 * midp) throw std::runtime_error("chain weights: taps and bias are not contiguous");
             }
             bo[bi].c1 = pack_b(wb, hw + b.c1w, b.cin, b.mid, b.mid, b.cin / 8, midp);
             bo[bi].c1b = pack_f(wf, hw + b.c1b, b.mid, midp);

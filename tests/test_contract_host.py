@@ -41,8 +41,10 @@ def test_create_tracker_rejects_unknown_and_out_of_scope_names():
         create_tracker(tracker_type="nonexistent_tracker", tracker_config=None, reid_weights="x.pt", device="cpu",
                        half=False, per_class=False)
     with pytest.raises(ValueError, match="Unknown tracker type"):
-        create_tracker("ocsort")
-    assert set(TRACKER_DEFAULTS) == {"bytetrack", "botsort", "deepocsort", "strongsort"}
+        create_tracker("hybridsort")
+    assert set(TRACKER_DEFAULTS) == {"bytetrack", "botsort", "deepocsort", "strongsort", "ocsort"}
+    # configs/trackers/ocsort.yaml defaults
+    assert TRACKER_DEFAULTS["ocsort"]["use_byte"] is False and TRACKER_DEFAULTS["ocsort"]["delta_t"] == 3
     # the YAML defaults the reference's create_tracker would read
     assert TRACKER_DEFAULTS["botsort"]["track_high_thresh"] == 0.6296854875023994
     assert TRACKER_DEFAULTS["botsort"]["removed_stracks_buffer"] == 329
