@@ -195,22 +195,22 @@ struct ChainTcArgs {
     GatesTcArgs gate;                // ChannelGate + conv3 fold, done by the crop's last CTA
 };
 
-template <int CP, int W, int R>
+template <int CP, int CR, int W, int R>
 struct ChainGeom {
     static constexpr int TW = W + 2, ROWS = R + 8, NPX = ROWS * TW;
     static constexpr int NT_MAX = (NPX + 127) / 128;
     static constexpr int NPXT = ((NPX + 7) / 8) * 8 + 2;
     static constexpr int X_BYTES = (CP / 8) * NPX * 16;               // one of hi / lo
-    static constexpr int T_BYTES = (CP / 4) * NPXT * 16;
+    static constexpr int T_BYTES = (CR / 4) * NPXT * 16;               // only the real channels pass through T
     static constexpr int WSLOT_BYTES = (CP / 8) * 2 * CP * 16 + 9 * CP * 4 + CP * 4;
     static constexpr int TMEM_COLS = NT_MAX * 2 * CP;
     // the last M tile may read past the planes: keep one tile of slack after X so those reads stay inside the allocation
     static constexpr size_t SMEM = 2 * (size_t)X_BYTES + T_BYTES + 2 * WSLOT_BYTES + 128;
 };
 
-template <int CP, int CR, int W, int R>
+template <int CP, int CR, int W, int R, int NSPLIT>
 __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainTcArgs a, const int* __restrict__ d_n, int off, int cap) {
-    using G = ChainGeom<CP, W, R>;
+    using G = ChainGeom<CP, CR, W, R>;
     const int n = blockIdx.z;
     if (n >= tc_chunk_count(d_n, off, cap)) return;
     const int br = 3 - (int)blockIdx.y, depth = br + 1, tile = blockIdx.x;
@@ -273,7 +273,10 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
     constexpr int walkers = W * C4;
     constexpr int n_grp = 256 / C4;
     constexpr int act = n_grp * C4;
-    constexpr int n_split = (act / walkers) < 1 ? 1 : (act / walkers);
+    // row splits per walker column: as many as there are threads (NSPLIT = 0), or fewer, longer walks -- a walker's
+    // 9 tap vectors and its first two window rows are a fixed cost per walk
+    constexpr int n_split_max = (act / walkers) < 1 ? 1 : (act / walkers);
+    constexpr int n_split = NSPLIT > 0 && NSPLIT < n_split_max ? NSPLIT : n_split_max;
     float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t mma_phase = 0;
 
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                                                           make_float2(__uint_as_float(v2[4 * j]), __uint_as_float(v2[4 * j + 1])));
                             const float2 hi2 = __fadd2_rn(make_float2(__uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3])),
                                                           make_float2(__uint_as_float(v2[4 * j + 2]), __uint_as_float(v2[4 * j + 3])));
-                            sT[(c0 / 4 + j) * NPXT + p] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                            if (c0 / 4 + j < C4) sT[(c0 / 4 + j) * NPXT + p] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
                         }
                     }
                 }
@@ -481,6 +484,35 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
     }
 }
 
+// the three instances of OSNet_x0_25 (<CP, CR, W, R, NSPLIT>): stage 2 = 16 channels on 64 x 32, stage 3 = 24 (padded to 32)
+// on 32 x 16, stage 4 = 32 on 16 x 8
+// (tuning knobs for scripts/variant_build.sh: -DBMB_S3_R=8 ...)
+#ifndef BMB_S2_NS
+#define BMB_S2_NS 0
+#endif
+#ifndef BMB_S3_R
+#define BMB_S3_R 16
+#endif
+#ifndef BMB_S3_NS
+#define BMB_S3_NS 0
+#endif
+#ifndef BMB_S4_NS
+#define BMB_S4_NS 0
+#endif
+#define BMB_CHAIN_S2 16, 16, 32, 16, BMB_S2_NS
+#define BMB_CHAIN_S3 32, 24, 16, BMB_S3_R, BMB_S3_NS
+#define BMB_CHAIN_S4 32, 32, 8, 16, BMB_S4_NS
+template <int CP, int CR, int W, int R, int NSPLIT>
+inline cudaError_t chain_prepare() {
+    return cudaFuncSetAttribute(k_chain_tc<CP, CR, W, R, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<CP, CR, W, R>::SMEM);
+}
+template <int CP, int CR, int W, int R, int NSPLIT>
+inline void chain_launch(const ChainTcArgs& a, int tiles, int crops, const int* d_n, int off, cudaStream_t st) {
+    k_chain_tc<CP, CR, W, R, NSPLIT><<<dim3(tiles, 4, crops), 256, ChainGeom<CP, CR, W, R>::SMEM, st>>>(a, d_n, off, crops);
+}
+template <int CP, int CR, int W, int R, int NSPLIT>
+constexpr int chain_rows() { return R; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // k_gemm_tc: out[p][n] = act( sum_src sum_k A_src[p][k] * B[k][n] + bias[n] ) over 128-pixel tiles of a crop.
 // grid = (tile groups, crops), 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner),
@@ -496,6 +528,7 @@ struct GemmTcArgs {
     int rows_per_tile;                  // 128 / W
     int tiles_per_crop, tiles_per_cta;
     int n_stage;                        // ring depth
+    int acc_bufs;                       // accumulators of the first GEMM in TMEM (2: the next tile's MMAs overlap this tile's epilogue)
     // B: rows [0, gate_rows) are built in the kernel as  gate[b][c] * w3[c][n]  (row = b * midp + c), the rest is copied
     const bf16* b_packed;               // [K8][2*NP][8] packed [hi | lo]; rows below gate_rows are ignored
     int K8;                             // total planes of K
@@ -547,7 +580,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
     const int n = blockIdx.y;
     if (n >= tc_chunk_count(d_n, off, cap)) return;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full, bar_acc_empty, bar_a2_full, bar_acc2_full, bar_b_ready, bar_w;
+    __shared__ __align__(8) uint64_t bar_full[4], bar_empty[4], bar_acc_full[2], bar_acc_empty[2], bar_acc2_full, bar_b_ready, bar_w;
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = a.NP, NP2 = a.NP2;
@@ -560,14 +593,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
     unsigned char* sA2 = smem + L.a2;
     float* sF = reinterpret_cast<float*>(smem + L.f);
     float* sGate = reinterpret_cast<float*>(smem + L.gate);      // [4][32] gates, then [4][32] means
-    const uint32_t acc_cols = 2u * NP, acc2_cols = tail ? 2u * NP2 : 0u;
+    // TMEM: acc_bufs accumulators of NP columns (the three split products of a K step land on the same columns), then
+    // the tail's NP2 columns
+    const uint32_t nbuf = (uint32_t)a.acc_bufs;
+    const uint32_t acc_cols = nbuf * NP, acc2_cols = tail ? (uint32_t)NP2 : 0u;
     const uint32_t tmem_cols = um::tmem_cols_pow2(acc_cols + acc2_cols);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.n_stage; ++i) { um::mbar_init(&bar_full[i], 1); um::mbar_init(&bar_empty[i], 1); }
-        um::mbar_init(&bar_acc_full, 1);
-        um::mbar_init(&bar_acc_empty, 256);
-        um::mbar_init(&bar_a2_full, 256);
+        for (int i = 0; i < 2; ++i) { um::mbar_init(&bar_acc_full[i], 1); um::mbar_init(&bar_acc_empty[i], 256); }
         um::mbar_init(&bar_acc2_full, 1);
         um::mbar_init(&bar_b_ready, 256);
         um::mbar_init(&bar_w, 1);
@@ -583,6 +617,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
     long long gk[40];
     int ngk = 0;
     const bool gprint = blockIdx.x == 0 && n == 5;
+    __shared__ long long s_gk[2][40];
+    __shared__ int s_ngk[2];
 #define GCK() do { if (ngk < 40) gk[ngk++] = clock64() - gk0; } while (0)
 #else
 #define GCK() do { } while (0)
@@ -605,6 +641,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
             }
             uint32_t it = 0;
             for (int tile = tile0; tile < tile1; ++tile) {
+#ifdef BMB_GEMM_L2PF
+                // the ring holds a fraction of a tile: pull the next tile's boxes into L2 while this one streams
+                if (tile + 1 < tile1)
+                    for (int s = 0; s < a.n_src; ++s)
+                        for (int p0 = 0; p0 < a.src_planes[s]; p0 += a.src_kc[s]) {
+                            um::tma_prefetch_4d(&a.map_hi[s], 0, (tile + 1) * 2, p0, n);
+                            um::tma_prefetch_4d(&a.map_lo[s], 0, (tile + 1) * 2, p0, n);
+                        }
+#endif
                 for (int s = 0; s < a.n_src; ++s) {
                     const int kc = a.src_kc[s];
                     for (int p0 = 0; p0 < a.src_planes[s]; p0 += kc, ++it) {
@@ -621,17 +666,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t id2 = um::idesc_bf16(128, 2 * NP), id1 = um::idesc_bf16(128, NP);
-            const uint32_t lbo_b = 2u * NP * 16u;
+            const uint32_t id1 = um::idesc_bf16(128, NP);
+            const uint32_t lbo_b = 2u * NP * 16u, lo_off = (uint32_t)NP * 16u;       // a K plane of B = NP rows W_hi, then NP rows W_lo
             um::mbar_wait(&bar_b_ready, 0);
             um::mbar_wait(&bar_w, 0);
             um::tc_fence_after();
             GCK();
             uint32_t it = 0, ti = 0;
             for (int tile = tile0; tile < tile1; ++tile, ++ti) {
-                um::mbar_wait(&bar_acc_empty, (ti & 1u) ^ 1u);
+                const uint32_t buf = ti % nbuf, use = ti / nbuf;
+                um::mbar_wait(&bar_acc_empty[buf], (use & 1u) ^ 1u);
                 um::tc_fence_after();
                 GCK();
+                const uint32_t acc = tmem + buf * (uint32_t)NP;
                 uint32_t kplane = 0, first = 1;
                 for (int s = 0; s < a.n_src; ++s) {
                     const int kc = a.src_kc[s];
@@ -641,38 +688,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
                         um::tc_fence_after();
                         const uint32_t ah = um::smem_u32(sRing + (size_t)slot * a.slot_bytes), al = ah + a.slot_bytes / 2;
                         for (int ks = 0; ks < kc / 2; ++ks) {
-                            const uint64_t db = um::make_desc(um::smem_u32(sB) + (kplane + 2 * ks) * lbo_b, lbo_b, 128);
-                            um::mma_bf16(tmem, um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), db, id2, first ? 0u : 1u);
-                            um::mma_bf16(tmem, um::make_desc(al + ks * 2 * 2048u, 2048u, 128), db, id1, 1u);
+                            const uint32_t bb = um::smem_u32(sB) + (kplane + 2 * ks) * lbo_b;
+                            const uint64_t dh = um::make_desc(bb, lbo_b, 128), dl = um::make_desc(bb + lo_off, lbo_b, 128);
+                            const uint64_t xh = um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), xl = um::make_desc(al + ks * 2 * 2048u, 2048u, 128);
+                            um::mma_bf16(acc, xh, dh, id1, first ? 0u : 1u);      // A_hi W_hi
+                            um::mma_bf16(acc, xl, dh, id1, 1u);                   // A_lo W_hi
+                            um::mma_bf16(acc, xh, dl, id1, 1u);                   // A_hi W_lo
                             first = 0;
                         }
                         kplane += kc;
                         um::mma_commit(&bar_empty[slot]);
                     }
                 }
-                um::mma_commit(&bar_acc_full);
+                um::mma_commit(&bar_acc_full[buf]);
                 GCK();
-                if (tail) {
-                    const uint32_t jd2 = um::idesc_bf16(128, 2 * NP2), jd1 = um::idesc_bf16(128, NP2);
-                    const uint32_t lbo_b2 = 2u * NP2 * 16u;
-                    um::mbar_wait(&bar_a2_full, ti & 1u);
-                    um::tc_fence_after();
-                    const uint32_t ah = um::smem_u32(sA2), al = ah + (uint32_t)(NP / 8) * 2048u;
-                    for (int ks = 0; ks < NP / 16; ++ks) {
-                        const uint64_t db = um::make_desc(um::smem_u32(sB2) + ks * 2 * lbo_b2, lbo_b2, 128);
-                        um::mma_bf16(tmem + acc_cols, um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), db, jd2, ks > 0);
-                        um::mma_bf16(tmem + acc_cols, um::make_desc(al + ks * 2 * 2048u, 2048u, 128), db, jd1, 1u);
-                    }
-                    um::mma_commit(&bar_acc2_full);
-                    GCK();
-                }
             }
 #ifdef BMB_TC_CLOCKS
-            if (gprint) {
-                printf("gemm K8 %d NP %d tail %d MMA thread: b_ready %lld |", a.K8, NP, (int)tail, gk[0]);
-                for (int i = 1; i < ngk; ++i) printf(" %lld", gk[i]);
-                printf("\n");
-            }
+            if (gprint) { for (int i = 0; i < ngk; ++i) s_gk[0][i] = gk[i]; s_ngk[0] = ngk; }
 #endif
         }
     } else {
@@ -688,17 +720,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
         const int cw = NP / 2;                                  // columns this warp owns: [half * cw, half * cw + cw)
         uint32_t ti = 0;
         for (int tile = tile0; tile < tile1; ++tile, ++ti) {
-            um::mbar_wait(&bar_acc_full, ti & 1u);
+            const uint32_t buf = ti % nbuf, use = ti / nbuf;
+            um::mbar_wait(&bar_acc_full[buf], use & 1u);
             um::tc_fence_after();
             GCK();
             const int px = tile * 128 + m;                      // pixel of the crop
-            auto emit = [&](const uint32_t* v1, const uint32_t* v2, const int c0) {
+            auto emit = [&](const uint32_t* v1, const int c0) {
                 const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c0), b1 = *reinterpret_cast<const float4*>(a.bias + c0 + 4);
                 float o[8];
-                o[0] = __uint_as_float(v1[0]) + __uint_as_float(v2[0]) + b0.x; o[1] = __uint_as_float(v1[1]) + __uint_as_float(v2[1]) + b0.y;
-                o[2] = __uint_as_float(v1[2]) + __uint_as_float(v2[2]) + b0.z; o[3] = __uint_as_float(v1[3]) + __uint_as_float(v2[3]) + b0.w;
-                o[4] = __uint_as_float(v1[4]) + __uint_as_float(v2[4]) + b1.x; o[5] = __uint_as_float(v1[5]) + __uint_as_float(v2[5]) + b1.y;
-                o[6] = __uint_as_float(v1[6]) + __uint_as_float(v2[6]) + b1.z; o[7] = __uint_as_float(v1[7]) + __uint_as_float(v2[7]) + b1.w;
+                o[0] = __uint_as_float(v1[0]) + b0.x; o[1] = __uint_as_float(v1[1]) + b0.y;
+                o[2] = __uint_as_float(v1[2]) + b0.z; o[3] = __uint_as_float(v1[3]) + b0.w;
+                o[4] = __uint_as_float(v1[4]) + b1.x; o[5] = __uint_as_float(v1[5]) + b1.y;
+                o[6] = __uint_as_float(v1[6]) + b1.z; o[7] = __uint_as_float(v1[7]) + b1.w;
                 if (a.relu) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
@@ -735,23 +768,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
             };
             {   // TMEM -> registers two 8-column groups deep: the loads of the next group fly while this one is processed
                 const int cb = half * cw, ce = cb + cw;
-                const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
-                uint32_t pa[8], pb[8], qa[8], qb[8];
+                const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)NP;
+                uint32_t pa[8], qa[8];
                 um::tmem_ld8(tq + cb, pa);
-                um::tmem_ld8(tq + cb + NP, pb);
                 for (int c0 = cb; c0 < ce; c0 += 16) {
                     um::tmem_ld_wait();
-                    if (c0 + 8 < ce) { um::tmem_ld8(tq + c0 + 8, qa); um::tmem_ld8(tq + c0 + 8 + NP, qb); }
-                    emit(pa, pb, c0);
+                    if (c0 + 8 < ce) um::tmem_ld8(tq + c0 + 8, qa);
+                    emit(pa, c0);
                     if (c0 + 8 < ce) {
                         um::tmem_ld_wait();
-                        if (c0 + 16 < ce) { um::tmem_ld8(tq + c0 + 16, pa); um::tmem_ld8(tq + c0 + 16 + NP, pb); }
-                        emit(qa, qb, c0 + 8);
+                        if (c0 + 16 < ce) um::tmem_ld8(tq + c0 + 16, pa);
+                        emit(qa, c0 + 8);
                     }
                 }
             }
             um::tc_fence_before();
-            mbar_arrive(&bar_acc_empty);
+            mbar_arrive(&bar_acc_empty[buf]);
             GCK();
             // 2x2 average pool of the tile in sF (rows_per_tile x W, row stride NPx + 4) -> (rows/2 x W/2) planes; same
             // operation order as the float32 kernel of round 1: (a + b + c + d) * 0.25, a=(y,x) b=(y,x+1) c=(y+1,x) d=(y+1,x+1)
@@ -783,23 +815,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
             };
             if (a.pool) pool_store(NP, a.out_hi, a.out_lo);
             if (tail) {
+                // the fresh tile (hi | lo planes in sA2) is the A operand of the second GEMM: every epilogue thread publishes
+                // its rows to the async proxy, one of them issues the MMAs (the MMA warp is already on the next tile)
                 um::fence_async_smem();
-                mbar_arrive(&bar_a2_full);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et == 0) {
+                    um::tc_fence_after();
+                    const uint32_t jd1 = um::idesc_bf16(128, NP2);
+                    const uint32_t lbo_b2 = 2u * NP2 * 16u, lo2 = (uint32_t)NP2 * 16u;
+                    const uint32_t ah = um::smem_u32(sA2), al = ah + (uint32_t)(NP / 8) * 2048u;
+                    for (int ks = 0; ks < NP / 16; ++ks) {
+                        const uint32_t bb = um::smem_u32(sB2) + ks * 2 * lbo_b2;
+                        const uint64_t dh = um::make_desc(bb, lbo_b2, 128), dl = um::make_desc(bb + lo2, lbo_b2, 128);
+                        const uint64_t xh = um::make_desc(ah + ks * 2 * 2048u, 2048u, 128), xl = um::make_desc(al + ks * 2 * 2048u, 2048u, 128);
+                        um::mma_bf16(tmem + acc_cols, xh, dh, jd1, ks > 0);
+                        um::mma_bf16(tmem + acc_cols, xl, dh, jd1, 1u);
+                        um::mma_bf16(tmem + acc_cols, xh, dl, jd1, 1u);
+                    }
+                    um::mma_commit(&bar_acc2_full);
+                }
                 um::mbar_wait(&bar_acc2_full, ti & 1u);
                 um::tc_fence_after();
                 GCK();
                 const int cw2 = NP2 / 2;
                 for (int c0 = half * cw2; c0 < half * cw2 + cw2; c0 += 8) {
-                    uint32_t v1[8], v2[8];
+                    uint32_t v1[8];
                     const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)c0;
                     um::tmem_ld8(ta, v1);
-                    um::tmem_ld8(ta + NP2, v2);
                     um::tmem_ld_wait();
                     const float4 b0 = *reinterpret_cast<const float4*>(a.bias2 + c0), b1 = *reinterpret_cast<const float4*>(a.bias2 + c0 + 4);
                     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                     float o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(v1[j]) + __uint_as_float(v2[j]) + bb[j], 0.f);
+                    for (int j = 0; j < 8; ++j) o[j] = fmaxf(__uint_as_float(v1[j]) + bb[j], 0.f);
                     if (a.pool2) {
                         float* f = sF + (size_t)m * (NP2 + 4) + c0;     // aliases the tail's A tile: its MMAs have completed
                         *reinterpret_cast<float4*>(f) = make_float4(o[0], o[1], o[2], o[3]);
@@ -819,16 +867,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
             }
         }
 #ifdef BMB_TC_CLOCKS
-        if (gprint && et == 0) {
-            printf("gemm K8 %d NP %d tail %d epilogue thread: b_built %lld |", a.K8, NP, (int)tail, gk[0]);
-            for (int i = 1; i < ngk; ++i) printf(" %lld", gk[i]);
-            printf("\n");
-        }
+        if (gprint && et == 0) { for (int i = 0; i < ngk; ++i) s_gk[1][i] = gk[i]; s_ngk[1] = ngk; }
 #endif
     }
     um::tc_fence_before();
     __syncthreads();
     if (warp == 1) um::tmem_dealloc(tmem, tmem_cols);
+#ifdef BMB_TC_CLOCKS
+    if (gprint && threadIdx.x == 0) {
+        // MMA thread: B ready | per tile: accumulator free, MMAs issued (, tail MMAs issued)
+        // epilogue thread 0: | per tile: accumulator full, epilogue 1 done (, tail accumulator full, epilogue 2 done)
+        for (int w = 0; w < 2; ++w) {
+            printf("gemm K8 %d NP %d tail %d groups %d stages %d %s:", a.K8, NP, (int)tail, (int)gridDim.x, a.n_stage, w ? "EPI" : "MMA");
+            for (int i = 0; i < s_ngk[w]; ++i) printf(" %lld", s_gk[w][i]);
+            printf("\n");
+        }
+    }
+#endif
 }
 
 

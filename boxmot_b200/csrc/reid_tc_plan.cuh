@@ -7,7 +7,8 @@ namespace tcx {
 
 // stage geometry of the chain kernel instances (osnet_x0_25: mid 16 / 24 / 32 at 64x32 / 32x16 / 16x8)
 struct ChainShape { int CP, CR, W, H, R, kind; };
-static const ChainShape kChainShapes[3] = {{16, 16, 32, 64, 16, LK_CHAIN_S2}, {32, 24, 16, 32, 8, LK_CHAIN_S3}, {32, 32, 8, 16, 16, LK_CHAIN_S4}};
+static const ChainShape kChainShapes[3] = {{16, 16, 32, 64, chain_rows<BMB_CHAIN_S2>(), LK_CHAIN_S2}, {32, 24, 16, 32, chain_rows<BMB_CHAIN_S3>(), LK_CHAIN_S3},
+                                           {32, 32, 8, 16, chain_rows<BMB_CHAIN_S4>(), LK_CHAIN_S4}};
 
 inline bool plan_supported(const ReidModel* m) {
     return m->arch == 1 && m->c[0] == 16 && m->c[1] == 64 && m->c[2] == 96 && m->c[3] == 128;
@@ -116,9 +117,9 @@ Plan* plan_build(ReidModel* m, const float* hw) {
         const float* W32 = m->d_w;
 
         // ---- kernel attributes ----
-        RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<16, 16, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<16, 32, 16>::SMEM));
-        RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<32, 24, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<32, 16, 8>::SMEM));
-        RCUDA_OK(cudaFuncSetAttribute(k_chain_tc<32, 32, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ChainGeom<32, 8, 16>::SMEM));
+        RCUDA_OK(chain_prepare<BMB_CHAIN_S2>());
+        RCUDA_OK(chain_prepare<BMB_CHAIN_S3>());
+        RCUDA_OK(chain_prepare<BMB_CHAIN_S4>());
         RCUDA_OK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, P->smem_limit));
         RCUDA_OK(cudaFuncSetAttribute(k_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
 
@@ -182,7 +183,12 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                     if ((int)layout(cand).total <= P->smem_limit) ns = cand;
             }
             if (!ns) throw std::runtime_error("tensor-core GEMM does not fit shared memory");
-            if (2 * g.NP + (tail ? 2 * g.NP2 : 0) > 512) throw std::runtime_error("tensor-core GEMM does not fit TMEM");
+            if (g.NP + (tail ? g.NP2 : 0) > 512) throw std::runtime_error("tensor-core GEMM does not fit TMEM");
+            {   // a second accumulator when the CTA has more than one tile and the columns fit next to a co-resident CTA's
+                const bool two_ctas = (int)layout(ns).total <= half_limit;
+                const int cols = 2 * g.NP + (tail ? g.NP2 : 0);
+                g.acc_bufs = (g.tiles_per_cta > 1 && cols <= (two_ctas ? 256 : 512)) ? 2 : 1;
+            }
             for (int s = 0; s < g.n_src; ++s) {   // the boxes follow the chunk size
                 make_tile_map(&g.map_hi[s], L.src_hi[s], P->chunk, g.src_planes[s], g.HW, g.src_kc[s]);
                 make_tile_map(&g.map_lo[s], L.src_lo[s], P->chunk, g.src_planes[s], g.HW, g.src_kc[s]);
@@ -278,7 +284,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                         // block's own output never goes to HBM (nothing else reads it); diagnostic stops keep the two launches
                         const int C = m->c[s + 1];
                         const GemmSmem probe = gemm_smem_layout(g.K8, g.NP, C, 2, true, false, 2 * 128 * 16 * 2, true);
-                        if ((int)probe.total <= P->smem_limit && 2 * g.NP + 2 * C <= 512) {
+                        if ((int)probe.total <= P->smem_limit && g.NP + C <= 512) {
                             g.b2_packed = WB + tr[s];
                             g.bias2 = WF + trb[s];
                             g.N2 = C; g.NP2 = C;
@@ -367,13 +373,13 @@ int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int up
                 k_maxpool_planes<<<148 * 4, 256, 0, st>>>(m->bufA, 128, 64, m->c[0], d_n, off, upper, P->P.hi, P->P.lo);
                 break;
             case LK_CHAIN_S2:
-                k_chain_tc<16, 16, 32, 16><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<16, 32, 16>::SMEM, st>>>(L.chain, d_n, off, upper);
+                chain_launch<BMB_CHAIN_S2>(L.chain, L.chain_tiles, upper, d_n, off, st);
                 break;
             case LK_CHAIN_S3:
-                k_chain_tc<32, 24, 16, 8><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<32, 16, 8>::SMEM, st>>>(L.chain, d_n, off, upper);
+                chain_launch<BMB_CHAIN_S3>(L.chain, L.chain_tiles, upper, d_n, off, st);
                 break;
             case LK_CHAIN_S4:
-                k_chain_tc<32, 32, 8, 16><<<dim3(L.chain_tiles, 4, upper), 256, ChainGeom<32, 8, 16>::SMEM, st>>>(L.chain, d_n, off, upper);
+                chain_launch<BMB_CHAIN_S4>(L.chain, L.chain_tiles, upper, d_n, off, st);
                 break;
             case LK_GEMM:
                 k_gemm_tc<<<dim3(L.gemm_groups, upper), GEMM_THREADS, L.gl.total, st>>>(L.gemm, d_n, off, upper, L.gl);
