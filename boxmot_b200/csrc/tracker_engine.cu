@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "host_stage.h"
 #include "tracker_core.cuh"
 #include "tracker_layout.h"
 
@@ -868,10 +869,15 @@ void Engine::update_batch(const float* const* dets, const int* det_rows, const f
             const bool pinned = cudaPointerGetAttributes(&attr, images[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
             if (!pinned) {
                 cudaGetLastError();   // unregistered host pointers report an error on some drivers: clear it
-                memcpy(h_images + ib * i, images[i], ib);
+                // staged in pieces by a few host threads (host_stage.h); each piece's DMA is queued as soon as it lands
+                uint8_t* stage = h_images + ib * i;
+                uint8_t* dev = d_images + ib * i;
+                StagePool::instance().copy(stage, images[i], ib, [&](size_t off, size_t len) {
+                    CUDA_OK(cudaMemcpyAsync(dev + off, stage + off, len, cudaMemcpyHostToDevice, stream));
+                });
+            } else {
+                CUDA_OK(cudaMemcpyAsync(d_images + ib * i, images[i], ib, cudaMemcpyHostToDevice, stream));
             }
-            CUDA_OK(cudaMemcpyAsync(d_images + ib * i, pinned ? images[i] : h_images + ib * i, ib,
-                                    cudaMemcpyHostToDevice, stream));
         }
         img_dev = d_images;
     }
