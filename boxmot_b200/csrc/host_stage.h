@@ -1,9 +1,14 @@
 // host_stage.h -- parallel staging copies of pageable frames into the engine's page-locked buffer.
 //
-// A 1280x720 BGR frame is 2.76 MB; one thread moves it at ~8 GB/s (0.33 ms), which is 15-20 % of an end-to-end
-// BotSort.update(dets, img) at 256 detections.  StagePool splits the copy into cache-line aligned pieces over a few
-// persistent worker threads plus the caller; the caller is told when each piece lands (in order) so that it can queue
-// that piece's host-to-device DMA while the rest is still being copied.
+// A 1280x720 BGR frame is 2.76 MB; one thread moves it in 0.17 ms on the B200 host (0.33 ms in the build container), which
+// is ~10 % of an end-to-end BotSort.update(dets, img) at 256 detections.  StagePool splits the copy into cache-line
+// aligned pieces over a few persistent worker threads plus the caller; the caller is told when each piece lands (in
+// order) so that it can queue that piece's host-to-device DMA while the rest is still being copied.
+//
+// MEASURED (round 2, scripts/sweep_stage.sh on the B200 box): the isolated copy drops to 0.06 ms with 3 helpers
+// (scripts/microbench/stage_pool_test.cpp), but the whole update() gets SLOWER -- 1.72 ms with the caller alone, 1.84 ms with
+// one helper, 2.00 ms with three (helpers woken from a condition variable once per frame, four small DMAs instead of
+// one).  Helpers are therefore opt-in: BOXMOT_B200_STAGE_THREADS=N (caller included), default 1.
 //
 // Host-only C++ (no CUDA types).  The pool is created lazily, re-created after a fork (worker threads do not survive
 // one), and joined when the process-wide instance is destroyed.
@@ -28,14 +33,14 @@ class StagePool {
     static constexpr int MAX_PIECES = 16;
     static constexpr size_t MIN_PIECE = 256 * 1024;   // below this a second thread costs more than it saves
 
-    // process-wide pool; `workers` < 0 reads BOXMOT_B200_STAGE_THREADS (default 3 helpers + the caller)
+    // process-wide pool; BOXMOT_B200_STAGE_THREADS = copying threads including the caller (default 1: no helpers)
     static StagePool& instance() {
         static StagePool* pool = nullptr;
         static pid_t owner = 0;
         static std::mutex guard;
         std::lock_guard<std::mutex> lk(guard);
         if (!pool || owner != getpid()) {   // first use, or a forked child (the parent's threads are not here)
-            int w = 3;
+            int w = 0;
             if (const char* e = std::getenv("BOXMOT_B200_STAGE_THREADS")) w = std::atoi(e) - 1;
             if (w < 0) w = 0;
             if (w > MAX_PIECES - 1) w = MAX_PIECES - 1;

@@ -1749,9 +1749,9 @@ int reid_forward(ReidModel* m, const uint8_t* d_images, size_t image_stride, int
             // tensor-core path: crop staging, stem and max pool are one fused kernel (k_front_tc); diagnostic stops at the
             // blob / stem tensors (0, 1) run the float32 kernels below instead
             bool tc_stopped = false;
-            const tcx::FrontInput fi{d_images, image_stride, rows, cols, d_crops};
+            const tcx::FrontInput fi{d_images, image_stride, rows, cols, d_crops, d_out, out_ld};
             L.launches += tcx::plan_run(m, fi, d_ncrops, off, upper, st, &tc_stopped, L);
-            if (!tc_stopped) {
+            if (!tc_stopped && !(m->tc->head_fused && m->debug_stop < 0)) {
                 const int C = m->c[3];
                 L.begin(CLS_HEAD);
                 k_head<<<upper, 256, sizeof(float) * (C + 32 + (256 / C > 0 ? 256 / C : 1) * C), st>>>(

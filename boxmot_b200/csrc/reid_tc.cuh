@@ -373,6 +373,11 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                 unsigned char* xl = sXl + ((c4 >> 1) * NPX + (ra - g0) * TW + x + 1) * 16 + (c4 & 1) * 8;
                 size_t go = ((((size_t)n * (4 * C8) + br * C8 + (c4 >> 1)) * H + ra) * W + x) * 8 + (c4 & 1) * 4;
                 float2 ps0 = make_float2(0.f, 0.f), ps1 = make_float2(0.f, 0.f);
+#ifdef BMB_DW_SPLIT_RN
+#define BMB_DW_SPLIT um::split2
+#else
+#define BMB_DW_SPLIT um::split2_tz
+#endif
 #define BMB_DW_ROW(U)                                                                                                  \
                 {                                                                                                      \
                     constexpr int i0 = (U) % 3, i1 = ((U) + 1) % 3, i2 = ((U) + 2) % 3;                                \
@@ -401,8 +406,8 @@ __global__ void __launch_bounds__(256) k_chain_tc(const __grid_constant__ ChainT
                     a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f);                                                  \
                     a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f);                                                  \
                     uint32_t h0, h1, e0, e1;                                                                           \
-                    um::split2(a0.x, a0.y, h0, e0);                                                                    \
-                    um::split2(a1.x, a1.y, h1, e1);                                                                    \
+                    BMB_DW_SPLIT(a0.x, a0.y, h0, e0);                                                                  \
+                    BMB_DW_SPLIT(a1.x, a1.y, h1, e1);                                                                  \
                     if (last) {                                                                                        \
                         *reinterpret_cast<uint2*>(a.y_hi + go) = make_uint2(h0, h1);                                   \
                         *reinterpret_cast<uint2*>(a.y_lo + go) = make_uint2(e0, e1);                                   \
@@ -550,6 +555,17 @@ struct GemmTcArgs {
     const float* bias2;
     int N2, NP2;
     bf16* out2_hi; bf16* out2_lo;
+    // head fused behind conv5 (one 128-pixel tile per crop): global average pool over the tile, fc (+ folded BatchNorm1d)
+    // + ReLU, L2 normalisation, scatter to the caller's row (base_backend.py:197-207, osnet.py:404-421)
+    const float* head_w;                // [N][head_feat] (null: no head)
+    const float* head_b;                // [head_feat]
+    int head_feat;
+};
+// per-call part of the fused head: the chunk's crop descriptors (out_row) and the caller's feature matrix
+struct GemmHeadIO {
+    const CropDesc* crops;
+    float* out;
+    int out_ld;
 };
 
 struct GemmSmem {
@@ -576,7 +592,7 @@ inline GemmSmem gemm_smem_layout(int K8, int NP, int NP2, int n_stage, bool tail
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_constant__ GemmTcArgs a, const int* __restrict__ d_n, int off, int cap,
-                                                            const GemmSmem L) {
+                                                            const GemmSmem L, const GemmHeadIO hio) {
     const int n = blockIdx.y;
     if (n >= tc_chunk_count(d_n, off, cap)) return;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -725,6 +741,64 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_tc(const __grid_consta
             um::tc_fence_after();
             GCK();
             const int px = tile * 128 + m;                      // pixel of the crop
+            if (a.head_w) {
+                // ---- conv5 + head: the tile is the whole 16 x 8 map.  Column sums over the 128 TMEM lanes (= pixels):
+                // butterfly over the 32 lanes of a warp, the four lane quadrants through shared memory (the ring is idle:
+                // every slot was consumed before the accumulator was committed) ----
+                float* part = reinterpret_cast<float*>(sRing);          // [4][NP]
+                float* pooled = part + 4 * NP;                          // [NP]
+                float* red = pooled + NP;                               // [8]
+                float* feat = red + 8;                                  // [head_feat]
+                const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)NP;
+                for (int c0 = half * cw; c0 < half * cw + cw; c0 += 8) {
+                    uint32_t v[8];
+                    um::tmem_ld8(tq + c0, v);
+                    um::tmem_ld_wait();
+                    const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c0), b1 = *reinterpret_cast<const float4*>(a.bias + c0 + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        o[j] = fmaxf(__uint_as_float(v[j]) + bb[j], 0.f);
+#pragma unroll
+                        for (int sh = 16; sh > 0; sh >>= 1) o[j] += __shfl_xor_sync(0xffffffffu, o[j], sh);
+                    }
+                    if (lane == 0) {
+                        *reinterpret_cast<float4*>(part + q * NP + c0) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(part + q * NP + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+                um::tc_fence_before();
+                mbar_arrive(&bar_acc_empty[buf]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int c = et; c < NP; c += 256) pooled[c] = ((part[c] + part[NP + c]) + (part[2 * NP + c] + part[3 * NP + c])) / 128.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int FEAT = a.head_feat, C = a.N;
+                float sq = 0.f;
+                for (int f = et; f < FEAT; f += 256) {
+                    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    int c = 0;
+                    for (; c + 8 <= C; c += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = fmaf(pooled[c + u], a.head_w[(size_t)(c + u) * FEAT + f], t[u]);
+                    }
+                    for (; c < C; ++c) t[0] = fmaf(pooled[c], a.head_w[(size_t)c * FEAT + f], t[0]);
+                    float sv = a.head_b[f] + (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])));
+                    sv = fmaxf(sv, 0.f);
+                    feat[f] = sv;
+                    sq = fmaf(sv, sv, sq);
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+                if (lane == 0) red[warp - 2] = sq;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                float tot = 0.f;
+                for (int w = 0; w < 8; ++w) tot += red[w];
+                const float nrm = sqrtf(tot);
+                float* dst = hio.out + (size_t)hio.crops[off + n].out_row * hio.out_ld;
+                for (int f = et; f < FEAT; f += 256) dst[f] = feat[f] / nrm;
+                continue;
+            }
             auto emit = [&](const uint32_t* v1, const int c0) {
                 const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c0), b1 = *reinterpret_cast<const float4*>(a.bias + c0 + 4);
                 float o[8];

@@ -112,6 +112,7 @@ struct Launch {
 
 struct Plan {
     int chunk = 0;
+    bool head_fused = false;    // `launches` ends with conv5 + head in one kernel (`launches_dbg` keeps conv5 -> k_head)
     bf16* d_wb = nullptr;       // packed BF16 weights
     float* d_wf = nullptr;      // padded float32 side tables (bias, depthwise taps)
     Planes P, X1, Y, XA, XB;

@@ -332,9 +332,18 @@ Plan* plan_build(ReidModel* m, const float* hw) {
                 finish(L);
             }
         }
-        {   // conv5 -> float32 NHWC for the head kernel
+        {   // conv5: with the head (global average pool, fc, L2 norm) in its epilogue, or -- in the diagnostic list -- as
+            // float32 NHWC for k_head
             Launch L = gemm(H, Wd, {{X, xC8}}, c5, m->c[3], c5b, true);
-            L.gemm.out_f32 = P->c5;
+            if (fuse_trans && H * Wd == 128) {
+                L.gemm.head_w = W32 + m->fcw;
+                L.gemm.head_b = W32 + m->fcb;
+                L.gemm.head_feat = m->feat;
+                L.cls = CLS_HEAD;
+                P->head_fused = true;
+            } else {
+                L.gemm.out_f32 = P->c5;
+            }
             L.stage_after = 11;
             finish(L);
         }
@@ -349,7 +358,7 @@ Plan* plan_build(ReidModel* m, const float* hw) {
 }
 
 // Replays the plan for one chunk of crops (the stem output of that chunk is in m->bufA).  Returns launches made.
-struct FrontInput { const uint8_t* images; size_t image_stride; int rows, cols; const CropDesc* crops; };
+struct FrontInput { const uint8_t* images; size_t image_stride; int rows, cols; const CropDesc* crops; float* out; int out_ld; };
 
 template <class Prof>
 int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int upper, cudaStream_t st, bool* stopped, Prof& prof) {
@@ -382,7 +391,7 @@ int plan_run(ReidModel* m, const FrontInput& fi, const int* d_n, int off, int up
                 chain_launch<BMB_CHAIN_S4>(L.chain, L.chain_tiles, upper, d_n, off, st);
                 break;
             case LK_GEMM:
-                k_gemm_tc<<<dim3(L.gemm_groups, upper), GEMM_THREADS, L.gl.total, st>>>(L.gemm, d_n, off, upper, L.gl);
+                k_gemm_tc<<<dim3(L.gemm_groups, upper), GEMM_THREADS, L.gl.total, st>>>(L.gemm, d_n, off, upper, L.gl, GemmHeadIO{fi.crops, fi.out, fi.out_ld});
                 break;
         }
         prof.end();

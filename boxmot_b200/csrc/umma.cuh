@@ -134,6 +134,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ---- split-BF16 ("hi + lo") arithmetic: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x| ----
+// cheaper variant for the depthwise walkers: hi = the float's upper 16 bits (truncation instead of rounding: one PRMT packs
+// the pair, one LOP3 per value recovers hi as a float), lo = bf16_rn(x - hi); |x - hi - lo| <= 2^-16 |x|
+__device__ __forceinline__ void split2_tz(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+    hi = __byte_perm(ua, ub, 0x7632);                           // low half = a's upper bits, high half = b's
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(ua & 0xffff0000u), b - __uint_as_float(ub & 0xffff0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);       // .x = a (low half), .y = b
     const float2 hf = __bfloat1622float2(h);
