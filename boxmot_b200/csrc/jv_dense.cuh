@@ -234,8 +234,36 @@ BMB_FN void jv_augment_wide(S& s, int n, int ld, int zrow, int n_free, int* mbx)
 #define JV_CHUNKS 4104
 #endif
 
+//
+// Mode 3 (the default) adds exact shortcuts selected by the bits of `feat` (all on by default; the bits exist so that a
+// hardware run can bisect them), found by counting on the BASELINE config-3 frames (oracle instrumented: 5.5e5 band
+// columns and 1.3e6 list swaps per frame):
+//   * NO-OP BAND COLUMNS.  In a search that starts from a zero-padding row every open column has
+//     d <= (0.0 - v) (its initial value; d only decreases).  A band column owned by another zero-padding row whose own
+//     distance never improved has h = ((0.0 - v[j]) - d[j]) == 0.0, so its relaxation value is r = (0.0 - v[jj]) - 0.0
+//     >= d[jj] for every open column: nothing changes, bit for bit.  91 % of the band columns of those frames are of
+//     this kind; the warps walk over runs of them (32 positions per ballot, no barrier, nothing is written).
+//   * PARALLEL _find_dense TAIL.  After the last strict decrease of the running minimum (position k*, found with the
+//     chunk minima) lapjv's swaps are a queue rotation: the m-th column at the minimum goes to cell lo + m and the
+//     element it displaces goes to that column's old position k_m, possibly to be displaced again by swap k_m - lo.
+//     The final cell of a displaced element is therefore the first iterate >= H of q -> k_q - lo (H = columns at the
+//     minimum), computed by pointer jumping over all cells at once; the columns at the minimum go to lo + rank.
+//     93-99 % of the swaps of those frames sit in such tails (570-740 swaps each); thread 0 still replays the part
+//     before k* and short tails.
+//   * HIT LIST.  A band-minimum hit of the relaxation is usually alone: the owning thread appends its list position
+//     (pos[]) to a short shared list; thread 0 sorts and replays it instead of the CTA scanning every open position
+//     for "distance == band minimum" (the mask pass remains the overflow path).
+#define JV_F_SKIP 1
+#define JV_F_PARFIND 2
+#define JV_F_HITLIST 4
+#define JV_F_ARRWIDE 8  // CTA-wide augmenting row reduction (jv_arr_wide)
+#define JV_PAR_MIN 48   // shortest tail (columns at the minimum) handled by the parallel pass
+#define JV_HITCAP 32    // hit list capacity
 template <typename S>
-BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx) {
+BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx, const int feat) {
+    const bool fast = (feat & JV_F_PARFIND) != 0;
+    const bool skip_noop = (feat & JV_F_SKIP) != 0;
+    const bool hitlist = (feat & JV_F_HITLIST) != 0;
     int* x = s.lap_x; int* y = s.lap_y; double* v = s.lap_v; double* d = s.lap_spc;
     int* pred = s.lap_path; int* cols = s.lap_tl; const int* free_rows = s.lap_sc;
     int* pos = s.lap_insc;   // inverse of cols (the `once` flags are dead after the reduction transfer)
@@ -246,11 +274,25 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
     __shared__ double cmin[JV_CHUNKS];
     __shared__ unsigned hmask[JV_CHUNKS];
     __shared__ unsigned smask[JV_CHUNKS];
+    __shared__ unsigned emask[JV_CHUNKS];   // positions at the global minimum (fast mode)
+    __shared__ int erank[JV_CHUNKS];        // exclusive prefix count of emask
+    __shared__ double sh_min;
+    __shared__ int sh_aux[2];               // [0] k*: first position at the global minimum, [1] number of emask bits
+    __shared__ int sh_nhit;
+    __shared__ int hitpos[JV_HITCAP];
 #else
     static double cmin[JV_CHUNKS];
     static unsigned hmask[JV_CHUNKS];
     static unsigned smask[JV_CHUNKS];
+    static unsigned emask[JV_CHUNKS];
+    static int erank[JV_CHUNKS];
+    static double sh_min;
+    static int sh_aux[2];
+    static int sh_nhit;
+    static int hitpos[JV_HITCAP];
 #endif
+    if (BMB_TID == 0) sh_nhit = 0;   // ordered before the first relaxation by the barrier after the first init
+    long long n_skip = 0;   // no-op band columns walked over (diagnostic counter 7)
     double dq[JV_OWN];    // distance of the owned columns (registers on the device)
     double nvq[JV_OWN];   // 0.0 - v[jj]: a zero-padding row relaxes with r = (0.0 - v) - h, the same two operations
     long long n_steps = 0, c_find = 0, c_replay = 0, c_edge = 0;
@@ -262,8 +304,9 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
         unsigned char open_h[JV_OWN];
 #endif
         long long c0 = BMB_CLOCK();
+        const bool start_zr = start >= zrow;
         {
-            const bool zr = start >= zrow;
+            const bool zr = start_zr;
             const double* cs = c + (size_t)start * ld;
 #pragma unroll
             for (int q = 0; q < JV_OWN; ++q) {
@@ -341,6 +384,11 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                         if (cc < C) cmin[cc] = before;
                         if (tot < run) run = tot;
                     }
+                    if (lane == 0) {   // global minimum; k* = lo when the first column of the list already holds it
+                        sh_min = run;
+                        sh_aux[0] = d[cols[lo]] == run ? lo : 0x7fffffff;
+                        sh_aux[1] = 0;
+                    }
                 }
                 BMB_SYNC();
                 // (3) hit masks: a position is a hit when its distance is at or below the running minimum before it
@@ -362,8 +410,131 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                     const unsigned hm = BMB_BALLOT(k < n && dj <= before);
                     const unsigned sm = BMB_BALLOT(k < n && dj < at_start);   // the minimum moves inside this chunk
                     if (lane == 0) { hmask[cc] = hm; smask[cc] = sm; }
+                    if (fast) {
+                        const unsigned em = BMB_BALLOT(k < n && dj == sh_min);
+                        if (lane == 0) {
+                            emask[cc] = em;
+                            if (em) BMB_ATOMIC_MIN(&sh_aux[0], base + cc * BMB_NL + BMB_FFS(em));
+                        }
+                    }
                 }
                 BMB_SYNC();
+                if (fast) {
+                    // (4') thread 0 replays the hits BEFORE k* (earlier running minima), one warp counts the columns at
+                    // the global minimum per chunk; the tail from k* on is a queue rotation (see the header comment)
+                    const int kstar = sh_aux[0];
+                    const int off = kstar == lo ? 1 : 0;   // position lo itself is column 0 of the band, in place
+                    if (BMB_WARP == (BMB_NW > 1 ? 1 : 0)) {
+                        int carry = 0;
+                        for (int c0i = 0; c0i < C; c0i += BMB_NL) {
+                            const int cc = c0i + lane;
+                            const int cnt = cc < C ? BMB_POPC(emask[cc]) : 0;
+#if BMB_DEVICE
+                            int inc = cnt;
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                                if (lane >= o) inc += t;
+                            }
+                            const int tot = __shfl_sync(0xffffffffu, inc, 31);
+#else
+                            const int inc = cnt;
+                            const int tot = cnt;
+#endif
+                            if (cc < C) erank[cc] = carry + inc - cnt;
+                            carry += tot;
+                        }
+                        if (lane == 0) sh_aux[1] = carry;
+                    }
+                    if (BMB_TID == 0 && kstar > lo + 1) {
+                        int h2 = lo + 1;
+                        double mind = d[cols[lo]];
+                        for (int cc = 0; cc < C; ++cc) {
+                            const int kb = base + cc * BMB_NL;
+                            if (kb >= kstar) break;
+                            unsigned m = hmask[cc];
+                            if (kstar - kb < BMB_NL) m &= (1u << (kstar - kb)) - 1u;   // positions below k* only
+                            if (!m) continue;
+                            if (smask[cc] == 0u && kb == h2 && (m & (m + 1u)) == 0u) { h2 += BMB_POPC(m); continue; }
+                            while (m) {
+                                const int k = kb + BMB_FFS(m);
+                                m &= m - 1;
+                                const int j = cols[k];
+                                const double dj = d[j];
+                                if (dj < mind) { h2 = lo; mind = dj; }
+                                cols[k] = cols[h2];
+                                cols[h2] = j;
+                                ++h2;
+                            }
+                        }
+                    }
+                    BMB_SYNC();
+                    const int H = off + sh_aux[1];   // columns at the minimum: the new band is [lo, lo + H)
+                    if (H < JV_PAR_MIN) {
+                        if (BMB_TID == 0) {
+                            int h2 = lo + off;
+                            for (int cc = 0; cc < C; ++cc) {
+                                unsigned m = emask[cc];
+                                const int kb = base + cc * BMB_NL;
+                                while (m) {
+                                    const int k = kb + BMB_FFS(m);
+                                    m &= m - 1;
+                                    const int j = cols[k];
+                                    const int other = cols[h2];
+                                    cols[k] = other;
+                                    cols[h2] = j;
+                                    ++h2;
+                                }
+                            }
+                        }
+                    } else {
+                        int* J = pos;   // J[q] = k_q - lo: where swap q sends the element of cell lo + q (pos is rebuilt in (5))
+                        for (int cc = BMB_WARP; cc < C; cc += BMB_NW) {
+                            const unsigned em = emask[cc];
+                            if ((em >> lane) & 1u)
+                                J[off + erank[cc] + BMB_POPC(em & ((1u << lane) - 1u))] = base + cc * BMB_NL + lane - lo;
+                        }
+                        if (off && BMB_TID == 0) J[0] = 0;
+                        BMB_SYNC();
+                        int rounds = 1;
+                        while ((1 << rounds) < H) ++rounds;
+                        for (int r = 0; r <= rounds; ++r) {   // pointer jumping: first iterate >= H (in place: any value
+                            for (int q = BMB_TID; q < H; q += BMB_NT) {   // read is an iterate of its cell)
+                                const int t = J[q];
+                                if (t < H) J[q] = J[t];
+                            }
+                            BMB_SYNC();
+                        }
+                        int val[JV_OWN], dst[JV_OWN];
+#pragma unroll
+                        for (int q = 0; q < JV_OWN; ++q) {
+                            const int P = lo + BMB_TID + q * BMB_NT;
+                            dst[q] = -1;
+#if !BMB_DEVICE
+                            if (P >= n) break;
+#endif
+                            if (P < n) {
+                                val[q] = cols[P];
+                                if (P == lo) {
+                                    if (off) dst[q] = lo; else if (H > 0) dst[q] = lo + J[0];
+                                } else {
+                                    const int cc = (P - base) / BMB_NL, b = (P - base) % BMB_NL;
+                                    const unsigned em = emask[cc];
+                                    if ((em >> b) & 1u) dst[q] = lo + off + erank[cc] + BMB_POPC(em & ((1u << b) - 1u));
+                                    else if (P - lo < H) dst[q] = lo + J[P - lo];
+                                }
+                            }
+                        }
+                        BMB_SYNC();
+#pragma unroll
+                        for (int q = 0; q < JV_OWN; ++q) {
+#if !BMB_DEVICE
+                            if (lo + BMB_TID + q * BMB_NT >= n) break;
+#endif
+                            if (dst[q] >= 0) cols[dst[q]] = val[q];
+                        }
+                    }
+                    if (BMB_TID == 0) { mbx[0] = lo + H; mbx[1] = -1; }
+                } else
                 // (4) the swaps are sequential by nature: one thread replays the hits in position order
                 if (BMB_TID == 0) {
                     int h2 = lo + 1;
@@ -421,6 +592,24 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
             }
             // ---- _scan_dense over the ready band: register arithmetic and one barrier per band column ----
             while (lo != hi && final_j == -1) {
+                if (skip_noop && start_zr) {
+                    // walk over no-op band columns: zero-padding owner, distance never improved (h == 0.0 exactly).
+                    // Every warp does the same walk on its own; nothing is written, later steps only write open columns.
+                    while (lo != hi) {
+                        const int k = lo + lane;
+                        bool stop = false;
+                        if (k < hi) {
+                            const int jb = cols[k];
+                            stop = !(y[jb] >= zrow && ((0.0 - v[jb]) - d[jb]) == 0.0);
+                        }
+                        const unsigned m = BMB_BALLOT(stop);
+                        if (m) { const int adv = BMB_FFS(m); lo += adv; n_skip += adv; break; }
+                        const int adv = hi - lo < BMB_NL ? hi - lo : BMB_NL;
+                        lo += adv;
+                        n_skip += adv;
+                    }
+                    if (lo == hi) break;
+                }
                 ++n_steps;
                 const int j = cols[lo++];
                 const int i = y[j];
@@ -467,7 +656,11 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                     imp &= imp - 1u;
                     const int jj = BMB_TID + q * BMB_NT;
                     pred[jj] = i;
-                    if ((hitq >> q) & 1u) { d[jj] = mind; any = 1; }
+                    if ((hitq >> q) & 1u) {
+                        d[jj] = mind;
+                        any = 1;
+                        if (hitlist) { const int sl = atomicAdd(&sh_nhit, 1); if (sl < JV_HITCAP) hitpos[sl] = pos[jj]; }
+                    }
                 }
 #else
                 for (int q = 0; q < JV_OWN; ++q) {
@@ -478,7 +671,11 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                         if (r < dq[q]) {
                             dq[q] = r;
                             pred[jj] = i;
-                            if (r == mind) { d[jj] = r; any = 1; }
+                            if (r == mind) {
+                                d[jj] = r;
+                                any = 1;
+                                if (hitlist) { const int sl = sh_nhit++; if (sl < JV_HITCAP) hitpos[sl] = pos[jj]; }
+                            }
                         }
                     }
                 }
@@ -488,6 +685,31 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                     c0 = BMB_CLOCK();
                     // the hits, in position order: open positions whose distance now equals the band minimum
                     const int hi0 = hi;
+                    const int nh = hitlist ? sh_nhit : JV_HITCAP + 1;   // reset by thread 0 after the next barrier
+                    if (nh <= JV_HITCAP) {
+                        if (BMB_TID == 0) {
+                            for (int a = 1; a < nh; ++a) {   // the list is short: insertion sort by position
+                                const int pa = hitpos[a];
+                                int b = a - 1;
+                                while (b >= 0 && hitpos[b] > pa) { hitpos[b + 1] = hitpos[b]; --b; }
+                                hitpos[b + 1] = pa;
+                            }
+                            int h2 = hi0, fj = -1;
+                            for (int a = 0; a < nh; ++a) {
+                                const int kq = hitpos[a];
+                                const int jq = cols[kq];
+                                if (y[jq] < 0) { fj = jq; break; }
+                                const int other = cols[h2];
+                                cols[kq] = other;
+                                pos[other] = kq;
+                                cols[h2] = jq;
+                                pos[jq] = h2;
+                                ++h2;
+                            }
+                            mbx[0] = h2;
+                            mbx[1] = fj;
+                        }
+                    } else {
                     int slot = BMB_WARP;
                     for (int k0 = hi0; k0 < n; k0 += BMB_NT, slot += BMB_NW) {
                         const int k = k0 + BMB_TID;
@@ -517,9 +739,11 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
                         mbx[0] = h2;
                         mbx[1] = fj;
                     }
+                    }
                     BMB_SYNC();
                     hi = mbx[0];
                     final_j = mbx[1];
+                    if (hitlist && BMB_TID == 0) sh_nhit = 0;   // everyone has read it; next push is after the barrier below
 #pragma unroll
                     for (int q = 0; q < JV_OWN; ++q) {
                         const int jj = BMB_TID + q * BMB_NT;
@@ -554,7 +778,98 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
         BMB_SYNC();
         c_edge += BMB_CLOCK() - c0;
     }
-    if (BMB_TID == 0) { s.timers[13] += n_steps; s.timers[11] += c_find; s.timers[14] += c_replay; s.timers[15] += c_edge; }
+    if (BMB_TID == 0) {
+        s.timers[13] += n_steps; s.timers[11] += c_find; s.timers[14] += c_replay; s.timers[15] += c_edge;
+        s.timers[7] += n_skip;
+    }
+}
+
+// CTA-wide augmenting row reduction (feature JV_F_ARRWIDE): the same sequential rounds as the one-warp loop in
+// jv_dense_solve, but the lexicographic two-smallest search of a round runs on every thread (the one-warp loop waits for
+// one dependent global load per 32 columns: 13 k cycles per round on the config-3 frames), per-warp results are merged
+// through shared memory by every thread alike (top-2 under the strict order (value, index) is associative), and thread 0
+// applies the round's writes between two barriers.
+struct JvTop2 { double a1, a2; int i1, i2; };
+BMB_FN bool jv_less(double va, int ia, double vb, int ib) {
+    if (ib < 0) return ia >= 0;
+    if (ia < 0) return false;
+    return va < vb || (va == vb && ia < ib);
+}
+BMB_FN JvTop2 jv_merge(const JvTop2& p, const JvTop2& q) {   // both sorted pairs; missing entries have index -1
+    JvTop2 r;
+    if (jv_less(p.a1, p.i1, q.a1, q.i1)) {
+        r.a1 = p.a1; r.i1 = p.i1;
+        if (jv_less(p.a2, p.i2, q.a1, q.i1)) { r.a2 = p.a2; r.i2 = p.i2; } else { r.a2 = q.a1; r.i2 = q.i1; }
+    } else {
+        r.a1 = q.a1; r.i1 = q.i1;
+        if (jv_less(q.a2, q.i2, p.a1, p.i1)) { r.a2 = q.a2; r.i2 = q.i2; } else { r.a2 = p.a1; r.i2 = p.i1; }
+    }
+    return r;
+}
+
+template <typename S>
+BMB_FN int jv_arr_wide(S& s, int n, int ld, int zrow, int n_free) {
+    int* x = s.lap_x; int* y = s.lap_y; double* v = s.lap_v; int* free_rows = s.lap_sc;
+    const double* c = s.cost;
+    const double BIG = 1.7976931348623157e308;
+    const int lane = BMB_LANE;
+#if BMB_DEVICE
+    __shared__ JvTop2 part[32];
+#else
+    static JvTop2 part[1];
+#endif
+    for (int pass = 0; pass < 2 && n_free > 0; ++pass) {
+        int cur = 0, kept = 0;
+        long long rounds = 0;
+        while (cur < n_free) {
+            ++rounds;
+            const int fi = free_rows[cur++];
+            const double* ci = c + (size_t)fi * ld;
+            const bool zr = fi >= zrow;
+            JvTop2 t;
+            t.a1 = BIG; t.a2 = BIG; t.i1 = -1; t.i2 = -1;
+            for (int j = BMB_TID; j < n; j += BMB_NT) {
+                const double r = (zr ? 0.0 : ci[j]) - v[j];
+                if (t.i1 < 0 || r < t.a1) { t.a2 = t.a1; t.i2 = t.i1; t.a1 = r; t.i1 = j; }
+                else if (t.i2 < 0 || r < t.a2) { t.a2 = r; t.i2 = j; }
+            }
+#if BMB_DEVICE
+            for (int o = 16; o > 0; o >>= 1) {
+                JvTop2 u;
+                u.a1 = __shfl_xor_sync(0xffffffffu, t.a1, o); u.a2 = __shfl_xor_sync(0xffffffffu, t.a2, o);
+                u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o); u.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+                t = jv_merge(t, u);
+            }
+#endif
+            if (lane == 0) part[BMB_WARP] = t;
+            BMB_SYNC();   // (1) per-warp results published; the prices read above are final for this round
+            t = part[0];
+            for (int w = 1; w < BMB_NW; ++w) t = jv_merge(t, part[w]);
+            int j1 = t.i1;
+            const int j2 = t.i2;
+            const double v1 = t.a1, v2 = (j2 >= 0) ? t.a2 : BIG;
+            int i0 = y[j1];
+            const int y2 = j2 >= 0 ? y[j2] : -1;
+            const double vj1 = v[j1];
+            const double lowered = vj1 - (v2 - v1);
+            const int moves = lowered < vj1;
+            BMB_SYNC();   // (2) everyone has read y / v of this round before thread 0 rewrites them
+            if (rounds < (long long)cur * n) {
+                if (moves) { if (BMB_TID == 0) v[j1] = lowered; }
+                else if (i0 >= 0 && j2 >= 0) { j1 = j2; i0 = y2; }
+                if (i0 >= 0) {
+                    if (moves) { --cur; if (BMB_TID == 0) free_rows[cur] = i0; }
+                    else { if (BMB_TID == 0) free_rows[kept] = i0; ++kept; }
+                }
+            } else {
+                if (i0 >= 0) { if (BMB_TID == 0) free_rows[kept] = i0; ++kept; }
+            }
+            if (BMB_TID == 0) { x[fi] = j1; y[j1] = fi; }
+            BMB_SYNC();   // (3) the round's writes are visible to the next round
+        }
+        n_free = kept;
+    }
+    return n_free;
 }
 
 // S provides: cost (n x n, leading dimension ld), lap_x, lap_y, lap_v, lap_spc (d), lap_path (pred),
@@ -565,9 +880,14 @@ BMB_FN void jv_augment_owned(S& s, int n, int ld, int zrow, int n_free, int* mbx
 template <typename S>
 BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide = 0) {
     if (n <= 0) return;
-    const bool wide_eff = wide && n >= 64;
+    // wide = mode | (feature bits << 2): mode 0 one warp, 1 CTA-wide over list positions, 2 column-owned, 3 column-owned
+    // with the shortcuts of `feat` (JV_F_*)
+    const int mode = wide & 3;
+    const int feat = mode == 3 ? (wide >> 2) : 0;
+    const bool wide_eff = mode && n >= 64;
     // column-owned variant: every thread keeps JV_OWN columns in registers, _find_dense holds JV_CHUNKS chunks
-    const bool owned_eff = wide_eff && wide == 2 && n <= JV_OWN * BMB_NT && n <= (JV_CHUNKS - 8) * BMB_NL;
+    const bool owned_eff = wide_eff && mode >= 2 && n <= JV_OWN * BMB_NT && n <= (JV_CHUNKS - 8) * BMB_NL;
+    const bool arr_wide = owned_eff && (feat & JV_F_ARRWIDE) != 0 && BMB_NW <= 32;
 #if BMB_DEVICE
     __shared__ int jv_mbx[2];
 #else
@@ -621,7 +941,7 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide 
         }
         tick(8);
         // ---- augmenting row reduction, two passes ----
-        for (int pass = 0; pass < 2 && n_free > 0; ++pass) {
+        for (int pass = 0; pass < 2 && n_free > 0 && !arr_wide; ++pass) {
             int cur = 0, kept = 0;
             long long rounds = 0;
             while (cur < n_free) {
@@ -678,8 +998,8 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide 
             }
             n_free = kept;
         }
-        tick(9);
-        if (lane == 0) { s.timers[12] += n_free; jv_mbx[0] = n_free; }
+        if (!arr_wide) tick(9);
+        if (lane == 0) { if (!arr_wide) s.timers[12] += n_free; jv_mbx[0] = n_free; }
         // ---- augmentation (one warp; the CTA-wide variant follows the barrier below) ----
         for (int f = 0; f < (wide_eff ? 0 : n_free); ++f) {
             const int start = free_rows[f];
@@ -815,9 +1135,17 @@ BMB_FN void jv_dense_solve(S& s, int n, int ld, int zrow = 0x7fffffff, int wide 
         if (!wide_eff) tick(10);
     }
     BMB_SYNC();
+    if (arr_wide) {
+        const long long t0 = BMB_CLOCK();
+        const int nf0 = jv_mbx[0];
+        BMB_SYNC();
+        const int nf = jv_arr_wide(s, n, ld, zrow, nf0);
+        if (BMB_TID == 0) { jv_mbx[0] = nf; s.timers[12] += nf; s.timers[9] += BMB_CLOCK() - t0; }
+        BMB_SYNC();
+    }
     if (wide_eff) {
         const long long t0 = BMB_CLOCK();
-        if (owned_eff) jv_augment_owned(s, n, ld, zrow, jv_mbx[0], jv_mbx);
+        if (owned_eff) jv_augment_owned(s, n, ld, zrow, jv_mbx[0], jv_mbx, feat);
         else jv_augment_wide(s, n, ld, zrow, jv_mbx[0], jv_mbx);
         if (BMB_TID == 0) s.timers[10] += BMB_CLOCK() - t0;
     }

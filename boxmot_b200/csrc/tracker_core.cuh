@@ -40,8 +40,10 @@
 #define BMB_DEVICE 1
 #define BMB_CLOCK() clock64()
 #define BMB_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define BMB_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #else
 #define BMB_ATOMIC_MAX(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
+#define BMB_ATOMIC_MIN(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
 #define BMB_CLOCK() 0ll
 #define BMB_FN static inline
 #define BMB_TID 0

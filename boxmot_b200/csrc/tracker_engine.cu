@@ -173,12 +173,15 @@ __global__ void __launch_bounds__(256) k_docs_embcost(const DocsCfg cfg, DocsStr
 // CTA-wide augmentation of the dense JV solver (jv_dense.cuh::jv_augment_wide): measured 4.2 s -> 0.65 s per frame
 // on the BASELINE config-3 shape (512 detections, 1 500 live tracks), identical results; the column-owned variant
 // (jv_augment_owned, mode 2) 0.53 s and is the default since its tracker-level GPU run (goldens + config-3 ids) went
-// green in round 2.  BOXMOT_B200_JV_WIDE=0/1/2 sets the initial value, boxmot_b200_jv_dense_mode() changes it
-// (parity tests run every variant).
+// green in round 2.  Mode 3 (the default) is mode 2 plus the two exact shortcuts described at jv_augment_owned
+// (no-op band columns walked over, parallel tail of _find_dense).  BOXMOT_B200_JV_WIDE=0/1/2/3 sets the initial
+// value, boxmot_b200_jv_dense_mode() changes it (parity tests run every variant).
+// 0..2: the older variants; 3: mode 3 with every shortcut; >= 4: raw `mode | feature bits << 2` (bisecting on hardware)
+static int jv_mode_value(int m) { return m < 0 ? 0 : (m == 3 ? (3 | (0xF << 2)) : (m > 63 ? 63 : m)); }
 static int& jv_wide_flag() {
     static int v = [] {
         const char* e = getenv("BOXMOT_B200_JV_WIDE");
-        return e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
+        return jv_mode_value(e ? atoi(e) : 3);
     }();
     return v;
 }
@@ -192,7 +195,7 @@ __host__ __device__ inline size_t jv_smem_bytes(int MX) {
 __global__ void __launch_bounds__(256) k_docs_frame(const DocsCfg cfg, DocsStream* streams, int jv_in_smem) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     DocsStream s = streams[blockIdx.x];
-    s.jv_wide = (jv_in_smem >> 1) & 3;
+    s.jv_wide = jv_in_smem >> 1;
     if (jv_in_smem & 1) {
         const int MX = cfg.cap_tracks > cfg.cap_dets ? cfg.cap_tracks : cfg.cap_dets;
         double* pd = reinterpret_cast<double*>(dyn_smem);
@@ -1054,7 +1057,7 @@ __global__ void __launch_bounds__(256) k_jv_only(DocsStream* streams, int n, int
     jv_dense_solve(s, n, ld, zrow, wide);
 }
 
-void set_jv_wide(int mode) { jv_wide_flag() = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+void set_jv_wide(int mode) { jv_wide_flag() = jv_mode_value(mode); }
 
 // lapjv(cost, extend_cost=True) on an (R, C) float64 host matrix with lapjv's own tie-breaking
 void standalone_jv(const double* cost, int R, int C, int* x, int* y) {

@@ -1,7 +1,8 @@
 """Phase clocks of the DeepOCSORT frame kernel on the BASELINE config-3 shape (512 detections / frame drawn from 2048
 objects in 4 cohorts): SM-clock cycles per phase of the last frame (0 dets+predict, 1 iou/appearance, 2 first
 assignment incl. solver, 3 updates, 4 second round, 5 misses+births, 6 emit; solver: 8 column reduction + transfer,
-9 row reduction, 10 augmentation, 12 free rows entering augmentation, 13 band columns scanned)."""
+9 row reduction, 10 augmentation (11 _find_dense, 14 hit replays, 15 init + prices + path inside it), 12 free rows entering
+augmentation, 13 band columns relaxed, 7 no-op band columns walked over (mode 3)).  BOXMOT_B200_JV_WIDE selects the solver variant."""
 import ctypes
 import sys
 import time

@@ -9,6 +9,7 @@
 
 #include "tracker_core.cuh"
 #include "tracker_layout.h"
+#include "cmc_ecc.cuh"
 
 using namespace bmb;
 
@@ -162,7 +163,7 @@ int docs_snapshot(DocsSim* h, int* ids, double* xs, double* Ps, int cap) {
     return n;
 }
 
-void docs_set_jv_wide(DocsSim* h, int wide) { h->s.jv_wide = wide; }
+void docs_set_jv_wide(DocsSim* h, int wide) { h->s.jv_wide = wide == 3 ? (3 | (0xF << 2)) : wide; }   // as Engine::set_jv_wide
 
 int docs_jv(DocsSim* h, const double* cost, int R, int C, int* x, int* y) {
     const int n = R > C ? R : C;
@@ -293,5 +294,19 @@ int ss_pyset_difference(SsSim* h, const int* a, int na, const unsigned char* in_
     const size_t stride = (size_t)8 * c.cap_tracks + 16;
     return pyset_difference(a, na, nb, [&](int key) { return flag[key] != 0; }, out, h->s.tmp_a, h->s.set_buf,
                             h->s.set_buf + stride, h->s.set_buf + 2 * stride, h->s.set_buf + 3 * stride);
+}
+
+// ---- camera-motion estimation (cmc_ecc.cuh) ---------------------------------------------------------------------
+// BaseCMC.preprocess on one BGR frame: out is rint(rows * scale) x rint(cols * scale) uint8
+void hostsim_cmc_prepare(const uint8_t* img, int rows, int cols, double scale, uint8_t* out, int h, int w) {
+    const double inv = 1.0 / scale;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) out[(size_t)y * w + x] = cmc_prepare_pixel(img, rows, cols, inv, y, x);
+}
+
+int hostsim_ecc(const uint8_t* T, const uint8_t* I, int h, int w, double eps, int max_iter, float* txy) {
+    double red[8];
+    txy[0] = txy[1] = 0.f;
+    return ecc_translation(T, I, h, w, eps, max_iter, red, txy);
 }
 }

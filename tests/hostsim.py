@@ -281,3 +281,29 @@ class HostSimStrongSort:
         covs = np.empty((cap, 8, 8))
         n = self.lib.ss_snapshot(self.h, ids.ctypes.data, means.ctypes.data, covs.ctypes.data, cap)
         return {int(ids[i]): (means[i].copy(), covs[i].copy()) for i in range(n)}
+
+
+# ---- camera-motion estimation (cmc_ecc.cuh) ------------------------------------------------------------------
+def cmc_prepare(img: np.ndarray, scale: float = 0.15) -> np.ndarray:
+    """BaseCMC.preprocess through the device source compiled for the host."""
+    lib = ctypes.CDLL(str(build()))
+    img = np.ascontiguousarray(img, np.uint8)
+    rows, cols = img.shape[:2]
+    h, w = int(np.rint(rows * scale)), int(np.rint(cols * scale))
+    out = np.empty((h, w), np.uint8)
+    lib.hostsim_cmc_prepare.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                        ctypes.c_int, ctypes.c_int]
+    lib.hostsim_cmc_prepare(img.ctypes.data, rows, cols, float(scale), out.ctypes.data, h, w)
+    return out
+
+
+def ecc_translation(template: np.ndarray, image: np.ndarray, eps: float = 1e-5, max_iter: int = 100):
+    """(status, tx, ty): ecc_translation() of cmc_ecc.cuh on two uint8 registration images."""
+    lib = ctypes.CDLL(str(build()))
+    t = np.ascontiguousarray(template, np.uint8)
+    i = np.ascontiguousarray(image, np.uint8)
+    txy = np.zeros(2, np.float32)
+    lib.hostsim_ecc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                ctypes.c_void_p]
+    st = lib.hostsim_ecc(t.ctypes.data, i.ctypes.data, t.shape[0], t.shape[1], float(eps), int(max_iter), txy.ctypes.data)
+    return st, txy[0], txy[1]

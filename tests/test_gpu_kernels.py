@@ -120,13 +120,15 @@ def test_iou_and_cosine_cost():
     np.testing.assert_allclose(out, embedding_cost(a, b), rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize("wide", [2, 1, 0])
+@pytest.mark.parametrize("wide", [3, 7, 11, 19, 35, 2, 1, 0])
 @pytest.mark.parametrize("seed,r,c", [(0, 1, 1), (1, 7, 30), (2, 33, 32), (3, 64, 64), (4, 65, 200), (5, 200, 65),
                                       (6, 130, 131), (7, 300, 300), (8, 97, 512), (9, 512, 97), (10, 40, 700)])
 def test_dense_jv_reproduces_lapjv_ties(seed, r, c, wide):
     """GPU dense Jonker-Volgenant vs the oracle's lapjv on tie-heavy matrices: identical x / y, i.e. identical
-    tie-breaking, which DeepOCSORT's birth order (ids) depends on.  Every augmentation variant: 2 = CTA-wide with
-    owned columns in registers, 1 = CTA-wide over list positions, 0 = one warp."""
+    tie-breaking, which DeepOCSORT's birth order (ids) depends on.  Every augmentation variant: 3 = column-owned with
+    every exact shortcut (the default), 7 / 11 / 19 / 35 = mode 3 with ONE shortcut (no-op band columns / parallel
+    _find_dense tail / hit list / CTA-wide row reduction: `3 | bit << 2`), 2 = CTA-wide with owned columns in registers,
+    1 = CTA-wide over list positions, 0 = one warp."""
     lib = _lib()
     assert lib.boxmot_b200_jv_dense_mode(wide) == 1
     try:
@@ -145,4 +147,4 @@ def test_dense_jv_reproduces_lapjv_ties(seed, r, c, wide):
             _, xo, yo = lapjv(cost, extend_cost=True)
             assert np.array_equal(x, xo) and np.array_equal(y, yo)
     finally:
-        lib.boxmot_b200_jv_dense_mode(1)
+        lib.boxmot_b200_jv_dense_mode(3)

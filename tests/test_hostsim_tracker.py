@@ -85,7 +85,7 @@ def test_hostsim_dense_jv_reproduces_lapjv_ties(seed):
     assert np.array_equal(x, xo) and np.array_equal(y, yo)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3, 7, 11, 19, 35])
 @pytest.mark.parametrize("seed", range(24))
 def test_hostsim_dense_jv_wide_augmentation_reproduces_lapjv_ties(seed, mode):
     """The CTA-wide augmentation (jv_augment_wide: relax every open position, then replay the band-minimum hits in
@@ -105,7 +105,7 @@ def test_hostsim_dense_jv_wide_augmentation_reproduces_lapjv_ties(seed, mode):
         assert np.array_equal(x, xo) and np.array_equal(y, yo)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3, 7, 11, 19, 35])
 @pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n][0] == "deepocsort"))
 def test_hostsim_deepocsort_golden_with_wide_augmentation(name, mode):
     kind, kwargs, make_frames, make_embs = CASES[name]
