@@ -152,6 +152,9 @@ int boxmot_b200_tracker_set_warp(BoxMOTB200Tracker* h, int stream, const double*
         as_engine(h)->set_warp(stream, warp2x3);
     });
 }
+int boxmot_b200_tracker_set_cmc(BoxMOTB200Tracker* h, const char* method) {
+    return guard([&] { as_engine(h)->set_cmc(method); });
+}
 int boxmot_b200_tracker_mark(BoxMOTB200Tracker* h, int which) {
     return guard([&] { as_engine(h)->mark_event(which); });
 }
@@ -212,8 +215,9 @@ BoxMOTBotSortHandle* boxmot_botsort_create(const BoxMOTBotSortConfig* c) {
     Engine* e = nullptr;
     guard([&] {
         if (!c) throw std::runtime_error("NULL config");
-        if (cmc_requested(c->cmc_method))
-            throw std::runtime_error("camera-motion compensation is out of scope for the B200 path: pass cmc_method=NULL");
+        if (cmc_requested(c->cmc_method) && strcmp(c->cmc_method, "ecc") != 0)
+            throw std::runtime_error("only the 'ecc' camera-motion estimator runs on the device: pass cmc_method=\"ecc\" or NULL "
+                                     "(warps of other estimators can be supplied through boxmot_b200_tracker_set_warp)");
         const int prep = preprocess_mode(c->reid_preprocess);
         BoxMOTB200TrackerConfig p{};
         p.tracker = BOXMOT_B200_TRACKER_BOTSORT;
@@ -238,6 +242,9 @@ BoxMOTBotSortHandle* boxmot_botsort_create(const BoxMOTBotSortConfig* c) {
         p.reid_model_path = c->reid_model_path;
         p.reid_preprocess = prep;
         e = new Engine(p);
+        if (cmc_requested(c->cmc_method)) {
+            try { e->set_cmc(c->cmc_method); } catch (...) { delete e; e = nullptr; throw; }
+        }
     });
     return reinterpret_cast<BoxMOTBotSortHandle*>(e);
 }
@@ -265,6 +272,13 @@ int boxmot_botsort_last_reid_postprocess_time_ms(BoxMOTBotSortHandle* h, double*
 // ---- standalone kernels ----------------------------------------------------------------------------------------
 int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y) {
     return guard([&] { standalone_jv(cost, rows, cols, x, y); });
+}
+int boxmot_b200_cmc_ecc(const uint8_t* prev_bgr, const uint8_t* cur_bgr, int rows, int cols, double scale, double eps,
+                        int max_iter, float* warp2x3, int* status, uint8_t* prepared) {
+    return guard([&] {
+        if (!prev_bgr || !cur_bgr || !warp2x3) throw std::runtime_error("NULL argument");
+        standalone_ecc(prev_bgr, cur_bgr, rows, cols, scale, eps, max_iter, warp2x3, status, prepared);
+    });
 }
 int boxmot_b200_jv_dense_mode(int cta_wide) {
     return guard([&] { set_jv_wide(cta_wide); });

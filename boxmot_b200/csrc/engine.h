@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <string>
@@ -71,6 +72,15 @@ struct Engine {
     float* d_embs = nullptr;
     double* d_warp = nullptr;      // [S][8] pending camera-motion warps (slot 6 = pending flag)
     bool warp_dirty = false;
+    // on-device camera-motion estimation (cmc_ecc.cuh): 0 = off (warps are supplied), 1 = the reference's ECC defaults
+    int cmc_mode = 0;
+    double cmc_scale = 0.15, cmc_eps = 1e-5;
+    int cmc_iters = 100;
+    int cmc_h = 0, cmc_w = 0;            // registration image size of the frames seen so far
+    uint8_t* d_cmc_prev = nullptr;       // [S][cmc_h * cmc_w] previous registration image per stream
+    uint8_t* d_cmc_cur = nullptr;
+    int* d_cmc_has_prev = nullptr;       // [S]
+    const int** d_cmc_gate = nullptr;    // [S] device pointers to the live-track count (StrongSORT) or null
     float* d_out = nullptr;
     int* d_scalars_out = nullptr;
     CropDesc* d_crops = nullptr;
@@ -133,6 +143,7 @@ struct Engine {
     int snapshot(int stream_index, int* ids, double* means, double* covs, int cap);
     int track_ids(int stream_index, int which, int* ids, int cap);
     void set_warp(int stream_index, const double* warp6);
+    void set_cmc(const char* method);   // "ecc" | "none" / "" / NULL
     void read_timers(int stream_index, long long* out16, bool reset);
     void set_profile(bool on);
     void profile_read(double* ms, int* launch_counts);  // REID_N_CLASSES + 1 entries (last = association)
@@ -143,6 +154,7 @@ struct Engine {
     void construct(const BoxMOTB200TrackerConfig& p);
     void release();
     void ensure_images(int rows, int cols, bool host_too);
+    void enqueue_cmc(const uint8_t* images_dev, int rows, int cols);
     void enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int rows, int cols, int max_dets_total);
     bool can_pipeline() const { return reid_stream != nullptr && !profile; }
     void enqueue_association(TrkStream* streams_dev, const float* embs_src);
@@ -159,6 +171,18 @@ void ss_build_crops(const SsCfg& cfg, SsStream* d_streams, int S, CropDesc* crop
 // unit detection rows -> gallery distances -> per-stream frame -> appearance / gallery update; returns launches
 int ss_enqueue_frame(const SsCfg& cfg, SsStream* d_streams, int S, cudaStream_t stream);
 int standalone_lsa(const double* cost, int R, int C, int* row_ind, int* col_ind);
+
+// ---- camera-motion estimation (cmc_kernels.cu) ---------------------------------------------------------------
+// dsize of cv2.resize(src, (0, 0), fx=scale, fy=scale): saturate_cast<int>(n * scale), round half to even
+inline void cmc_scaled_size(int rows, int cols, double scale, int* h, int* w) {
+    *h = (int)nearbyint(rows * scale);
+    *w = (int)nearbyint(cols * scale);
+}
+void cmc_enqueue_ecc(const uint8_t* images, size_t image_stride, int rows, int cols, int S, double scale, double eps,
+                     int max_iter, uint8_t* prev, uint8_t* cur, int* has_prev, const int* const* gate, double* warp,
+                     cudaStream_t st);
+void standalone_ecc(const uint8_t* prev_bgr, const uint8_t* cur_bgr, int rows, int cols, double scale, double eps,
+                    int max_iter, float* warp6, int* status, uint8_t* prepared_out);
 
 void standalone_jv(const double* cost, int R, int C, int* x, int* y);
 void set_jv_wide(int mode);   // dense-JV augmentation variant used by every later launch of this process

@@ -512,6 +512,7 @@ void Engine::release() {
         cudaFree(d_docs_alt); cudaFree(d_ss_alt);
     }
     if (reid) reid_free(reid);
+    cudaFree(d_cmc_prev); cudaFree(d_cmc_cur); cudaFree(d_cmc_has_prev); cudaFree(d_cmc_gate);
     cudaFree(d_warp); cudaFree(d_mem); cudaFree(d_dets); cudaFree(d_ndets); cudaFree(d_embs); cudaFree(d_out);
     cudaFree(d_scalars_out); cudaFree(d_streams); cudaFree(d_docs); cudaFree(d_ss); cudaFree(d_crops); cudaFree(d_ncrops); cudaFree(d_images);
     cudaFreeHost(h_dets); cudaFreeHost(h_ndets); cudaFreeHost(h_out); cudaFreeHost(h_scalars);
@@ -525,6 +526,7 @@ void Engine::release() {
 
 void Engine::reset() {
     if (reid_stream) CUDA_OK(cudaStreamSynchronize(reid_stream));
+    if (d_cmc_has_prev) CUDA_OK(cudaMemsetAsync(d_cmc_has_prev, 0, sizeof(int) * S, stream));   // ECC.prev_img = None
     if (is_docs || is_ss) {
         CUDA_OK(cudaStreamSynchronize(stream));
         for (int i = 0; i < S; ++i) CUDA_OK(cudaMemsetAsync(d_mem + stream_bytes * i, 0, persistent_bytes, stream));
@@ -552,6 +554,7 @@ void Engine::enqueue_frame(const float* embs_dev, const uint8_t* images_dev, int
     launches = 0;
     CUDA_OK(cudaEventRecord(ev[0], stream));
     ev_recorded = true;
+    if (cmc_mode) enqueue_cmc(images_dev, rows, cols);
     if (is_ss) {
         const size_t CD = cfg.cap_dets, F = cfg.feat_dim;
         if (!embs_dev) {
@@ -739,6 +742,46 @@ void Engine::enqueue_association(TrkStream* streams_dev, const float* embs_src) 
     }
 }
 
+// On-device camera-motion estimation: the reference's ECC estimator with its defaults (motion/cmc/ecc.py:23-31), used
+// by StrongSORT on every frame that starts with tracks (strongsort.py:67,83-86) and by BoT-SORT with cmc_method "ecc"
+// (botsort.py:78,116-117,142).  The estimated warp lands in d_warp like a supplied one and is consumed by the same frame.
+void Engine::set_cmc(const char* method) {
+    const bool off = !method || !method[0] || strcmp(method, "none") == 0 || strcmp(method, "None") == 0;
+    if (off) { cmc_mode = 0; return; }
+    if (strcmp(method, "ecc") != 0)
+        throw std::runtime_error(std::string("camera-motion method '") + method + "' is not built on the device (ecc, none); "
+                                 "sof / orb / sift warps can be supplied through set_warp");
+    if ((!is_ss && !is_docs && cfg.kind != KIND_XYWH) || is_docs)
+        throw std::runtime_error("on-device ECC applies to BoT-SORT and StrongSORT (ByteTrack has no CMC, DeepOCSORT's is sof)");
+    if (is_ss && !d_cmc_gate) {   // StrongSORT estimates only while tracks exist
+        std::vector<const int*> g(S);
+        for (int i = 0; i < S; ++i) g[i] = h_ss[i].scalars + SC_N_ACTIVE;
+        CUDA_OK(cudaMalloc(&d_cmc_gate, sizeof(const int*) * S));
+        CUDA_OK(cudaMemcpy(d_cmc_gate, g.data(), sizeof(const int*) * S, cudaMemcpyHostToDevice));
+    }
+    cmc_mode = 1;
+}
+
+void Engine::enqueue_cmc(const uint8_t* images_dev, int rows, int cols) {
+    if (!images_dev || rows <= 0 || cols <= 0) throw std::runtime_error("camera-motion estimation needs the frame");
+    int h, w;
+    cmc_scaled_size(rows, cols, cmc_scale, &h, &w);
+    if (h < 3 || w < 3) throw std::runtime_error("camera-motion estimation: frame too small for the registration scale");
+    if (h != cmc_h || w != cmc_w) {
+        CUDA_OK(cudaStreamSynchronize(stream));
+        cudaFree(d_cmc_prev); cudaFree(d_cmc_cur); d_cmc_prev = d_cmc_cur = nullptr;
+        CUDA_OK(cudaMalloc(&d_cmc_prev, (size_t)h * w * S));
+        CUDA_OK(cudaMalloc(&d_cmc_cur, (size_t)h * w * S));
+        if (!d_cmc_has_prev) CUDA_OK(cudaMalloc(&d_cmc_has_prev, sizeof(int) * S));
+        CUDA_OK(cudaMemsetAsync(d_cmc_has_prev, 0, sizeof(int) * S, stream));
+        cmc_h = h; cmc_w = w;
+    }
+    cmc_enqueue_ecc(images_dev, (size_t)rows * cols * 3, rows, cols, S, cmc_scale, cmc_eps, cmc_iters, d_cmc_prev, d_cmc_cur,
+                    d_cmc_has_prev, d_cmc_gate, d_warp, stream);
+    launches += 2;
+    warp_dirty = true;   // the estimate applies to this frame only
+}
+
 void Engine::set_warp(int sidx, const double* warp6) {
     if (sidx < 0 || sidx >= S) throw std::runtime_error("stream index out of range");
     if (!is_ss && !is_docs && cfg.kind != KIND_XYWH)
@@ -859,9 +902,11 @@ void Engine::update_batch(const float* const* dets, const int* det_rows, const f
                                     sizeof(float) * F * h_ndets[i], cudaMemcpyHostToDevice, stream));
     }
     const uint8_t* img_dev = nullptr;
-    if (cfg.with_reid && !have_embs) {
-        if (!reid) throw std::runtime_error("with_reid tracker needs embeddings or a ReID model");
-        if (!images || rows <= 0 || cols <= 0) throw std::runtime_error("ReID inside update() needs an image");
+    const bool reid_here = cfg.with_reid && !have_embs;
+    if (reid_here || cmc_mode) {
+        if (reid_here && !reid) throw std::runtime_error("with_reid tracker needs embeddings or a ReID model");
+        if (!images || rows <= 0 || cols <= 0)
+            throw std::runtime_error(reid_here ? "ReID inside update() needs an image" : "camera-motion estimation needs the frame");
         ensure_images(rows, cols, true);
         const size_t ib = (size_t)rows * cols * 3;
         for (int i = 0; i < S; ++i) {
@@ -899,7 +944,7 @@ void Engine::update_device(const float* dets_dev, const int* det_rows, const flo
         slot[i] = det_rows[i];
         total += det_rows[i];
     }
-    if (can_pipeline() && cfg.with_reid && !embs_dev && images_dev && !sync) {
+    if (can_pipeline() && cfg.with_reid && !embs_dev && images_dev && !sync && !cmc_mode) {
         // frame pipeline: crops + ReID of this frame on reid_stream (input set p), association on `stream` once the
         // embeddings are there; the ReID of the next frame overlaps this frame's association
         const int pp = pipe_parity;

@@ -197,3 +197,57 @@ def cohort_stream(n_objects=2048, cohorts=4, frames=10, hw=(1080, 1920), seed=3,
         dets.append(d)
         embs.append((e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32))
     return dets, embs
+
+
+def camera_pan_sequence(n_frames: int = 16, hw=(360, 640), n_objects: int = 24, seed: int = 5, max_step: float = 4.0,
+                        dim: int = 0):
+    """Moving-camera test input: a smooth textured canvas seen through a window that pans by a few whole
+    pixels per frame (plus per-frame sensor noise), and detections of objects that stand still on the canvas -- so they
+    move in the image by exactly the camera motion.  Pure numpy, seeded.  Returns (frames [H,W,3] uint8 BGR, dets (n,6)
+    float32 per frame, window offsets (n_frames, 2) int, embeddings per frame or None)."""
+    h, w = hw
+    rng = np.random.default_rng(seed)
+    margin = int(max_step * n_frames) + 8
+    H, W = h + 2 * margin, w + 2 * margin
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    canvas = np.zeros((H, W, 3), np.float32)
+    def smooth_field(cell):   # random grid of `cell`-pixel cells, bilinearly interpolated: smooth at the 0.15 scale
+        gh, gw = H // cell + 3, W // cell + 3
+        g = rng.random((gh, gw)).astype(np.float32)
+        fy, fx = yy / cell, xx / cell
+        y0, x0 = fy.astype(np.int64), fx.astype(np.int64)
+        ay, ax = fy - y0, fx - x0
+        return (g[y0, x0] * (1 - ay) * (1 - ax) + g[y0, x0 + 1] * (1 - ay) * ax
+                + g[y0 + 1, x0] * ay * (1 - ax) + g[y0 + 1, x0 + 1] * ay * ax)
+
+    for c in range(3):
+        canvas[..., c] = smooth_field(56) + 0.5 * smooth_field(28) + 0.08 * rng.random((H, W)).astype(np.float32)
+    canvas -= canvas.min()
+    canvas = canvas / canvas.max() * 215.0 + 20.0
+    ox, oy = float(margin), float(margin)
+    offs, frames, dets, embs = [], [], [], []
+    cx = rng.uniform(margin + 40, margin + w - 40, n_objects)
+    cy = rng.uniform(margin + 40, margin + h - 40, n_objects)
+    bw = rng.uniform(18, 46, n_objects)
+    bh = rng.uniform(36, 90, n_objects)
+    protos = np.abs(rng.normal(size=(n_objects, max(dim, 1)))).astype(np.float32)
+    vx, vy = rng.uniform(-max_step, max_step, 2)
+    for f in range(n_frames):
+        if f % 5 == 0:
+            vx, vy = rng.uniform(-max_step, max_step, 2)
+        ox = float(np.clip(ox + vx, 2, 2 * margin - 2))
+        oy = float(np.clip(oy + vy, 2, 2 * margin - 2))
+        ix, iy = int(round(ox)), int(round(oy))
+        offs.append((ix, iy))
+        win = canvas[iy:iy + h, ix:ix + w] + rng.normal(0.0, 1.5, (h, w, 3)).astype(np.float32)
+        frames.append(np.clip(np.rint(win), 0, 255).astype(np.uint8))
+        keep = rng.random(n_objects) > 0.1
+        x1 = cx - bw / 2 - ix + rng.normal(0, 0.4, n_objects)
+        y1 = cy - bh / 2 - iy + rng.normal(0, 0.4, n_objects)
+        d = np.stack([x1, y1, x1 + bw, y1 + bh, rng.uniform(0.55, 0.95, n_objects), np.zeros(n_objects)], 1)
+        vis = keep & (d[:, 0] > 0) & (d[:, 1] > 0) & (d[:, 2] < w) & (d[:, 3] < h)
+        dets.append(d[vis].astype(np.float32))
+        if dim:
+            e = np.maximum(protos[vis] + 0.3 * rng.normal(size=(int(vis.sum()), dim)).astype(np.float32), 0.0)
+            embs.append((e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32))
+    return frames, dets, np.asarray(offs), (embs if dim else None)

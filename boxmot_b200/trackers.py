@@ -286,6 +286,17 @@ class MultiStreamTracker:
         if not self.handle:
             raise B200Error(f"tracker create failed: {_lib.last_error(self.lib)}")
         self.frame_count = 0
+        self.cmc = None
+
+    def set_cmc(self, method: Optional[str]) -> None:
+        """Camera-motion ESTIMATION on the device from the frames passed to `update` (BoT-SORT, StrongSORT): "ecc" = the
+        reference's ECC estimator with its defaults (motion/cmc/ecc.py:23-108: translation model, eps 1e-5, 100 iterations,
+        gray image at scale 0.15), run where the reference runs it (botsort.py:142, strongsort.py:83-86); None / "none"
+        turns it off (warps are then supplied through `set_warp`)."""
+        m = None if method in (None, "", "none", "None") else str(method)
+        if not self.lib.boxmot_b200_tracker_set_cmc(self.handle, m.encode() if m else None):
+            raise B200Error(_lib.last_error(self.lib))
+        self.cmc = m
 
     def close(self):
         if getattr(self, "handle", None):
@@ -338,9 +349,10 @@ class MultiStreamTracker:
                 e_ptr[i] = e.ctypes.data
         i_ptr, ih, iw = None, 0, 0
         i_arr = []
-        if self.with_reid and e_ptr is None:
+        if (self.with_reid and e_ptr is None) or self.cmc:
             if imgs is None:
-                raise B200Error("BoT-SORT with_reid needs `embs` or frames (and a ReID blob) to embed detections")
+                raise B200Error("camera-motion estimation needs the frames" if self.cmc and not (self.with_reid and e_ptr is None)
+                                else "BoT-SORT with_reid needs `embs` or frames (and a ReID blob) to embed detections")
             i_ptr = (ctypes.c_void_p * S)()
             for i, im in enumerate(imgs):
                 im = np.ascontiguousarray(im, dtype=np.uint8)
@@ -576,8 +588,10 @@ class ByteTrack(_SingleStreamTracker):
 class BotSort(_SingleStreamTracker):
     """BoT-SORT on the GPU; arguments as boxmot/trackers/bbox/botsort/botsort.py:66-118.
 
-    `use_cmc` must be False: camera-motion estimation is OpenCV image registration outside this hot path
-    (SURVEY N6); the reference's parity and baseline runs disable it the same way."""
+    `use_cmc=True` with `cmc_method="ecc"` (the reference constructor's method) estimates the camera warp on the device
+    every frame from `img` (`MultiStreamTracker.set_cmc`); the other estimators (sof, orb, sift) are OpenCV
+    feature pipelines outside this path: pass `use_cmc=False` and, if you have their warp, `update(..., warp=)`.
+    `use_cmc` defaults to False here (the reference: True)."""
 
     _kind = "botsort"
 
@@ -588,8 +602,9 @@ class BotSort(_SingleStreamTracker):
                  with_reid: bool = True, second_match_thresh: float = 0.5,
                  unconfirmed_match_thresh: float = 0.7, unconfirmed_emb_scale: float = 2.0,
                  removed_stracks_buffer: int = 100, **kwargs: Any):
-        if use_cmc:
-            raise NotImplementedError("use_cmc=True: camera-motion compensation is out of scope (pass use_cmc=False)")
+        if use_cmc and cmc_method != "ecc":
+            raise NotImplementedError(f"use_cmc=True with cmc_method='{cmc_method}': only 'ecc' is estimated on the device "
+                                      "(pass use_cmc=False and supply the warp through update(..., warp=))")
         super().__init__(reid_model=reid_model if with_reid else None, track_high_thresh=track_high_thresh,
                          track_low_thresh=track_low_thresh, new_track_thresh=new_track_thresh,
                          track_buffer=track_buffer, match_thresh=match_thresh, proximity_thresh=proximity_thresh,
@@ -599,6 +614,8 @@ class BotSort(_SingleStreamTracker):
                          unconfirmed_match_thresh=unconfirmed_match_thresh,
                          unconfirmed_emb_scale=unconfirmed_emb_scale,
                          removed_stracks_buffer=removed_stracks_buffer, **kwargs)
+        if use_cmc:
+            self._engine.set_cmc("ecc")
 
 
 class DeepOcSort(_SingleStreamTracker):
@@ -648,17 +665,22 @@ class OcSort(_SingleStreamTracker):
 class StrongSort(_SingleStreamTracker):
     """StrongSORT on the GPU; arguments as boxmot/trackers/bbox/strongsort/strongsort.py:38-67 (`max_age` is the
     BaseTracker setting the reference forwards to its Tracker).  The reference estimates a camera warp with ECC on
-    every frame that has tracks; here the warp is an input (`update(..., warp=)`, identity when omitted) and
+    every frame that has tracks (strongsort.py:67,83-86): `cmc="ecc"` does the same on the device from `img`
+    (SURVEY 8f-3); with the default `cmc=None` the warp is an input (`update(..., warp=)`, identity when omitted).
     `camera_update` itself always runs, as in the reference."""
 
     _kind = "strongsort"
 
     def __init__(self, reid_model: Any = None, min_conf: float = 0.1, max_cos_dist: float = 0.2,
                  max_iou_dist: float = 0.7, n_init: int = 3, nn_budget: int = 100, mc_lambda: float = 0.98,
-                 ema_alpha: float = 0.9, **kwargs: Any):
+                 ema_alpha: float = 0.9, cmc: Optional[str] = None, **kwargs: Any):
+        if cmc not in (None, "", "none", "ecc"):
+            raise NotImplementedError(f"cmc='{cmc}': StrongSORT's estimator is 'ecc' (or None: supplied warps)")
         super().__init__(reid_model=reid_model, min_conf=min_conf, max_cos_dist=max_cos_dist,
                          max_iou_dist=max_iou_dist, n_init=n_init, nn_budget=nn_budget, mc_lambda=mc_lambda,
                          ema_alpha=ema_alpha, **kwargs)
+        if cmc == "ecc":
+            self._engine.set_cmc("ecc")
 
 
 def _flatten_yaml_defaults(node, acc=None):
@@ -707,23 +729,30 @@ def resolve_tracker_args(tracker_type, tracker_config=None, evolve_param_dict=No
         inspect.signature(_SingleStreamTracker.__init__).parameters) | {"cap_tracks", "cap_dets", "feat_dim"}
     accepted -= {"self", "params", "kwargs"}
     args = {k: v for k, v in args.items() if k in accepted}   # the reference's **kwargs swallows the rest
-    # Camera-motion estimation (motion/cmc/*, OpenCV) is outside the path: the reference's YAML defaults turn it on
-    # (botsort.yaml use_cmc: true / sof; DeepOCSORT and StrongSORT always), here the estimator is replaced by a warp
-    # the caller supplies through update(..., warp=).  Say so once instead of diverging silently.
-    wants_cmc = (kind == "botsort" and args.get("use_cmc", False)) or (kind == "deepocsort" and not args.get("cmc_off", False)) \
-        or kind == "strongsort"
+    # Camera-motion estimation: ECC runs on the device (StrongSORT always uses it in the reference; BoT-SORT when
+    # cmc_method is "ecc").  The feature-based estimators (sof -- botsort.yaml's and DeepOCSORT's default --, orb, sift) are
+    # OpenCV pipelines outside the path: there the estimator is replaced by a warp the caller supplies through
+    # update(..., warp=).  Say so once instead of diverging silently.
+    method = args.get("cmc_method", "ecc")
+    bot_ecc = kind == "botsort" and bool(args.get("use_cmc", False)) and method == "ecc"
+    wants_cmc = (kind == "botsort" and args.get("use_cmc", False) and not bot_ecc) or \
+        (kind == "deepocsort" and not args.get("cmc_off", False))
     if wants_cmc and not _CMC_WARNED.get(kind):
         import warnings
 
         _CMC_WARNED[kind] = True
         warnings.warn(f"boxmot_b200.create_tracker('{kind}'): the reference configuration runs camera-motion compensation "
-                      f"({args.get('cmc_method', 'sof' if kind != 'strongsort' else 'ecc')}); this library applies only a warp "
-                      "supplied through update(..., warp=) -- without one the tracker behaves as with CMC off", stacklevel=3)
+                      f"({method if kind == 'botsort' else 'sof'}); only 'ecc' is estimated on the device -- this tracker applies "
+                      "a warp supplied through update(..., warp=), without one it behaves as with CMC off", stacklevel=3)
     args.pop("cmc_method", None)
     if kind == "botsort":
-        args["use_cmc"] = False
+        args["use_cmc"] = bot_ecc
+        if bot_ecc:
+            args["cmc_method"] = "ecc"
     if kind == "deepocsort":
         args["cmc_off"] = True
+    if kind == "strongsort":
+        args.setdefault("cmc", "ecc")   # strongsort.py:67: always ECC
     args.pop("per_class", None)
     return kind, cls, args
 

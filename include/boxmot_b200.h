@@ -82,7 +82,7 @@ typedef struct BoxMOTBotSortConfig {
     float match_thresh;
     float proximity_thresh;
     float appearance_thresh;
-    const char* cmc_method; /* must be NULL, "" or "none": CMC estimation is out of scope */
+    const char* cmc_method; /* "ecc" runs on the device; NULL, "" or "none" = off (sof / orb / sift: supply the warp) */
     int frame_rate;
     int fuse_first_associate;
     int with_reid;
@@ -212,8 +212,15 @@ BOXMOT_B200_API int boxmot_b200_tracker_last_device_ms(BoxMOTB200Tracker* handle
  * (trackers/bbox/strongsort/sort/track.py:139-148; without a supplied warp it runs with the identity, as the
  * reference does whenever tracks exist); DeepOCSORT through KalmanBoxTracker.apply_affine_correction before the
  * predict step (trackers/bbox/deepocsort/deepocsort.py:189-206, 345-348; motion/kalman_filters/xysr.py:311-366).
- * Estimating the warp (motion/cmc/*) is out of scope. */
+ * A supplied warp is how the estimators that are not built on the device (sof, orb, sift) reach the trackers. */
 BOXMOT_B200_API int boxmot_b200_tracker_set_warp(BoxMOTB200Tracker* handle, int stream, const double* warp2x3);
+/* Camera-motion ESTIMATION on the device, every frame, from the frame passed to update: method "ecc" is
+ * the reference's ECC estimator with its defaults -- cv2.findTransformECC translation model, eps 1e-5, 100 iterations,
+ * gray registration image at scale 0.15 (boxmot/motion/cmc/ecc.py:23-108, base_cmc.py:29-60) -- as StrongSORT runs it on
+ * every frame that starts with tracks (trackers/bbox/strongsort/strongsort.py:67,83-86) and BoT-SORT with
+ * cmc_method="ecc" (trackers/bbox/botsort/botsort.py:78,116-117,142).  "none" / "" / NULL turns it off again.  The
+ * estimate replaces a warp supplied for the same frame.  BoT-SORT and StrongSORT handles only. */
+BOXMOT_B200_API int boxmot_b200_tracker_set_cmc(BoxMOTB200Tracker* handle, const char* method);
 /* Device timing on the handle's own CUDA stream: record mark 0 / mark 1 around a region, then read the elapsed
  * milliseconds (synchronises on mark 1). */
 BOXMOT_B200_API int boxmot_b200_tracker_mark(BoxMOTB200Tracker* handle, int which);
@@ -236,9 +243,17 @@ BOXMOT_B200_API int boxmot_b200_lap_solve(const double* cost, int rows, int cols
 /* lapjv(cost, extend_cost=True) (no cost limit, zero-padded to square) with lapjv's own tie-breaking -- the dense
  * Jonker-Volgenant solver DeepOCSORT's association needs for bit-exact ids. cost (rows, cols) float64 host. */
 BOXMOT_B200_API int boxmot_b200_jv_dense(const double* cost, int rows, int cols, int* x, int* y);
-/* Augmentation variant of the dense solver for this process: 2 = CTA-wide search with the columns owned by threads
- * (distances in registers), 1 = CTA-wide search over list positions, 0 = one-warp search; all reproduce lapjv's
- * results, the parity tests run every variant (env BOXMOT_B200_JV_WIDE sets the initial value). */
+/* ECC().apply(prev) followed by ECC().apply(cur) on two BGR frames (rows x cols x 3 uint8, host): the float32 2x3 warp
+ * the second call returns (row major), status 0 = estimated, 1 = OpenCV would have raised StsNoConv (identity, as
+ * ecc.py:69-79 returns); `prepared` (optional, rint(rows*scale) x rint(cols*scale) uint8) receives the registration
+ * image of `cur` (BaseCMC.preprocess). */
+BOXMOT_B200_API int boxmot_b200_cmc_ecc(const uint8_t* prev_bgr, const uint8_t* cur_bgr, int rows, int cols, double scale,
+                                        double eps, int max_iter, float* warp2x3, int* status, uint8_t* prepared);
+/* Augmentation variant of the dense solver for this process: 3 = column-owned CTA-wide search with the exact shortcuts
+ * (no-op band columns, parallel _find_dense tail, hit list, CTA-wide row reduction; the default), 2 = column-owned
+ * (distances in registers), 1 = CTA-wide search over list positions, 0 = one-warp search; values >= 4 are
+ * `3 | shortcut bits << 2` for bisecting.  All reproduce lapjv's results, the parity tests run every variant (env
+ * BOXMOT_B200_JV_WIDE sets the initial value). */
 BOXMOT_B200_API int boxmot_b200_jv_dense_mode(int cta_wide);
 /* scipy.optimize.linear_sum_assignment(cost) with scipy's own tie-breaking (StrongSORT's min_cost_matching,
  * trackers/bbox/strongsort/sort/linear_assignment.py:62): cost (rows, cols) float64 host -> min(rows, cols) pairs

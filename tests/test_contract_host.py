@@ -202,6 +202,9 @@ def test_create_tracker_call_chain_with_a_stub_engine(monkeypatch):
             self.with_reid, self.has_reid_model = kind != "bytetrack", reid_blob is not None
             made.append((kind, cap_tracks, cap_dets, feat_dim, reid_blob, params))
 
+        def set_cmc(self, method):
+            self.cmc = method
+
     monkeypatch.setattr(T, "MultiStreamTracker", Engine)
 
     class OnDevice:
@@ -229,7 +232,12 @@ def test_create_tracker_call_chain_with_a_stub_engine(monkeypatch):
     assert made[-2][5]["det_thresh"] == 0.5 and made[-2][5]["w_association_emb"] == 0.75      # deepocsort YAML values
     T.create_tracker("deepocsort", evolve_param_dict={"det_thresh": 0.4, "embedding_off": True}, reid_weights="never_loaded.pt")
     assert made[-1][5]["det_thresh"] == 0.4 and made[-1][5]["w_association_emb"] == 0.5     # constructor default now
-    T.create_tracker("strongsort", reid_model=Foreign())
+    t = T.create_tracker("strongsort", reid_model=Foreign())
     assert warmed == [1] and made[-1][4] is None
+    assert t._engine.cmc == "ecc"   # strongsort.py:67: the reference always estimates with ECC -> on the device here
+    t = T.create_tracker("botsort", evolve_param_dict={"use_cmc": True, "cmc_method": "ecc", "with_reid": False})
+    assert t._engine.cmc == "ecc"
+    with pytest.raises(NotImplementedError, match="only 'ecc'"):
+        T.BotSort(use_cmc=True, cmc_method="sof", with_reid=False)
     with pytest.raises(NotImplementedError, match="per_class"):
         T.create_tracker("bytetrack", per_class=True)
