@@ -63,10 +63,12 @@ def test_ecc_restatements_match_opencv_on_a_panning_camera():
         assert abs(tx - true[0]) < 0.08 and abs(ty - true[1]) < 0.08
 
 
-def test_ecc_non_convergence_is_reported_like_opencv():
-    rng = np.random.default_rng(9)
-    a = rng.integers(0, 256, (54, 96), dtype=np.uint8)
-    b = rng.integers(0, 256, (54, 96), dtype=np.uint8)
+@pytest.mark.parametrize("kind", ["constant", "inverted", "flipped"])
+def test_ecc_non_convergence_is_reported_like_opencv(kind):
+    """cv2 raises StsNoConv on a constant image (NaN correlation) and on anti-correlated images (lambda_d <= 0): the oracle
+    raises NoConvergence, the device source returns status 1."""
+    a = cmc.preprocess(camera_pan_sequence(1, hw=(360, 640), seed=5)[0][0])
+    b = {"constant": np.full_like(a, 128), "inverted": 255 - a, "flipped": a[::-1, ::-1].copy()}[kind]
     assert _cv2_ecc(a, b)[0] == 1
     with pytest.raises(cmc.NoConvergence):
         cmc.find_transform_ecc_translation(a, b)

@@ -77,13 +77,15 @@ def test_device_ecc_matches_opencv(hw, seed):
     assert worst < 1e-4
 
 
-def test_device_ecc_reports_non_convergence_as_identity():
-    rng = np.random.default_rng(2)
-    a = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
-    b = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
+@pytest.mark.parametrize("kind", ["constant", "inverted"])
+def test_device_ecc_reports_non_convergence_as_identity(kind):
+    """Both StsNoConv exits of cv::findTransformECC: a constant frame (zero variance -> NaN correlation) and the inverted
+    frame (anti-correlated -> lambda_d <= 0).  ECC.apply then returns the identity (ecc.py:69-79); so does the device."""
+    a = camera_pan_sequence(1, hw=(360, 640), seed=5)[0][0]
+    b = np.full_like(a, 128) if kind == "constant" else 255 - a
     ref = Cv2Ecc()
     ref.apply(a)
-    assert np.array_equal(ref.apply(b), np.eye(2, 3, dtype=np.float32))   # cv2 raises StsNoConv -> identity
+    assert np.array_equal(ref.apply(b), np.eye(2, 3, dtype=np.float32))   # cv2 raised StsNoConv
     st, got, _ = _device_ecc(a, b)
     assert st == 1 and np.array_equal(got, np.eye(2, 3, dtype=np.float32))
 
