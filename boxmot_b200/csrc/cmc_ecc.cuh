@@ -32,13 +32,15 @@ namespace bmb {
 #define BMB_F2I_RN(x) ((int)nearbyintf(x))
 #endif
 
-// source index and 11-bit weights of cv2.resize(INTER_LINEAR) on uint8 (oracle/cmc.py::_coeffs)
-BMB_FN void cmc_coeff(int d, int src_n, double inv_scale, int& idx, int& a0, int& a1) {
+// source index and 11-bit weights of cv2.resize(INTER_LINEAR) on uint8 (oracle/cmc.py::_coeffs).  OpenCV resets the
+// weights at the image border only along x (`clamp`); along y both taps keep their weights and the ROW INDICES are clipped
+// (it matters when rint(rows * scale) rounds up and the last output row samples past the last input row).
+BMB_FN void cmc_coeff(int d, int src_n, double inv_scale, bool clamp, int& idx, int& a0, int& a1) {
     float f = (float)((d + 0.5) * inv_scale - 0.5);
     int s = (int)floorf(f);
     f = f - (float)s;
-    if (s < 0) { s = 0; f = 0.f; }
-    if (s >= src_n - 1) { s = src_n - 1; f = 0.f; }
+    if (clamp && s < 0) { s = 0; f = 0.f; }
+    if (clamp && s >= src_n - 1) { s = src_n - 1; f = 0.f; }
     idx = s;
     a0 = BMB_F2I_RN((1.0f - f) * 2048.0f);
     a1 = BMB_F2I_RN(f * 2048.0f);
@@ -51,11 +53,12 @@ BMB_FN int cmc_gray(const uint8_t* p) {   // BGR -> gray, cv2.cvtColor on uint8
 // one pixel of preprocess(): gray of the four source pixels, horizontal then vertical fixed-point blend
 BMB_FN uint8_t cmc_prepare_pixel(const uint8_t* img, int rows, int cols, double inv_scale, int dy, int dx) {
     int xi, xa0, xa1, yi, ya0, ya1;
-    cmc_coeff(dx, cols, inv_scale, xi, xa0, xa1);
-    cmc_coeff(dy, rows, inv_scale, yi, ya0, ya1);
+    cmc_coeff(dx, cols, inv_scale, true, xi, xa0, xa1);
+    cmc_coeff(dy, rows, inv_scale, false, yi, ya0, ya1);
     const int x1 = xi + 1 < cols ? xi + 1 : cols - 1;
-    const int y1 = yi + 1 < rows ? yi + 1 : rows - 1;
-    const uint8_t* r0 = img + (size_t)yi * cols * 3;
+    const int y0 = yi < 0 ? 0 : (yi > rows - 1 ? rows - 1 : yi);
+    const int y1 = yi + 1 < 0 ? 0 : (yi + 1 > rows - 1 ? rows - 1 : yi + 1);
+    const uint8_t* r0 = img + (size_t)y0 * cols * 3;
     const uint8_t* r1 = img + (size_t)y1 * cols * 3;
     const int hor0 = cmc_gray(r0 + 3 * xi) * xa0 + cmc_gray(r0 + 3 * x1) * xa1;
     const int hor1 = cmc_gray(r1 + 3 * xi) * xa0 + cmc_gray(r1 + 3 * x1) * xa1;

@@ -31,8 +31,9 @@ def bgr2gray_u8(img: np.ndarray) -> np.ndarray:
     return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
 
 
-def _coeffs(dst_n: int, src_n: int, scale: float):
-    """Source index and 11-bit weights of cv2.resize(INTER_LINEAR) on uint8 for an explicit scale = 1 / fx."""
+def _coeffs(dst_n: int, src_n: int, scale: float, clamp: bool = True):
+    """Source index and 11-bit weights of cv2.resize(INTER_LINEAR) on uint8 for an explicit scale = 1 / fx.  OpenCV resets the
+    weights at the border only along x (`clamp`); along y the weights stay and the row indices are clipped."""
     idx = np.zeros(dst_n, np.int64)
     a0 = np.zeros(dst_n, np.int64)
     a1 = np.zeros(dst_n, np.int64)
@@ -40,9 +41,9 @@ def _coeffs(dst_n: int, src_n: int, scale: float):
         f = np.float32((d + 0.5) * scale - 0.5)
         s = int(np.floor(f))
         f = np.float32(f - np.float32(s))
-        if s < 0:
+        if clamp and s < 0:
             s, f = 0, np.float32(0)
-        if s >= src_n - 1:
+        if clamp and s >= src_n - 1:
             s, f = src_n - 1, np.float32(0)
         idx[d] = s
         a0[d] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
@@ -61,12 +62,13 @@ def resize_gray_u8(src: np.ndarray, scale: float) -> np.ndarray:
     dh, dw = scaled_size(sh, sw, scale)
     inv = 1.0 / scale
     xi, xa0, xa1 = _coeffs(dw, sw, inv)
-    yi, ya0, ya1 = _coeffs(dh, sh, inv)
+    yi, ya0, ya1 = _coeffs(dh, sh, inv, clamp=False)
     s = src.astype(np.int64)
     x1 = np.minimum(xi + 1, sw - 1)
     hor = s[:, xi] * xa0[None, :] + s[:, x1] * xa1[None, :]
-    y1 = np.minimum(yi + 1, sh - 1)
-    out = (((ya0[:, None] * (hor[yi] >> 4)) >> 16) + ((ya1[:, None] * (hor[y1] >> 4)) >> 16) + 2) >> 2
+    y0 = np.clip(yi, 0, sh - 1)
+    y1 = np.clip(yi + 1, 0, sh - 1)
+    out = (((ya0[:, None] * (hor[y0] >> 4)) >> 16) + ((ya1[:, None] * (hor[y1] >> 4)) >> 16) + 2) >> 2
     return np.clip(out, 0, 255).astype(np.uint8)
 
 

@@ -23,10 +23,12 @@ def _cv2_ecc(prev, cur):
         return 1, np.float32(0), np.float32(0)
 
 
-@pytest.mark.parametrize("hw,scale", [((720, 1280), 0.15), ((1080, 1920), 0.15), ((719, 1277), 0.15), ((360, 640), 0.1),
+@pytest.mark.parametrize("hw,scale", [((720, 1280), 0.15), ((1080, 1920), 0.15), ((719, 1277), 0.15), ((360, 640), 0.1), ((377, 700), 0.15), ((597, 802), 0.15),
                                       ((333, 517), 0.15)])
 def test_preprocess_is_bit_exact_against_opencv(hw, scale):
-    """cvtColor(BGR2GRAY) + resize(fx, fy, INTER_LINEAR) on uint8: oracle and host-compiled device source == cv2."""
+    """cvtColor(BGR2GRAY) + resize(fx, fy, INTER_LINEAR) on uint8: oracle and host-compiled device source == cv2.  377 and 597
+    rows are sizes where rint(rows * 0.15) rounds up and the last output row samples past the last input row: OpenCV clips the
+    row indices there but keeps both weights (found by tests/tools/soak_cmc.py)."""
     img = np.random.default_rng(hw[0]).integers(0, 256, (*hw, 3), dtype=np.uint8)
     gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
     want = cv2.resize(gray, (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_LINEAR)

@@ -85,7 +85,8 @@ def case(seed, build=True):
             int(rng.integers(0, 3))
             return kind, kw, frames, embs, None, None
         sim = HostSimDeepOcSort(deepocsort_cfg(feat_dim=dim, **kw))
-        sim.set_jv_wide(int(rng.integers(0, 3)))
+        mode = int(rng.integers(0, 3))
+        sim.set_jv_wide(int(os.environ.get("SOAK_JV_MODE", mode)))   # SOAK_JV_MODE=3: the default variant with every shortcut
         return kind, kw, frames, embs, sim, DeepOcSortOracle(**kw)
     kw = dict(STRONGSORT_YAML, min_conf=float(rng.uniform(0.2, 0.6)), max_cos_dist=float(rng.uniform(0.2, 0.5)),
               n_init=int(rng.integers(1, 4)), nn_budget=int(rng.choice([5, 30, 100])), max_age=int(rng.integers(5, 35)),
